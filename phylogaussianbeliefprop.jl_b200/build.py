@@ -1,0 +1,69 @@
+"""Builds libpgbp_b200.so (CUDA, sm_100a) in-tree with nvcc.
+
+    python phylogaussianbeliefprop.jl_b200/build.py            # the product
+    python phylogaussianbeliefprop.jl_b200/build.py --emul     # host emulation of the kernel bodies,
+                                                               # used ONLY by CPU tests of the host logic
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+SOURCES = ["pgbp_plan.cu", "pgbp_batch.cu", "pgbp_message.cu", "pgbp_factors.cu"]
+HEADERS = ["pgbp_backend.h", "pgbp_internal.h", "pgbp_kernels.cuh", "pgbp_launch.h", "pgbp_shapes.h",
+           "pgbp_factors.cuh", os.path.join("..", "..", "include", "pgbp_b200.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("build failed: " + os.path.basename(cmd[-1]))
+    return r.stdout + r.stderr
+
+
+def build(emul=False, verbose=False, force=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(LIBDIR, "obj_emul" if emul else "obj")
+    os.makedirs(objdir, exist_ok=True)
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    lib = os.path.join(LIBDIR, "libpgbp_emul.so" if emul else "libpgbp_b200.so")
+    objs, jobs = [], []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(objdir, s + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [src] + hdrs):
+            if emul:
+                cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-DPGBP_HOST_EMUL", "-x", "c++", "-c", src, "-o", obj]
+            else:
+                cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            jobs.append(cmd)
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(4, len(jobs))) as ex:
+            for out in ex.map(_run, jobs):
+                if verbose:
+                    print(out)
+    if jobs or not os.path.exists(lib):
+        if emul:
+            _run(["g++", "-shared", "-o", lib] + objs)
+        else:
+            _run([NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib
+
+
+if __name__ == "__main__":
+    print(build(emul="--emul" in sys.argv, verbose="-v" in sys.argv, force="--force" in sys.argv))

@@ -1,0 +1,368 @@
+// Batch = device state of B independent replicas of one cluster graph.
+// HBM layout: structure-of-arrays, batch innermost.  Row k of an
+// array is `ld` doubles (ld = B rounded up to 32 elements = 256 bytes), so a
+// warp working on 32 consecutive elements reads one aligned 256-byte line per
+// slot.  A belief owns S(m) rows of packed-upper J, m rows of h, 1 row of g.
+#include <algorithm>
+
+#include "pgbp_launch.h"
+#include "pgbp_shapes.h"
+
+using namespace pgbp;
+
+namespace pgbp {
+
+template <class T>
+static int alloc(pgbp_batch* b, T** p, size_t n) {
+  void* v = nullptr;
+  PGBP_TRY(dev_malloc(&v, n * sizeof(T)));
+  *p = (T*)v;
+  b->device_bytes += (int64_t)(n * sizeof(T));
+  return 0;
+}
+
+int batch_need_scratch(pgbp_batch* b, size_t bytes) {
+  if (bytes <= b->scratch_bytes) return 0;
+  PGBP_TRY(stream_sync(b->stream));
+  dev_free(b->scratch);
+  b->device_bytes -= (int64_t)b->scratch_bytes;
+  b->scratch = nullptr;
+  b->scratch_bytes = 0;
+  void* v = nullptr;
+  PGBP_TRY(dev_malloc(&v, bytes));
+  b->scratch = (double*)v;
+  b->scratch_bytes = bytes;
+  b->device_bytes += (int64_t)bytes;
+  return 0;
+}
+
+static int need_slot_table(pgbp_batch* b, size_t n) {
+  if (n <= b->d_slot_len) return 0;
+  PGBP_TRY(stream_sync(b->stream));
+  dev_free(b->d_slot);
+  void* v = nullptr;
+  PGBP_TRY(dev_malloc(&v, n * sizeof(int32_t)));
+  b->d_slot = (int32_t*)v;
+  b->d_slot_len = n;
+  return 0;
+}
+
+int batch_upload_tables(pgbp_batch* b) {
+  const pgbp_plan* p = b->plan;
+  PGBP_TRY(stream_sync(b->stream));
+  dev_free(b->d_tab);
+  b->d_tab = nullptr;
+  void* v = nullptr;
+  PGBP_TRY(dev_malloc(&v, std::max<size_t>(1, p->tab.size()) * sizeof(int32_t)));
+  b->d_tab = (int32_t*)v;
+  PGBP_TRY(h2d(b->d_tab, p->tab.data(), p->tab.size() * sizeof(int32_t), b->stream));
+  return stream_sync(b->stream);
+}
+
+// ---- AoS <-> SoA transposes (32 x 32 shared-memory tiles) -----------------
+#ifndef PGBP_HOST_EMUL
+__global__ void k_aos_to_soa(const double* __restrict__ aos, int K, const int32_t* __restrict__ slot,
+                             double* __restrict__ soa, int64_t ld, int64_t B) {
+  __shared__ double tile[32][33];
+  const int64_t e0 = (int64_t)blockIdx.x * 32;
+  const int k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t e = e0 + r;
+    const int k = k0 + threadIdx.x;
+    if (e < B && k < K) tile[r][threadIdx.x] = aos[e * K + k];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r;
+    const int64_t e = e0 + threadIdx.x;
+    if (e < B && k < K) {
+      const int sl = slot ? slot[k] : k;
+      if (sl >= 0) soa[(int64_t)sl * ld + e] = tile[threadIdx.x][r];
+    }
+  }
+}
+__global__ void k_soa_to_aos(const double* __restrict__ soa, int64_t ld, const int32_t* __restrict__ slot,
+                             double* __restrict__ aos, int K, int64_t B) {
+  __shared__ double tile[32][33];
+  const int64_t e0 = (int64_t)blockIdx.x * 32;
+  const int k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r;
+    const int64_t e = e0 + threadIdx.x;
+    if (e < B && k < K) {
+      const int sl = slot ? slot[k] : k;
+      tile[r][threadIdx.x] = soa[(int64_t)sl * ld + e];
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t e = e0 + r;
+    const int k = k0 + threadIdx.x;
+    if (e < B && k < K) aos[e * K + k] = tile[threadIdx.x][r];
+  }
+}
+#endif
+
+int aos_to_soa(pgbp_batch* b, const double* d_aos, int K, const int32_t* d_slot, double* d_soa, int64_t ld) {
+  if (K <= 0) return 0;
+#ifdef PGBP_HOST_EMUL
+  for (int64_t e = 0; e < b->B; e++)
+    for (int k = 0; k < K; k++) {
+      const int sl = d_slot ? d_slot[k] : k;
+      if (sl >= 0) d_soa[(int64_t)sl * ld + e] = d_aos[e * K + k];
+    }
+#else
+  dim3 grid((unsigned)((b->B + 31) / 32), (unsigned)((K + 31) / 32));
+  k_aos_to_soa<<<grid, dim3(32, 8), 0, b->stream>>>(d_aos, K, d_slot, d_soa, ld, b->B);
+#endif
+  b->launches++;
+  return check_launch("k_aos_to_soa");
+}
+
+int soa_to_aos(pgbp_batch* b, const double* d_soa, int64_t ld, double* d_aos, int K, const int32_t* d_slot) {
+  if (K <= 0) return 0;
+#ifdef PGBP_HOST_EMUL
+  for (int64_t e = 0; e < b->B; e++)
+    for (int k = 0; k < K; k++) d_aos[e * K + k] = d_soa[(int64_t)(d_slot ? d_slot[k] : k) * ld + e];
+#else
+  dim3 grid((unsigned)((b->B + 31) / 32), (unsigned)((K + 31) / 32));
+  k_soa_to_aos<<<grid, dim3(32, 8), 0, b->stream>>>(d_soa, ld, d_slot, d_aos, K, b->B);
+#endif
+  b->launches++;
+  return check_launch("k_soa_to_aos");
+}
+
+// copy K host columns <-> device rows given by `slots` (host table)
+static int put_columns(pgbp_batch* b, const double* host, int K, const std::vector<int32_t>& slots, double* d_soa) {
+  if (K <= 0) return 0;
+  PGBP_TRY(batch_need_scratch(b, sizeof(double) * (size_t)b->B * K));
+  PGBP_TRY(need_slot_table(b, K));
+  PGBP_TRY(h2d(b->scratch, host, sizeof(double) * (size_t)b->B * K, b->stream));
+  PGBP_TRY(h2d(b->d_slot, slots.data(), sizeof(int32_t) * K, b->stream));
+  PGBP_TRY(aos_to_soa(b, b->scratch, K, b->d_slot, d_soa, b->ld));
+  return stream_sync(b->stream);  // `slots` may be a temporary
+}
+static int get_columns(pgbp_batch* b, double* host, int K, const std::vector<int32_t>& slots, const double* d_soa) {
+  if (K <= 0) return 0;
+  PGBP_TRY(batch_need_scratch(b, sizeof(double) * (size_t)b->B * K));
+  PGBP_TRY(need_slot_table(b, K));
+  PGBP_TRY(h2d(b->d_slot, slots.data(), sizeof(int32_t) * K, b->stream));
+  PGBP_TRY(soa_to_aos(b, d_soa, b->ld, b->scratch, K, b->d_slot));
+  PGBP_TRY(d2h(host, b->scratch, sizeof(double) * (size_t)b->B * K, b->stream));
+  return stream_sync(b->stream);
+}
+
+static void square_slots(int m, int64_t base, bool upper_only, std::vector<int32_t>* out) {
+  out->resize((size_t)m * m);
+  for (int c = 0; c < m; c++)
+    for (int r = 0; r < m; r++) {
+      int32_t v;
+      if (r <= c) v = (int32_t)(base + pk(r, c));
+      else v = upper_only ? -1 : (int32_t)(base + pk(c, r));
+      (*out)[(size_t)c * m + r] = v;
+    }
+}
+
+static int access_hJg(pgbp_batch* b, bool put, double* d_arr, int m, int64_t js, int64_t hs, int64_t gs,
+                      double* J, double* h, double* g) {
+  PGBP_TRY(set_device(b->device));
+  std::vector<int32_t> sl;
+  if (J && m > 0) {
+    square_slots(m, js, put, &sl);
+    PGBP_TRY(put ? put_columns(b, J, m * m, sl, d_arr) : get_columns(b, J, m * m, sl, d_arr));
+  }
+  if (h && m > 0) {
+    sl.resize(m);
+    for (int k = 0; k < m; k++) sl[k] = (int32_t)(hs + k);
+    PGBP_TRY(put ? put_columns(b, h, m, sl, d_arr) : get_columns(b, h, m, sl, d_arr));
+  }
+  if (g && gs >= 0) {
+    if (put) PGBP_TRY(h2d(d_arr + gs * b->ld, g, sizeof(double) * b->B, b->stream));
+    else PGBP_TRY(d2h(g, d_arr + gs * b->ld, sizeof(double) * b->B, b->stream));
+    PGBP_TRY(stream_sync(b->stream));
+  }
+  return 0;
+}
+
+}  // namespace pgbp
+
+extern "C" {
+
+int32_t pgbp_batch_create(const pgbp_plan* plan, int64_t B, int32_t device, uint32_t flags, pgbp_batch** out) {
+  if (!plan || !out || B <= 0) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
+  if (plan->nslots_state >= (int64_t)1 << 31) PGBP_FAIL(PGBP_EINVAL, "cluster graph too large for int32 slot tables");
+  PGBP_TRY(set_device(device));
+  std::unique_ptr<pgbp_batch> b(new pgbp_batch);
+  b->plan = plan;
+  b->B = B;
+  b->ld = (B + 31) / 32 * 32;
+  b->device = device;
+  b->flags = flags;
+#ifndef PGBP_HOST_EMUL
+  PGBP_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+  b->own_stream = true;
+#endif
+  const size_t ld = (size_t)b->ld;
+  PGBP_TRY(alloc(b.get(), &b->state, (size_t)plan->nslots_state * ld));
+  PGBP_TRY(dev_memset(b->state, 0, sizeof(double) * (size_t)plan->nslots_state * ld, b->stream));
+  if (flags & PGBP_BATCH_FACTORS) {
+    PGBP_TRY(alloc(b.get(), &b->factor, (size_t)plan->nslots_factor * ld));
+    PGBP_TRY(dev_memset(b->factor, 0, sizeof(double) * (size_t)plan->nslots_factor * ld, b->stream));
+  }
+  if (flags & PGBP_BATCH_RESIDUALS) {
+    const size_t nd = 2 * (size_t)plan->nsepsets;
+    PGBP_TRY(alloc(b.get(), &b->resid, std::max<size_t>(1, (size_t)plan->nslots_resid) * ld));
+    PGBP_TRY(dev_memset(b->resid, 0, sizeof(double) * std::max<size_t>(1, (size_t)plan->nslots_resid) * ld, b->stream));
+    PGBP_TRY(alloc(b.get(), &b->kldiv, std::max<size_t>(1, nd) * ld));
+    PGBP_TRY(alloc(b.get(), &b->calflag, std::max<size_t>(1, nd) * ld));
+    PGBP_TRY(alloc(b.get(), &b->done, ld));
+    PGBP_TRY(alloc(b.get(), &b->iscal, ld));
+    PGBP_TRY(alloc(b.get(), &b->itertree, 2 * ld));
+    PGBP_TRY(dev_memset(b->done, 0, ld, b->stream));
+    PGBP_TRY(dev_memset(b->iscal, 0, sizeof(int32_t) * ld, b->stream));
+    PGBP_TRY(dev_memset(b->itertree, 0, sizeof(int32_t) * 2 * ld, b->stream));
+  }
+  PGBP_TRY(alloc(b.get(), &b->status, ld));
+  PGBP_TRY(dev_memset(b->status, 0, sizeof(int32_t) * ld, b->stream));
+  PGBP_TRY(alloc(b.get(), &b->d_one, 1));
+  PGBP_TRY(batch_upload_tables(b.get()));
+  b->device_bytes += (int64_t)(plan->tab.size() * sizeof(int32_t));
+  b->d_msgs.assign(2 * plan->trees.size(), nullptr);
+  for (size_t t = 0; t < plan->trees.size(); t++)
+    for (int dir = 0; dir < 2; dir++) {
+      const Traversal& tv = plan->trees[t].trav[dir];
+      PGBP_TRY(alloc(b.get(), &b->d_msgs[2 * t + dir], std::max<size_t>(1, tv.msgs.size())));
+      PGBP_TRY(h2d(b->d_msgs[2 * t + dir], tv.msgs.data(), tv.msgs.size() * sizeof(MsgDesc), b->stream));
+    }
+  PGBP_TRY(stream_sync(b->stream));
+  *out = b.release();
+  if (flags & PGBP_BATCH_RESIDUALS) PGBP_TRY(pgbp_reset_calibration_flags(*out, 1));
+  return 0;
+}
+
+int32_t pgbp_batch_destroy(pgbp_batch* b) {
+  if (!b) return 0;
+  set_device(b->device);
+  stream_sync(b->stream);
+  dev_free(b->state); dev_free(b->factor); dev_free(b->resid); dev_free(b->kldiv);
+  dev_free(b->calflag); dev_free(b->done); dev_free(b->status); dev_free(b->iscal); dev_free(b->itertree);
+  dev_free(b->d_tab); dev_free(b->d_one); dev_free(b->scratch); dev_free(b->d_slot); free_tables(b);
+  for (auto* p : b->d_msgs) dev_free(p);
+#ifndef PGBP_HOST_EMUL
+  if (b->own_stream) cudaStreamDestroy(b->stream);
+#endif
+  delete b;
+  return 0;
+}
+
+int32_t pgbp_batch_set_stream(pgbp_batch* b, void* s) {
+  if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
+  PGBP_TRY(stream_sync(b->stream));
+#ifndef PGBP_HOST_EMUL
+  if (b->own_stream) cudaStreamDestroy(b->stream);
+  b->stream = (cudaStream_t)s;
+#endif
+  b->own_stream = false;
+  return 0;
+}
+
+int32_t pgbp_batch_synchronize(pgbp_batch* b) {
+  if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
+  return stream_sync(b->stream);
+}
+int64_t pgbp_batch_size(const pgbp_batch* b) { return b ? b->B : 0; }
+int64_t pgbp_batch_device_bytes(const pgbp_batch* b) { return b ? b->device_bytes : 0; }
+int64_t pgbp_batch_launch_count(pgbp_batch* b, int32_t reset) {
+  if (!b) return 0;
+  const int64_t n = b->launches;
+  if (reset) b->launches = 0;
+  return n;
+}
+
+int32_t pgbp_set_belief(pgbp_batch* b, int32_t i, const double* J, const double* h, const double* g) {
+  if (!b || i < 0 || i >= b->plan->nbeliefs) PGBP_FAIL(PGBP_EINVAL, "bad batch / belief index");
+  const pgbp_plan* p = b->plan;
+  return access_hJg(b, true, b->state, p->dim[i], p->jslot[i], p->hslot[i], p->gslot[i], (double*)J, (double*)h, (double*)g);
+}
+int32_t pgbp_get_belief(pgbp_batch* b, int32_t i, double* J, double* h, double* g) {
+  if (!b || i < 0 || i >= b->plan->nbeliefs) PGBP_FAIL(PGBP_EINVAL, "bad batch / belief index");
+  const pgbp_plan* p = b->plan;
+  return access_hJg(b, false, b->state, p->dim[i], p->jslot[i], p->hslot[i], p->gslot[i], J, h, g);
+}
+int32_t pgbp_get_factor(pgbp_batch* b, int32_t i, double* J, double* h, double* g) {
+  if (!b || i < 0 || i >= b->plan->nclusters) PGBP_FAIL(PGBP_EINVAL, "bad batch / cluster index");
+  if (!b->factor) PGBP_FAIL(PGBP_ESTATE, "batch was created without PGBP_BATCH_FACTORS");
+  const pgbp_plan* p = b->plan;
+  return access_hJg(b, false, b->factor, p->dim[i], p->jslot[i], p->hslot[i], p->gslot[i], J, h, g);
+}
+int32_t pgbp_get_residual(pgbp_batch* b, int32_t j, int32_t to_cluster, double* dJ, double* dh, uint8_t* iscal_resid,
+                          double* kldiv) {
+  if (!b || j < 0 || j >= b->plan->nsepsets) PGBP_FAIL(PGBP_EINVAL, "bad batch / sepset index");
+  if (!b->resid) PGBP_FAIL(PGBP_ESTATE, "batch was created without PGBP_BATCH_RESIDUALS");
+  const pgbp_plan* p = b->plan;
+  int side;
+  if (to_cluster == p->sep_a[j]) side = 0;
+  else if (to_cluster == p->sep_b[j]) side = 1;
+  else PGBP_FAIL(PGBP_EINVAL, "cluster %d is not an end of sepset %d", to_cluster, j);
+  const int d = 2 * j + side;
+  PGBP_TRY(access_hJg(b, false, b->resid, p->dim[p->nclusters + j], p->rjslot[d], p->rhslot[d], -1, dJ, dh, nullptr));
+  if (iscal_resid) PGBP_TRY(d2h(iscal_resid, b->calflag + (int64_t)d * b->ld, (size_t)b->B, b->stream));
+  if (kldiv) PGBP_TRY(d2h(kldiv, b->kldiv + (int64_t)d * b->ld, sizeof(double) * (size_t)b->B, b->stream));
+  return stream_sync(b->stream);
+}
+int32_t pgbp_get_status(pgbp_batch* b, int32_t* status) {
+  if (!b || !status) PGBP_FAIL(PGBP_EINVAL, "null argument");
+  PGBP_TRY(set_device(b->device));
+  PGBP_TRY(d2h(status, b->status, sizeof(int32_t) * (size_t)b->B, b->stream));
+  return stream_sync(b->stream);
+}
+int32_t pgbp_clear_status(pgbp_batch* b) {
+  if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
+  PGBP_TRY(set_device(b->device));
+  return dev_memset(b->status, 0, sizeof(int32_t) * (size_t)b->ld, b->stream);
+}
+
+int32_t pgbp_reset_beliefs(pgbp_batch* b) {
+  if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
+  PGBP_TRY(set_device(b->device));
+  return dev_memset(b->state, 0, sizeof(double) * (size_t)b->plan->nslots_state * (size_t)b->ld, b->stream);
+}
+int32_t pgbp_factors_from_beliefs(pgbp_batch* b) {
+  if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
+  if (!b->factor) PGBP_FAIL(PGBP_ESTATE, "batch was created without PGBP_BATCH_FACTORS");
+  PGBP_TRY(set_device(b->device));
+  return d2d(b->factor, b->state, sizeof(double) * (size_t)b->plan->nslots_factor * (size_t)b->ld, b->stream);
+}
+int32_t pgbp_reset_from_factors(pgbp_batch* b) {
+  if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
+  if (!b->factor) PGBP_FAIL(PGBP_ESTATE, "batch was created without PGBP_BATCH_FACTORS");
+  PGBP_TRY(set_device(b->device));
+  const pgbp_plan* p = b->plan;
+  const size_t ld = (size_t)b->ld;
+  PGBP_TRY(d2d(b->state, b->factor, sizeof(double) * (size_t)p->nslots_factor * ld, b->stream));
+  return dev_memset(b->state + (size_t)p->nslots_factor * ld, 0,
+                    sizeof(double) * (size_t)(p->nslots_state - p->nslots_factor) * ld, b->stream);
+}
+int32_t pgbp_reset_calibration_flags(pgbp_batch* b, int32_t reset_kl) {
+  if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
+  if (!b->calflag) PGBP_FAIL(PGBP_ESTATE, "batch was created without PGBP_BATCH_RESIDUALS");
+  PGBP_TRY(set_device(b->device));
+  // empty messages are born calibrated and are never reset (src/beliefs.jl:919-922, 973-974)
+  const pgbp_plan* p = b->plan;
+  PGBP_TRY(dev_memset(b->calflag, 0, 2 * (size_t)p->nsepsets * (size_t)b->ld, b->stream));
+  for (int j = 0; j < p->nsepsets; j++)
+    if (p->dim[p->nclusters + j] == 0)
+      PGBP_TRY(dev_memset(b->calflag + (int64_t)2 * j * b->ld, 1, 2 * (size_t)b->ld, b->stream));
+  (void)reset_kl;
+  return 0;
+}
+
+int32_t pgbp_device_view(pgbp_batch* b, double** base, int64_t* ld, int64_t* nslots) {
+  if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
+  if (base) *base = b->state;
+  if (ld) *ld = b->ld;
+  if (nslots) *nslots = b->plan->nslots_state;
+  return 0;
+}
+
+}  // extern "C"

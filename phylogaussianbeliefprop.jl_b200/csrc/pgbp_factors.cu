@@ -1,0 +1,846 @@
+// K1 factor assignment, K4 factored energy, K5 regularisation.
+#include <algorithm>
+#include <set>
+
+#include "pgbp_factors.cuh"
+#include "pgbp_kernels.cuh"
+#include "pgbp_launch.h"
+
+using namespace pgbp;
+
+namespace pgbp {
+
+// --------------------------------------------------------------------------
+// generic launcher: body(e, y) for e < B, y < ny
+// --------------------------------------------------------------------------
+#ifndef PGBP_HOST_EMUL
+template <class F>
+__global__ void __launch_bounds__(128) k_generic(F f, int64_t B) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B) return;
+  f(e, (int)blockIdx.y);
+}
+#endif
+
+template <class F>
+static int launch_generic(pgbp_batch* b, const char* name, int64_t n, int ny, F f) {
+  if (ny <= 0 || n <= 0) return 0;
+#ifdef PGBP_HOST_EMUL
+  for (int y = 0; y < ny; y++)
+    for (int64_t e = 0; e < n; e++) f(e, y);
+  b->launches++;
+#else
+  for (int y0 = 0; y0 < ny; y0 += 65535) {
+    const int cnt = std::min(65535, ny - y0);
+    F g = f;
+    g.y0 = y0;
+    dim3 grid((unsigned)((n + 127) / 128), (unsigned)cnt);
+    k_generic<<<grid, 128, 0, b->stream>>>(g, n);
+    b->launches++;
+  }
+#endif
+  return check_launch(name);
+}
+
+// --------------------------------------------------------------------------
+// K1: per-parameter-set preparation
+// --------------------------------------------------------------------------
+struct ThetaPrep {
+  const double* params;  // AoS [np][nc*p*p + p + p*p]
+  double* theta;         // SoA [rows][ldp]
+  int64_t ldp;
+  ThetaRows tr;
+  int y0 = 0;
+  PGBP_HD void operator()(int64_t ip, int) const {
+    const int p = tr.p, nc = tr.nc, pp = p * p;
+    const double* src = params + ip * (int64_t)(nc * pp + p + pp);
+    double w[PGBP_MAX_TRAITS * PGBP_MAX_TRAITS], out[PGBP_MAX_TRAITS * PGBP_MAX_TRAITS];
+    double* th = theta + ip;
+    double kind = 0.0;
+    for (int c = 0; c < nc; c++) {
+      for (int k = 0; k < pp; k++) {
+        w[k] = src[c * pp + k];
+        th[(int64_t)(tr.R(c) + k) * ldp] = w[k];
+      }
+      double ld;
+      const int info = spd_inverse_logdet(w, out, p, &ld);
+      if (info) kind = -(double)info;
+      for (int k = 0; k < pp; k++) th[(int64_t)(tr.P(c) + k) * ldp] = out[k];
+      th[(int64_t)tr.g0(c) * ldp] = -0.5 * (p * PGBP_LOG2PI + ld);  // branch_logdet_variance
+    }
+    const double* mu = src + nc * pp;
+    const double* v = mu + p;
+    for (int k = 0; k < p; k++) th[(int64_t)(tr.mu() + k) * ldp] = mu[k];
+    bool allzero = true, anyinf = false;
+    for (int k = 0; k < pp; k++) if (v[k] != 0.0) allzero = false;
+    for (int k = 0; k < p; k++) if (v[k * p + k] == INFINITY) anyinf = true;
+    double rootg = 0.0;
+    for (int k = 0; k < pp; k++) out[k] = 0.0;
+    double rh[PGBP_MAX_TRAITS];
+    for (int k = 0; k < p; k++) rh[k] = 0.0;
+    if (kind >= 0.0) {
+      if (allzero) kind = 0.0;
+      else if (anyinf) kind = 2.0;
+      else {
+        kind = 1.0;
+        for (int k = 0; k < pp; k++) w[k] = v[k];
+        double ld;
+        const int info = spd_inverse_logdet(w, out, p, &ld);  // j = inv(v); logdet(j) = -ld
+        if (info) kind = -(double)info;
+        double quad = 0.0;
+        for (int r = 0; r < p; r++) {
+          double s = 0.0;
+          for (int c = 0; c < p; c++) s += out[c * p + r] * mu[c];
+          rh[r] = s;
+          quad += mu[r] * s;
+        }
+        rootg = 0.5 * (-p * PGBP_LOG2PI - ld - quad);  // src/evomodels/evomodels.jl:394
+      }
+    }
+    for (int k = 0; k < pp; k++) th[(int64_t)(tr.rootP() + k) * ldp] = out[k];
+    for (int k = 0; k < p; k++) th[(int64_t)(tr.rooth() + k) * ldp] = rh[k];
+    th[(int64_t)tr.rootg() * ldp] = rootg;
+    th[(int64_t)tr.kind() * ldp] = kind;
+  }
+};
+
+// K1 main: one thread = (cluster y, element e).  Zeroes the cluster, then adds
+// the factor of every node family assigned to it, in node order
+// (src/beliefs.jl:798-859), with evidence absorbed in closed form:
+//   phi_v = N(sum_a c_a x_a ; 0, j^-1),  c = (1, -gamma_1, ..),  fixed members
+//   contribute z = sum c_a y_a:  J_ab += c_a c_b j,  h_b -= c_b j z,
+//   g += g_v - z'jz/2   (absorbevidence!, src/beliefupdates.jl:210-231).
+struct AssignBody {
+  FamDev F;
+  const double* theta;
+  int64_t ldp;
+  const double* tip;  // SoA [ntips*p][ldd]
+  int64_t ldd;
+  double* state;
+  int32_t* status;
+  int64_t ld;
+  int64_t np, nd;
+  int pairing;
+  ThetaRows tr;
+  int y0 = 0;
+  PGBP_HD void operator()(int64_t e, int y) const {
+    const int c = y + y0;
+    const int p = F.p, pp = p * p;
+    int64_t ip, id;
+    if (pairing == PGBP_PAIR_PRODUCT) { ip = e / nd; id = e % nd; }
+    else { ip = np == 1 ? 0 : e; id = nd == 1 ? 0 : e; }
+    const double* th = theta + ip;
+    const double* td = tip + id;
+    double* st = state + e;
+    const int64_t js = F.cl_jslot[c], hs = F.cl_hslot[c], gs = F.cl_gslot[c];
+    const int m = F.cl_dim[c];
+    for (int q = 0; q < tri(m) + m; q++) st[(js + q) * ld] = 0.0;  // J then h are contiguous
+    double g = 0.0;
+    const double kind = th[(int64_t)tr.kind() * ldp];
+    if (kind < 0.0) {
+      if (c == 0) status_fail(status, e, PGBP_STATUS(0x7ffffd, (int)(-kind)));
+      st[gs * ld] = NAN;
+      return;
+    }
+    double j[PGBP_MAX_TRAITS * PGBP_MAX_TRAITS], w[PGBP_MAX_TRAITS * PGBP_MAX_TRAITS];
+    double z[PGBP_MAX_TRAITS], jz[PGBP_MAX_TRAITS];
+    for (int iv = F.clu_off[c]; iv < F.clu_off[c + 1]; iv++) {
+      const int v = F.clu_node[iv];
+      const int k0 = F.mem_off[v], nm = F.mem_off[v + 1] - k0;
+      if (nm == 1) {  // root family (src/beliefs.jl:803-807)
+        const int pos = F.mem_pos[k0];
+        if (pos < 0 || kind != 1.0) continue;  // fixed root, or improper prior: factor == 1
+        for (int cc = 0; cc < p; cc++) {
+          for (int r = 0; r <= cc; r++) st[(js + pk(pos + r, pos + cc)) * ld] += th[(int64_t)(tr.rootP() + cc * p + r) * ldp];
+          st[(hs + pos + cc) * ld] += th[(int64_t)(tr.rooth() + cc) * ldp];
+        }
+        g += th[(int64_t)tr.rootg() * ldp];
+        continue;
+      }
+      // precision block j and log-normaliser of the family
+      double gv;
+      bool samecolor = true;
+      for (int k = k0 + 2; k < k0 + nm; k++) if (F.mem_color[k] != F.mem_color[k0 + 1]) samecolor = false;
+      if (samecolor) {
+        const int col = F.mem_color[k0 + 1];
+        double t0 = 0.0;
+        if (nm == 2) t0 = F.mem_length[k0 + 1];
+        else for (int k = k0 + 1; k < k0 + nm; k++) t0 += F.mem_gamma[k] * F.mem_gamma[k] * F.mem_length[k];
+        for (int q = 0; q < pp; q++) j[q] = th[(int64_t)(tr.P(col) + q) * ldp] / t0;
+        gv = th[(int64_t)tr.g0(col) * ldp] - 0.5 * p * log(t0);
+      } else {  // heterogeneous hybrid: j = (sum gamma^2 t R_c)^-1 (src/evomodels/heterogeneousmodels.jl:135-150)
+        for (int q = 0; q < pp; q++) w[q] = 0.0;
+        for (int k = k0 + 1; k < k0 + nm; k++) {
+          const double f = F.mem_gamma[k] * F.mem_gamma[k] * F.mem_length[k];
+          const int col = F.mem_color[k];
+          for (int q = 0; q < pp; q++) w[q] += f * th[(int64_t)(tr.R(col) + q) * ldp];
+        }
+        double ldv;
+        const int info = spd_inverse_logdet(w, j, p, &ldv);
+        if (info) { status_fail(status, e, PGBP_STATUS(0x7ffffc, info)); st[gs * ld] = NAN; return; }
+        gv = -0.5 * (p * PGBP_LOG2PI + ldv);
+      }
+      // evidence: z = sum over fixed members of c_a * value_a
+      bool anyfixed = false;
+      for (int t = 0; t < p; t++) z[t] = 0.0;
+      for (int a = 0; a < nm; a++) {
+        if (F.mem_pos[k0 + a] >= 0) continue;
+        anyfixed = true;
+        const double ca = a == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + a]);
+        if (a == 0) {
+          const int row = F.node_datarow[v];
+          for (int t = 0; t < p; t++) z[t] += ca * td[(int64_t)(row * p + t) * ldd];
+        } else {
+          for (int t = 0; t < p; t++) z[t] += ca * th[(int64_t)(tr.mu() + t) * ldp];
+        }
+      }
+      if (anyfixed) {
+        double quad = 0.0;
+        for (int r = 0; r < p; r++) {
+          double s = 0.0;
+          for (int cc = 0; cc < p; cc++) s += j[cc * p + r] * z[cc];
+          jz[r] = s;
+          quad += z[r] * s;
+        }
+        gv -= 0.5 * quad;
+      }
+      g += gv;
+      for (int a = 0; a < nm; a++) {
+        const int pa = F.mem_pos[k0 + a];
+        if (pa < 0) continue;
+        const double ca = a == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + a]);
+        if (anyfixed)
+          for (int t = 0; t < p; t++) st[(hs + pa + t) * ld] -= ca * jz[t];
+        for (int bq = a; bq < nm; bq++) {
+          const int pb = F.mem_pos[k0 + bq];
+          if (pb < 0) continue;
+          const double cb = bq == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + bq]);
+          const double cab = ca * cb;
+          for (int tb = 0; tb < p; tb++)
+            for (int ta = 0; ta < (bq == a ? tb + 1 : p); ta++) {
+              const int r = pa + ta, cc = pb + tb;  // pa <= pb: member positions increase along the family
+              st[(js + (r <= cc ? pk(r, cc) : pk(cc, r))) * ld] += cab * j[tb * p + ta];
+            }
+        }
+      }
+    }
+    st[gs * ld] = g;
+  }
+};
+
+// --------------------------------------------------------------------------
+// K4: factored energy (src/score.jl:162-182)
+// --------------------------------------------------------------------------
+template <int MAXM>
+struct EnergyClusterBody {
+  const double* state;
+  const double* factor;
+  int32_t* status;
+  const int64_t* cl_jslot;
+  const int64_t* cl_hslot;
+  const int64_t* cl_gslot;
+  const int32_t* cl_dim;
+  const int32_t* list;  // clusters handled by this instantiation
+  double* part;         // [2*nclusters + nsepsets][ld]: energy_c, entropy_c, entropy_s
+  int nclusters;
+  int64_t ld;
+  int y0 = 0;
+  PGBP_HD void operator()(int64_t e, int y) const {
+    const int c = list[y + y0];
+    const int M = cl_dim[c];
+    const double* st = state + e;
+    const double* fa = factor + e;
+    const int64_t js = cl_jslot[c], hs = cl_hslot[c], gs = cl_gslot[c];
+    const double gf = fa[gs * ld];
+    if (M == 0) {  // src/score.jl:170-171
+      part[(int64_t)c * ld + e] = -gf;
+      part[(int64_t)(nclusters + c) * ld + e] = 0.0;
+      return;
+    }
+    constexpr int NA = MAXM * (MAXM + 1) / 2;
+    double A[NA], mu[MAXM], x[MAXM];
+    const int SM = tri(M);
+    for (int q = 0; q < SM; q++) A[q] = st[(js + q) * ld];
+    for (int k = 0; k < M; k++) mu[k] = st[(hs + k) * ld];
+    double logdet = 0.0;
+    for (int k = 0; k < M; k++) {  // U'U = J_b; forward solve w = U^-T h
+      const double d = A[pk(k, k)];
+      if (!(d > 0.0)) {
+        status_fail(status, e, PGBP_STATUS(0x7ffffb, k + 1));
+        part[(int64_t)c * ld + e] = NAN;
+        part[(int64_t)(nclusters + c) * ld + e] = NAN;
+        return;
+      }
+      logdet += log(d);
+      const double rinv = 1.0 / sqrt(d);
+      A[pk(k, k)] = rinv;  // store 1/U_kk
+      for (int cc = k + 1; cc < M; cc++) A[pk(k, cc)] *= rinv;
+      mu[k] *= rinv;
+      for (int cc = k + 1; cc < M; cc++) {
+        const double akc = A[pk(k, cc)];
+        for (int r = k + 1; r <= cc; r++) A[pk(r, cc)] -= A[pk(k, r)] * akc;
+        mu[cc] -= akc * mu[k];
+      }
+    }
+    for (int k = M - 1; k >= 0; k--) {  // U mu = w
+      double s = mu[k];
+      for (int cc = k + 1; cc < M; cc++) s -= A[pk(k, cc)] * mu[cc];
+      mu[k] = s * A[pk(k, k)];
+    }
+    // tr(J_b^-1 J_f) = sum_k |U^-T f_k|^2-weighted ... computed as sum_k e_k' U^-1 U^-T J_f e_k:
+    // for each column k of J_f solve U' x = f_k, U y = x, take y_k.
+    double trace = 0.0, quad = 0.0, hfmu = 0.0;
+    for (int k = 0; k < M; k++) {
+      double fk_mu = 0.0;
+      for (int r = 0; r < M; r++) {
+        const double f = fa[(js + (r <= k ? pk(r, k) : pk(k, r))) * ld];
+        x[r] = f;
+        fk_mu += f * mu[r];
+      }
+      quad += mu[k] * fk_mu;
+      for (int r = 0; r < M; r++) {  // U' x = f_k
+        double s = x[r];
+        for (int q = 0; q < r; q++) s -= A[pk(q, r)] * x[q];
+        x[r] = s * A[pk(r, r)];
+      }
+      for (int r = M - 1; r >= k; r--) {  // U y = x, only down to row k
+        double s = x[r];
+        for (int q = r + 1; q < M; q++) s -= A[pk(r, q)] * x[q];
+        x[r] = s * A[pk(r, r)];
+      }
+      trace += x[k];
+      hfmu += fa[(hs + k) * ld] * mu[k];
+    }
+    part[(int64_t)c * ld + e] = 0.5 * (trace + quad) - hfmu - gf;               // average_energy, :114-117
+    part[(int64_t)(nclusters + c) * ld + e] = 0.5 * (M * (PGBP_LOG2PI + 1.0) - logdet);  // entropy, :58-62
+  }
+};
+
+template <int MAXM>
+struct EntropySepsetBody {
+  const double* state;
+  const int64_t* jslot;  // per belief
+  const int32_t* dim;
+  const int32_t* list;
+  double* part;
+  int nclusters;
+  int64_t ld;
+  int y0 = 0;
+  PGBP_HD void operator()(int64_t e, int y) const {
+    const int j = list[y + y0];
+    const int M = dim[nclusters + j];
+    double* out = part + (int64_t)(2 * nclusters + j) * ld + e;
+    if (M == 0) { *out = 0.0; return; }
+    constexpr int NA = MAXM * (MAXM + 1) / 2;
+    double A[NA];
+    const double* st = state + e;
+    const int64_t js = jslot[nclusters + j];
+    for (int q = 0; q < tri(M); q++) A[q] = st[(js + q) * ld];
+    double logdet = 0.0;
+    for (int k = 0; k < M; k++) {
+      const double d = A[pk(k, k)];
+      if (!(d > 0.0)) {  // logdet(Symmetric(J)) of a singular / indefinite sepset (src/score.jl:66)
+        logdet = (d == 0.0) ? -INFINITY : NAN;
+        break;
+      }
+      logdet += log(d);
+      const double rinv = 1.0 / sqrt(d);
+      for (int cc = k + 1; cc < M; cc++) A[pk(k, cc)] *= rinv;
+      for (int cc = k + 1; cc < M; cc++) {
+        const double akc = A[pk(k, cc)];
+        for (int r = k + 1; r <= cc; r++) A[pk(r, cc)] -= A[pk(k, r)] * akc;
+      }
+    }
+    *out = 0.5 * (M * (PGBP_LOG2PI + 1.0) - logdet);
+  }
+};
+
+struct EnergyReduceBody {
+  const double* part;
+  double* out;  // SoA [3][ldo]
+  int nclusters, nsepsets;
+  int64_t ld, ldo;
+  int y0 = 0;
+  PGBP_HD void operator()(int64_t e, int) const {
+    double en = 0.0, ent = 0.0;
+    for (int c = 0; c < nclusters; c++) en += part[(int64_t)c * ld + e];
+    for (int c = 0; c < nclusters; c++) ent += part[(int64_t)(nclusters + c) * ld + e];
+    for (int j = 0; j < nsepsets; j++) ent -= part[(int64_t)(2 * nclusters + j) * ld + e];
+    out[e] = en;
+    out[ldo + e] = ent;
+    out[2 * ldo + e] = -(en - ent);  // factored_energy = -free_energy, src/score.jl:151-154
+  }
+};
+
+// --------------------------------------------------------------------------
+// K5: regularisation
+// --------------------------------------------------------------------------
+PGBP_HD double maxabs_packed(const double* st, int64_t js, int M, int64_t ld) {
+  double mx = 0.0;
+  for (int q = 0; q < tri(M); q++) absmax(mx, st[(js + q) * ld]);
+  return mx;
+}
+
+// by cluster, step A: eps_c = max(eps, max|J_c|) once, then bump the cluster's
+// diagonal once per incident sepset variable (src/clustergraphbeliefs.jl:240-249, 264-273)
+struct RegClusterBody {
+  double* state;
+  double* eps;  // [nclusters][ld]
+  const int64_t* jslot;
+  const int32_t* dim;
+  const int32_t* reg_off;
+  const int32_t* reg_pos;
+  int64_t ld;
+  double floor_eps;
+  int y0 = 0;
+  PGBP_HD void operator()(int64_t e, int y) const {
+    const int c = y + y0;
+    double* st = state + e;
+    const int64_t js = jslot[c];
+    double ep = maxabs_packed(st, js, dim[c], ld);
+    if (!(ep >= floor_eps)) ep = (ep != ep) ? ep : floor_eps;
+    eps[(int64_t)c * ld + e] = ep;
+    for (int k = reg_off[c]; k < reg_off[c + 1]; k++) {
+      const int u = reg_pos[k];
+      st[(js + pk(u, u)) * ld] += ep;
+    }
+  }
+};
+// by cluster, step B: sepset diagonal += eps of its two clusters, in cluster order
+struct RegSepsetBody {
+  double* state;
+  const double* eps;
+  const int64_t* jslot;
+  const int32_t* dim;
+  const int32_t* sep_a;
+  const int32_t* sep_b;
+  int nclusters;
+  int64_t ld;
+  int y0 = 0;
+  PGBP_HD void operator()(int64_t e, int y) const {
+    const int j = y + y0;
+    const int M = dim[nclusters + j];
+    if (M == 0) return;
+    const int a = sep_a[j] < sep_b[j] ? sep_a[j] : sep_b[j];
+    const int b2 = sep_a[j] < sep_b[j] ? sep_b[j] : sep_a[j];
+    const double e1 = eps[(int64_t)a * ld + e], e2 = eps[(int64_t)b2 * ld + e];
+    double* st = state + e;
+    const int64_t js = jslot[nclusters + j];
+    for (int k = 0; k < M; k++) {
+      double* d = st + (js + pk(k, k)) * ld;
+      *d = (*d + e1) + e2;
+    }
+  }
+};
+
+// on schedule: eps of one cluster (src/clustergraphbeliefs.jl:386)
+struct EpsOneBody {
+  const double* state;
+  double* eps;  // [ld]
+  int64_t js, ld;
+  int M;
+  double floor_eps;
+  int y0 = 0;
+  PGBP_HD void operator()(int64_t e, int) const {
+    double ep = maxabs_packed(state + e, js, M, ld);
+    if (!(ep >= floor_eps)) ep = (ep != ep) ? ep : floor_eps;
+    eps[e] = ep;
+  }
+};
+// regularizebeliefs_1clustersepset! with a per-element eps (:264-275)
+struct RegOneBody {
+  double* state;
+  const double* eps;
+  const int32_t* upind;  // device table: cluster positions of the sepset's variables
+  int64_t cjs, sjs, ld;
+  int S;
+  int y0 = 0;
+  PGBP_HD void operator()(int64_t e, int) const {
+    double* st = state + e;
+    const double ep = eps[e];
+    for (int k = 0; k < S; k++) {
+      const int u = upind[k];
+      st[(cjs + pk(u, u)) * ld] += ep;
+      st[(sjs + pk(k, k)) * ld] += ep;
+    }
+  }
+};
+
+// by node subtree: one launch per network node (src/clustergraphbeliefs.jl:314-340)
+struct RegNodeBody {
+  double* state;
+  const int64_t* jslot;
+  const int32_t* dim;
+  const int32_t *eps_cluster, *step_off, *step_cluster, *step_sepset, *idx_off, *idx_cluster, *idx_sepset;
+  int e0, e1, s0, s1;  // ranges of this node in eps_cluster / steps
+  int nclusters;
+  int64_t ld;
+  int y0 = 0;
+  PGBP_HD void operator()(int64_t e, int) const {
+    double* st = state + e;
+    double ep = PGBP_EPS;
+    for (int k = e0; k < e1; k++) {
+      const int c = eps_cluster[k];
+      const double m = maxabs_packed(st, jslot[c], dim[c], ld);
+      if (m > ep || m != m) ep = m;
+    }
+    for (int s = s0; s < s1; s++) {
+      const int64_t cj = jslot[step_cluster[s]], sj = jslot[nclusters + step_sepset[s]];
+      for (int k = idx_off[s]; k < idx_off[s + 1]; k++) {
+        const int uc = idx_cluster[k], us = idx_sepset[k];
+        st[(cj + pk(uc, uc)) * ld] += ep;
+        st[(sj + pk(us, us)) * ld] += ep;
+      }
+    }
+  }
+};
+
+// --------------------------------------------------------------------------
+// device copies of plan tables, built lazily per batch
+// --------------------------------------------------------------------------
+struct DevTables {
+  int64_t* jslot = nullptr;  // per belief
+  int64_t* hslot = nullptr;
+  int64_t* gslot = nullptr;
+  int32_t* dim = nullptr;
+  int32_t *sep_a = nullptr, *sep_b = nullptr;
+  int32_t *reg_off = nullptr, *reg_pos = nullptr;
+  // families
+  int32_t *node_cluster = nullptr, *mem_off = nullptr, *mem_pos = nullptr, *mem_color = nullptr,
+          *node_datarow = nullptr, *clu_off = nullptr, *clu_node = nullptr;
+  double *mem_length = nullptr, *mem_gamma = nullptr;
+  // parameter / data staging
+  double* theta = nullptr;
+  int64_t theta_rows = 0, ldp = 0;
+  double* tip = nullptr;
+  int64_t tip_rows = 0, ldd = 0;
+  std::vector<void*> owned;
+};
+
+template <class T>
+static int upload(pgbp_batch* b, DevTables* dt, T** dst, const std::vector<T>& src) {
+  void* v = nullptr;
+  PGBP_TRY(dev_malloc(&v, std::max<size_t>(1, src.size()) * sizeof(T)));
+  dt->owned.push_back(v);
+  *dst = (T*)v;
+  b->device_bytes += (int64_t)(src.size() * sizeof(T));
+  return h2d(v, src.data(), src.size() * sizeof(T), b->stream);
+}
+
+static int get_tables(pgbp_batch* b, DevTables** out) {
+  if (b->d_fam) { *out = (DevTables*)b->d_fam; return 0; }
+  const pgbp_plan* p = b->plan;
+  std::unique_ptr<DevTables> dt(new DevTables);
+  PGBP_TRY(upload(b, dt.get(), &dt->jslot, p->jslot));
+  PGBP_TRY(upload(b, dt.get(), &dt->hslot, p->hslot));
+  PGBP_TRY(upload(b, dt.get(), &dt->gslot, p->gslot));
+  PGBP_TRY(upload(b, dt.get(), &dt->dim, p->dim));
+  PGBP_TRY(upload(b, dt.get(), &dt->sep_a, p->sep_a));
+  PGBP_TRY(upload(b, dt.get(), &dt->sep_b, p->sep_b));
+  std::vector<int32_t> ro(1, 0), rp;
+  for (int c = 0; c < p->nclusters; c++) {
+    for (auto& nb : p->nbrs[c]) {  // neighbor_labels order
+      const int j = nb.second;
+      const std::vector<int32_t>& up = (p->sep_a[j] == c) ? p->up_a[j] : p->up_b[j];
+      rp.insert(rp.end(), up.begin(), up.end());
+    }
+    ro.push_back((int32_t)rp.size());
+  }
+  PGBP_TRY(upload(b, dt.get(), &dt->reg_off, ro));
+  PGBP_TRY(upload(b, dt.get(), &dt->reg_pos, rp));
+  if (p->has_families) {
+    const FamilyTable& F = p->fam;
+    PGBP_TRY(upload(b, dt.get(), &dt->node_cluster, F.node_cluster));
+    PGBP_TRY(upload(b, dt.get(), &dt->mem_off, F.mem_off));
+    PGBP_TRY(upload(b, dt.get(), &dt->mem_pos, F.mem_pos));
+    PGBP_TRY(upload(b, dt.get(), &dt->mem_color, F.mem_color));
+    PGBP_TRY(upload(b, dt.get(), &dt->node_datarow, F.node_datarow));
+    PGBP_TRY(upload(b, dt.get(), &dt->clu_off, F.clu_off));
+    PGBP_TRY(upload(b, dt.get(), &dt->clu_node, F.clu_node));
+    PGBP_TRY(upload(b, dt.get(), &dt->mem_length, F.mem_length));
+    PGBP_TRY(upload(b, dt.get(), &dt->mem_gamma, F.mem_gamma));
+  }
+  PGBP_TRY(stream_sync(b->stream));
+  b->d_fam = dt.release();
+  *out = (DevTables*)b->d_fam;
+  return 0;
+}
+
+void free_tables(pgbp_batch* b) {
+  DevTables* dt = (DevTables*)b->d_fam;
+  if (!dt) return;
+  for (void* v : dt->owned) dev_free(v);
+  dev_free(dt->theta);
+  dev_free(dt->tip);
+  delete dt;
+  b->d_fam = nullptr;
+}
+
+static int ensure_rows(pgbp_batch* b, double** arr, int64_t* rows_have, int64_t* ld_have, int64_t rows, int64_t n) {
+  const int64_t ld = (n + 31) / 32 * 32;
+  if (*arr && *rows_have >= rows && *ld_have == ld) return 0;
+  PGBP_TRY(stream_sync(b->stream));
+  dev_free(*arr);
+  void* v = nullptr;
+  PGBP_TRY(dev_malloc(&v, sizeof(double) * (size_t)rows * (size_t)ld));
+  *arr = (double*)v;
+  *rows_have = rows;
+  *ld_have = ld;
+  return 0;
+}
+
+template <int MAXM>
+static int launch_energy_bucket(pgbp_batch* b, DevTables* dt, const std::vector<int32_t>& cl, const std::vector<int32_t>& sp,
+                                double* part, int32_t* d_list) {
+  const pgbp_plan* p = b->plan;
+  if (!cl.empty()) {
+    PGBP_TRY(h2d(d_list, cl.data(), cl.size() * sizeof(int32_t), b->stream));
+    EnergyClusterBody<MAXM> body{b->state, b->factor, b->status, dt->jslot, dt->hslot, dt->gslot, dt->dim, d_list,
+                                 part, p->nclusters, b->ld};
+    PGBP_TRY(launch_generic(b, "k_energy_cluster", b->B, (int)cl.size(), body));
+  }
+  if (!sp.empty()) {
+    int32_t* d_list2 = d_list + p->nclusters;
+    PGBP_TRY(h2d(d_list2, sp.data(), sp.size() * sizeof(int32_t), b->stream));
+    EntropySepsetBody<MAXM> body{b->state, dt->jslot, dt->dim, d_list2, part, p->nclusters, b->ld};
+    PGBP_TRY(launch_generic(b, "k_entropy_sepset", b->B, (int)sp.size(), body));
+  }
+  return 0;
+}
+
+static int factored_energy_launch(pgbp_batch* b, double* d_out_soa, int64_t ldo) {
+  const pgbp_plan* p = b->plan;
+  if (!b->factor) PGBP_FAIL(PGBP_ESTATE, "batch was created without PGBP_BATCH_FACTORS");
+  DevTables* dt;
+  PGBP_TRY(get_tables(b, &dt));
+  const size_t nrows = 2 * (size_t)p->nclusters + p->nsepsets;
+  const size_t part_bytes = sizeof(double) * nrows * (size_t)b->ld;
+  const size_t list_bytes = sizeof(int32_t) * (size_t)(p->nclusters + p->nsepsets) * 4;
+  PGBP_TRY(batch_need_scratch(b, part_bytes + list_bytes + 3 * sizeof(double) * (size_t)b->ld));
+  double* part = b->scratch;
+  int32_t* d_list = (int32_t*)((char*)b->scratch + part_bytes);
+  // bucket clusters / sepsets by dimension so small ones use small local arrays
+  const int caps[4] = {4, 12, 32, PGBP_MAX_DIM};
+  std::vector<int32_t> cl[4], sp[4];
+  auto bucket = [&](int m) { for (int k = 0; k < 4; k++) if (m <= caps[k]) return k; return 3; };
+  for (int c = 0; c < p->nclusters; c++) cl[bucket(p->dim[c])].push_back(c);
+  for (int j = 0; j < p->nsepsets; j++) sp[bucket(p->dim[p->nclusters + j])].push_back(j);
+  const int stride = p->nclusters + p->nsepsets;
+  PGBP_TRY(launch_energy_bucket<4>(b, dt, cl[0], sp[0], part, d_list));
+  PGBP_TRY(launch_energy_bucket<12>(b, dt, cl[1], sp[1], part, d_list + stride));
+  PGBP_TRY(launch_energy_bucket<32>(b, dt, cl[2], sp[2], part, d_list + 2 * stride));
+  PGBP_TRY(launch_energy_bucket<PGBP_MAX_DIM>(b, dt, cl[3], sp[3], part, d_list + 3 * stride));
+  PGBP_TRY(stream_sync(b->stream));  // host lists are temporaries
+  EnergyReduceBody red{part, d_out_soa, p->nclusters, p->nsepsets, b->ld, ldo};
+  return launch_generic(b, "k_energy_reduce", b->B, 1, red);
+}
+
+}  // namespace pgbp
+
+extern "C" {
+
+int32_t pgbp_assign_factors(pgbp_batch* b, int32_t ncolors, const double* params, int64_t nparamsets,
+                            const double* tipdata, int64_t ndatasets, int32_t pairing) {
+  if (!b || !params) PGBP_FAIL(PGBP_EINVAL, "null argument");
+  const pgbp_plan* p = b->plan;
+  if (!p->has_families) PGBP_FAIL(PGBP_ESTATE, "the plan has no node-family table");
+  const FamilyTable& F = p->fam;
+  const int pt = p->ntraits;
+  if (pt > PGBP_MAX_TRAITS) PGBP_FAIL(PGBP_EINVAL, "ntraits %d > %d", pt, PGBP_MAX_TRAITS);
+  if (ncolors < F.ncolors_min) PGBP_FAIL(PGBP_EINVAL, "ncolors %d but the family table uses colour %d", ncolors, F.ncolors_min - 1);
+  if (F.ntips > 0 && !tipdata) PGBP_FAIL(PGBP_EINVAL, "null tip data");
+  const int64_t B = b->B;
+  if (pairing == PGBP_PAIR_PRODUCT) {
+    if (nparamsets * ndatasets != B) PGBP_FAIL(PGBP_EINVAL, "product pairing needs nparamsets*ndatasets == B");
+  } else if (pairing == PGBP_PAIR_ZIP) {
+    if ((nparamsets != 1 && nparamsets != B) || (ndatasets != 1 && ndatasets != B))
+      PGBP_FAIL(PGBP_EINVAL, "zip pairing needs nparamsets, ndatasets in {1, B}");
+  } else PGBP_FAIL(PGBP_EINVAL, "unknown pairing %d", pairing);
+  PGBP_TRY(set_device(b->device));
+  DevTables* dt;
+  PGBP_TRY(get_tables(b, &dt));
+  ThetaRows tr{pt, ncolors};
+  // parameters: upload AoS, prepare per-set tables
+  const int64_t plen = (int64_t)ncolors * pt * pt + pt + (int64_t)pt * pt;
+  PGBP_TRY(ensure_rows(b, &dt->theta, &dt->theta_rows, &dt->ldp, tr.nrows(), nparamsets));
+  const int64_t tiprows = (int64_t)F.ntips * pt;
+  PGBP_TRY(ensure_rows(b, &dt->tip, &dt->tip_rows, &dt->ldd, std::max<int64_t>(1, tiprows), ndatasets));
+  const size_t need = sizeof(double) * (size_t)std::max(plen * nparamsets, tiprows * ndatasets);
+  PGBP_TRY(batch_need_scratch(b, need));
+  PGBP_TRY(h2d(b->scratch, params, sizeof(double) * (size_t)(plen * nparamsets), b->stream));
+  ThetaPrep prep{b->scratch, dt->theta, dt->ldp, tr};
+  PGBP_TRY(launch_generic(b, "k_theta_prep", nparamsets, 1, prep));
+  if (tiprows > 0) {
+    // tip data AoS [nd][ntips*p] -> SoA [ntips*p][ldd]
+    PGBP_TRY(stream_sync(b->stream));
+    PGBP_TRY(h2d(b->scratch, tipdata, sizeof(double) * (size_t)(tiprows * ndatasets), b->stream));
+    const int64_t saveB = b->B;
+    b->B = ndatasets;  // transpose over the data-set axis
+    int rc = aos_to_soa(b, b->scratch, (int)tiprows, nullptr, dt->tip, dt->ldd);
+    b->B = saveB;
+    PGBP_TRY(rc);
+  }
+  FamDev fd{dt->node_cluster, dt->mem_off, dt->mem_pos, dt->mem_length, dt->mem_gamma, dt->mem_color,
+            dt->node_datarow, dt->clu_off, dt->clu_node, dt->jslot, dt->hslot, dt->gslot, dt->dim,
+            pt, ncolors, F.root_fixed};
+  AssignBody body{fd, dt->theta, dt->ldp, dt->tip, dt->ldd, b->state, b->status, b->ld, nparamsets, ndatasets, pairing, tr};
+  PGBP_TRY(launch_generic(b, "k_assign_factors", B, p->nclusters, body));
+  // sepsets <- 0 (src/beliefs.jl:796), factor snapshot (src/clustergraphbeliefs.jl:106)
+  PGBP_TRY(dev_memset(b->state + (size_t)p->nslots_factor * (size_t)b->ld, 0,
+                      sizeof(double) * (size_t)(p->nslots_state - p->nslots_factor) * (size_t)b->ld, b->stream));
+  if (b->factor) PGBP_TRY(d2d(b->factor, b->state, sizeof(double) * (size_t)p->nslots_factor * (size_t)b->ld, b->stream));
+  return stream_sync(b->stream);
+}
+
+int32_t pgbp_factored_energy_device(pgbp_batch* b, double* d_out_soa) {
+  if (!b || !d_out_soa) PGBP_FAIL(PGBP_EINVAL, "null argument");
+  PGBP_TRY(set_device(b->device));
+  return factored_energy_launch(b, d_out_soa, b->ld);
+}
+
+int32_t pgbp_factored_energy(pgbp_batch* b, double* out) {
+  if (!b || !out) PGBP_FAIL(PGBP_EINVAL, "null argument");
+  PGBP_TRY(set_device(b->device));
+  const pgbp_plan* p = b->plan;
+  // output rows live behind the partial sums in the scratch buffer
+  const size_t nrows = 2 * (size_t)p->nclusters + p->nsepsets;
+  const size_t part_bytes = sizeof(double) * nrows * (size_t)b->ld;
+  const size_t list_bytes = sizeof(int32_t) * (size_t)(p->nclusters + p->nsepsets) * 4;
+  const size_t off = (part_bytes + list_bytes + 7) / 8 * 8;
+  PGBP_TRY(batch_need_scratch(b, off + 6 * sizeof(double) * (size_t)b->ld));
+  double* d_soa = (double*)((char*)b->scratch + off);
+  PGBP_TRY(factored_energy_launch(b, d_soa, b->ld));
+  double* d_aos = d_soa + 3 * b->ld;
+  PGBP_TRY(soa_to_aos(b, d_soa, b->ld, d_aos, 3, nullptr));
+  PGBP_TRY(d2h(out, d_aos, sizeof(double) * 3 * (size_t)b->B, b->stream));
+  return stream_sync(b->stream);
+}
+
+int32_t pgbp_regularize_bycluster(pgbp_batch* b) {
+  if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
+  PGBP_TRY(set_device(b->device));
+  const pgbp_plan* p = b->plan;
+  DevTables* dt;
+  PGBP_TRY(get_tables(b, &dt));
+  PGBP_TRY(batch_need_scratch(b, sizeof(double) * (size_t)p->nclusters * (size_t)b->ld));
+  RegClusterBody a{b->state, b->scratch, dt->jslot, dt->dim, dt->reg_off, dt->reg_pos, b->ld, PGBP_EPS};
+  PGBP_TRY(launch_generic(b, "k_reg_cluster", b->B, p->nclusters, a));
+  RegSepsetBody s{b->state, b->scratch, dt->jslot, dt->dim, dt->sep_a, dt->sep_b, p->nclusters, b->ld};
+  return launch_generic(b, "k_reg_sepset", b->B, p->nsepsets, s);
+}
+
+int32_t pgbp_regularize_onschedule(pgbp_batch* b) {
+  if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
+  PGBP_TRY(set_device(b->device));
+  pgbp_plan* p = const_cast<pgbp_plan*>(b->plan);
+  DevTables* dt;
+  PGBP_TRY(get_tables(b, &dt));
+  // the op list of src/clustergraphbeliefs.jl:376-403
+  struct Op { int kind, c, j, nb; };
+  std::vector<Op> ops;
+  std::set<std::pair<int, int>> sent;  // (from, to)
+  std::vector<MsgDesc> msgs;
+  std::vector<int32_t> uptab;
+  std::vector<int32_t> upoff;
+  for (int c = 0; c < p->nclusters; c++) {
+    ops.push_back({0, c, 0, 0});
+    std::vector<Op> tosend;
+    for (auto& nbj : p->nbrs[c]) {
+      const int nb = nbj.first, j = nbj.second;
+      if (!sent.count({nb, c})) {
+        ops.push_back({1, c, j, (int)upoff.size()});
+        const std::vector<int32_t>& up = (p->sep_a[j] == c) ? p->up_a[j] : p->up_b[j];
+        upoff.push_back((int32_t)uptab.size());
+        uptab.insert(uptab.end(), up.begin(), up.end());
+        sent.insert({nb, c});
+      }
+      if (!sent.count({c, nb})) {
+        tosend.push_back({2, c, j, nb});
+        sent.insert({c, nb});
+      }
+    }
+    for (auto& o : tosend) {
+      MsgDesc md;
+      PGBP_TRY(p->make_msg(o.c, o.j, o.nb, &md));
+      md.ref = (int32_t)msgs.size();
+      ops.push_back({2, o.c, o.j, (int)msgs.size()});
+      msgs.push_back(md);
+    }
+  }
+  PGBP_TRY(batch_upload_tables(b));
+  void* v = nullptr;
+  PGBP_TRY(dev_malloc(&v, std::max<size_t>(1, msgs.size()) * sizeof(MsgDesc)));
+  MsgDesc* d_msgs = (MsgDesc*)v;
+  PGBP_TRY(dev_malloc(&v, std::max<size_t>(1, uptab.size()) * sizeof(int32_t)));
+  int32_t* d_up = (int32_t*)v;
+  int rc = h2d(d_msgs, msgs.data(), msgs.size() * sizeof(MsgDesc), b->stream);
+  if (!rc) rc = h2d(d_up, uptab.data(), uptab.size() * sizeof(int32_t), b->stream);
+  if (!rc) rc = batch_need_scratch(b, sizeof(double) * (size_t)b->ld);
+  const double eps0 = sqrt(PGBP_EPS);
+  for (size_t k = 0; k < ops.size() && !rc; k++) {
+    const Op& o = ops[k];
+    if (o.kind == 0) {
+      EpsOneBody body{b->state, b->scratch, p->jslot[o.c], b->ld, p->dim[o.c], eps0};
+      rc = launch_generic(b, "k_eps_one", b->B, 1, body);
+    } else if (o.kind == 1) {
+      const int S = p->dim[p->nclusters + o.j];
+      if (S == 0) continue;  // isempty(upind) && return
+      RegOneBody body{b->state, b->scratch, d_up + upoff[o.nb], p->jslot[o.c], p->jslot[p->nclusters + o.j], b->ld, S};
+      rc = launch_generic(b, "k_reg_one", b->B, 1, body);
+    } else {
+      const MsgDesc& md = msgs[o.nb];
+      LaunchGroup g;
+      g.step = 0; g.first = o.nb; g.count = 1;
+      shape_class(md.mF - md.s, md.s, &g.ci, &g.cs, &g.maxm);
+      MsgArgs a = make_args(b, 0, 0x3ffff0, false);  // residual stored, flags untouched (:400)
+      rc = launch_group(b, a, d_msgs, g);
+    }
+  }
+  if (!rc) rc = stream_sync(b->stream);
+  dev_free(d_msgs);
+  dev_free(d_up);
+  return rc;
+}
+
+int32_t pgbp_regularize_bynodesubtree(pgbp_batch* b, int32_t nnodes, const int32_t* eps_off, const int32_t* eps_cluster,
+                                      const int32_t* step_off, const int32_t* step_cluster, const int32_t* step_sepset,
+                                      const int32_t* idx_off, const int32_t* idx_cluster, const int32_t* idx_sepset) {
+  if (!b || nnodes < 0 || !eps_off || !step_off) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
+  PGBP_TRY(set_device(b->device));
+  const pgbp_plan* p = b->plan;
+  DevTables* dt;
+  PGBP_TRY(get_tables(b, &dt));
+  const int ne = eps_off[nnodes], ns = step_off[nnodes];
+  const int ni = ns ? idx_off[ns] : 0;
+  for (int k = 0; k < ne; k++) if (eps_cluster[k] < 0 || eps_cluster[k] >= p->nclusters) PGBP_FAIL(PGBP_EINVAL, "eps_cluster out of range");
+  for (int s = 0; s < ns; s++) {
+    if (step_cluster[s] < 0 || step_cluster[s] >= p->nclusters || step_sepset[s] < 0 || step_sepset[s] >= p->nsepsets)
+      PGBP_FAIL(PGBP_EINVAL, "step %d out of range", s);
+    for (int k = idx_off[s]; k < idx_off[s + 1]; k++)
+      if (idx_cluster[k] < 0 || idx_cluster[k] >= p->dim[step_cluster[s]] || idx_sepset[k] < 0 ||
+          idx_sepset[k] >= p->dim[p->nclusters + step_sepset[s]])
+        PGBP_FAIL(PGBP_EINVAL, "step %d: diagonal index out of range", s);
+  }
+  std::vector<int32_t> all;
+  all.insert(all.end(), eps_cluster, eps_cluster + ne);
+  const size_t o_sc = all.size(); all.insert(all.end(), step_cluster, step_cluster + ns);
+  const size_t o_ss = all.size(); all.insert(all.end(), step_sepset, step_sepset + ns);
+  const size_t o_io = all.size(); all.insert(all.end(), idx_off, idx_off + ns + 1);
+  const size_t o_ic = all.size(); all.insert(all.end(), idx_cluster, idx_cluster + ni);
+  const size_t o_is = all.size(); all.insert(all.end(), idx_sepset, idx_sepset + ni);
+  void* v = nullptr;
+  PGBP_TRY(dev_malloc(&v, std::max<size_t>(1, all.size()) * sizeof(int32_t)));
+  int32_t* d = (int32_t*)v;
+  int rc = h2d(d, all.data(), all.size() * sizeof(int32_t), b->stream);
+  for (int n = 0; n < nnodes && !rc; n++) {
+    if (step_off[n + 1] == step_off[n]) continue;
+    RegNodeBody body{b->state, dt->jslot, dt->dim, d, nullptr, d + o_sc, d + o_ss, d + o_io, d + o_ic, d + o_is,
+                     eps_off[n], eps_off[n + 1], step_off[n], step_off[n + 1], p->nclusters, b->ld};
+    rc = launch_generic(b, "k_reg_node", b->B, 1, body);
+  }
+  if (!rc) rc = stream_sync(b->stream);
+  dev_free(d);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// Internal structures of libpgbp_b200: the plan (static index work, host) and
+// the batch (device state).  See DESIGN.md for the HBM layout.
+#pragma once
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "../../include/pgbp_b200.h"
+#include "pgbp_backend.h"
+
+namespace pgbp {
+
+PGBP_HD int tri(int m) { return m * (m + 1) / 2; }
+// packed upper, column-major: (r <= c) -> c(c+1)/2 + r
+PGBP_HD int pk(int r, int c) { return c * (c + 1) / 2 + r; }
+
+// One message F -> T through sepset S (src/beliefupdates.jl:650-665), as index
+// data only.  Slots index rows of the batch's SoA arrays.
+struct MsgDesc {
+  int64_t fJ, fh, fg;  // sender cluster slots (state)
+  int64_t sJ, sh, sg;  // sepset slots (state)
+  int64_t tJ, th, tg;  // receiver cluster slots (state)
+  int64_t rJ, rh;      // residual slots (resid array)
+  int32_t dmsg;        // directed-message id = 2*sepset + side (flags / kldiv row)
+  int32_t mF, s;       // sender and sepset dimension; i = mF - s is integrated out
+  int32_t gat;         // table: S(mF) packed J slots of the sender in [I;K] order, then mF h slots
+  int32_t sca;         // table: S(s) packed J slots of the receiver, then s h slots
+  int32_t ref;         // position in the reference's sequential order of this traversal
+};
+
+struct LaunchGroup {
+  int32_t step;        // launch step (groups of one step are independent)
+  int32_t ci, cs;      // shape class (i, s) if specialised, (-1,-1) generic
+  int32_t maxm;        // for the generic kernel: max sender dimension in the group
+  int32_t first, count;  // range in Traversal::msgs
+};
+
+struct Traversal {
+  std::vector<MsgDesc> msgs;          // execution order
+  std::vector<int32_t> step_of_msg;   // step of msgs[i]
+  std::vector<LaunchGroup> groups;    // launch order
+  int32_t nsteps = 0;
+  double bytes_noresid = 0, bytes_resid = 0, flops = 0;  // algorithmic, per element
+};
+
+struct Tree {
+  std::vector<int32_t> parent, child, sepset;
+  Traversal trav[2];  // 0 postorder, 1 preorder
+};
+
+struct FamilyTable {
+  int32_t nnodes = 0, ntips = 0, root_fixed = 0;
+  std::vector<int32_t> node_cluster, mem_off, mem_pos, mem_color, node_datarow;
+  std::vector<double> mem_length, mem_gamma;
+  // derived: nodes of each cluster, ascending (order of the loop at src/beliefs.jl:798)
+  std::vector<int32_t> clu_off, clu_node;
+  int32_t ncolors_min = 1;
+};
+
+}  // namespace pgbp
+
+struct pgbp_plan {
+  int32_t nclusters = 0, nsepsets = 0, nbeliefs = 0, ntraits = 0;
+  std::vector<int32_t> dim;
+  std::vector<int64_t> jslot, hslot, gslot;  // state layout per belief
+  int64_t nslots_state = 0, nslots_factor = 0;
+  std::vector<int64_t> rjslot, rhslot;       // residual layout per directed message
+  int64_t nslots_resid = 0;
+  std::vector<int32_t> sep_a, sep_b;
+  std::vector<std::vector<int32_t>> up_a, up_b;
+  std::map<std::pair<int32_t, int32_t>, int32_t> sep_of;  // (min,max cluster) -> sepset
+  std::vector<pgbp::Tree> trees;
+  std::vector<int32_t> tab;                  // deduplicated index tables
+  std::map<std::vector<int32_t>, int32_t> tab_index;
+  // neighbours of each cluster ordered by neighbour code (neighbor_labels order)
+  std::vector<std::vector<std::pair<int32_t, int32_t>>> nbrs;  // (neighbour cluster, sepset)
+  bool has_families = false;
+  pgbp::FamilyTable fam;
+  int32_t max_dim = 0;
+
+  int32_t intern_table(const std::vector<int32_t>& t);
+  // build the descriptor of message from -> to through sepset j
+  int make_msg(int32_t from, int32_t j, int32_t to, pgbp::MsgDesc* out);
+};
+
+struct pgbp_batch {
+  const pgbp_plan* plan = nullptr;
+  int64_t B = 0, ld = 0;
+  int32_t device = 0;
+  uint32_t flags = 0;
+  pgbp_stream_t stream = 0;
+  bool own_stream = false;
+  double* state = nullptr;
+  double* factor = nullptr;
+  double* resid = nullptr;
+  double* kldiv = nullptr;
+  uint8_t* calflag = nullptr;  // [2*nsepsets][ld]
+  uint8_t* done = nullptr;     // [ld] (auto-stop mask)
+  int32_t* status = nullptr;   // [ld]
+  int32_t* iscal = nullptr;    // [ld]
+  int32_t* itertree = nullptr; // [2][ld]
+  int32_t* d_tab = nullptr;
+  // per-tree, per-direction descriptor arrays on the device
+  std::vector<pgbp::MsgDesc*> d_msgs;  // index 2*tree+dir
+  pgbp::MsgDesc* d_one = nullptr;      // scratch descriptor for pgbp_propagate
+  double* scratch = nullptr;           // staging for host<->device transposes / outputs
+  size_t scratch_bytes = 0;
+  // K1 device tables
+  void* d_fam = nullptr;
+  int64_t device_bytes = 0;
+  int64_t launches = 0;
+  bool want_info = false;
+  int32_t* d_slot = nullptr;  // device scratch for transpose slot tables
+  size_t d_slot_len = 0;
+};

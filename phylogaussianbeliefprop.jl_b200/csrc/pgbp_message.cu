@@ -1,0 +1,297 @@
+// K2 (message passing), K3 (integrate) and the calibrate! driver.
+#include "pgbp_kernels.cuh"
+#include "pgbp_launch.h"
+#include "pgbp_shapes.h"
+
+using namespace pgbp;
+
+namespace pgbp {
+
+#define PGBP_MSG_THREADS 128
+
+#ifndef PGBP_HOST_EMUL
+template <int CI, int CS, int MAXM>
+__global__ void __launch_bounds__(PGBP_MSG_THREADS) k_message(MsgArgs a) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.B) return;
+  message_thread<CI, CS, MAXM>(a, blockIdx.y, e);
+}
+__global__ void __launch_bounds__(256) k_message_copy(MsgArgs a) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.B) return;
+  message_copy_thread(a, blockIdx.y, e);
+}
+template <int MAXM>
+__global__ void __launch_bounds__(128) k_integrate(const double* state, int32_t* status, int64_t B, int64_t ld,
+                                                   int64_t jslot, int64_t hslot, int64_t gslot, int M,
+                                                   double* mu_soa, double* norm, int64_t ld_out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B) return;
+  integrate_thread<MAXM>(state, status, ld, e, jslot, hslot, gslot, M, mu_soa, norm, ld_out);
+}
+#endif
+
+template <int CI, int CS, int MAXM>
+static int launch_message(pgbp_batch* b, const MsgArgs& a, int nmsg) {
+#ifdef PGBP_HOST_EMUL
+  for (int m = 0; m < nmsg; m++)
+    for (int64_t e = 0; e < a.B; e++) message_thread<CI, CS, MAXM>(a, m, e);
+#else
+  dim3 grid((unsigned)((a.B + PGBP_MSG_THREADS - 1) / PGBP_MSG_THREADS), (unsigned)nmsg);
+  k_message<CI, CS, MAXM><<<grid, PGBP_MSG_THREADS, 0, b->stream>>>(a);
+#endif
+  b->launches++;
+  return check_launch("k_message");
+}
+
+static int launch_copy(pgbp_batch* b, const MsgArgs& a, int nmsg) {
+#ifdef PGBP_HOST_EMUL
+  for (int m = 0; m < nmsg; m++)
+    for (int64_t e = 0; e < a.B; e++) message_copy_thread(a, m, e);
+#else
+  dim3 grid((unsigned)((a.B + 255) / 256), (unsigned)nmsg);
+  k_message_copy<<<grid, 256, 0, b->stream>>>(a);
+#endif
+  b->launches++;
+  return check_launch("k_message_copy");
+}
+
+// One launch group (same step, same shape class).  blockIdx.y is limited to
+// 65535: split larger groups.
+int launch_group(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGroup& g) {
+  int done = 0;
+  while (done < g.count) {
+    const int n = std::min(g.count - done, 65535);
+    a.msgs = d_msgs + g.first + done;
+    int rc = 0;
+    if (g.ci == 0) {
+      rc = launch_copy(b, a, n);
+    } else if (g.ci > 0) {
+      bool hit = false;
+#define X(I_, S_)                                   \
+  if (!hit && g.ci == I_ && g.cs == S_) {           \
+    rc = launch_message<I_, S_, 0>(b, a, n);        \
+    hit = true;                                     \
+  }
+      PGBP_T0_SHAPES(X)
+#undef X
+      if (!hit) PGBP_FAIL(PGBP_ESTATE, "no specialised kernel for shape (%d,%d)", g.ci, g.cs);
+    } else if (g.maxm <= 16) {
+      rc = launch_message<-1, -1, 16>(b, a, n);
+    } else if (g.maxm <= 32) {
+      rc = launch_message<-1, -1, 32>(b, a, n);
+    } else {
+      rc = launch_message<-1, -1, 64>(b, a, n);
+    }
+    PGBP_TRY(rc);
+    done += n;
+  }
+  return 0;
+}
+
+MsgArgs make_args(pgbp_batch* b, uint32_t opts, int32_t ref_base, bool use_done) {
+  MsgArgs a;
+  a.msgs = nullptr;
+  a.tab = b->d_tab;
+  a.state = b->state;
+  a.resid = b->resid;
+  a.calflag = b->calflag;
+  a.status = b->status;
+  a.done = use_done ? b->done : nullptr;
+  a.B = b->B;
+  a.ld = b->ld;
+  a.opts = opts;
+  a.ref_base = ref_base;
+  return a;
+}
+
+int run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_t ref_base, bool use_done) {
+  const Traversal& tv = b->plan->trees[tree].trav[dir];
+  MsgArgs a = make_args(b, opts, ref_base, use_done);
+  const MsgDesc* d = b->d_msgs[2 * tree + dir];
+  for (const LaunchGroup& g : tv.groups) PGBP_TRY(launch_group(b, a, d, g));
+  return 0;
+}
+
+// iscalibrated_residnorm(beliefs) = AND over all directed messages
+// (src/clustergraphbeliefs.jl:168-169); with auto, freeze calibrated elements.
+PGBP_HD void iscal_thread(const uint8_t* calflag, int nd, int64_t ld, const int32_t* status, uint8_t* done,
+                          int32_t* iscal, int32_t* itertree, int32_t it, int32_t tr, int autostop, int64_t e) {
+  if (done && done[e]) return;  // frozen: keeps its (true) result
+  int ok = status[e] == 0;
+  for (int d = 0; d < nd && ok; d++) ok = calflag[(int64_t)d * ld + e] != 0;
+  iscal[e] = ok;
+  if (ok) {
+    if (itertree && itertree[e] == 0) {
+      itertree[e] = it;
+      itertree[ld + e] = tr;
+    }
+    if (autostop && done) done[e] = 1;
+  }
+}
+
+#ifndef PGBP_HOST_EMUL
+__global__ void k_iscal(const uint8_t* calflag, int nd, int64_t B, int64_t ld, const int32_t* status,
+                        uint8_t* done, int32_t* iscal, int32_t* itertree, int32_t it, int32_t tr, int autostop) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B) return;
+  iscal_thread(calflag, nd, ld, status, done, iscal, itertree, it, tr, autostop, e);
+}
+#endif
+
+static int launch_iscal(pgbp_batch* b, int it, int tr, int autostop) {
+  const int nd = 2 * b->plan->nsepsets;
+#ifdef PGBP_HOST_EMUL
+  for (int64_t e = 0; e < b->B; e++)
+    iscal_thread(b->calflag, nd, b->ld, b->status, b->done, b->iscal, b->itertree, it, tr, autostop, e);
+#else
+  k_iscal<<<(unsigned)((b->B + 255) / 256), 256, 0, b->stream>>>(b->calflag, nd, b->B, b->ld, b->status, b->done,
+                                                                  b->iscal, b->itertree, it, tr, autostop);
+#endif
+  b->launches++;
+  return check_launch("k_iscal");
+}
+
+int integrate_launch(pgbp_batch* b, int belief, double* d_mu_soa, double* d_norm, int64_t ld_out) {
+  const pgbp_plan* p = b->plan;
+  const int M = p->dim[belief];
+  const int64_t js = p->jslot[belief], hs = p->hslot[belief], gs = p->gslot[belief];
+#ifdef PGBP_HOST_EMUL
+  for (int64_t e = 0; e < b->B; e++)
+    integrate_thread<PGBP_MAX_DIM>(b->state, b->status, b->ld, e, js, hs, gs, M, d_mu_soa, d_norm, ld_out);
+#else
+  const unsigned grid = (unsigned)((b->B + 127) / 128);
+  if (M <= 4)
+    k_integrate<4><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out);
+  else if (M <= 12)
+    k_integrate<12><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out);
+  else if (M <= 32)
+    k_integrate<32><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out);
+  else
+    k_integrate<PGBP_MAX_DIM><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out);
+#endif
+  b->launches++;
+  return check_launch("k_integrate");
+}
+
+}  // namespace pgbp
+
+extern "C" {
+
+int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntrees, int32_t niter, uint32_t flags) {
+  if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
+  const pgbp_plan* p = b->plan;
+  if (!(flags & PGBP_CAL_BOTH)) PGBP_FAIL(PGBP_EINVAL, "flags select neither postorder nor preorder");
+  if (niter < 1) PGBP_FAIL(PGBP_EINVAL, "niter < 1");
+  if ((flags & (PGBP_CAL_RESIDNORM | PGBP_CAL_AUTO)) && !b->calflag)
+    PGBP_FAIL(PGBP_ESTATE, "residual tracking requested but the batch was created without PGBP_BATCH_RESIDUALS");
+  if (flags & PGBP_CAL_RESIDKLDIV) PGBP_FAIL(PGBP_EINVAL, "update_residualkldiv is not implemented yet");
+  std::vector<int32_t> ids;
+  if (tree_ids) ids.assign(tree_ids, tree_ids + ntrees);
+  else for (int t = 0; t < (int)p->trees.size(); t++) ids.push_back(t);
+  if (ids.empty()) PGBP_FAIL(PGBP_EINVAL, "empty schedule");
+  for (int t : ids) if (t < 0 || t >= (int)p->trees.size()) PGBP_FAIL(PGBP_EINVAL, "tree id %d out of range", t);
+  PGBP_TRY(set_device(b->device));
+  const bool autostop = (flags & PGBP_CAL_AUTO) != 0;
+  const bool track = (flags & PGBP_CAL_RESIDNORM) != 0;
+  if (b->done) PGBP_TRY(dev_memset(b->done, 0, (size_t)b->ld, b->stream));
+  if (b->itertree) PGBP_TRY(dev_memset(b->itertree, 0, sizeof(int32_t) * 2 * (size_t)b->ld, b->stream));
+  if (b->iscal) PGBP_TRY(dev_memset(b->iscal, 0, sizeof(int32_t) * (size_t)b->ld, b->stream));
+  const uint32_t opts = flags & PGBP_CAL_RESIDNORM;
+  int32_t ref = 0;
+  for (int it = 1; it <= niter; it++) {
+    for (size_t j = 0; j < ids.size(); j++) {
+      const int t = ids[j];
+      const int n = (int)p->trees[t].parent.size();
+      if (flags & PGBP_CAL_POSTORDER) { PGBP_TRY(run_traversal(b, t, 0, opts, ref, autostop)); ref += n; }
+      if (flags & PGBP_CAL_PREORDER) { PGBP_TRY(run_traversal(b, t, 1, opts, ref, autostop)); ref += n; }
+      const bool last = (it == niter && j + 1 == ids.size());
+      if (track && (autostop || last || b->want_info)) PGBP_TRY(launch_iscal(b, it, (int)j + 1, autostop));
+      if (ref > (1 << 22)) ref = 0;  // keep the status word positive
+    }
+  }
+  return 0;
+}
+
+int32_t pgbp_calibrate(pgbp_batch* b, const int32_t* tree_ids, int32_t ntrees, int32_t niter, uint32_t flags,
+                       int32_t* succ, int32_t* iscal, int32_t* iter_tree) {
+  if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
+  b->want_info = iter_tree != nullptr;
+  int rc = pgbp_calibrate_async(b, tree_ids, ntrees, niter, flags);
+  b->want_info = false;
+  PGBP_TRY(rc);
+  const int64_t B = b->B;
+  std::vector<int32_t> st;
+  if (succ || iscal) {
+    st.resize(B);
+    PGBP_TRY(d2h(st.data(), b->status, sizeof(int32_t) * B, b->stream));
+  }
+  if (iscal) {
+    if (b->iscal && (flags & PGBP_CAL_RESIDNORM)) PGBP_TRY(d2h(iscal, b->iscal, sizeof(int32_t) * B, b->stream));
+    else memset(iscal, 0, sizeof(int32_t) * B);
+  }
+  std::vector<int32_t> itr;
+  if (iter_tree) {
+    if (b->itertree) {
+      itr.resize(2 * b->ld);
+      PGBP_TRY(d2h(itr.data(), b->itertree, sizeof(int32_t) * 2 * b->ld, b->stream));
+    }
+  }
+  PGBP_TRY(stream_sync(b->stream));
+  if (succ) for (int64_t e = 0; e < B; e++) succ[e] = st[e] == 0;
+  if (iscal) for (int64_t e = 0; e < B; e++) if (st[e] != 0) iscal[e] = 0;  // (false,false) on failure
+  if (iter_tree) for (int64_t e = 0; e < B; e++) {
+    iter_tree[2 * e] = itr.empty() ? 0 : itr[e];
+    iter_tree[2 * e + 1] = itr.empty() ? 0 : itr[b->ld + e];
+  }
+  return 0;
+}
+
+int32_t pgbp_propagate(pgbp_batch* b, int32_t from_cluster, int32_t sepset, int32_t to_cluster, uint32_t flags) {
+  if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
+  pgbp_plan* p = const_cast<pgbp_plan*>(b->plan);
+  if (from_cluster < 0 || from_cluster >= p->nclusters || to_cluster < 0 || to_cluster >= p->nclusters)
+    PGBP_FAIL(PGBP_EINVAL, "cluster index out of range");
+  const int j = sepset >= p->nclusters ? sepset - p->nclusters : sepset;  // accept belief index or sepset index
+  MsgDesc md;
+  const size_t tab_before = p->tab.size();
+  PGBP_TRY(p->make_msg(from_cluster, j, to_cluster, &md));
+  PGBP_TRY(set_device(b->device));
+  if (p->tab.size() != tab_before) PGBP_TRY(batch_upload_tables(b));
+  PGBP_TRY(h2d(b->d_one, &md, sizeof md, b->stream));
+  PGBP_TRY(stream_sync(b->stream));  // md is a stack object
+  LaunchGroup g;
+  g.step = 0; g.first = 0; g.count = 1;
+  shape_class(md.mF - md.s, md.s, &g.ci, &g.cs, &g.maxm);
+  MsgArgs a = make_args(b, flags & PGBP_CAL_RESIDNORM, 0x3ffff0, false);
+  if (!b->calflag) a.opts = 0;
+  return launch_group(b, a, b->d_one, g);
+}
+
+int32_t pgbp_integrate_device(pgbp_batch* b, int32_t belief, double* d_mu_soa, double* d_norm) {
+  if (!b || !d_norm) PGBP_FAIL(PGBP_EINVAL, "null argument");
+  if (belief < 0 || belief >= b->plan->nbeliefs) PGBP_FAIL(PGBP_EINVAL, "belief index out of range");
+  PGBP_TRY(set_device(b->device));
+  return integrate_launch(b, belief, d_mu_soa, d_norm, b->ld);
+}
+
+int32_t pgbp_integrate(pgbp_batch* b, int32_t belief, double* mu, double* norm) {
+  if (!b || !norm) PGBP_FAIL(PGBP_EINVAL, "null argument");
+  if (belief < 0 || belief >= b->plan->nbeliefs) PGBP_FAIL(PGBP_EINVAL, "belief index out of range");
+  PGBP_TRY(set_device(b->device));
+  const int M = b->plan->dim[belief];
+  const int64_t ld = b->ld;
+  PGBP_TRY(batch_need_scratch(b, sizeof(double) * (size_t)ld * (size_t)(M + 1) * (mu ? 2 : 1)));
+  double* d_norm = b->scratch;
+  double* d_mu = mu ? b->scratch + ld : nullptr;
+  PGBP_TRY(integrate_launch(b, belief, d_mu, d_norm, ld));
+  PGBP_TRY(d2h(norm, d_norm, sizeof(double) * b->B, b->stream));
+  if (mu && M > 0) {
+    double* d_aos = b->scratch + ld * (int64_t)(M + 1);
+    PGBP_TRY(soa_to_aos(b, d_mu, ld, d_aos, M, nullptr));
+    PGBP_TRY(d2h(mu, d_aos, sizeof(double) * b->B * M, b->stream));
+  }
+  return stream_sync(b->stream);
+}
+
+}  // extern "C"

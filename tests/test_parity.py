@@ -1,0 +1,460 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and against
+the reference's golden values.
+
+Every test runs twice: `emul` (host emulation of the kernel bodies; CPU; checks
+the host logic -- plan compiler, index tables, ABI) and `cuda` (marked gpu; the
+product).  Tolerance: north_star asks for <= 1e-10 relative on beliefs and
+log-likelihoods; the assertions below use TOL = 1e-10 (observed ~1e-15).
+Schedules and scope indices are compared bit-exactly.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import pgbp_b200
+from harness import BACKENDS, Case, get_lib, relerr
+from oracle import beliefs as OB
+from oracle import bp as OBP
+from oracle import clustergraph as CG
+from oracle import models as M
+
+TOL = 1e-10
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_goldens.json")))
+NAN = math.nan
+TBL = np.array([[10, 1.0], [10, 0.9], [NAN, 1.0], [0, -1.0]])
+TAXA = ["A", "B1", "B2", "C"]
+HINT9 = GOLD["canonicalform_beliefnodelabels"][:7]
+
+
+def check_all_beliefs(case, batch, cgbs, tol=TOL, elems=None):
+    elems = range(len(cgbs)) if elems is None else elems
+    worst = 0.0
+    for j in range(1, len(case.b) + 1):
+        J, h, g = batch.get_belief(j)
+        for e in elems:
+            ob = cgbs[e].belief[j - 1]
+            worst = max(worst, relerr(J[e], ob.J), relerr(h[e], ob.h), relerr(g[e], ob.g))
+    assert worst <= tol, worst
+    return worst
+
+
+# ------------------------------------------------------------------ plan / schedule (bit-exact)
+def mirror_steps(nbeliefs, nclusters, frm, sep, to):
+    """Independent restatement of the launch-step rule: a message
+    runs one step after the last write of its sender and after the last access
+    of its receiver / sepset."""
+    lw, lr, steps = [-1] * nbeliefs, [-1] * nbeliefs, []
+    for f, s, t in zip(frm, sep, to):
+        st = max(lw[f] + 1, max(lw[t], lr[t]) + 1, max(lw[s], lr[s]) + 1)
+        steps.append(st)
+        lr[f] = max(lr[f], st)
+        lw[t] = st
+        lw[s] = st
+    return steps
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_plan_schedule_and_scope_bit_exact(backend):
+    lib = get_lib(backend)
+    tbl = np.array(GOLD["lazaridis_x"]).reshape(-1, 1).repeat(3, axis=1)
+    net_taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
+    m = M.MvFullBrownianMotion(np.eye(3), np.zeros(3))
+    case = Case(GOLD["lazaridis"], "cliquetree", tbl, net_taxa, m, lib, order_hint=GOLD["lazaridis_cluster_labels"])
+    assert case.sched[0][2] == GOLD["lazaridis_sched_parent"] and case.sched[0][3] == GOLD["lazaridis_sched_child"]
+    # in-scope node counts with a fixed root, times p = 3
+    assert case.plan.belief_dim[:17] == [3 * k for k in (3, 3, 1, 1, 0, 3, 4, 4, 1, 1, 1, 4, 4, 4, 4, 1, 1)]
+    pa, ch = [j - 1 for j in case.sched[0][2]], [j - 1 for j in case.sched[0][3]]
+    nb, nc = len(case.b), case.nclusters
+    sepidx = {frozenset(b.metadata): j for j, b in enumerate(case.b) if j >= nc}
+    labs = case.cg.labels
+    for direction in (0, 1):
+        lv = case.plan.levels(0, direction)
+        n = len(pa)
+        order = range(n - 1, -1, -1) if direction == 0 else range(n)
+        frm = [(ch if direction == 0 else pa)[i] for i in order]
+        to = [(pa if direction == 0 else ch)[i] for i in order]
+        sep = [sepidx[frozenset((labs[f], labs[t]))] for f, t in zip(frm, to)]
+        steps = mirror_steps(nb, nc, frm, sep, to)
+        # library output is in execution order; index it back by reference position
+        by_ref = {int(r): k for k, r in enumerate(lv["ref"])}
+        assert sorted(by_ref) == list(range(n))
+        for r in range(n):
+            k = by_ref[r]
+            assert (lv["frm"][k], lv["sepset"][k], lv["to"][k], lv["step"][k]) == (frm[r], sep[r], to[r], steps[r])
+        assert lv["nsteps"] == max(steps) + 1
+        assert list(lv["step"]) == sorted(lv["step"])
+    # algorithmic bytes of one calibration (SURVEY 8d worked example): 49 232 B
+    by = case.plan.traversal_cost(0, 0, True)[0] + case.plan.traversal_cost(0, 1, True)[0]
+    assert by == 49232.0
+    # scope maps == oracle's scopeindex
+    for j in range(nc, nb):
+        s = case.b[j]
+        for lab in s.metadata:
+            c = case.b[labs.index(lab)]
+            assert list(pgbp_b200.scopeindex(s.nodelabel, s.inscope, c.nodelabel, c.inscope)) == list(OB.scopeindex(s, c))
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_set_get_roundtrip_and_api_errors(backend):
+    lib = get_lib(backend)
+    case = Case(GOLD["netstr_named"], "cliquetree", TBL, TAXA, M.MvDiagBrownianMotion([2, 1], [3, -3], [0.1, 10]), lib,
+                order_hint=HINT9, with_families=False)
+    B = 37  # ragged: not a multiple of 32
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+    rng = np.random.default_rng(1)
+    for j in range(1, len(case.b) + 1):
+        m = bt.dimension(j)
+        A = rng.normal(size=(B, m, m))
+        J = A + A.transpose(0, 2, 1)
+        h, g = rng.normal(size=(B, m)), rng.normal(size=B)
+        bt.set_belief(j, J, h, g)
+        J2, h2, g2 = bt.get_belief(j)
+        assert np.array_equal(J, J2) and np.array_equal(h, h2) and np.array_equal(g, g2)
+    assert (bt.status() == 0).all()
+    with pytest.raises(pgbp_b200.PgbpError):
+        bt.assignfactors(pgbp_b200.bm_params([np.eye(2)], [0, 0]), np.zeros((1, 4, 2)))  # plan has no family table
+    with pytest.raises(pgbp_b200.PgbpError):
+        bt.propagate_belief(1, len(case.b), 2)  # that sepset does not join clusters 1 and 2
+    with pytest.raises(pgbp_b200.PgbpError):
+        bt.calibrate([5])
+    bt0 = pgbp_b200.BatchedClusterGraphBelief(case.plan, 3, factors=False, residuals=False)
+    with pytest.raises(pgbp_b200.PgbpError):
+        bt0.factored_energy()
+    with pytest.raises(pgbp_b200.PgbpError):
+        bt0.calibrate()  # residual tracking needs the residual arrays
+    assert bt0.calibrate(update_residualnorm=False)[0].all()
+
+
+# ------------------------------------------------------------------ reference known answers
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_canonicalform_six_messages(backend):
+    # test/test_canonicalform.jl:65-109: six explicit propagate_belief! calls, then integratebelief!
+    lib = get_lib(backend)
+    m = M.UnivariateBrownianMotion(2, 3, 0)
+    case = Case(GOLD["netstr_named"], "cliquetree", TBL[:, 1:], TAXA, m, lib, order_hint=HINT9)
+    B = 3
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+    bt.assignfactors(pgbp_b200.bm_params([2.0], [3.0]), TBL[None, :, 1:])
+    e = {k.number: k for k in case.net.edges}
+    J, h, g = bt.get_belief(1)
+    np.testing.assert_allclose(J[0], 0.5 / e[4].length * np.array([[1, -1], [-1, 1]]), rtol=1e-14)
+    assert (h == 0).all() and g[0] == pytest.approx(-math.log(2 * math.pi * e[4].length * 2) / 2, rel=1e-14)
+    bpv = 0.5 / (e[7].gamma ** 2 * e[7].length + e[5].gamma ** 2 * e[5].length)
+    J, h, g = bt.get_belief(4)
+    np.testing.assert_allclose(J[1], bpv * np.array([[1, -.9, -.1], [-.9, .81, .09], [-.1, .09, .01]]), rtol=1e-13)
+    for to, s, fr in [(1, 8, 2), (1, 9, 3), (4, 10, 1), (4, 12, 6), (4, 13, 7), (5, 11, 4)]:
+        pgbp_b200.propagate_belief(bt, to, s, fr)
+    mu, ll = pgbp_b200.integratebelief(bt, 5)
+    assert (bt.status() == 0).all()
+    assert np.all(np.abs(ll / GOLD["canonicalform_loglik"] - 1) < 1e-14)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("case_", GOLD["evomodels"], ids=lambda c: c["id"])
+def test_evomodels_postorder_loglik(backend, case_):
+    # test/test_evomodels.jl:52-264; factors assigned by the host-side model code and uploaded
+    # (covers OU, missing data and every root type), one postorder + integratebelief! on the device
+    lib = get_lib(backend)
+    cols = {"y": [1], "x": [0], "xy": [0, 1]}[case_["traits"]]
+    model = getattr(M, case_["model"])(*eval(case_["args"], {"inf": math.inf, "np": np}))
+    case = Case(GOLD["netstr_named"], "cliquetree", TBL[:, cols], TAXA, model, lib, schedule="spanningtree",
+                with_families=False)
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, 2)
+    case.upload(bt, [case.oracle_cgb()] * 2)
+    spt = case.sched[0]
+    assert pgbp_b200.propagate_1traversal_postorder(bt, spt).all()
+    _, ll = pgbp_b200.integratebelief(bt, spt[2][0])
+    assert np.all(np.abs(ll / case_["loglik"] - 1) < 1e-9)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_lazaridis_docs_numbers(backend):
+    # docs/src/man/getting_started.md:184-189, 283-291
+    lib = get_lib(backend)
+    taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
+    tbl = np.array(GOLD["lazaridis_x"]).reshape(-1, 1)
+    case = Case(GOLD["lazaridis"], "cliquetree", tbl, taxa, M.UnivariateBrownianMotion(1, 0), lib,
+                order_hint=GOLD["lazaridis_cluster_labels"])
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, 4)
+    pgbp_b200.assignfactors(bt, pgbp_b200.bm_params([1.0], [0.0]), tbl[None])
+    J, h, g = bt.get_belief(1)
+    np.testing.assert_allclose(J[3], np.array(GOLD["lazaridis_b1_J"]), rtol=1e-13)
+    assert g[3] == pytest.approx(GOLD["lazaridis_b1_g"], rel=1e-13)
+    succ, iscal = pgbp_b200.calibrate(bt, case.sched)
+    assert succ.all() and not iscal.any()
+    _, norm = pgbp_b200.integratebelief(bt, 1)
+    assert np.all(np.abs(norm / GOLD["lazaridis_norm"] - 1) < 1e-12)
+    fe = pgbp_b200.factored_energy(bt)
+    assert np.all(np.abs(fe[:, 2] / GOLD["lazaridis_fe"] - 1) < 1e-12)
+    succ, iscal = pgbp_b200.calibrate(bt, case.sched)  # second pass: residuals are now ~0
+    assert succ.all() and iscal.all()
+
+
+# ------------------------------------------------------------------ device factor assignment
+ASSIGN_CASES = [
+    ("uni_fixed", lambda: M.UnivariateBrownianMotion(2, 3, 0), [1], lambda: ([[[2.0]]], [3.0], None)),
+    ("uni_improper", lambda: M.UnivariateBrownianMotion(2, 3, math.inf), [1], lambda: ([[[2.0]]], [3.0], [[math.inf]])),
+    ("uni_random", lambda: M.UnivariateBrownianMotion(2, 3, 0.4), [1], lambda: ([[[2.0]]], [3.0], [[0.4]])),
+    ("full_fixed", lambda: M.MvFullBrownianMotion([[2.0, 0.5], [0.5, 1.0]], [3.0, -3.0]), [0, 1],
+     lambda: ([[[2.0, 0.5], [0.5, 1.0]]], [3.0, -3.0], None)),
+    ("full_random", lambda: M.MvFullBrownianMotion([[2.0, 0.5], [0.5, 1.0]], [3.0, -3.0], [[0.1, 0.01], [0.01, 0.2]]), [0, 1],
+     lambda: ([[[2.0, 0.5], [0.5, 1.0]]], [3.0, -3.0], [[0.1, 0.01], [0.01, 0.2]])),
+    ("full_improper", lambda: M.MvFullBrownianMotion([[2.0, 0.5], [0.5, 1.0]], [3.0, -3.0], [[math.inf, 0], [0, math.inf]]), [0, 1],
+     lambda: ([[[2.0, 0.5], [0.5, 1.0]]], [3.0, -3.0], [[math.inf, 0], [0, math.inf]])),
+    ("diag_random", lambda: M.MvDiagBrownianMotion([2, 1], [3, -3], [0.1, 10]), [0, 1],
+     lambda: ([[2.0, 1.0]], [3.0, -3.0], [0.1, 10.0])),
+]
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("name,mk,cols,par", ASSIGN_CASES, ids=[c[0] for c in ASSIGN_CASES])
+def test_assignfactors_device_vs_oracle(backend, name, mk, cols, par):
+    lib = get_lib(backend)
+    tbl = TBL.copy()
+    tbl[2, 0] = 7.5  # device assignment: no missing data
+    tbl = tbl[:, cols]
+    model = mk()
+    case = Case(GOLD["netstr_named"], "cliquetree", tbl, TAXA, model, lib, schedule="spanningtree")
+    B = 5
+    rng = np.random.default_rng(3)
+    data = tbl[None] + rng.normal(size=(B,) + tbl.shape)
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+    rates, mu, v = par()
+    bt.assignfactors(pgbp_b200.bm_params(rates, mu, v), data)
+    cgbs = [case.oracle_cgb(tbl=data[e]) for e in range(B)]
+    check_all_beliefs(case, bt, cgbs)
+    for j in range(1, case.nclusters + 1):  # factor snapshot
+        J, h, g = bt.get_factor(j)
+        assert relerr(J[1], cgbs[1].factor[j - 1].J) <= TOL and relerr(g[1], cgbs[1].factor[j - 1].g) <= TOL
+    spt = case.sched[0]
+    assert bt.propagate_1traversal_postorder(spt).all()
+    _, ll = bt.integratebelief(spt[2][0])
+    for e in range(B):
+        OBP.propagate_1traversal_postorder(cgbs[e], *spt)
+        assert abs(ll[e] / OBP.integratebelief_cgb(cgbs[e], spt[2][0])[1] - 1) <= TOL
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_assignfactors_heterogeneous_theta_grid(backend):
+    # config-4 shape in miniature: painted rates (one hybrid with parents of different colours),
+    # a grid of parameter vectors x one data set (product pairing)
+    lib = get_lib(backend)
+    tbl = TBL.copy()
+    tbl[2, 0] = 7.5
+    colors = {9: 2, 7: 2, 8: 2, 1: 3}
+    rng = np.random.default_rng(7)
+    NP = 6
+
+    def rnd_spd(p):
+        A = rng.normal(size=(p, p))
+        return A @ A.T / p + 0.1 * np.eye(p)
+
+    thetas = [[rnd_spd(2) for _ in range(3)] for _ in range(NP)]
+    mus = rng.normal(size=(NP, 2))
+    model0 = M.HeterogeneousBrownianMotion(thetas[0], colors, mus[0])
+    case = Case(GOLD["netstr_named"], "cliquetree", tbl, TAXA, model0, lib, schedule="spanningtree",
+                edge_color=lambda num: colors.get(num, 1) - 1)
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, NP)
+    params = np.stack([pgbp_b200.bm_params(thetas[k], mus[k]) for k in range(NP)])
+    bt.assignfactors(params, tbl[None], ncolors=3, pairing="product")
+    cgbs = [case.oracle_cgb(model=M.HeterogeneousBrownianMotion(thetas[k], colors, mus[k])) for k in range(NP)]
+    check_all_beliefs(case, bt, cgbs)
+    spt = case.sched[0]
+    assert bt.propagate_1traversal_postorder(spt, update_residualnorm=False).all()
+    _, ll = bt.integratebelief(spt[2][0], want_mu=False)
+    for k in range(NP):
+        OBP.propagate_1traversal_postorder(cgbs[k], *spt)
+        assert abs(ll[k] / OBP.integratebelief_cgb(cgbs[k], spt[2][0])[1] - 1) <= TOL
+    # a non-PD rate matrix fails only its own element
+    params[2, :4] = [1.0, 2.0, 2.0, 1.0]
+    bt.assignfactors(params, tbl[None], ncolors=3, pairing="product")
+    st = bt.status()
+    assert st[2] != 0 and (np.delete(st, 2) == 0).all()
+
+
+# ------------------------------------------------------------------ calibration
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_calibrate_cliquetree_all_beliefs(backend):
+    # test/test_calibration.jl:36-78
+    lib = get_lib(backend)
+    tbl_y = np.array([[1.0], [.9], [1], [-1]])
+    m = M.UnivariateBrownianMotion(0.471474, 0, math.inf)
+    case = Case(GOLD["netstr_named"], "cliquetree", tbl_y, TAXA, m, lib, schedule="spanningtree")
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, 2)
+    bt.assignfactors(pgbp_b200.bm_params([0.471474], [0.0], [math.inf]), tbl_y[None])
+    pgbp_b200.calibrate(bt, case.sched)
+    ll = -4.877930583154144
+    for j in range(1, len(case.b) + 1):
+        assert np.all(np.abs(bt.integratebelief(j)[1] / ll - 1) < 1e-7)
+    assert np.all(np.abs(pgbp_b200.factored_energy(bt)[:, 2] / ll - 1) < 1e-7)
+    root_ind = next(i for i, be in enumerate(case.b) if 1 in be.nodelabel) + 1
+    mu, _ = bt.integratebelief(root_ind)
+    assert mu[0, -1] == pytest.approx(-0.26000871507162693, rel=1e-5)
+    cgb = case.oracle_cgb()
+    OBP.calibrate(cgb, case.sched)
+    check_all_beliefs(case, bt, [cgb, cgb])
+    # residuals and flags of every directed message
+    labs = case.cg.labels
+    for j in range(case.nclusters, len(case.b)):
+        for lab_to in case.b[j].metadata:
+            lab_from = [l for l in case.b[j].metadata if l != lab_to][0]
+            dJ, dh, fl, _ = bt.get_residual(j + 1, labs.index(lab_to) + 1)
+            r = cgb.messageresidual[(lab_to, lab_from)]
+            assert relerr(dJ[0], r.dJ) <= 1e-9 and relerr(dh[0], r.dh) <= 1e-9 and bool(fl[0]) == r.iscalibrated_resid
+    # the graph invariant survives both regularisations (test/test_calibration.jl:65-77)
+    for reg in ("bynodesubtree", "bycluster"):
+        bt.init_beliefs_reset_fromfactors()
+        cgb2 = case.oracle_cgb()
+        if reg == "bycluster":
+            bt.regularizebeliefs_bycluster()
+            OBP.regularizebeliefs_bycluster(cgb2, case.cg)
+        else:
+            bt.regularizebeliefs_bynodesubtree(OBP.bynodesubtree_program(cgb2, case.cg))
+            OBP.regularizebeliefs_bynodesubtree(cgb2, case.cg)
+        check_all_beliefs(case, bt, [cgb2, cgb2])
+        pgbp_b200.calibrate(bt, case.sched)
+        assert np.all(np.abs(bt.integratebelief(1)[1] / ll - 1) < 1e-7)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_loopy_bethe_onschedule_autostop(backend):
+    # test/test_calibration.jl:79-105: "calibration reached: iteration 5, schedule tree 1"
+    lib = get_lib(backend)
+    tbl_y = np.array([[-1.81358], [0.468158], [0.658486], [0.643821]])
+    taxa = ["A", "B", "C", "D"]
+    m = M.UnivariateBrownianMotion(0.0861249, 0)
+    case = Case(GOLD["netstr_unnamed"], "bethe", tbl_y, taxa, m, lib)
+    B = 4
+    rng = np.random.default_rng(11)
+    data = np.repeat(tbl_y[None], B, axis=0)
+    data[1:] += 0.3 * rng.normal(size=(B - 1, 4, 1))
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+    bt.assignfactors(pgbp_b200.bm_params([0.0861249], [0.0]), data)
+    bt.regularizebeliefs_onschedule()
+    cgbs = [case.oracle_cgb(tbl=data[e]) for e in range(B)]
+    for c in cgbs:
+        OBP.regularizebeliefs_onschedule(c, case.cg)
+    check_all_beliefs(case, bt, cgbs)
+    succ, iscal, it = pgbp_b200.calibrate(bt, case.sched, 20, auto=True, info=True)
+    assert succ.all() and iscal.all()
+    assert tuple(it[0]) == (5, 1)
+    infos = []
+    for c in cgbs:
+        assert all(OBP.calibrate(c, case.sched, 20, auto=True))
+        infos.append(OBP.calibrate.last_info)
+    assert [tuple(x) for x in it] == infos  # per-element auto-stop point, bit-exact
+    check_all_beliefs(case, bt, cgbs, tol=1e-9)
+    ind = case.cg.labels.index("I3") + 1
+    assert bt.integratebelief(ind)[0][0, -1] == pytest.approx(0.21511454631828986, rel=1e-5)
+    fe = bt.factored_energy()
+    for e in range(B):
+        assert relerr(fe[e], np.array(OBP.factored_energy(cgbs[e]))) <= 1e-9
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_joingraph_missing_data_bynodesubtree(backend):
+    # test/test_calibration.jl:131-185: level-3 network, missing trait, improper root,
+    # JoinGraphStructuring(3), one schedule tree per variable
+    lib = get_lib(backend)
+    tbl = np.array([[2.11, 30.0], [2.15, NAN]])
+    m = M.MvFullBrownianMotion([[1, 0.5], [0.5, 1]], [0, 0], [[math.inf, 0], [0, math.inf]])
+
+    def sched(case):
+        out = []
+        for n in case.net.vec_node:
+            st = CG.nodesubtree_clusterlist(case.cg, n.name)
+            if st[0]:
+                out.append(st)
+        return out
+
+    case = Case(GOLD["netstr_level3"], "jgs", tbl, ["A", "B"], m, lib, schedule=sched, with_families=False, maxclustersize=3)
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, 2)
+    cgb = case.oracle_cgb()
+    case.upload(bt, [cgb, cgb])
+    bt.init_factors_frombeliefs()
+    bt.regularizebeliefs_bynodesubtree(OBP.bynodesubtree_program(cgb, case.cg))
+    OBP.regularizebeliefs_bynodesubtree(cgb, case.cg)
+    succ, iscal, it = bt.calibrate(case.sched, 10, auto=True, info=True)
+    assert succ.all() and iscal.all()
+    assert all(OBP.calibrate(cgb, case.sched, 10, auto=True))
+    assert tuple(it[0]) == OBP.calibrate.last_info
+    i6 = case.cg.labels.index("I1I2I3") + 1
+    mu, nrm = bt.integratebelief(i6)
+    assert nrm[0] == pytest.approx(-1.390595772423, rel=1e-7)
+    np.testing.assert_allclose(mu[0], [2.121105154896223, 30.005552577448075, 2.1360649504455984,
+                                       30.013032475222563, 2.128585052670943, 30.00929252633547], rtol=1e-7)
+    check_all_beliefs(case, bt, [cgb, cgb], tol=1e-9)
+
+
+# ------------------------------------------------------------------ failure semantics
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_failed_cholesky_is_per_element_status(backend):
+    # src/beliefupdates.jl:68-76, 640-644: the exception is returned, not thrown; here: status word
+    lib = get_lib(backend)
+    m = M.UnivariateBrownianMotion(2, 3, 0)
+    case = Case(GOLD["netstr_named"], "cliquetree", TBL[:, 1:], TAXA, m, lib, order_hint=HINT9, schedule="spanningtree")
+    B = 6
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+    cgb = case.oracle_cgb()
+    case.upload(bt, [cgb] * B)
+    # element 4: make cluster 1's precision indefinite in the variable integrated out by its first message
+    J, h, g = bt.get_belief(1)
+    J[4] = np.array([[-1.0, 0.3], [0.3, 2.0]])
+    bt.set_belief(1, J, h, g)
+    spt = case.sched[0]
+    succ = bt.propagate_1traversal_postorder(spt)
+    assert list(succ) == [True] * 4 + [False] + [True]
+    st = bt.status()
+    lv = case.plan.levels(0, 0)
+    k = next(i for i in range(len(lv["ref"])) if lv["frm"][i] == 0)
+    assert st[4] != 0 and (st[4] >> 8) - 1 == lv["ref"][k] and (st[4] & 0xff) == 1
+    _, ll = bt.integratebelief(spt[2][0])
+    ok = [0, 1, 2, 3, 5]
+    assert np.all(np.abs(ll[ok] / GOLD["canonicalform_loglik"] - 1) < 1e-13)
+    # oracle agrees on which message fails
+    b2 = [x.copy() for x in cgb.belief]
+    b2[0].J[:] = J[4]
+    ex = None
+    n = len(spt[0])
+    for r, i in enumerate(range(n - 1, -1, -1)):
+        ss = b2[cgb.sepsetindex(spt[0][i], spt[1][i]) - 1]
+        ex = OBP.propagate_belief(b2[spt[2][i] - 1], ss, b2[spt[3][i] - 1])
+        if ex is not None:
+            assert r == (st[4] >> 8) - 1 and ex.info == (st[4] & 0xff)
+            break
+    assert ex is not None
+
+
+# ------------------------------------------------------------------ shapes: generic kernel, larger traits
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("p", [3, 5, 8, 16])
+def test_multivariate_shapes_vs_oracle(backend, p):
+    # p=3: register-resident kernels (config 2 shapes); p=5: mixed; p=8, 16: generic kernel
+    # (config 4 / 5 shapes: m up to 3p or 4p, s up to 3p)
+    lib = get_lib(backend)
+    rng = np.random.default_rng(100 + p)
+    A = rng.normal(size=(p, p))
+    R = A @ A.T / p + 0.1 * np.eye(p)
+    mu = rng.normal(size=p)
+    taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
+    B = 3
+    data = rng.normal(size=(B, 7, p))
+    model = M.MvFullBrownianMotion(R, mu)
+    case = Case(GOLD["lazaridis"], "cliquetree", data[0], taxa, model, lib, order_hint=GOLD["lazaridis_cluster_labels"])
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+    bt.assignfactors(pgbp_b200.bm_params([R], mu), data)
+    cgbs = [case.oracle_cgb(tbl=data[e]) for e in range(B)]
+    check_all_beliefs(case, bt, cgbs)
+    succ, _ = bt.calibrate(case.sched)
+    assert succ.all()
+    for c in cgbs:
+        OBP.calibrate(c, case.sched)
+    worst = check_all_beliefs(case, bt, cgbs, tol=1e-9)
+    _, ll = bt.integratebelief(case.sched[0][2][0])
+    fe = bt.factored_energy()
+    for e in range(B):
+        ref = OBP.integratebelief_cgb(cgbs[e], case.sched[0][2][0])[1]
+        assert abs(ll[e] / ref - 1) <= TOL and abs(fe[e, 2] / ref - 1) <= 1e-9
