@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the batched Gaussian-BP hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+
+Workload (BASELINE.json configs[1]): lazaridis_2014 admixture graph, clique
+tree (17 clusters / 16 sepsets / 32 messages per calibration), full
+multivariate Brownian motion with p = 3 traits, fixed root, 65,536 synthetic
+trait replicates per GPU simulated down the network (seed 0xB200 + 2).
+Metric: clique-tree calibrations per second, whole job (all ranks).
+
+One step =  beliefs <- factors (init_beliefs_reset_fromfactors!),
+            calibrate!(beliefs, [spt]) = 16 postorder + 16 preorder messages with
+            residual tracking and the iscalibrated reduction,
+            integratebelief! at the root cluster (per-replicate log-likelihood),
+            [N > 1: NCCL all-gather of the log-likelihoods]
+for all B replicates of the rank.  `value` times that with the factors
+resident in HBM; `e2e` times the public host-buffer API per step:
+pinned host tip data -> H2D -> assignfactors (K1) -> calibrate -> integratebelief
+-> D2H of the log-likelihoods.
+
+`--impl reference`: the reference is Julia (not in this image), so the
+reference arm is the C/OpenMP restatement of the reference's algorithm
+(oracle/c, kind "port") on all host cores, on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "clique-tree calibrations/sec (batched replicates)"
+UNIT = "calibrations/s"
+WORKLOAD = ("lazaridis_2014 admixture graph, MvFullBrownianMotion p=3, 65,536 synthetic trait replicates per GPU, "
+            "clique tree, calibrate! (post+pre order, residual tracking) + integratebelief! [BASELINE configs[1]]")
+SEED = 0xB200 + 2
+
+
+def load_plan_dict():
+    return json.load(open(os.path.join(ROOT, "workloads", "lazaridis_cliquetree_p3.json")))
+
+
+def make_inputs(d, B, seed=SEED):
+    """R = A A'/3 + 0.1 I, mu = 0, fixed root; replicates simulated down the
+    network: X_v = sum_k gamma_k X_pa_k + N(0, sum_k gamma_k^2 t_k R)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    p = d["ntraits"]
+    A = rng.normal(size=(p, p))
+    R = A @ A.T / 3 + 0.1 * np.eye(p)
+    Lr = np.linalg.cholesky(R)
+    n = len(d["simulate"])
+    X = np.zeros((n, B, p))
+    for v in range(1, n):
+        par = d["simulate"][v]
+        var = sum(g * g * t for _, t, g in par)
+        mean = sum(g * X[q] for q, t, g in par)
+        X[v] = mean + np.sqrt(var) * (rng.normal(size=(B, p)) @ Lr.T)
+    tips = np.ascontiguousarray(X[d["tip_nodes"]].transpose(1, 0, 2))  # [B][ntips][p]
+    params = np.concatenate([R.T.ravel(), np.zeros(p), np.zeros(p * p)])[None]
+    return params, tips
+
+
+# ----------------------------------------------------------------------------- reference arm / cpu baseline
+def cpu_port_rate(d, params, tips, seconds, nthreads=0):
+    """calibrations/s of the C/OpenMP oracle port on a bounded sample."""
+    from oracle.cport import COracle, dll
+    co = COracle.from_plan_dict(d)
+    kw = dict(root_belief=d["root_cluster"], nthreads=nthreads)
+    n0 = min(2048, tips.shape[0])
+    co.run_batch(params, tips[:n0], **kw)  # warm-up (thread pool, page faults)
+    t = time.perf_counter()
+    co.run_batch(params, tips[:n0], **kw)
+    r0 = n0 / (time.perf_counter() - t)
+    n = int(min(tips.shape[0], max(n0, r0 * seconds)))
+    t = time.perf_counter()
+    out = co.run_batch(params, tips[:n], **kw)
+    dt = time.perf_counter() - t
+    assert (out["status"] == 0).all()
+    cores = dll().pgbpo_num_threads() if nthreads <= 0 else nthreads
+    return n / dt, cores, n, dt, out["loglik"]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d = load_plan_dict()
+    per_step = 3.0
+    params, tips = make_inputs(d, 65536)
+    from oracle.cport import COracle, dll
+    co = COracle.from_plan_dict(d)
+    kw = dict(root_belief=d["root_cluster"])
+    n0 = 2048
+    co.run_batch(params, tips[:n0], **kw)
+    t = time.perf_counter()
+    co.run_batch(params, tips[:n0], **kw)
+    r0 = n0 / (time.perf_counter() - t)
+    n = int(min(tips.shape[0], max(n0, r0 * per_step)))
+    for _ in range(args.warmup):
+        co.run_batch(params, tips[:n], **kw)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        co.run_batch(params, tips[:n], **kw)
+    dt = time.perf_counter() - t
+    cores = dll().pgbpo_num_threads()
+    value = n * args.steps / dt
+    sample = f"{n} of 65536 replicates per step (assignfactors + calibrate + integratebelief per replicate)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference is Julia (absent from the image): C/OpenMP restatement of "
+                   "its algorithm (oracle/c), all host threads, bounded sample per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                c, m = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            mx = m
+            if t0 - 0.05 <= t <= t1 + 0.05:
+                sm.append(c)
+                for nme, val in zip(names, f[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nme)
+        if not sm:  # timed region shorter than the sampling period: use every sample
+            for t, line in self.rows:
+                try:
+                    sm.append(float(line.split(",")[0]))
+                except ValueError:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import pgbp_b200
+    from pgbp_b200 import _lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world:
+        if rank == 0:
+            print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; reporting n_gpus={world}", file=sys.stderr)
+    d = load_plan_dict()
+    B = args.batch
+    p = d["ntraits"]
+    params, tips = make_inputs(d, B, SEED + 1000 * rank)
+    lib = pgbp_b200.default_library()
+    plan = pgbp_b200.ClusterGraphPlan(d["nclusters"], d["belief_dim"], d["sepset_clusters"], d["upind"], d["trees"], p,
+                                      d["families"], lib)
+    stream = torch.cuda.current_stream()
+    bt = pgbp_b200.BatchedClusterGraphBelief(plan, B, device=local, stream=stream.cuda_stream)
+    root = d["root_cluster"] + 1
+    bytes_cal = plan.traversal_cost(0, 0, True)[0] + plan.traversal_cost(0, 1, True)[0]
+    flops_cal = plan.traversal_cost(0, 0, True)[1] + plan.traversal_cost(0, 1, True)[1]
+
+    # ---- device-resident arm -------------------------------------------------
+    bt.assignfactors(params, tips)  # factors resident in HBM before the timed region
+    _, ld, _ = bt.device_view()
+    d_norm = torch.empty(ld, dtype=torch.float64, device=dev)
+    gathered = torch.empty(world * ld, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step(ev=None):
+        bt.init_beliefs_reset_fromfactors()
+        if ev:
+            ev[0].record(stream)
+        bt.calibrate_async(None, 1, update_residualnorm=True)
+        if ev:
+            ev[1].record(stream)
+        bt.integrate_device(root, d_norm.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_norm)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    bt.launch_count(reset=True)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for k in range(args.steps):
+        step(evs[k])
+    e1.record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    launches = bt.launch_count()
+    ms_total = e0.elapsed_time(e1)
+    ms_msgs = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    tt = torch.tensor([ms_total, ms_msgs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, ms_msgs = float(tt[0]), float(tt[1])
+    value = world * B * args.steps / (ms_total * 1e-3)
+    st = bt.status()
+    assert (st == 0).all(), "numerical failure inside the timed region"
+    loglik_dev = d_norm[:B].cpu().numpy()
+
+    # ---- end-to-end arm: public host-buffer API --------------------------------
+    nbuf = 2
+    pinned = [torch.from_numpy(tips.copy()).pin_memory() for _ in range(nbuf)]
+    pin_np = [t.numpy() for t in pinned]
+    ll_host = None
+    for k in range(2):
+        bt.assignfactors(params, pin_np[k % nbuf])
+        bt.calibrate(None, 1)
+        _, ll_host = bt.integratebelief(root, want_mu=False)
+    barrier()
+    t0e = time.perf_counter()
+    for k in range(args.steps):
+        bt.assignfactors(params, pin_np[k % nbuf])            # H2D of this step's inputs + K1
+        succ, iscal = bt.calibrate(None, 1)                    # D2H of succ / iscal
+        _, ll_host = bt.integratebelief(root, want_mu=False)   # D2H of the result
+    barrier()
+    dte = time.perf_counter() - t0e
+    te = torch.tensor([dte], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(te[0])
+    h2d = tips.nbytes + params.nbytes
+    d2h = ll_host.nbytes + 2 * 4 * B
+    assert np.allclose(ll_host, loglik_dev, rtol=1e-12, atol=0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel family (k_message*) ----------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = bytes_cal * B * args.steps / (ms_msgs * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_calibration_per_replicate")
+        if traffic is not None:
+            traffic = traffic * B
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "k_message<i,s> family (all 32 messages of a calibration)",
+                "algorithmic_bytes_per_calibration_per_replicate": bytes_cal,
+                "algorithmic_flops_per_calibration_per_replicate": flops_cal,
+                "share_of_step": ms_msgs / ms_total}
+
+    # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        rate, cores, n, dt, ll_cpu = cpu_port_rate(d, params, tips, args.cpu_seconds)
+        err = float(np.max(np.abs(ll_cpu / loglik_dev[:n] - 1)))
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} of {B} replicates in {dt:.1f} s (assignfactors + calibrate + integratebelief per replicate, "
+                         f"C/OpenMP restatement of the Julia reference)",
+               "max_rel_err_gpu_vs_cpu_loglik": err}
+        assert err < 1e-10, err
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "replicates_per_gpu": B, "ntraits": p, "messages_per_calibration": 32,
+                   "step": "reset_from_factors + calibrate (post+pre, residuals, iscal) + integrate(root)"
+                           + (" + nccl all_gather(loglik)" if world > 1 else ""),
+                   "l2": "inputs larger than L2 (state %.2f GB per GPU)" % (bt.device_bytes() / 1e9),
+                   "parallelism": f"replicate batch sharded over {world} GPU(s), plan replicated"},
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "path": "pinned host tip data -> assignfactors (H2D + K1) -> calibrate -> integratebelief -> D2H loglik"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="replicates per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
