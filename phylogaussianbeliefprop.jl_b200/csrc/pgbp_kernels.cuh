@@ -3,6 +3,9 @@
 // threads touch consecutive doubles (batch-innermost SoA), so every warp load
 // or store is one fully coalesced 256-byte transaction.
 #pragma once
+#include <type_traits>
+#include <utility>
+
 #include "pgbp_internal.h"
 
 namespace pgbp {
@@ -29,6 +32,247 @@ PGBP_HD void absmax(double& m, double x) {
   if (a > m || a != a) m = a;
 }
 
+// compile-time loop: f(std::integral_constant<int, k>) for k = 0..N-1
+template <class F, int... Is>
+PGBP_HD void static_for_impl(F&& f, std::integer_sequence<int, Is...>) {
+  (f(std::integral_constant<int, Is>{}), ...);
+}
+template <int N, class F>
+PGBP_HD void static_for(F&& f) {
+  static_for_impl(f, std::make_integer_sequence<int, (N > 0 ? N : 0)>{});
+}
+// column of packed index q (q = c(c+1)/2 + r, r <= c)
+PGBP_HD constexpr int colof(int q) {
+  int c = 0;
+  while ((c + 1) * (c + 2) / 2 <= q) ++c;
+  return c;
+}
+
+#define PGBP_CHUNK 8
+
+// calibration flag of one residual (src/beliefs.jl:994-1003):
+// max|dh|/sqrt(s) <= 1e-5 && max|dJ|/sqrt(s^2) <= 1e-5.  max_i(|x_i|/c) == (max_i|x_i|)/c
+// exactly (division by c > 0 is monotone, so is rounding).
+PGBP_HD void store_flag(const MsgArgs& a, int dmsg, int64_t e, int S, double maxJ, double maxh) {
+  if ((a.opts & PGBP_CAL_RESIDNORM) && a.calflag) {
+    bool ok = true;
+    if (S > 0) ok = (maxh / sqrt((double)S) <= 1e-5) && (maxJ / (double)S <= 1e-5);
+    a.calflag[(int64_t)dmsg * a.ld + e] = ok ? 1 : 0;
+  }
+}
+
+// Register-resident message kernel body, compile-time shape (I >= 1 integrated
+// out, S kept).  marginalize (src/beliefupdates.jl:55-83) -> divide! (:579-587)
+// -> mult! (:483-488) -> residual (:646-647) -> flag (src/beliefs.jl:994-1003).
+//
+// Only J_II (packed), J_IK and h_I stay in registers.  They are factorised in
+// place (right-looking U'U on the I rows): afterwards AI holds U, Bm holds
+// Z' = U^-T J_IK and hI holds w = U^-T h_I.  The kept block is then STREAMED in
+// chunks of PGBP_CHUNK packed entries: the sender's J_KK entry, the sepset's old
+// value and the receiver's old value are all loaded first (3*CHUNK independent
+// loads in flight per thread), then  new = J_KK - z_r.z_c,  delta = new - old,
+// and the three stores.  h and g follow the same pattern.
+template <int CI, int CS>
+PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
+  constexpr int I = CI, S = CS, M = I + S, SI = I * (I + 1) / 2, SS = S * (S + 1) / 2;
+  const MsgDesc md = a.msgs[msg_index];  // by value: lives in registers, never re-read after a store
+  if (a.status[e] != 0) return;
+  if (a.done && a.done[e]) return;
+  const int64_t ld = a.ld;
+  double* st = a.state + e;
+  double* rs = a.resid ? a.resid + e : nullptr;
+  const int32_t* __restrict__ gat = a.tab + md.gat;
+  const int32_t* __restrict__ sca = a.tab + md.sca;
+  constexpr int SMM = M * (M + 1) / 2;
+  double AI[SI > 0 ? SI : 1];
+  double Bm[I * S > 0 ? I * S : 1];  // Bm[k*S + c] = J[I_k, K_c]
+  double hI[I > 0 ? I : 1];
+#pragma unroll
+  for (int c = 0; c < I; c++) {
+#pragma unroll
+    for (int r = 0; r <= c; r++) AI[pk(r, c)] = st[(md.fJ + gat[pk(r, c)]) * ld];
+  }
+#pragma unroll
+  for (int c = 0; c < S; c++) {
+#pragma unroll
+    for (int k = 0; k < I; k++) Bm[k * S + c] = st[(md.fJ + gat[pk(k, I + c)]) * ld];
+  }
+#pragma unroll
+  for (int k = 0; k < I; k++) hI[k] = st[(md.fh + gat[SMM + k]) * ld];
+  double g = st[md.fg * ld];
+  const double sg_old = st[md.sg * ld];
+  const double tg_old = st[md.tg * ld];
+
+  // "Ji = Jki = hi = 0 if missing data" shortcut, src/beliefupdates.jl:62-66
+  bool allzero = true;
+#pragma unroll
+  for (int q = 0; q < SI; q++)
+    if (!(fabs(AI[q]) <= PGBP_EPS)) allzero = false;
+#pragma unroll
+  for (int q = 0; q < I * S; q++)
+    if (!(fabs(Bm[q]) <= PGBP_EPS)) allzero = false;
+#pragma unroll
+  for (int k = 0; k < I; k++)
+    if (!(fabs(hI[k]) <= PGBP_EPS)) allzero = false;
+
+  if (!allzero) {
+    double logdet = 0.0, ww = 0.0;
+#pragma unroll
+    for (int k = 0; k < I; k++) {
+      const double d = AI[pk(k, k)];
+      if (!(d > 0.0)) {  // LAPACK potrf: info = k+1 (also catches NaN)
+        status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, k + 1));
+        return;
+      }
+      logdet += log(d);
+      const double rinv = 1.0 / sqrt(d);
+#pragma unroll
+      for (int c = k + 1; c < I; c++) AI[pk(k, c)] *= rinv;
+#pragma unroll
+      for (int c = 0; c < S; c++) Bm[k * S + c] *= rinv;
+      const double wk = hI[k] * rinv;
+      hI[k] = wk;
+      ww += wk * wk;
+#pragma unroll
+      for (int c = k + 1; c < I; c++) {
+        const double akc = AI[pk(k, c)];
+#pragma unroll
+        for (int r = k + 1; r <= c; r++) AI[pk(r, c)] -= AI[pk(k, r)] * akc;
+        hI[c] -= akc * wk;
+      }
+#pragma unroll
+      for (int c = 0; c < S; c++) {
+        const double bkc = Bm[k * S + c];
+#pragma unroll
+        for (int r = k + 1; r < I; r++) Bm[r * S + c] -= AI[pk(k, r)] * bkc;
+      }
+    }
+    g += 0.5 * ((double)I * PGBP_LOG2PI - logdet + ww);
+  } else {
+#pragma unroll
+    for (int q = 0; q < I * S; q++) Bm[q] = 0.0;  // message = (h_K, J_KK, g) unchanged
+#pragma unroll
+    for (int k = 0; k < I; k++) hI[k] = 0.0;
+  }
+
+  double maxJ = 0.0, maxh = 0.0;
+  constexpr int NCH = (SS + PGBP_CHUNK - 1) / PGBP_CHUNK;
+  static_for<NCH>([&](auto chc) {
+    constexpr int q0 = decltype(chc)::value * PGBP_CHUNK;
+    constexpr int n = (SS - q0) < PGBP_CHUNK ? (SS - q0) : PGBP_CHUNK;
+    double jo[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
+    int64_t ta[PGBP_CHUNK];
+    static_for<n>([&](auto kc) {
+      constexpr int k = decltype(kc)::value, q = q0 + k, c = colof(q), r = q - c * (c + 1) / 2;
+      ta[k] = (md.tJ + sca[q]) * ld;
+      jo[k] = st[(md.fJ + gat[pk(I + r, I + c)]) * ld];
+      so[k] = st[(md.sJ + q) * ld];
+      to[k] = st[ta[k]];
+    });
+    static_for<n>([&](auto kc) {
+      constexpr int k = decltype(kc)::value, q = q0 + k, c = colof(q), r = q - c * (c + 1) / 2;
+      double nv = jo[k];
+#pragma unroll
+      for (int i = 0; i < I; i++) nv -= Bm[i * S + r] * Bm[i * S + c];
+      const double d = nv - so[k];
+      st[(md.sJ + q) * ld] = nv;
+      st[ta[k]] = to[k] + d;
+      if (rs) rs[(md.rJ + q) * ld] = d;
+      absmax(maxJ, d);
+    });
+  });
+  {
+    double ho[S > 0 ? S : 1], so[S > 0 ? S : 1], to[S > 0 ? S : 1];
+    int64_t ta[S > 0 ? S : 1];
+#pragma unroll
+    for (int k = 0; k < S; k++) {
+      ta[k] = (md.th + sca[SS + k]) * ld;
+      ho[k] = st[(md.fh + gat[SMM + I + k]) * ld];
+      so[k] = st[(md.sh + k) * ld];
+      to[k] = st[ta[k]];
+    }
+#pragma unroll
+    for (int k = 0; k < S; k++) {
+      double nv = ho[k];
+#pragma unroll
+      for (int i = 0; i < I; i++) nv -= Bm[i * S + k] * hI[i];
+      const double d = nv - so[k];
+      st[(md.sh + k) * ld] = nv;
+      st[ta[k]] = to[k] + d;
+      if (rs) rs[(md.rh + k) * ld] = d;
+      absmax(maxh, d);
+    }
+  }
+  st[md.sg * ld] = g;
+  st[md.tg * ld] = tg_old + (g - sg_old);
+  store_flag(a, md.dmsg, e, S, maxJ, maxh);
+}
+
+// Runtime-shape variants share this tail: divide / multiply / residual / flag with
+// chunked prefetch.  newJ(r,c,q), newh(k) give the outgoing message.
+template <class FJ, class FH>
+PGBP_HD void divide_mult_store(const MsgArgs& a, const MsgDesc& md, int64_t e, int S, FJ newJ, FH newh,
+                               double newg) {
+  const int64_t ld = a.ld;
+  double* st = a.state + e;
+  double* rs = a.resid ? a.resid + e : nullptr;
+  const int32_t* __restrict__ sca = a.tab + md.sca;
+  const int SS = tri(S);
+  const double sg_old = st[md.sg * ld], tg_old = st[md.tg * ld];
+  double maxJ = 0.0, maxh = 0.0;
+  int r = 0, c = 0;  // (r,c) of packed index q, advanced incrementally
+  for (int q0 = 0; q0 < SS; q0 += PGBP_CHUNK) {
+    double nv[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
+    int64_t ta[PGBP_CHUNK];
+#pragma unroll
+    for (int k = 0; k < PGBP_CHUNK; k++) {
+      const int q = q0 + k;
+      if (q < SS) {
+        ta[k] = (md.tJ + sca[q]) * ld;
+        nv[k] = newJ(r, c, q);
+        so[k] = st[(md.sJ + q) * ld];
+        to[k] = st[ta[k]];
+        if (++r > c) { r = 0; c++; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PGBP_CHUNK; k++) {
+      const int q = q0 + k;
+      if (q < SS) {
+        const double d = nv[k] - so[k];
+        st[(md.sJ + q) * ld] = nv[k];
+        st[ta[k]] = to[k] + d;
+        if (rs) rs[(md.rJ + q) * ld] = d;
+        absmax(maxJ, d);
+      }
+    }
+  }
+  for (int k0 = 0; k0 < S; k0 += PGBP_CHUNK) {
+    double nv[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
+    int64_t ta[PGBP_CHUNK];
+#pragma unroll
+    for (int k = 0; k < PGBP_CHUNK; k++)
+      if (k0 + k < S) {
+        ta[k] = (md.th + sca[SS + k0 + k]) * ld;
+        nv[k] = newh(k0 + k);
+        so[k] = st[(md.sh + k0 + k) * ld];
+        to[k] = st[ta[k]];
+      }
+#pragma unroll
+    for (int k = 0; k < PGBP_CHUNK; k++)
+      if (k0 + k < S) {
+        const double d = nv[k] - so[k];
+        st[(md.sh + k0 + k) * ld] = nv[k];
+        st[ta[k]] = to[k] + d;
+        if (rs) rs[(md.rh + k0 + k) * ld] = d;
+        absmax(maxh, d);
+      }
+  }
+  st[md.sg * ld] = newg;
+  st[md.tg * ld] = tg_old + (newg - sg_old);
+  store_flag(a, md.dmsg, e, S, maxJ, maxh);
+}
+
 struct TrailJ {
   const double* A;
   int I;
@@ -52,141 +296,69 @@ struct GatherH {
   PGBP_HD double operator()(int k) const { return st[(base + gat[k]) * ld]; }
 };
 
-// Divide by the sepset, multiply into the receiver, store the residual and the
-// calibration flag: src/beliefupdates.jl:579-587 (divide!), :483-488 (mult!),
-// :646-647 (residual), src/beliefs.jl:994-1003 (iscalibrated_residnorm!).
-// `newJ(q)`, `newh(k)` give the outgoing message in sepset order.
-template <class FJ, class FH>
-PGBP_HD void divide_mult_store(const MsgArgs& a, const MsgDesc& md, int64_t e, int S, FJ newJ, FH newh,
-                               double newg) {
-  const int64_t ld = a.ld;
-  double* st = a.state + e;
-  double* rs = a.resid ? a.resid + e : nullptr;
-  const int32_t* sca = a.tab + md.sca;
-  const int SS = tri(S);
-  double maxJ = 0.0, maxh = 0.0;
-#pragma unroll
-  for (int c = 0; c < S; c++) {
-#pragma unroll
-    for (int r = 0; r <= c; r++) {
-      const int q = pk(r, c);
-      const double nv = newJ(r, c, q);
-      double* sp = st + (md.sJ + q) * ld;
-      const double d = nv - *sp;
-      *sp = nv;
-      st[(md.tJ + sca[q]) * ld] += d;
-      if (rs) rs[(md.rJ + q) * ld] = d;
-      absmax(maxJ, d);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < S; k++) {
-    const double nv = newh(k);
-    double* sp = st + (md.sh + k) * ld;
-    const double d = nv - *sp;
-    *sp = nv;
-    st[(md.th + sca[SS + k]) * ld] += d;
-    if (rs) rs[(md.rh + k) * ld] = d;
-    absmax(maxh, d);
-  }
-  {
-    double* sp = st + md.sg * ld;
-    const double d = newg - *sp;
-    *sp = newg;
-    st[md.tg * ld] += d;
-  }
-  if ((a.opts & PGBP_CAL_RESIDNORM) && a.calflag) {
-    bool ok = true;
-    if (S > 0) {
-      // max_i |x_i| / sqrt(n) == max_i (|x_i| / sqrt(n)) exactly (monotone rounding)
-      ok = (maxh / sqrt((double)S) <= 1e-5) && (maxJ / (double)S <= 1e-5);
-    }
-    a.calflag[(int64_t)md.dmsg * ld + e] = ok ? 1 : 0;
-  }
-}
-
-// Message with i >= 1 variables integrated out (marginalize,
-// src/beliefupdates.jl:55-83).  The sender is gathered in [I;K] order so that
-// the Schur complement is the first i pivots of a right-looking Cholesky; the
-// trailing s x s block then holds J_K - J_KI J_I^-1 J_IK, the eliminated h gives
-// h_K - J_KI J_I^-1 h_I, and w = U^-T h_I gives h_I' J_I^-1 h_I = |w|^2.
-// CI/CS >= 0: compile-time shape, arrays live in registers.  CI < 0: runtime
-// shape, arrays live in thread-local memory sized for MAXM.
-template <int CI, int CS, int MAXM>
-PGBP_HD void message_thread(const MsgArgs& a, int msg_index, int64_t e) {
-  constexpr bool RT = (CI < 0);
-  constexpr int CM = RT ? MAXM : (CI + CS);
-  constexpr int NA = CM * (CM + 1) / 2;
-  const MsgDesc& md = a.msgs[msg_index];
+// Generic message kernel body: runtime shape, the whole sender belief gathered in
+// [I;K] order into thread-local memory sized for MAXM, right-looking partial
+// Cholesky over the first i pivots; the trailing block is the outgoing message.
+template <int MAXM>
+PGBP_HD void message_thread_rt(const MsgArgs& a, int msg_index, int64_t e) {
+  constexpr int NA = MAXM * (MAXM + 1) / 2;
+  const MsgDesc md = a.msgs[msg_index];
   if (a.status[e] != 0) return;
   if (a.done && a.done[e]) return;
-  const int I = RT ? (md.mF - md.s) : CI;
-  const int S = RT ? md.s : CS;
-  const int M = I + S;
+  const int I = md.mF - md.s, S = md.s, M = md.mF;
   const int64_t ld = a.ld;
   const double* st = a.state + e;
-  const int32_t* gat = a.tab + md.gat;
-  double A[NA > 0 ? NA : 1];
-  double hv[CM > 0 ? CM : 1];
+  const int32_t* __restrict__ gat = a.tab + md.gat;
+  double A[NA];
+  double hv[MAXM];
   const int SM = tri(M);
-#pragma unroll
+#pragma unroll 8
   for (int q = 0; q < SM; q++) A[q] = st[(md.fJ + gat[q]) * ld];
-#pragma unroll
+#pragma unroll 8
   for (int k = 0; k < M; k++) hv[k] = st[(md.fh + gat[SM + k]) * ld];
   double g = st[md.fg * ld];
-
-  // "Ji = Jki = hi = 0 if missing data" shortcut, src/beliefupdates.jl:62-66
   bool allzero = true;
-#pragma unroll
   for (int c = 0; c < M; c++) {
     const int rmax = c < I ? c + 1 : I;
-#pragma unroll
     for (int r = 0; r < rmax; r++)
       if (!(fabs(A[pk(r, c)]) <= PGBP_EPS)) allzero = false;
   }
-#pragma unroll
   for (int k = 0; k < I; k++)
     if (!(fabs(hv[k]) <= PGBP_EPS)) allzero = false;
-
   if (!allzero) {
     double logdet = 0.0, ww = 0.0;
-#pragma unroll
     for (int k = 0; k < I; k++) {
       const double d = A[pk(k, k)];
-      if (!(d > 0.0)) {  // LAPACK potrf: info = k+1 (also catches NaN)
+      if (!(d > 0.0)) {
         status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, k + 1));
         return;
       }
       logdet += log(d);
       const double rinv = 1.0 / sqrt(d);
-#pragma unroll
       for (int c = k + 1; c < M; c++) A[pk(k, c)] *= rinv;
       const double wk = hv[k] * rinv;
       ww += wk * wk;
-#pragma unroll
       for (int c = k + 1; c < M; c++) {
         const double akc = A[pk(k, c)];
-#pragma unroll
         for (int r = k + 1; r <= c; r++) A[pk(r, c)] -= A[pk(k, r)] * akc;
         hv[c] -= akc * wk;
       }
     }
     g += 0.5 * ((double)I * PGBP_LOG2PI - logdet + ww);
   }
-  // trailing block -> sepset order
   divide_mult_store(a, md, e, S, TrailJ{A, I}, TrailH{hv, I}, g);
 }
 
 // Message with nothing to integrate out (src/beliefupdates.jl:56): the outgoing
 // message is the sender's belief re-ordered; streamed, no local storage.
 PGBP_HD void message_copy_thread(const MsgArgs& a, int msg_index, int64_t e) {
-  const MsgDesc& md = a.msgs[msg_index];
+  const MsgDesc md = a.msgs[msg_index];
   if (a.status[e] != 0) return;
   if (a.done && a.done[e]) return;
   const int S = md.s;
   const int64_t ld = a.ld;
   const double* st = a.state + e;
-  const int32_t* gat = a.tab + md.gat;
+  const int32_t* __restrict__ gat = a.tab + md.gat;
   const int SS = tri(S);
   const double g = st[md.fg * ld];
   divide_mult_store(a, md, e, S, GatherJ{st, gat, md.fJ, ld}, GatherH{st, gat + SS, md.fh, ld}, g);

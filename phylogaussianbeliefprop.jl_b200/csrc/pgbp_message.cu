@@ -14,7 +14,8 @@ template <int CI, int CS, int MAXM>
 __global__ void __launch_bounds__(PGBP_MSG_THREADS) k_message(MsgArgs a) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.B) return;
-  message_thread<CI, CS, MAXM>(a, blockIdx.y, e);
+  if constexpr (CI >= 0) message_thread_t0<CI, CS>(a, blockIdx.y, e);
+  else message_thread_rt<MAXM>(a, blockIdx.y, e);
 }
 __global__ void __launch_bounds__(256) k_message_copy(MsgArgs a) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -35,7 +36,10 @@ template <int CI, int CS, int MAXM>
 static int launch_message(pgbp_batch* b, const MsgArgs& a, int nmsg) {
 #ifdef PGBP_HOST_EMUL
   for (int m = 0; m < nmsg; m++)
-    for (int64_t e = 0; e < a.B; e++) message_thread<CI, CS, MAXM>(a, m, e);
+    for (int64_t e = 0; e < a.B; e++) {
+      if constexpr (CI >= 0) message_thread_t0<CI, CS>(a, m, e);
+      else message_thread_rt<MAXM>(a, m, e);
+    }
 #else
   dim3 grid((unsigned)((a.B + PGBP_MSG_THREADS - 1) / PGBP_MSG_THREADS), (unsigned)nmsg);
   k_message<CI, CS, MAXM><<<grid, PGBP_MSG_THREADS, 0, b->stream>>>(a);
