@@ -127,12 +127,26 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML polled in-process every
+    2 ms (the timed region of the small config lasts ~20 ms, shorter than nvidia-smi's period);
+    falls back to `nvidia-smi -lms 100` if NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nv, self.stop_flag, self.mx = [], None, None, False, None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.nv = nv
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -142,39 +156,48 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
+    def _poll(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self.stop_flag:
+            try:
+                c = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.perf_counter(), c, [k for k, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
-    def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+    def _read(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for t, line in self.rows:
+        for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
             try:
                 c, m = float(f[0]), float(f[1])
-            except ValueError:
+            except (ValueError, IndexError):
                 continue
-            mx = m
-            if t0 - 0.05 <= t <= t1 + 0.05:
-                sm.append(c)
-                for nme, val in zip(names, f[3:7]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nme)
-        if not sm:  # timed region shorter than the sampling period: use every sample
-            for t, line in self.rows:
-                try:
-                    sm.append(float(line.split(",")[0]))
-                except ValueError:
-                    pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            self.mx = m
+            self.rows.append((time.perf_counter(), c, [n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
+
+    def stop(self, t0, t1):
+        if self.nv is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        self.stop_flag = True
+        inside = [(c, r) for t, c, r in self.rows if t0 <= t <= t1]
+        where = "timed region"
+        if not inside:  # only possible with the nvidia-smi fallback on a very short region
+            inside, where = [(c, r) for t, c, r in self.rows], "whole run (region shorter than the sampling period)"
+        sm = [c for c, _ in inside]
+        reasons = sorted({x for _, r in inside for x in r})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                "samples": len(sm), "sampled": where, "source": "nvml" if self.nv else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -205,6 +228,8 @@ def run_gpu(args):
                                       d["families"], lib)
     stream = torch.cuda.current_stream()
     bt = pgbp_b200.BatchedClusterGraphBelief(plan, B, device=local, stream=stream.cuda_stream)
+    if args.walk is not None:
+        bt.set_walk_mode(args.walk)
     root = d["root_cluster"] + 1
     bytes_cal = plan.traversal_cost(0, 0, True)[0] + plan.traversal_cost(0, 1, True)[0]
     flops_cal = plan.traversal_cost(0, 0, True)[1] + plan.traversal_cost(0, 1, True)[1]
@@ -343,12 +368,13 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="replicates per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--walk", type=int, default=None, help="kernel strategy override: 0 level-parallel, 1 walk kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -139,6 +139,13 @@ int64_t pgbp_batch_device_bytes(const pgbp_batch* batch);
 /* kernels launched on this batch since creation / since the last reset (reset != 0) */
 int64_t pgbp_batch_launch_count(pgbp_batch* batch, int32_t reset);
 
+/* Kernel strategy of calibrate / traversals: -1 automatic (default; currently always 0),
+ * 0 level-parallel launches (one launch per step and shape class; parallel over messages and
+ * replicates), 1 walk kernel (one launch per traversal; each thread walks all messages of its
+ * replicate; needs every message shape to be whole nodes of ntraits <= 4 traits, else falls
+ * back to 0).  Results are bit-identical. */
+int32_t pgbp_batch_set_walk_mode(pgbp_batch* batch, int32_t mode);
+
 /* Host <-> device belief access (CanonicalBelief fields, src/beliefs.jl:72-132).
  * J: [B][m][m] column-major full square, h: [B][m], g: [B]; any pointer may be
  * NULL.  set symmetrises nothing: the upper triangle is taken, as the

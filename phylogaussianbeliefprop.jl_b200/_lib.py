@@ -51,6 +51,7 @@ SIGNATURES = {
     "pgbp_batch_size": (i64, [vp]),
     "pgbp_batch_device_bytes": (i64, [vp]),
     "pgbp_batch_launch_count": (i64, [vp, i32]),
+    "pgbp_batch_set_walk_mode": (i32, [vp, i32]),
     "pgbp_set_belief": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
     "pgbp_get_belief": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
     "pgbp_get_factor": (i32, [vp, i32, P(f64), P(f64), P(f64)]),

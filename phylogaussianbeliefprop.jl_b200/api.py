@@ -282,6 +282,10 @@ class BatchedClusterGraphBelief:
     def launch_count(self, reset=False):
         return self.lib.pgbp_batch_launch_count(self.handle, int(reset))
 
+    def set_walk_mode(self, mode):
+        """-1 auto, 0 level-parallel launches, 1 single walk kernel per traversal."""
+        self.lib.check(self.lib.pgbp_batch_set_walk_mode(self.handle, int(mode)))
+
     def synchronize(self):
         self.lib.check(self.lib.pgbp_batch_synchronize(self.handle))
 

@@ -17,7 +17,10 @@ HEADERS = ["pgbp_backend.h", "pgbp_internal.h", "pgbp_kernels.cuh", "pgbp_launch
            "pgbp_factors.cuh", os.path.join("..", "..", "include", "pgbp_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+              # no implicit mul+add contraction: the only fused operations are the explicit fma() calls, so all
+              # kernel variants of one operation are bit-identical to each other
+              "-fmad=false"]
 
 
 def _stale(target, deps):
@@ -48,7 +51,7 @@ def build(emul=False, verbose=False, force=False):
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
             if emul:
-                cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-DPGBP_HOST_EMUL", "-x", "c++", "-c", src, "-o", obj]
+                cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-DPGBP_HOST_EMUL", "-x", "c++", "-c", src, "-o", obj]
             else:
                 cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)

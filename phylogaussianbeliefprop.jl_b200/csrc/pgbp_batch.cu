@@ -234,6 +234,12 @@ int32_t pgbp_batch_create(const pgbp_plan* plan, int64_t B, int32_t device, uint
       PGBP_TRY(alloc(b.get(), &b->d_msgs[2 * t + dir], std::max<size_t>(1, tv.msgs.size())));
       PGBP_TRY(h2d(b->d_msgs[2 * t + dir], tv.msgs.data(), tv.msgs.size() * sizeof(MsgDesc), b->stream));
     }
+  b->d_walk.assign(plan->trees.size(), nullptr);
+  for (size_t t = 0; t < plan->trees.size(); t++) {
+    const auto& w = plan->trees[t].walk;
+    PGBP_TRY(alloc(b.get(), &b->d_walk[t], std::max<size_t>(1, w.size())));
+    PGBP_TRY(h2d(b->d_walk[t], w.data(), w.size() * sizeof(MsgDesc), b->stream));
+  }
   PGBP_TRY(stream_sync(b->stream));
   *out = b.release();
   if (flags & PGBP_BATCH_RESIDUALS) PGBP_TRY(pgbp_reset_calibration_flags(*out, 1));
@@ -248,6 +254,7 @@ int32_t pgbp_batch_destroy(pgbp_batch* b) {
   dev_free(b->calflag); dev_free(b->done); dev_free(b->status); dev_free(b->iscal); dev_free(b->itertree);
   dev_free(b->d_tab); dev_free(b->d_one); dev_free(b->scratch); dev_free(b->d_slot); free_tables(b);
   for (auto* p : b->d_msgs) dev_free(p);
+  for (auto* p : b->d_walk) dev_free(p);
 #ifndef PGBP_HOST_EMUL
   if (b->own_stream) cudaStreamDestroy(b->stream);
 #endif

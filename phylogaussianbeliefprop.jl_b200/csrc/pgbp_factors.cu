@@ -278,13 +278,13 @@ struct EnergyClusterBody {
       mu[k] *= rinv;
       for (int cc = k + 1; cc < M; cc++) {
         const double akc = A[pk(k, cc)];
-        for (int r = k + 1; r <= cc; r++) A[pk(r, cc)] -= A[pk(k, r)] * akc;
-        mu[cc] -= akc * mu[k];
+        for (int r = k + 1; r <= cc; r++) A[pk(r, cc)] = nfma(A[pk(k, r)], akc, A[pk(r, cc)]);
+        mu[cc] = nfma(akc, mu[k], mu[cc]);
       }
     }
     for (int k = M - 1; k >= 0; k--) {  // U mu = w
       double s = mu[k];
-      for (int cc = k + 1; cc < M; cc++) s -= A[pk(k, cc)] * mu[cc];
+      for (int cc = k + 1; cc < M; cc++) s = nfma(A[pk(k, cc)], mu[cc], s);
       mu[k] = s * A[pk(k, k)];
     }
     // tr(J_b^-1 J_f) = sum_k |U^-T f_k|^2-weighted ... computed as sum_k e_k' U^-1 U^-T J_f e_k:
@@ -295,17 +295,17 @@ struct EnergyClusterBody {
       for (int r = 0; r < M; r++) {
         const double f = fa[(js + (r <= k ? pk(r, k) : pk(k, r))) * ld];
         x[r] = f;
-        fk_mu += f * mu[r];
+        fk_mu = fma(f, mu[r], fk_mu);
       }
       quad += mu[k] * fk_mu;
       for (int r = 0; r < M; r++) {  // U' x = f_k
         double s = x[r];
-        for (int q = 0; q < r; q++) s -= A[pk(q, r)] * x[q];
+        for (int q = 0; q < r; q++) s = nfma(A[pk(q, r)], x[q], s);
         x[r] = s * A[pk(r, r)];
       }
       for (int r = M - 1; r >= k; r--) {  // U y = x, only down to row k
         double s = x[r];
-        for (int q = r + 1; q < M; q++) s -= A[pk(r, q)] * x[q];
+        for (int q = r + 1; q < M; q++) s = nfma(A[pk(r, q)], x[q], s);
         x[r] = s * A[pk(r, r)];
       }
       trace += x[k];
@@ -348,7 +348,7 @@ struct EntropySepsetBody {
       for (int cc = k + 1; cc < M; cc++) A[pk(k, cc)] *= rinv;
       for (int cc = k + 1; cc < M; cc++) {
         const double akc = A[pk(k, cc)];
-        for (int r = k + 1; r <= cc; r++) A[pk(r, cc)] -= A[pk(k, r)] * akc;
+        for (int r = k + 1; r <= cc; r++) A[pk(r, cc)] = nfma(A[pk(k, r)], akc, A[pk(r, cc)]);
       }
     }
     *out = 0.5 * (M * (PGBP_LOG2PI + 1.0) - logdet);

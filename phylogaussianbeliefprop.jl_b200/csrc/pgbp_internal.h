@@ -26,6 +26,7 @@ struct MsgDesc {
   int32_t gat;         // table: S(mF) packed J slots of the sender in [I;K] order, then mF h slots
   int32_t sca;         // table: S(s) packed J slots of the receiver, then s h slots
   int32_t ref;         // position in the reference's sequential order of this traversal
+  int32_t wid;         // walk-kernel shape id (pgbp_shapes.h), -1 if outside the family
 };
 
 struct LaunchGroup {
@@ -46,6 +47,8 @@ struct Traversal {
 struct Tree {
   std::vector<int32_t> parent, child, sepset;
   Traversal trav[2];  // 0 postorder, 1 preorder
+  std::vector<MsgDesc> walk;  // postorder then preorder messages in reference order
+  bool walkable = false;      // every message is inside the walk family of ntraits
 };
 
 struct FamilyTable {
@@ -102,6 +105,7 @@ struct pgbp_batch {
   int32_t* d_tab = nullptr;
   // per-tree, per-direction descriptor arrays on the device
   std::vector<pgbp::MsgDesc*> d_msgs;  // index 2*tree+dir
+  std::vector<pgbp::MsgDesc*> d_walk;  // per tree, reference order (walk kernel)
   pgbp::MsgDesc* d_one = nullptr;      // scratch descriptor for pgbp_propagate
   double* scratch = nullptr;           // staging for host<->device transposes / outputs
   size_t scratch_bytes = 0;
@@ -110,6 +114,7 @@ struct pgbp_batch {
   int64_t device_bytes = 0;
   int64_t launches = 0;
   bool want_info = false;
+  int32_t walk_mode = -1;  // -1 auto, 0 never, 1 always (when walkable)
   int32_t* d_slot = nullptr;  // device scratch for transpose slot tables
   size_t d_slot_len = 0;
 };

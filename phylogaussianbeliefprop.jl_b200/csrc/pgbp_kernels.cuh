@@ -32,6 +32,12 @@ PGBP_HD void absmax(double& m, double x) {
   if (a > m || a != a) m = a;
 }
 
+// c - a*b with ONE rounding.  The library is compiled with -fmad=false, so the
+// only fused operations are the explicit ones: every kernel variant (register,
+// generic, walk, cooperative) that applies the same per-entry update order gives
+// bit-identical results.
+PGBP_HD double nfma(double a, double b, double c) { return fma(-a, b, c); }
+
 // compile-time loop: f(std::integral_constant<int, k>) for k = 0..N-1
 template <class F, int... Is>
 PGBP_HD void static_for_impl(F&& f, std::integer_sequence<int, Is...>) {
@@ -132,19 +138,19 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
       for (int c = 0; c < S; c++) Bm[k * S + c] *= rinv;
       const double wk = hI[k] * rinv;
       hI[k] = wk;
-      ww += wk * wk;
+      ww = fma(wk, wk, ww);
 #pragma unroll
       for (int c = k + 1; c < I; c++) {
         const double akc = AI[pk(k, c)];
 #pragma unroll
-        for (int r = k + 1; r <= c; r++) AI[pk(r, c)] -= AI[pk(k, r)] * akc;
-        hI[c] -= akc * wk;
+        for (int r = k + 1; r <= c; r++) AI[pk(r, c)] = nfma(AI[pk(k, r)], akc, AI[pk(r, c)]);
+        hI[c] = nfma(akc, wk, hI[c]);
       }
 #pragma unroll
       for (int c = 0; c < S; c++) {
         const double bkc = Bm[k * S + c];
 #pragma unroll
-        for (int r = k + 1; r < I; r++) Bm[r * S + c] -= AI[pk(k, r)] * bkc;
+        for (int r = k + 1; r < I; r++) Bm[r * S + c] = nfma(AI[pk(k, r)], bkc, Bm[r * S + c]);
       }
     }
     g += 0.5 * ((double)I * PGBP_LOG2PI - logdet + ww);
@@ -173,7 +179,7 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
       constexpr int k = decltype(kc)::value, q = q0 + k, c = colof(q), r = q - c * (c + 1) / 2;
       double nv = jo[k];
 #pragma unroll
-      for (int i = 0; i < I; i++) nv -= Bm[i * S + r] * Bm[i * S + c];
+      for (int i = 0; i < I; i++) nv = nfma(Bm[i * S + r], Bm[i * S + c], nv);
       const double d = nv - so[k];
       st[(md.sJ + q) * ld] = nv;
       st[ta[k]] = to[k] + d;
@@ -195,7 +201,7 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
     for (int k = 0; k < S; k++) {
       double nv = ho[k];
 #pragma unroll
-      for (int i = 0; i < I; i++) nv -= Bm[i * S + k] * hI[i];
+      for (int i = 0; i < I; i++) nv = nfma(Bm[i * S + k], hI[i], nv);
       const double d = nv - so[k];
       st[(md.sh + k) * ld] = nv;
       st[ta[k]] = to[k] + d;
@@ -337,11 +343,11 @@ PGBP_HD void message_thread_rt(const MsgArgs& a, int msg_index, int64_t e) {
       const double rinv = 1.0 / sqrt(d);
       for (int c = k + 1; c < M; c++) A[pk(k, c)] *= rinv;
       const double wk = hv[k] * rinv;
-      ww += wk * wk;
+      ww = fma(wk, wk, ww);
       for (int c = k + 1; c < M; c++) {
         const double akc = A[pk(k, c)];
-        for (int r = k + 1; r <= c; r++) A[pk(r, c)] -= A[pk(k, r)] * akc;
-        hv[c] -= akc * wk;
+        for (int r = k + 1; r <= c; r++) A[pk(r, c)] = nfma(A[pk(k, r)], akc, A[pk(r, c)]);
+        hv[c] = nfma(akc, wk, hv[c]);
       }
     }
     g += 0.5 * ((double)I * PGBP_LOG2PI - logdet + ww);
@@ -406,18 +412,18 @@ PGBP_HD void integrate_thread(const double* state, int32_t* status, int64_t ld, 
     for (int c = k + 1; c < M; c++) A[pk(k, c)] *= rinv;
     const double wk = hv[k] * rinv;
     hv[k] = wk;
-    ww += wk * wk;
+    ww = fma(wk, wk, ww);
     for (int c = k + 1; c < M; c++) {
       const double akc = A[pk(k, c)];
-      for (int r = k + 1; r <= c; r++) A[pk(r, c)] -= A[pk(k, r)] * akc;
-      hv[c] -= akc * wk;
+      for (int r = k + 1; r <= c; r++) A[pk(r, c)] = nfma(A[pk(k, r)], akc, A[pk(r, c)]);
+      hv[c] = nfma(akc, wk, hv[c]);
     }
   }
   norm[e] = g + 0.5 * ((double)M * PGBP_LOG2PI - logdet + ww);
   if (mu_soa) {
     for (int k = M - 1; k >= 0; k--) {  // U mu = w
       double s = hv[k];
-      for (int c = k + 1; c < M; c++) s -= A[pk(k, c)] * hv[c];
+      for (int c = k + 1; c < M; c++) s = nfma(A[pk(k, c)], hv[c], s);
       hv[k] = s * A[pk(k, k)];
       mu_soa[k * ld_out + e] = hv[k];
     }

@@ -8,6 +8,12 @@ using namespace pgbp;
 namespace pgbp {
 
 #define PGBP_MSG_THREADS 128
+#ifndef PGBP_WALK_THREADS
+#define PGBP_WALK_THREADS 128
+#endif
+#ifndef PGBP_WALK_MINBLOCKS
+#define PGBP_WALK_MINBLOCKS 2
+#endif
 
 #ifndef PGBP_HOST_EMUL
 template <int CI, int CS, int MAXM>
@@ -22,6 +28,53 @@ __global__ void __launch_bounds__(256) k_message_copy(MsgArgs a) {
   if (e >= a.B) return;
   message_copy_thread(a, blockIdx.y, e);
 }
+#endif
+
+// Walk kernel: one thread = one replicate walks the WHOLE message list of a
+// calibration (postorder then preorder) in the reference's sequential order.
+// Replicates are independent, so there is no inter-thread dependency at all:
+// one launch per calibration, no per-message launch latency, and a belief
+// written by message k is re-read by message k+1 from L1/L2 instead of HBM.
+// Shapes are restricted to the trait-multiple family of pgbp_shapes.h so that
+// every message still runs the register-resident specialised body.
+template <int P, int A_, int B_>
+PGBP_HD void walk_case(const MsgArgs& a, int m, int64_t e) {
+  if constexpr (A_ == 0) message_copy_thread(a, m, e);
+  else if constexpr ((A_ + B_) * P <= PGBP_T0_MAX) message_thread_t0<A_ * P, B_ * P>(a, m, e);
+}
+template <int P>
+PGBP_HD void walk_thread(const MsgArgs& a, int nmsg, int64_t e) {
+  if (a.status[e] != 0) return;
+  if (a.done && a.done[e]) return;
+  for (int m = 0; m < nmsg; m++) {
+    switch (a.msgs[m].wid) {
+      case 0: case 1: case 2: case 3: walk_case<P, 0, 0>(a, m, e); break;
+      case 4: walk_case<P, 1, 0>(a, m, e); break;
+      case 5: walk_case<P, 1, 1>(a, m, e); break;
+      case 6: walk_case<P, 1, 2>(a, m, e); break;
+      case 7: walk_case<P, 1, 3>(a, m, e); break;
+      case 8: walk_case<P, 2, 0>(a, m, e); break;
+      case 9: walk_case<P, 2, 1>(a, m, e); break;
+      case 10: walk_case<P, 2, 2>(a, m, e); break;
+      case 11: walk_case<P, 2, 3>(a, m, e); break;
+      case 12: walk_case<P, 3, 0>(a, m, e); break;
+      case 13: walk_case<P, 3, 1>(a, m, e); break;
+      case 14: walk_case<P, 3, 2>(a, m, e); break;
+      case 15: walk_case<P, 3, 3>(a, m, e); break;
+      default: break;
+    }
+    if (a.status[e] != 0) return;  // first failed message stops the traversal (src/calibration.jl:129-131)
+  }
+}
+
+#ifndef PGBP_HOST_EMUL
+template <int P>
+__global__ void __launch_bounds__(PGBP_WALK_THREADS, PGBP_WALK_MINBLOCKS) k_walk(MsgArgs a, int nmsg) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.B) return;
+  walk_thread<P>(a, nmsg, e);
+}
+
 template <int MAXM>
 __global__ void __launch_bounds__(128) k_integrate(const double* state, int32_t* status, int64_t B, int64_t ld,
                                                    int64_t jslot, int64_t hslot, int64_t gslot, int M,
@@ -107,6 +160,39 @@ MsgArgs make_args(pgbp_batch* b, uint32_t opts, int32_t ref_base, bool use_done)
   a.opts = opts;
   a.ref_base = ref_base;
   return a;
+}
+
+template <int P>
+static int launch_walk(pgbp_batch* b, const MsgArgs& a, int nmsg) {
+#ifdef PGBP_HOST_EMUL
+  for (int64_t e = 0; e < a.B; e++) walk_thread<P>(a, nmsg, e);
+#else
+  k_walk<P><<<(unsigned)((a.B + PGBP_WALK_THREADS - 1) / PGBP_WALK_THREADS), PGBP_WALK_THREADS, 0, b->stream>>>(a, nmsg);
+#endif
+  b->launches++;
+  return check_launch("k_walk");
+}
+
+// post (+ pre) traversal of one tree in a single launch; first/count select the
+// part of the walk list (postorder = [0,n), preorder = [n,2n))
+int run_walk(pgbp_batch* b, int tree, int first, int count, uint32_t opts, int32_t ref_base, bool use_done) {
+  MsgArgs a = make_args(b, opts, ref_base - first, use_done);
+  a.msgs = b->d_walk[tree] + first;
+  switch (b->plan->ntraits) {
+    case 1: return launch_walk<1>(b, a, count);
+    case 2: return launch_walk<2>(b, a, count);
+    case 3: return launch_walk<3>(b, a, count);
+    case 4: return launch_walk<4>(b, a, count);
+    default: PGBP_FAIL(PGBP_ESTATE, "walk kernel: unsupported ntraits");
+  }
+}
+
+bool use_walk(const pgbp_batch* b, int tree) {
+  const Tree& tr = b->plan->trees[tree];
+  if (!tr.walkable || b->plan->ntraits > PGBP_WALK_MAXP) return false;
+  // measured on B200 (lazaridis p=3, B=65536): level-parallel 70.3M calibrations/s, walk 46.5M
+  // (8 warps/SM at 255 registers cannot hide HBM latency) => the walk kernel is opt-in only
+  return b->walk_mode == 1;
 }
 
 int run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_t ref_base, bool use_done) {
@@ -207,8 +293,15 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
     for (size_t j = 0; j < ids.size(); j++) {
       const int t = ids[j];
       const int n = (int)p->trees[t].parent.size();
-      if (flags & PGBP_CAL_POSTORDER) { PGBP_TRY(run_traversal(b, t, 0, opts, ref, autostop)); ref += n; }
-      if (flags & PGBP_CAL_PREORDER) { PGBP_TRY(run_traversal(b, t, 1, opts, ref, autostop)); ref += n; }
+      if (use_walk(b, t)) {
+        const bool po = flags & PGBP_CAL_POSTORDER, pr = flags & PGBP_CAL_PREORDER;
+        const int first = po ? 0 : n, count = (po ? n : 0) + (pr ? n : 0);
+        PGBP_TRY(run_walk(b, t, first, count, opts, ref, autostop));
+        ref += count;
+      } else {
+        if (flags & PGBP_CAL_POSTORDER) { PGBP_TRY(run_traversal(b, t, 0, opts, ref, autostop)); ref += n; }
+        if (flags & PGBP_CAL_PREORDER) { PGBP_TRY(run_traversal(b, t, 1, opts, ref, autostop)); ref += n; }
+      }
       const bool last = (it == niter && j + 1 == ids.size());
       if (track && (autostop || last || b->want_info)) PGBP_TRY(launch_iscal(b, it, (int)j + 1, autostop));
       if (ref > (1 << 22)) ref = 0;  // keep the status word positive
@@ -248,6 +341,12 @@ int32_t pgbp_calibrate(pgbp_batch* b, const int32_t* tree_ids, int32_t ntrees, i
     iter_tree[2 * e] = itr.empty() ? 0 : itr[e];
     iter_tree[2 * e + 1] = itr.empty() ? 0 : itr[b->ld + e];
   }
+  return 0;
+}
+
+int32_t pgbp_batch_set_walk_mode(pgbp_batch* b, int32_t mode) {
+  if (!b || mode < -1 || mode > 1) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
+  b->walk_mode = mode;
   return 0;
 }
 

@@ -45,6 +45,7 @@ int pgbp_plan::make_msg(int32_t from, int32_t j, int32_t to, MsgDesc* out) {
   m.dmsg = 2 * j + side;
   m.rJ = rjslot[m.dmsg]; m.rh = rhslot[m.dmsg];
   m.mF = mF; m.s = s; m.ref = 0;
+  m.wid = walk_shape_id(ntraits, mF - s, s);
   // sender gather table in [I;K] order
   std::vector<char> keep(mF, 0);
   for (int k : *upF) keep[k] = 1;
@@ -229,6 +230,16 @@ int32_t pgbp_plan_create(const pgbp_plan_desc* d, pgbp_plan** out) {
     // preorder: i = 0..n-1, parent -> child (src/calibration.jl:147-151)
     for (int i = 0; i < n; i++) { f[i] = tr.parent[i]; s[i] = tr.sepset[i]; to[i] = tr.child[i]; }
     PGBP_TRY(build_traversal(p.get(), f, s, to, &tr.trav[1]));
+    // walk list: reference order, postorder then preorder
+    tr.walk.resize(2 * (size_t)n);
+    tr.walkable = n > 0;
+    for (int dir = 0; dir < 2; dir++)
+      for (const MsgDesc& m : tr.trav[dir].msgs) {
+        MsgDesc w = m;
+        w.ref = m.ref + dir * n;
+        tr.walk[w.ref] = w;
+        if (w.wid < 0) tr.walkable = false;
+      }
   }
   // node families
   if (d->families) {

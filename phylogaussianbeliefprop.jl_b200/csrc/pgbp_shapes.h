@@ -9,6 +9,7 @@
 #define PGBP_MAX_FAMILY 8
 #define PGBP_MAX_TRAITS 16
 #define PGBP_T0_MAX 12
+#define PGBP_WALK_MAXP 4
 
 namespace pgbp {
 inline void shape_class(int i, int s, int* ci, int* cs, int* maxm) {
@@ -17,6 +18,16 @@ inline void shape_class(int i, int s, int* ci, int* cs, int* maxm) {
   *ci = -1; *cs = -1;
   const int m = i + s;
   *maxm = m <= 16 ? 16 : (m <= 32 ? 32 : 64);
+}
+// "Walk" family for ntraits = P: a message whose integrated / kept dimensions are
+// a*P and b*P (a <= 3, b <= 3, whole nodes in scope) gets id 4a+b; anything else -1
+// (then the traversal uses the level-parallel launches).
+inline int walk_shape_id(int P, int i, int s) {
+  if (P < 1 || P > PGBP_WALK_MAXP || i % P || s % P) return -1;
+  const int a = i / P, b = s / P;
+  if (a > 3 || b > 3) return -1;
+  if (a > 0 && (a + b) * P > PGBP_T0_MAX) return -1;
+  return 4 * a + b;
 }
 }  // namespace pgbp
 

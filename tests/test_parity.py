@@ -458,3 +458,56 @@ def test_multivariate_shapes_vs_oracle(backend, p):
     for e in range(B):
         ref = OBP.integratebelief_cgb(cgbs[e], case.sched[0][2][0])[1]
         assert abs(ll[e] / ref - 1) <= TOL and abs(fe[e, 2] / ref - 1) <= 1e-9
+
+
+# ------------------------------------------------------------------ walk kernel == level-parallel launches
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_walk_kernel_matches_level_parallel_and_oracle(backend, p):
+    # one launch per calibration (each thread walks all messages of its replicate) must give the
+    # same beliefs, residuals, flags and failure status as one launch per step
+    lib = get_lib(backend)
+    rng = np.random.default_rng(200 + p)
+    A = rng.normal(size=(p, p))
+    R = A @ A.T / p + 0.1 * np.eye(p)
+    taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
+    B = 70
+    data = rng.normal(size=(B, 7, p))
+    model = M.MvFullBrownianMotion(R, np.zeros(p))
+    case = Case(GOLD["lazaridis"], "cliquetree", data[0], taxa, model, lib, order_hint=GOLD["lazaridis_cluster_labels"])
+    out = {}
+    for mode in (0, 1):
+        bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+        bt.set_walk_mode(mode)
+        bt.assignfactors(pgbp_b200.bm_params([R], np.zeros(p)), data)
+        # element 5: indefinite precision in cluster 10 (a leaf cluster of the clique tree)
+        J, h, g = bt.get_belief(10)
+        J[5] = -np.eye(p)
+        bt.set_belief(10, J, h, g)
+        n0 = bt.launch_count(reset=True)
+        succ, iscal = bt.calibrate(case.sched)
+        nl = bt.launch_count()
+        succ2, iscal2 = bt.calibrate(case.sched)
+        out[mode] = dict(succ=succ, iscal2=iscal2, st=bt.status(), nl=nl,
+                         beliefs=[bt.get_belief(j) for j in range(1, len(case.b) + 1)],
+                         res=[bt.get_residual(case.nclusters + 1 + j, case.plan.sepset_clusters[j][s] + 1)
+                              for j in range(case.plan.nsepsets) for s in (0, 1)])
+    if p <= 3:
+        assert out[1]["nl"] == 2 and out[0]["nl"] > 10  # walk kernel + iscal reduction
+    else:  # 4 nodes x 4 traits = 16 > register-resident limit: falls back to level-parallel launches
+        assert out[1]["nl"] == out[0]["nl"]
+    ok = np.arange(B) != 5
+    assert (out[0]["succ"] == ok).all() and (out[1]["succ"] == ok).all()
+    assert np.array_equal(out[0]["st"], out[1]["st"]) and out[0]["st"][5] != 0
+    assert out[0]["iscal2"][ok].all() and out[1]["iscal2"][ok].all()
+    for (J0, h0, g0), (J1, h1, g1) in zip(out[0]["beliefs"], out[1]["beliefs"]):
+        assert np.array_equal(J0[ok], J1[ok]) and np.array_equal(h0[ok], h1[ok]) and np.array_equal(g0[ok], g1[ok])
+    for r0, r1 in zip(out[0]["res"], out[1]["res"]):
+        assert np.array_equal(r0[0][ok], r1[0][ok]) and np.array_equal(r0[2][ok], r1[2][ok])
+    for e in (0, 6, B - 1):
+        cgb = case.oracle_cgb(tbl=data[e])
+        OBP.calibrate(cgb, case.sched)
+        OBP.calibrate(cgb, case.sched)
+        for j, (J1, h1, g1) in enumerate(out[1]["beliefs"]):
+            ob = cgb.belief[j]
+            assert max(relerr(J1[e], ob.J), relerr(h1[e], ob.h), relerr(g1[e], ob.g)) <= TOL
