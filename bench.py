@@ -37,51 +37,135 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "clique-tree calibrations/sec (batched replicates)"
-UNIT = "calibrations/s"
-WORKLOAD = ("lazaridis_2014 admixture graph, MvFullBrownianMotion p=3, 65,536 synthetic trait replicates per GPU, "
-            "clique tree, calibrate! (post+pre order, residual tracking) + integratebelief! [BASELINE configs[1]]")
-SEED = 0xB200 + 2
+SEED = 0xB200
 
 
-def load_plan_dict():
-    return json.load(open(os.path.join(ROOT, "workloads", "lazaridis_cliquetree_p3.json")))
+class C2:
+    """BASELINE configs[1]: lazaridis_2014, MvFullBM p=3, 65,536 trait replicates, clique tree."""
+    key = "c2"
+    unit = "calibrations/s"
+    workload = ("lazaridis_2014 admixture graph, MvFullBrownianMotion p=3, 65,536 synthetic trait replicates per GPU, "
+                "clique tree, calibrate! (post+pre order, residual tracking) + integratebelief! [BASELINE configs[1]]")
+    default_batch = 65536
+    ncolors = 1
+    residuals = True
+    step_text = "reset_from_factors + calibrate (post+pre, residuals, iscal) + integrate(root)"
+    e2e_text = "pinned host tip data -> assignfactors (H2D + K1) -> calibrate -> integratebelief -> D2H loglik"
+    kernel_text = "k_message<i,s> family (all 32 messages of a calibration)"
+    cpu_text = "assignfactors + calibrate + integratebelief per replicate"
+
+    def __init__(self):
+        self.d = json.load(open(os.path.join(ROOT, "workloads", "lazaridis_cliquetree_p3.json")))
+
+    def inputs(self, B, rank):
+        """R = A A'/3 + 0.1 I, mu = 0, fixed root; replicates simulated down the
+        network: X_v = sum_k gamma_k X_pa_k + N(0, sum_k gamma_k^2 t_k R).  One theta, B data sets."""
+        d = self.d
+        rng = np.random.Generator(np.random.PCG64(SEED + 2 + 1000 * rank))
+        p = d["ntraits"]
+        A = rng.normal(size=(p, p))
+        R = A @ A.T / 3 + 0.1 * np.eye(p)
+        Lr = np.linalg.cholesky(R)
+        n = len(d["simulate"])
+        X = np.zeros((n, B, p))
+        for v in range(1, n):
+            par = d["simulate"][v]
+            var = sum(g * g * t for _, t, g in par)
+            mean = sum(g * X[q] for q, t, g in par)
+            X[v] = mean + np.sqrt(var) * (rng.normal(size=(B, p)) @ Lr.T)
+        tips = np.ascontiguousarray(X[d["tip_nodes"]].transpose(1, 0, 2))  # [B][ntips][p]
+        params = np.concatenate([R.T.ravel(), np.zeros(p), np.zeros(p * p)])[None]
+        return params, tips
+
+    def cost(self, plan):
+        by = plan.traversal_cost(0, 0, True)[0] + plan.traversal_cost(0, 1, True)[0]
+        fl = plan.traversal_cost(0, 0, True)[1] + plan.traversal_cost(0, 1, True)[1]
+        return by, fl
+
+    cpu_kw = dict(post=True, pre=True, residnorm=True)
 
 
-def make_inputs(d, B, seed=SEED):
-    """R = A A'/3 + 0.1 I, mu = 0, fixed root; replicates simulated down the
-    network: X_v = sum_k gamma_k X_pa_k + N(0, sum_k gamma_k^2 t_k R)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    p = d["ntraits"]
-    A = rng.normal(size=(p, p))
-    R = A @ A.T / 3 + 0.1 * np.eye(p)
-    Lr = np.linalg.cholesky(R)
-    n = len(d["simulate"])
-    X = np.zeros((n, B, p))
-    for v in range(1, n):
-        par = d["simulate"][v]
-        var = sum(g * g * t for _, t, g in par)
-        mean = sum(g * X[q] for q, t, g in par)
-        X[v] = mean + np.sqrt(var) * (rng.normal(size=(B, p)) @ Lr.T)
-    tips = np.ascontiguousarray(X[d["tip_nodes"]].transpose(1, 0, 2))  # [B][ntips][p]
-    params = np.concatenate([R.T.ravel(), np.zeros(p), np.zeros(p * p)])[None]
-    return params, tips
+class C4(C2):
+    """BASELINE configs[3]: synthetic 10k-tip level-1 network, HeterogeneousBM p=8, grid of 4,096 theta."""
+    key = "c4"
+    unit = "likelihood evaluations/s"
+    workload = ("synthetic level-1 network, 10,000 tips + 1,000 reticulations (21,999 nodes; clique tree of 20,998 "
+                "clusters), HeterogeneousBrownianMotion p=8 with 4 rate colours, one shared data set, batched grid of "
+                "parameter vectors; unit = assignfactors! + postorder traversal + integratebelief!(root) "
+                "(the optimiser objective, src/calibration.jl:195-221) [BASELINE configs[3]]")
+    default_batch = 4096
+    ncolors = 4
+    residuals = False
+    step_text = "assign_factors (K1) + propagate_1traversal_postorder (20,997 messages) + integrate(root)"
+    e2e_text = "pinned host theta grid -> assignfactors (H2D + K1) -> postorder -> integratebelief -> D2H loglik"
+    kernel_text = "k_message* family (20,997 postorder messages of one likelihood evaluation)"
+    cpu_text = "assignfactors + postorder + integratebelief per parameter vector"
+
+    def __init__(self, ntips=10000, nretic=1000, p=8):
+        from workloads import synth
+        net = synth.level1_network(ntips, nretic, SEED + 4)
+        self.col = synth.edge_colors(net, self.ncolors)
+        self.d = synth.cliquetree_plan(net, p, True, self.col, name="synthetic_level1_%d" % ntips)
+        self.synth = synth
+
+    def inputs(self, B, rank):
+        d = self.d
+        p, nc = d["ntraits"], self.ncolors
+        rng = np.random.Generator(np.random.PCG64(SEED + 4 + 1000 * rank))
+
+        def rate():
+            A = rng.normal(size=(p, p))
+            return A @ A.T / p + 0.1 * np.eye(p)
+        R0 = [rate() for _ in range(nc)]
+        # families list parents by decreasing index; simulate lists them in edge order: map through parent id
+        par_col = {}
+        for v, fam in enumerate(d["simulate"]):
+            o = d["families"]["mem_off"][v]
+            order = sorted(range(len(fam)), key=lambda k: -fam[k][0])
+            for pos, k in enumerate(order):
+                par_col[(v, k)] = d["families"]["mem_color"][o + 1 + pos]
+        tips = self.synth.simulate_tips(d, lambda v, k: R0[par_col[(v, k)]], 1, SEED + 40)  # one shared data set
+        params = np.empty((B, nc * p * p + p + p * p))
+        for b in range(B):  # SURVEY 8(d) C4: R_c^(b) = A A'/p + 0.1 I
+            A = rng.normal(size=(nc, p, p))
+            R = A @ A.transpose(0, 2, 1) / p + 0.1 * np.eye(p)
+            params[b, :nc * p * p] = R.reshape(-1)  # symmetric: row- and column-major coincide
+            params[b, nc * p * p:] = 0.0
+        return params, tips
+
+    def cost(self, plan):
+        by, fl = plan.traversal_cost(0, 0, False)
+        return by, fl
+
+    cpu_kw = dict(post=True, pre=False, residnorm=False)
+
+
+WORKLOADS = {"c2": C2, "c4": C4}
 
 
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
-def cpu_port_rate(d, params, tips, seconds, nthreads=0):
-    """calibrations/s of the C/OpenMP oracle port on a bounded sample."""
+def cpu_port_rate(w, params, tips, seconds, nthreads=0, steps=1, warmup=0):
+    """units/s of the C/OpenMP oracle port on a bounded sample of the workload."""
     from oracle.cport import COracle, dll
-    co = COracle.from_plan_dict(d)
-    kw = dict(root_belief=d["root_cluster"], nthreads=nthreads)
-    n0 = min(2048, tips.shape[0])
-    co.run_batch(params, tips[:n0], **kw)  # warm-up (thread pool, page faults)
+    co = COracle.from_plan_dict(w.d)
+    kw = dict(root_belief=w.d["root_cluster"], nthreads=nthreads, ncolors=w.ncolors, **w.cpu_kw)
+    B = max(params.shape[0], tips.shape[0])
+
+    def run(n):
+        return co.run_batch(params[:n] if params.shape[0] > 1 else params, tips[:n] if tips.shape[0] > 1 else tips,
+                            B=n, **kw)
+    n0 = min(max(64, B // 32), B)
+    run(n0)  # warm-up (thread pool, page faults)
     t = time.perf_counter()
-    co.run_batch(params, tips[:n0], **kw)
+    run(n0)
     r0 = n0 / (time.perf_counter() - t)
-    n = int(min(tips.shape[0], max(n0, r0 * seconds)))
+    n = int(min(B, max(n0, r0 * seconds)))
+    for _ in range(warmup):
+        run(n)
     t = time.perf_counter()
-    out = co.run_batch(params, tips[:n], **kw)
-    dt = time.perf_counter() - t
+    for _ in range(steps):
+        out = run(n)
+    dt = (time.perf_counter() - t) / steps
     assert (out["status"] == 0).all()
     cores = dll().pgbpo_num_threads() if nthreads <= 0 else nthreads
     return n / dt, cores, n, dt, out["loglik"]
@@ -91,35 +175,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    d = load_plan_dict()
-    per_step = 3.0
-    params, tips = make_inputs(d, 65536)
-    from oracle.cport import COracle, dll
-    co = COracle.from_plan_dict(d)
-    kw = dict(root_belief=d["root_cluster"])
-    n0 = 2048
-    co.run_batch(params, tips[:n0], **kw)
-    t = time.perf_counter()
-    co.run_batch(params, tips[:n0], **kw)
-    r0 = n0 / (time.perf_counter() - t)
-    n = int(min(tips.shape[0], max(n0, r0 * per_step)))
-    for _ in range(args.warmup):
-        co.run_batch(params, tips[:n], **kw)
-    t = time.perf_counter()
-    for _ in range(args.steps):
-        co.run_batch(params, tips[:n], **kw)
-    dt = time.perf_counter() - t
-    cores = dll().pgbpo_num_threads()
-    value = n * args.steps / dt
-    sample = f"{n} of 65536 replicates per step (assignfactors + calibrate + integratebelief per replicate)"
+    w = WORKLOADS[args.workload]()
+    B = args.batch or w.default_batch
+    params, tips = w.inputs(B, 0)
+    value, cores, n, dt, _ = cpu_port_rate(w, params, tips, 3.0, steps=args.steps, warmup=args.warmup)
+    sample = f"{n} of {B} batch elements per step ({w.cpu_text})"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": w.unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference is Julia (absent from the image): C/OpenMP restatement of "
+        "config": {"workload": w.workload, "note": "reference is Julia (absent from the image): C/OpenMP restatement of "
                    "its algorithm (oracle/c), all host threads, bounded sample per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": value, "unit": w.unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": w.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -216,40 +284,56 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    if args.gpus != world:
-        if rank == 0:
-            print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; reporting n_gpus={world}", file=sys.stderr)
-    d = load_plan_dict()
-    B = args.batch
+    if args.gpus != world and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; reporting n_gpus={world}", file=sys.stderr)
+    w = WORKLOADS[args.workload]()
+    d = w.d
+    B = args.batch or w.default_batch
     p = d["ntraits"]
-    params, tips = make_inputs(d, B, SEED + 1000 * rank)
+    params, tips = w.inputs(B, rank)
     lib = pgbp_b200.default_library()
     plan = pgbp_b200.ClusterGraphPlan(d["nclusters"], d["belief_dim"], d["sepset_clusters"], d["upind"], d["trees"], p,
                                       d["families"], lib)
     stream = torch.cuda.current_stream()
-    bt = pgbp_b200.BatchedClusterGraphBelief(plan, B, device=local, stream=stream.cuda_stream)
+    bt = pgbp_b200.BatchedClusterGraphBelief(plan, B, device=local, stream=stream.cuda_stream,
+                                             factors=w.residuals, residuals=w.residuals)
     if args.walk is not None:
         bt.set_walk_mode(args.walk)
     root = d["root_cluster"] + 1
-    bytes_cal = plan.traversal_cost(0, 0, True)[0] + plan.traversal_cost(0, 1, True)[0]
-    flops_cal = plan.traversal_cost(0, 0, True)[1] + plan.traversal_cost(0, 1, True)[1]
+    bytes_unit, flops_unit = w.cost(plan)
+    nmsg = len(d["trees"][0][0]) * (2 if w.key == "c2" else 1)
 
-    # ---- device-resident arm -------------------------------------------------
-    bt.assignfactors(params, tips)  # factors resident in HBM before the timed region
+    # ---- device-resident arm: inputs in HBM before the timed region -----------------------
     _, ld, _ = bt.device_view()
     d_norm = torch.empty(ld, dtype=torch.float64, device=dev)
     gathered = torch.empty(world * ld, dtype=torch.float64, device=dev) if world > 1 else None
+    if w.key == "c2":
+        bt.assignfactors(params, tips)  # factors resident in HBM
 
-    def step(ev=None):
-        bt.init_beliefs_reset_fromfactors()
-        if ev:
-            ev[0].record(stream)
-        bt.calibrate_async(None, 1, update_residualnorm=True)
-        if ev:
-            ev[1].record(stream)
-        bt.integrate_device(root, d_norm.data_ptr())
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, d_norm)
+        def step(ev=None):
+            bt.init_beliefs_reset_fromfactors()
+            if ev:
+                ev[0].record(stream)
+            bt.calibrate_async(None, 1, update_residualnorm=True)
+            if ev:
+                ev[1].record(stream)
+            bt.integrate_device(root, d_norm.data_ptr())
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, d_norm)
+    else:
+        d_params = torch.from_numpy(params).to(dev)
+        d_tips = torch.from_numpy(tips).to(dev)
+
+        def step(ev=None):
+            bt.assignfactors_device(d_params.data_ptr(), params.shape[0], d_tips.data_ptr(), tips.shape[0], ncolors=w.ncolors)
+            if ev:
+                ev[0].record(stream)
+            bt.calibrate_async(None, 1, update_residualnorm=False, direction=L.CAL_POSTORDER)
+            if ev:
+                ev[1].record(stream)
+            bt.integrate_device(root, d_norm.data_ptr())
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, d_norm)
 
     def barrier():
         torch.cuda.synchronize()
@@ -284,29 +368,36 @@ def run_gpu(args):
     assert (st == 0).all(), "numerical failure inside the timed region"
     loglik_dev = d_norm[:B].cpu().numpy()
 
-    # ---- end-to-end arm: public host-buffer API --------------------------------
+    # ---- end-to-end arm: public host-buffer API, pinned host inputs, D2H of the result -------
     nbuf = 2
-    pinned = [torch.from_numpy(tips.copy()).pin_memory() for _ in range(nbuf)]
+    big = tips if w.key == "c2" else params
+    pinned = [torch.from_numpy(big.copy()).pin_memory() for _ in range(nbuf)]
     pin_np = [t.numpy() for t in pinned]
+    e2e_steps = args.steps if w.key == "c2" else min(args.steps, 5)
+
+    def e2e_step(k):
+        if w.key == "c2":
+            bt.assignfactors(params, pin_np[k % nbuf])            # H2D of this step's inputs + K1
+            succ, iscal = bt.calibrate(None, 1)                    # D2H of succ / iscal
+        else:
+            bt.assignfactors(pin_np[k % nbuf], tips, ncolors=w.ncolors)
+            succ = bt.propagate_1traversal_postorder(0, update_residualnorm=False)
+        return bt.integratebelief(root, want_mu=False)[1]          # D2H of the result
     ll_host = None
     for k in range(2):
-        bt.assignfactors(params, pin_np[k % nbuf])
-        bt.calibrate(None, 1)
-        _, ll_host = bt.integratebelief(root, want_mu=False)
+        ll_host = e2e_step(k)
     barrier()
     t0e = time.perf_counter()
-    for k in range(args.steps):
-        bt.assignfactors(params, pin_np[k % nbuf])            # H2D of this step's inputs + K1
-        succ, iscal = bt.calibrate(None, 1)                    # D2H of succ / iscal
-        _, ll_host = bt.integratebelief(root, want_mu=False)   # D2H of the result
+    for k in range(e2e_steps):
+        ll_host = e2e_step(k)
     barrier()
     dte = time.perf_counter() - t0e
     te = torch.tensor([dte], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(te[0])
+    e2e_value = world * B * e2e_steps / float(te[0])
     h2d = tips.nbytes + params.nbytes
-    d2h = ll_host.nbytes + 2 * 4 * B
+    d2h = ll_host.nbytes + (2 if w.key == "c2" else 1) * 4 * B
     assert np.allclose(ll_host, loglik_dev, rtol=1e-12, atol=0)
 
     if rank != 0:
@@ -320,43 +411,43 @@ def run_gpu(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = bytes_cal * B * args.steps / (ms_msgs * 1e-3) / 1e9
+    achieved = bytes_unit * B * args.steps / (ms_msgs * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_calibration_per_replicate")
+        traffic = json.load(open(tp)).get(w.key, {}).get("dram_bytes_per_unit_per_element")
         if traffic is not None:
             traffic = traffic * B
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "k_message<i,s> family (all 32 messages of a calibration)",
-                "algorithmic_bytes_per_calibration_per_replicate": bytes_cal,
-                "algorithmic_flops_per_calibration_per_replicate": flops_cal,
+                "traffic": traffic, "peak_source": peak_src, "kernel": w.kernel_text,
+                "algorithmic_bytes_per_unit_per_element": bytes_unit,
+                "algorithmic_flops_per_unit_per_element": flops_unit,
+                "fp64_gflops_achieved": flops_unit * B * args.steps / (ms_msgs * 1e-3) / 1e9,
                 "share_of_step": ms_msgs / ms_total}
 
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        rate, cores, n, dt, ll_cpu = cpu_port_rate(d, params, tips, args.cpu_seconds)
+        rate, cores, n, dt, ll_cpu = cpu_port_rate(w, params, tips, args.cpu_seconds)
         err = float(np.max(np.abs(ll_cpu / loglik_dev[:n] - 1)))
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n} of {B} replicates in {dt:.1f} s (assignfactors + calibrate + integratebelief per replicate, "
-                         f"C/OpenMP restatement of the Julia reference)",
+        cpu = {"value": rate, "unit": w.unit, "cores": cores, "kind": "port",
+               "sample": f"{n} of {B} batch elements in {dt:.1f} s ({w.cpu_text}, C/OpenMP restatement of the Julia "
+                         f"reference)",
                "max_rel_err_gpu_vs_cpu_loglik": err}
         assert err < 1e-10, err
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": w.unit, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "replicates_per_gpu": B, "ntraits": p, "messages_per_calibration": 32,
-                   "step": "reset_from_factors + calibrate (post+pre, residuals, iscal) + integrate(root)"
-                           + (" + nccl all_gather(loglik)" if world > 1 else ""),
+        "config": {"workload": w.workload, "batch_per_gpu": B, "ntraits": p, "messages_per_unit": nmsg,
+                   "step": w.step_text + (" + nccl all_gather(loglik)" if world > 1 else ""),
                    "l2": "inputs larger than L2 (state %.2f GB per GPU)" % (bt.device_bytes() / 1e9),
-                   "parallelism": f"replicate batch sharded over {world} GPU(s), plan replicated"},
+                   "parallelism": f"batch sharded over {world} GPU(s), plan replicated"},
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "path": "pinned host tip data -> assignfactors (H2D + K1) -> calibrate -> integratebelief -> D2H loglik"},
+        "e2e": {"value": e2e_value, "unit": w.unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "path": w.e2e_text},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -371,7 +462,9 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=65536, help="replicates per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="batch elements per GPU (default: the workload's)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = BASELINE configs[1] (headline), "
+                    "c4 = configs[3] (10k-tip synthetic network, p=8)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--walk", type=int, default=None, help="kernel strategy override: 0 level-parallel, 1 walk kernel")

@@ -145,6 +145,11 @@ int64_t pgbp_batch_launch_count(pgbp_batch* batch, int32_t reset);
  * replicate; needs every message shape to be whole nodes of ntraits <= 4 traits, else falls
  * back to 0).  Results are bit-identical. */
 int32_t pgbp_batch_set_walk_mode(pgbp_batch* batch, int32_t mode);
+/* Kernel for medium message shapes (sender dimension > 12): -1 automatic (= 1 where it fits),
+ * 1 shared-memory kernel (one thread per element, factor in shared memory), 4 / 8 cooperative
+ * kernel (that many lanes per element for sender dimensions <= 16, 8 above; sender dimension
+ * <= 32), 0 one thread per element with thread-local storage.  Results are bit-identical. */
+int32_t pgbp_batch_set_coop_mode(pgbp_batch* batch, int32_t mode);
 
 /* Host <-> device belief access (CanonicalBelief fields, src/beliefs.jl:72-132).
  * J: [B][m][m] column-major full square, h: [B][m], g: [B]; any pointer may be
@@ -192,6 +197,11 @@ int32_t pgbp_reset_calibration_flags(pgbp_batch* batch, int32_t reset_kl);
 int32_t pgbp_assign_factors(pgbp_batch* batch, int32_t ncolors, const double* params,
                             int64_t nparamsets, const double* tipdata, int64_t ndatasets,
                             int32_t pairing);
+/* same with DEVICE pointers (records already in HBM), enqueue only: the optimiser inner loop that
+ * keeps its theta grid on the GPU (src/calibration.jl:195-221) */
+int32_t pgbp_assign_factors_device(pgbp_batch* batch, int32_t ncolors, const double* d_params,
+                                   int64_t nparamsets, const double* d_tipdata, int64_t ndatasets,
+                                   int32_t pairing);
 
 /* ---------------------------------------------------------------- message passing */
 #define PGBP_CAL_POSTORDER 1u       /* propagate_1traversal_postorder! (src/calibration.jl:111-135) */

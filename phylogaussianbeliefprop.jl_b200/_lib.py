@@ -52,6 +52,7 @@ SIGNATURES = {
     "pgbp_batch_device_bytes": (i64, [vp]),
     "pgbp_batch_launch_count": (i64, [vp, i32]),
     "pgbp_batch_set_walk_mode": (i32, [vp, i32]),
+    "pgbp_batch_set_coop_mode": (i32, [vp, i32]),
     "pgbp_set_belief": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
     "pgbp_get_belief": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
     "pgbp_get_factor": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
@@ -63,6 +64,7 @@ SIGNATURES = {
     "pgbp_reset_from_factors": (i32, [vp]),
     "pgbp_reset_calibration_flags": (i32, [vp, i32]),
     "pgbp_assign_factors": (i32, [vp, i32, P(f64), i64, P(f64), i64, i32]),
+    "pgbp_assign_factors_device": (i32, [vp, i32, vp, i64, vp, i64, i32]),
     "pgbp_calibrate": (i32, [vp, P(i32), i32, i32, u32, P(i32), P(i32), P(i32)]),
     "pgbp_calibrate_async": (i32, [vp, P(i32), i32, i32, u32]),
     "pgbp_propagate": (i32, [vp, i32, i32, i32, u32]),

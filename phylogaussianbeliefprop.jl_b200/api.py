@@ -286,6 +286,10 @@ class BatchedClusterGraphBelief:
         """-1 auto, 0 level-parallel launches, 1 single walk kernel per traversal."""
         self.lib.check(self.lib.pgbp_batch_set_walk_mode(self.handle, int(mode)))
 
+    def set_coop_mode(self, mode):
+        """-1 auto, 1 shared-memory kernel, 4 / 8 cooperative lanes, 0 thread-local generic kernel."""
+        self.lib.check(self.lib.pgbp_batch_set_coop_mode(self.handle, int(mode)))
+
     def synchronize(self):
         self.lib.check(self.lib.pgbp_batch_synchronize(self.handle))
 
@@ -346,6 +350,13 @@ class BatchedClusterGraphBelief:
         self.lib.check(self.lib.pgbp_assign_factors(self.handle, int(ncolors), _fptr(pa), pa.shape[0], _fptr(td), nd, pr))
 
     init_factors_frommodel = assignfactors
+
+    def assignfactors_device(self, d_params_ptr, nparamsets, d_tip_ptr, ndatasets, ncolors=1, pairing="zip"):
+        """assignfactors! with the parameter / tip-data records already on the device (enqueue only)."""
+        pr = {"zip": L.PAIR_ZIP, "product": L.PAIR_PRODUCT}[pairing]
+        self.lib.check(self.lib.pgbp_assign_factors_device(
+            self.handle, int(ncolors), C.c_void_p(int(d_params_ptr)), int(nparamsets),
+            C.c_void_p(int(d_tip_ptr)) if d_tip_ptr else None, int(ndatasets), pr))
 
     def init_beliefs_reset(self):
         self.lib.check(self.lib.pgbp_reset_beliefs(self.handle))

@@ -1,0 +1,633 @@
+// K2, cooperative class: medium message shapes (sender dimension 13..32), G lanes per
+// batch element.
+//
+// Why: one thread per element needs S(m_F)+m_F doubles of live state (m_F = 24: 324 doubles =
+// 648 registers) -- it spills to local memory and thrashes L1/L2 (measured 260 GB/s on
+// (i,s) = (16,8)).  Here the sender belief is spread column-cyclically over G lanes of one
+// warp: lane g owns columns c = g, g+G, g+2G, .. of the [I;K]-ordered upper triangle (rows
+// 0..c) and the matching entries of h.  m_F = 24, G = 8: at most 8+16+24 (+3) doubles per lane.
+//
+// Memory: the state layout is unchanged (batch-innermost SoA).  A warp holds 32/G consecutive
+// elements; lanes with the same g are adjacent, so every warp-level load/store touches G slots x
+// (32/G consecutive doubles): full 32-byte sectors for G <= 8.
+//
+// Arithmetic: right-looking U'U elimination of the first I pivots.  At pivot k every lane scales
+// its own row-k entries (U[k,c] = A[k,c] / sqrt(d_k)) and publishes them in a per-element row
+// buffer in shared memory; after one __syncwarp every lane reads U[k,r] (broadcast reads: the G
+// lanes of an element read the same word) and applies  A[r,c] -= U[k,r] U[k,c]  to its columns.
+// Each entry therefore receives its updates in ascending k with the same operands as in the
+// register-resident (T0) and generic kernels: results are bit-identical to theirs.
+// After I pivots the trailing block IS the outgoing message (src/beliefupdates.jl:77-82); each
+// lane then does divide! / mult! / residual (src/beliefupdates.jl:579-587,483-488,646-647) for its
+// own columns.
+#pragma once
+#include "pgbp_kernels.cuh"
+
+namespace pgbp {
+
+#ifndef PGBP_HOST_EMUL
+
+template <int MAXM, int G>
+__global__ void __launch_bounds__(128) k_message_coop(MsgArgs a) {
+  constexpr int RPW = 32 / G;               // elements per warp
+  constexpr int RPB = 128 / G;              // elements per block
+  constexpr int NJ = (MAXM + G - 1) / G;    // column slots per lane
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ double rowbuf[2][MAXM + 1][RPB];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / RPW, rw = lane % RPW;  // lane = g * RPW + rw
+  const int rb = warp * RPW + rw;
+  const int64_t e = (int64_t)blockIdx.x * RPB + rb;
+  const MsgDesc md = a.msgs[blockIdx.y];
+  const int I = md.mF - md.s, S = md.s, M = md.mF;
+  const int64_t ld = a.ld;
+  bool active = e < a.B;
+  if (active) active = a.status[e] == 0 && !(a.done && a.done[e]);
+  double* st = a.state + (active ? e : 0);
+  double* rs = a.resid ? a.resid + (active ? e : 0) : nullptr;
+  const int32_t* __restrict__ gat = a.tab + md.gat;
+  const int32_t* __restrict__ sca = a.tab + md.sca;
+  const int SM = tri(M), SS = tri(S);
+  // lanes of this element: bit (gg * RPW + rw) for gg < G
+  unsigned repmask = 0;
+#pragma unroll
+  for (int gg = 0; gg < G; gg++) repmask |= 1u << (gg * RPW + rw);
+
+  // ---- gather my columns (rows 0..c) and my h entries ---------------------------------
+  double A[NJ][MAXM];
+  double hc[NJ];
+  bool nz = false;  // some entry of J_II, J_IK, h_I is not within eps of 0 (src/beliefupdates.jl:63)
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const int c = g + G * j;
+    const bool cv = active && c < M;
+    const int RJ = (G * j + G < MAXM) ? (G * j + G) : MAXM;
+#pragma unroll
+    for (int r = 0; r < RJ; r++) {
+      double v = 0.0;
+      if (cv && r <= c) v = st[(md.fJ + gat[pk(r, c)]) * ld];
+      A[j][r] = v;
+      if (r < I && !(fabs(v) <= PGBP_EPS)) nz = true;
+    }
+    double hv = 0.0;
+    if (cv) hv = st[(md.fh + gat[SM + c]) * ld];
+    hc[j] = hv;
+    if (c < I && !(fabs(hv) <= PGBP_EPS)) nz = true;
+  }
+  const double g_old = st[md.fg * ld];
+  const bool skip = (__ballot_sync(FULL, nz) & repmask) == 0;  // message = (h_K, J_KK, g) unchanged
+
+  // ---- eliminate the first I pivots -----------------------------------------------------
+  double dk[NJ];  // pivots I own (k = g + G*j), for the log-determinant
+#pragma unroll
+  for (int j = 0; j < NJ; j++) dk[j] = 1.0;
+  double ww = 0.0;
+  int fail_pivot = 0;
+#pragma unroll
+  for (int k = 0; k < MAXM; k++) {
+    if (k >= I) break;
+    const int jk = k / G, gk = k % G;  // compile-time after unrolling
+    const int src = gk * RPW + rw;
+    const double d = __shfl_sync(FULL, A[jk][k], src);
+    if (!skip && fail_pivot == 0 && !(d > 0.0)) fail_pivot = k + 1;  // LAPACK potrf info (also NaN)
+    if (g == gk) dk[jk] = d;
+    const double rinv = skip ? 0.0 : 1.0 / sqrt(d);
+    double(*row)[RPB] = rowbuf[k & 1];
+    // scale my row-k entries, publish them
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      const int RJ = (G * j + G < MAXM) ? (G * j + G) : MAXM;
+      if (k < RJ) {
+        const int c = g + G * j;
+        if (c > k) {
+          const double u = A[j][k] * rinv;
+          A[j][k] = u;
+          if (c < M) row[c][rb] = u;
+        } else if (c == k) {
+          row[MAXM][rb] = hc[j] * rinv;  // w_k
+        }
+      }
+    }
+    __syncwarp();
+    const double wk = row[MAXM][rb];
+    ww = fma(wk, wk, ww);
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      const int RJ = (G * j + G < MAXM) ? (G * j + G) : MAXM;
+      if (k + 1 < RJ) {
+        const int c = g + G * j;
+        if (c > k) {
+          const double ukc = A[j][k];
+#pragma unroll
+          for (int r = k + 1; r < RJ; r++)
+            if (r <= c && c < M) A[j][r] = nfma(row[r][rb], ukc, A[j][r]);
+          hc[j] = nfma(ukc, wk, hc[j]);
+        }
+      }
+    }
+  }
+  if (fail_pivot) {
+    if (active && g == 0) status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, fail_pivot));
+    active = false;
+  }
+
+  // ---- log-normaliser: logs of my pivots in parallel, summed in pivot order ---------------
+  double lg[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) lg[j] = (G * j < MAXM && g + G * j < I) ? log(dk[j]) : 0.0;
+  double logdet = 0.0;
+#pragma unroll
+  for (int k = 0; k < MAXM; k++) {
+    if (k >= I) break;
+    logdet += __shfl_sync(FULL, lg[k / G], (k % G) * RPW + rw);
+  }
+  double gnew = g_old;
+  if (!skip) gnew += 0.5 * ((double)I * PGBP_LOG2PI - logdet + ww);
+
+  // ---- divide! / mult! / residual for my kept columns -----------------------------------------
+  double maxJ = 0.0, maxh = 0.0;
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const int RJ = (G * j + G < MAXM) ? (G * j + G) : MAXM;
+    const int c = g + G * j;
+    const bool cv = active && c >= I && c < M;
+    const int cc = c - I;
+#pragma unroll
+    for (int r0 = 0; r0 < RJ; r0 += PGBP_CHUNK) {
+      double so[PGBP_CHUNK], to[PGBP_CHUNK];
+      int64_t ta[PGBP_CHUNK], sa[PGBP_CHUNK];
+#pragma unroll
+      for (int u = 0; u < PGBP_CHUNK; u++) {
+        const int r = r0 + u;
+        if (r < RJ) {
+          const bool v = cv && r >= I && r <= c;
+          const int q = v ? pk(r - I, cc) : 0;
+          sa[u] = (md.sJ + q) * ld;
+          ta[u] = (md.tJ + (v ? sca[q] : 0)) * ld;
+          so[u] = v ? st[sa[u]] : 0.0;
+          to[u] = v ? st[ta[u]] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PGBP_CHUNK; u++) {
+        const int r = r0 + u;
+        if (r < RJ) {
+          const bool v = cv && r >= I && r <= c;
+          if (v) {
+            const double nv = A[j][r];
+            const double d = nv - so[u];
+            st[sa[u]] = nv;
+            st[ta[u]] = to[u] + d;
+            if (rs) rs[(md.rJ + pk(r - I, cc)) * ld] = d;
+            absmax(maxJ, d);
+          }
+        }
+      }
+    }
+    if (cv) {
+      const int64_t sa = (md.sh + cc) * ld, ta = (md.th + sca[SS + cc]) * ld;
+      const double so = st[sa], to = st[ta];
+      const double nv = hc[j];
+      const double d = nv - so;
+      st[sa] = nv;
+      st[ta] = to + d;
+      if (rs) rs[(md.rh + cc) * ld] = d;
+      absmax(maxh, d);
+    }
+  }
+  // NaN-propagating max over the G lanes of the element
+#pragma unroll
+  for (int gg = 1; gg < G; gg <<= 1) {
+    const int src = ((g ^ gg) * RPW + rw);
+    const double oJ = __shfl_sync(FULL, maxJ, src), oh = __shfl_sync(FULL, maxh, src);
+    if (oJ > maxJ || oJ != oJ) maxJ = (maxJ != maxJ) ? maxJ : oJ;
+    if (oh > maxh || oh != oh) maxh = (maxh != maxh) ? maxh : oh;
+  }
+  if (active && g == 0) {
+    const double sg_old = st[md.sg * ld], tg_old = st[md.tg * ld];
+    st[md.sg * ld] = gnew;
+    st[md.tg * ld] = tg_old + (gnew - sg_old);
+    store_flag(a, md.dmsg, e, S, maxJ, maxh);
+  }
+}
+
+#endif  // !PGBP_HOST_EMUL
+
+// =====================================================================================
+// K2, shared-memory class ("T0S"): the register-resident algorithm of message_thread_t0 with its
+// working set (U = chol(J_II) rows, Z = U^-T J_IK, w = U^-T h_I) held in SHARED memory instead of
+// registers, one thread per batch element, one warp per block.
+//
+// Why this and not more lanes per element: the cooperative kernel above spends ~0.19 warp
+// instructions per byte moved (every lane repeats the pivot bookkeeping and runs predicated-off
+// work) and the SM's issue rate, not HBM, bounds it.  One thread per element costs ~0.04, so the
+// kernel can be HBM-bound; what a thread lacks is storage (m_F = 16: 108 live doubles), and that
+// is what shared memory provides: tri(I) + I*S + I doubles per element, laid out [entry][lane], so
+// every LDS/STS of a warp is one conflict-free 256-byte row and no two threads ever touch the same
+// word -- no barrier anywhere in the kernel.
+//
+//   A  the I-rows of the sender (J_II upper, J_IK, h_I) go global -> shared with 8-byte cp.async:
+//      all loads of the element are in flight at once, no registers staged;
+//   B  left-looking U'U: one column at a time in registers (at most MAXI doubles), previous rows
+//      read back from shared memory: one LDS per FMA, one STS per finished entry;
+//   C  the kept block is STREAMED column by column, like in message_thread_t0: sender J_KK, old
+//      sepset and old receiver values are loaded together (24 independent loads per thread), then
+//      new = J_KK - z_r.z_c, delta = new - old, three stores.
+// Per-entry update order and operands equal message_thread_t0 / message_thread_rt: bit-identical.
+// =====================================================================================
+#ifndef PGBP_HOST_EMUL
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// doubles of shared memory per element
+inline __host__ __device__ int smem_doubles(int I, int S) { return I * (I + 1) / 2 + I * S + I; }
+
+template <int MAXI>
+__global__ void __launch_bounds__(32) k_message_smem_rt(MsgArgs a) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x;
+  const int64_t e = (int64_t)blockIdx.x * 32 + tid;
+  if (e >= a.B) return;
+  if (a.status[e] != 0) return;
+  if (a.done && a.done[e]) return;
+  const MsgDesc md = a.msgs[blockIdx.y];
+  const int I = md.mF - md.s, S = md.s, M = md.mF;
+  const int64_t ld = a.ld;
+  double* st = a.state + e;
+  double* rs = a.resid ? a.resid + e : nullptr;
+  const int32_t* __restrict__ gat = a.tab + md.gat;
+  const int32_t* __restrict__ sca = a.tab + md.sca;
+  const int TI = tri(I), SMM = tri(M), SS = tri(S);
+  const int ZB = TI, WB = TI + I * S;  // region bases: Z(k, cc) = ZB + cc*I + k, w(k) = WB + k
+#define PGBP_SM(ent) sm[(ent) * 32 + tid]
+
+  // ---- A: I-rows of the sender -> shared (asynchronous) ---------------------------------
+  for (int c = 0; c < M; c++) {
+    const int kmax = c < I ? c + 1 : I;
+    const int base = c < I ? tri(c) : ZB + (c - I) * I;
+    const int32_t* gc = gat + tri(c);
+#pragma unroll 4
+    for (int k = 0; k < kmax; k++) cp_async8(&PGBP_SM(base + k), st + (md.fJ + gc[k]) * ld);
+  }
+#pragma unroll 4
+  for (int k = 0; k < I; k++) cp_async8(&PGBP_SM(WB + k), st + (md.fh + gat[SMM + k]) * ld);
+  double g = st[md.fg * ld];
+  const double sg_old = st[md.sg * ld], tg_old = st[md.tg * ld];
+  cp_async_wait_all();
+
+  // "Ji = Jki = hi = 0 if missing data" shortcut (src/beliefupdates.jl:62-66)
+  bool allzero = true;
+  {
+    const int n = WB + I;
+#pragma unroll 4
+    for (int q = 0; q < n; q++)
+      if (!(fabs(PGBP_SM(q)) <= PGBP_EPS)) allzero = false;
+  }
+
+  if (!allzero) {
+    // ---- B: left-looking factorisation, column c in registers ------------------------------
+    double rinv[MAXI];
+#pragma unroll
+    for (int k = 0; k < MAXI; k++) rinv[k] = 0.0;
+    double logdet = 0.0, ww = 0.0;
+    for (int c = 0; c <= M; c++) {  // c == M: the h column
+      const bool isp = c < I, ish = c == M;
+      const int kmax = isp ? c + 1 : I;      // rows held
+      const int nelim = isp ? c : I;         // pivots applied
+      const int base = isp ? tri(c) : (ish ? WB : ZB + (c - I) * I);
+      double v[MAXI];
+#pragma unroll
+      for (int k = 0; k < MAXI; k++) v[k] = k < kmax ? PGBP_SM(base + k) : 0.0;
+#pragma unroll
+      for (int k = 0; k < MAXI; k++) {
+        if (k >= nelim) break;
+        const double u = v[k] * rinv[k];
+        v[k] = u;
+        PGBP_SM(base + k) = u;
+        if (ish) ww = fma(u, u, ww);
+#pragma unroll
+        for (int r = k + 1; r < MAXI; r++)
+          if (r < kmax) v[r] = nfma(PGBP_SM(pk(k, r)), u, v[r]);
+      }
+      if (isp) {
+        double d = 0.0;
+#pragma unroll
+        for (int k = 0; k < MAXI; k++)
+          if (k == c) d = v[k];
+        if (!(d > 0.0)) {  // LAPACK potrf: info = c+1 (also catches NaN)
+          status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, c + 1));
+          return;
+        }
+        logdet += log(d);
+        const double ri = 1.0 / sqrt(d);
+#pragma unroll
+        for (int k = 0; k < MAXI; k++)
+          if (k == c) rinv[k] = ri;
+      }
+    }
+    g += 0.5 * ((double)I * PGBP_LOG2PI - logdet + ww);
+  } else {
+    const int n = WB + I;  // message = (h_K, J_KK, g) unchanged: Z = 0, w = 0
+    for (int q = TI; q < n; q++) PGBP_SM(q) = 0.0;
+  }
+
+  // ---- C: stream the kept block ---------------------------------------------------------------
+  double maxJ = 0.0, maxh = 0.0;
+  for (int cc = 0; cc < S; cc++) {
+    double zc[MAXI];
+#pragma unroll
+    for (int i = 0; i < MAXI; i++) zc[i] = i < I ? PGBP_SM(ZB + cc * I + i) : 0.0;
+    const int32_t* gc = gat + tri(I + cc) + I;  // sender slots of (I+rr, I+cc), rr = 0..cc
+    const int qc = tri(cc);
+    for (int r0 = 0; r0 <= cc; r0 += PGBP_CHUNK) {
+      double jo[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
+      int64_t ta[PGBP_CHUNK];
+#pragma unroll
+      for (int u = 0; u < PGBP_CHUNK; u++) {
+        const int rr = r0 + u;
+        if (rr <= cc) {
+          ta[u] = (md.tJ + sca[qc + rr]) * ld;
+          jo[u] = st[(md.fJ + gc[rr]) * ld];
+          so[u] = st[(md.sJ + qc + rr) * ld];
+          to[u] = st[ta[u]];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PGBP_CHUNK; u++) {
+        const int rr = r0 + u;
+        if (rr <= cc) {
+          double nv = jo[u];
+          const int zb = ZB + rr * I;
+#pragma unroll
+          for (int i = 0; i < MAXI; i++)
+            if (i < I) nv = nfma(PGBP_SM(zb + i), zc[i], nv);
+          const double d = nv - so[u];
+          st[(md.sJ + qc + rr) * ld] = nv;
+          st[ta[u]] = to[u] + d;
+          if (rs) rs[(md.rJ + qc + rr) * ld] = d;
+          absmax(maxJ, d);
+        }
+      }
+    }
+  }
+  {
+    double w[MAXI];
+#pragma unroll
+    for (int i = 0; i < MAXI; i++) w[i] = i < I ? PGBP_SM(WB + i) : 0.0;
+    const int32_t* gh = gat + SMM + I;
+    for (int k0 = 0; k0 < S; k0 += PGBP_CHUNK) {
+      double ho[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
+      int64_t ta[PGBP_CHUNK];
+#pragma unroll
+      for (int u = 0; u < PGBP_CHUNK; u++) {
+        const int k = k0 + u;
+        if (k < S) {
+          ta[u] = (md.th + sca[SS + k]) * ld;
+          ho[u] = st[(md.fh + gh[k]) * ld];
+          so[u] = st[(md.sh + k) * ld];
+          to[u] = st[ta[u]];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PGBP_CHUNK; u++) {
+        const int k = k0 + u;
+        if (k < S) {
+          double nv = ho[u];
+          const int zb = ZB + k * I;
+#pragma unroll
+          for (int i = 0; i < MAXI; i++)
+            if (i < I) nv = nfma(PGBP_SM(zb + i), w[i], nv);
+          const double d = nv - so[u];
+          st[(md.sh + k) * ld] = nv;
+          st[ta[u]] = to[u] + d;
+          if (rs) rs[(md.rh + k) * ld] = d;
+          absmax(maxh, d);
+        }
+      }
+    }
+  }
+  st[md.sg * ld] = g;
+  st[md.tg * ld] = tg_old + (g - sg_old);
+  store_flag(a, md.dmsg, e, S, maxJ, maxh);
+#undef PGBP_SM
+}
+
+
+// -------------------------------------------------------------------------------------
+// Same kernel with the integrated dimension I known at compile time (I <= 16): no predicated
+// work (every loop over pivots / rows has constant bounds), shared-memory offsets are immediates,
+// global addresses are one IMAD.WIDE.U32 each (slot * 8*ld + base), and the Z columns (and the h
+// column, which is simply column S of the right-hand sides) are solved TWO at a time so that one
+// LDS of U[k,r] feeds two independent FMA chains.  ncu on the runtime-I version: 12.8k warp
+// instructions per warp-message, 55% of them integer address / predicate work, IPC 1.2; this
+// version: see profiles/.
+// The "all zero" test of src/beliefupdates.jl:62-66 is folded into the loads of phase B; a failed
+// pivot is only reported once the whole I-part has been seen to be non-zero.
+// -------------------------------------------------------------------------------------
+__device__ __forceinline__ double* gaddr(char* base, uint32_t slot, uint32_t ld8) {
+  return (double*)(base + (uint64_t)slot * (uint64_t)ld8);  // IMAD.WIDE.U32
+}
+
+template <int I>
+__global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x;
+  const int64_t e = (int64_t)blockIdx.x * 32 + tid;
+  if (e >= a.B) return;
+  if (a.status[e] != 0) return;
+  if (a.done && a.done[e]) return;
+  const MsgDesc md = a.msgs[blockIdx.y];
+  const int S = md.s, M = md.mF;
+  const uint32_t ld8 = (uint32_t)(a.ld * 8);
+  char* stb = (char*)(a.state + e);
+  char* rsb = a.resid ? (char*)(a.resid + e) : nullptr;
+  const int32_t* __restrict__ gat = a.tab + md.gat;
+  const int32_t* __restrict__ sca = a.tab + md.sca;
+  constexpr int TI = I * (I + 1) / 2;
+  const int SMM = tri(M), SS = tri(S);
+  const uint32_t fJ = (uint32_t)md.fJ, fh = (uint32_t)md.fh, sJ = (uint32_t)md.sJ, sh = (uint32_t)md.sh,
+                 tJ = (uint32_t)md.tJ, th = (uint32_t)md.th, rJ = (uint32_t)md.rJ, rh = (uint32_t)md.rh;
+  double* smt = sm + tid;             // entry n of this thread: smt[n * 32]
+  double* Z = smt + TI * 32;          // Z(k, cc) = Z[(cc * I + k) * 32]; column S holds h_I / w
+
+  // ---- A: I-rows of the sender -> shared (asynchronous) ---------------------------------
+#pragma unroll
+  for (int c = 0; c < I; c++) {
+#pragma unroll
+    for (int k = 0; k <= c; k++) cp_async8(smt + pk(k, c) * 32, gaddr(stb, fJ + gat[pk(k, c)], ld8));
+  }
+  for (int cc = 0; cc < S; cc++) {
+    const int32_t* gc = gat + tri(I + cc);
+    double* zc = Z + cc * I * 32;
+#pragma unroll
+    for (int k = 0; k < I; k++) cp_async8(zc + k * 32, gaddr(stb, fJ + gc[k], ld8));
+  }
+  {
+    double* zc = Z + S * I * 32;
+#pragma unroll
+    for (int k = 0; k < I; k++) cp_async8(zc + k * 32, gaddr(stb, fh + gat[SMM + k], ld8));
+  }
+  double g = *gaddr(stb, (uint32_t)md.fg, ld8);
+  const double sg_old = *gaddr(stb, (uint32_t)md.sg, ld8), tg_old = *gaddr(stb, (uint32_t)md.tg, ld8);
+  cp_async_wait_all();
+
+  // ---- B1: U'U = J_II, left-looking, fully unrolled ------------------------------------------
+  double rinv[I];
+  double logdet = 0.0;
+  bool nz = false;
+  int fail = 0;
+#pragma unroll
+  for (int c = 0; c < I; c++) {
+    double v[I];
+#pragma unroll
+    for (int k = 0; k <= c; k++) {
+      v[k] = smt[pk(k, c) * 32];
+      if (!(fabs(v[k]) <= PGBP_EPS)) nz = true;
+    }
+#pragma unroll
+    for (int k = 0; k < c; k++) {
+      const double u = v[k] * rinv[k];
+      v[k] = u;
+      smt[pk(k, c) * 32] = u;
+#pragma unroll
+      for (int r = k + 1; r <= c; r++) v[r] = nfma(r == c ? u : smt[pk(k, r) * 32], u, v[r]);
+    }
+    const double d = v[c];
+    if (!(d > 0.0) && fail == 0) fail = c + 1;  // LAPACK potrf info (also NaN); reported below
+    logdet += log(d);
+    rinv[c] = 1.0 / sqrt(d);
+  }
+  // ---- B2: Z = U^-T [J_IK | h_I], two right-hand sides at a time --------------------------------
+  double ww = 0.0;
+  const int nrhs = S + 1;
+  constexpr int NPAIR = (I <= 10) ? 2 : 1;  // larger I: one column at a time (register budget)
+  for (int c0 = 0; c0 < nrhs; c0 += NPAIR) {
+    const bool two = NPAIR == 2 && c0 + 1 < nrhs;
+    double* z0 = Z + c0 * I * 32;
+    double* z1 = two ? z0 + I * 32 : z0;
+    double v0[I], v1[I];
+#pragma unroll
+    for (int k = 0; k < I; k++) {
+      v0[k] = z0[k * 32];
+      v1[k] = z1[k * 32];
+      if (!(fabs(v0[k]) <= PGBP_EPS) || !(fabs(v1[k]) <= PGBP_EPS)) nz = true;
+    }
+#pragma unroll
+    for (int k = 0; k < I; k++) {
+      const double u0 = v0[k] * rinv[k], u1 = v1[k] * rinv[k];
+      v0[k] = u0;
+      v1[k] = u1;
+#pragma unroll
+      for (int r = k + 1; r < I; r++) {
+        const double ukr = smt[pk(k, r) * 32];
+        v0[r] = nfma(ukr, u0, v0[r]);
+        if (NPAIR == 2) v1[r] = nfma(ukr, u1, v1[r]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < I; k++) {
+      z0[k * 32] = v0[k];
+      if (two) z1[k * 32] = v1[k];
+    }
+    if (c0 == S || (NPAIR == 2 && c0 + 1 == S)) {  // the h column: w = U^-T h_I
+      const double* w = (c0 == S) ? v0 : v1;
+#pragma unroll
+      for (int k = 0; k < I; k++) ww = fma(w[k], w[k], ww);
+    }
+  }
+  if (nz) {
+    if (fail) {
+      status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, fail));
+      return;
+    }
+    g += 0.5 * ((double)I * PGBP_LOG2PI - logdet + ww);
+  } else {  // "missing data" shortcut: message = (h_K, J_KK, g) unchanged
+    for (int q = 0; q < nrhs * I; q++) Z[q * 32] = 0.0;
+  }
+
+  // ---- C: stream the kept block ---------------------------------------------------------------
+  double maxJ = 0.0, maxh = 0.0;
+  for (int cc = 0; cc < S; cc++) {
+    double zc[I];
+#pragma unroll
+    for (int i = 0; i < I; i++) zc[i] = Z[(cc * I + i) * 32];
+    const int32_t* gc = gat + tri(I + cc) + I;  // sender slots of (I+rr, I+cc), rr = 0..cc
+    const int qc = tri(cc);
+    for (int r0 = 0; r0 <= cc; r0 += PGBP_CHUNK) {
+      double jo[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
+      double* ta[PGBP_CHUNK];
+#pragma unroll
+      for (int u = 0; u < PGBP_CHUNK; u++) {
+        const int rr = r0 + u;
+        if (rr <= cc) {
+          ta[u] = gaddr(stb, tJ + sca[qc + rr], ld8);
+          jo[u] = *gaddr(stb, fJ + gc[rr], ld8);
+          so[u] = *gaddr(stb, sJ + qc + rr, ld8);
+          to[u] = *ta[u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PGBP_CHUNK; u++) {
+        const int rr = r0 + u;
+        if (rr <= cc) {
+          double nv = jo[u];
+          const double* zr = Z + rr * I * 32;
+#pragma unroll
+          for (int i = 0; i < I; i++) nv = nfma(zr[i * 32], zc[i], nv);
+          const double d = nv - so[u];
+          *gaddr(stb, sJ + qc + rr, ld8) = nv;
+          *ta[u] = to[u] + d;
+          if (rsb) *gaddr(rsb, rJ + qc + rr, ld8) = d;
+          absmax(maxJ, d);
+        }
+      }
+    }
+  }
+  {
+    double w[I];
+#pragma unroll
+    for (int i = 0; i < I; i++) w[i] = Z[(S * I + i) * 32];
+    const int32_t* gh = gat + SMM + I;
+    for (int k0 = 0; k0 < S; k0 += PGBP_CHUNK) {
+      double ho[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
+      double* ta[PGBP_CHUNK];
+#pragma unroll
+      for (int u = 0; u < PGBP_CHUNK; u++) {
+        const int k = k0 + u;
+        if (k < S) {
+          ta[u] = gaddr(stb, th + sca[SS + k], ld8);
+          ho[u] = *gaddr(stb, fh + gh[k], ld8);
+          so[u] = *gaddr(stb, sh + k, ld8);
+          to[u] = *ta[u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PGBP_CHUNK; u++) {
+        const int k = k0 + u;
+        if (k < S) {
+          double nv = ho[u];
+          const double* zr = Z + k * I * 32;
+#pragma unroll
+          for (int i = 0; i < I; i++) nv = nfma(zr[i * 32], w[i], nv);
+          const double d = nv - so[u];
+          *gaddr(stb, sh + k, ld8) = nv;
+          *ta[u] = to[u] + d;
+          if (rsb) *gaddr(rsb, rh + k, ld8) = d;
+          absmax(maxh, d);
+        }
+      }
+    }
+  }
+  *gaddr(stb, (uint32_t)md.sg, ld8) = g;
+  *gaddr(stb, (uint32_t)md.tg, ld8) = tg_old + (g - sg_old);
+  store_flag(a, md.dmsg, e, S, maxJ, maxh);
+}
+
+#endif  // !PGBP_HOST_EMUL
+
+}  // namespace pgbp

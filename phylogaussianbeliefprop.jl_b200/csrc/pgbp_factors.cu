@@ -123,8 +123,8 @@ struct AssignBody {
   int pairing;
   ThetaRows tr;
   int y0 = 0;
-  PGBP_HD void operator()(int64_t e, int y) const {
-    const int c = y + y0;
+  PGBP_HD void operator()(int64_t e, int y) const { run(e, y + y0); }
+  PGBP_HD void run(int64_t e, int c) const {
     const int p = F.p, pp = p * p;
     int64_t ip, id;
     if (pairing == PGBP_PAIR_PRODUCT) { ip = e / nd; id = e % nd; }
@@ -225,6 +225,106 @@ struct AssignBody {
       }
     }
     st[gs * ld] = g;
+  }
+};
+
+// K1 fast path, compile-time trait count P.  A cluster that holds exactly ONE node family, with
+// one rate colour, whose in-scope members tile the whole cluster scope (host flag `fast`) -- every
+// tree-edge cluster of a clique tree -- is written ONCE: the family precision j = P_c / t0 lives in
+// registers, every (J, h, g) slot gets a single direct store (no zero fill, no read-modify-write,
+// no thread-local arrays).  Same arithmetic, operand for operand, as AssignBody::run; other
+// clusters take that generic path.
+template <int P>
+struct AssignFast {
+  AssignBody gen;
+  const uint8_t* fast;  // [nclusters]
+  int y0 = 0;
+  PGBP_HD void operator()(int64_t e, int y) const {
+    const int c = y + y0;
+    if (!fast[c]) { gen.run(e, c); return; }
+    const FamDev& F = gen.F;
+    const ThetaRows& tr = gen.tr;
+    const int64_t ldp = gen.ldp, ld = gen.ld, ldd = gen.ldd;
+    int64_t ip, id;
+    if (gen.pairing == PGBP_PAIR_PRODUCT) { ip = e / gen.nd; id = e % gen.nd; }
+    else { ip = gen.np == 1 ? 0 : e; id = gen.nd == 1 ? 0 : e; }
+    const double* th = gen.theta + ip;
+    const double* td = gen.tip + id;
+    double* st = gen.state + e;
+    const int64_t js = F.cl_jslot[c], hs = F.cl_hslot[c], gs = F.cl_gslot[c];
+    const double kind = th[(int64_t)tr.kind() * ldp];
+    if (kind < 0.0) { gen.run(e, c); return; }  // invalid parameters: generic path records the status
+    const int v = F.clu_node[F.clu_off[c]];
+    const int k0 = F.mem_off[v], nm = F.mem_off[v + 1] - k0;
+    const int col = F.mem_color[k0 + 1];
+    double t0 = 0.0;
+    if (nm == 2) t0 = F.mem_length[k0 + 1];
+    else for (int k = k0 + 1; k < k0 + nm; k++) t0 += F.mem_gamma[k] * F.mem_gamma[k] * F.mem_length[k];
+    double j[P * P];
+#pragma unroll
+    for (int cc = 0; cc < P; cc++) {
+#pragma unroll
+      for (int r = 0; r <= cc; r++) {
+        const double x = th[(int64_t)(tr.P(col) + cc * P + r) * ldp] / t0;
+        j[cc * P + r] = x;
+        j[r * P + cc] = x;
+      }
+    }
+    double gv = th[(int64_t)tr.g0(col) * ldp] - 0.5 * P * log(t0);
+    // evidence: z = sum over fixed members of c_a * value_a
+    bool anyfixed = false;
+    double z[P], jz[P];
+#pragma unroll
+    for (int t = 0; t < P; t++) z[t] = 0.0;
+    for (int a = 0; a < nm; a++) {
+      if (F.mem_pos[k0 + a] >= 0) continue;
+      anyfixed = true;
+      const double ca = a == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + a]);
+      if (a == 0) {
+        const int row = F.node_datarow[v];
+#pragma unroll
+        for (int t = 0; t < P; t++) z[t] += ca * td[(int64_t)(row * P + t) * ldd];
+      } else {
+#pragma unroll
+        for (int t = 0; t < P; t++) z[t] += ca * th[(int64_t)(tr.mu() + t) * ldp];
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < P; t++) jz[t] = 0.0;
+    if (anyfixed) {
+      double quad = 0.0;
+#pragma unroll
+      for (int r = 0; r < P; r++) {
+        double s = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < P; cc++) s += j[cc * P + r] * z[cc];
+        jz[r] = s;
+        quad += z[r] * s;
+      }
+      gv -= 0.5 * quad;
+    }
+    for (int a = 0; a < nm; a++) {
+      const int pa = F.mem_pos[k0 + a];
+      if (pa < 0) continue;
+      const double ca = a == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + a]);
+#pragma unroll
+      for (int t = 0; t < P; t++) st[(hs + pa + t) * ld] = anyfixed ? 0.0 - ca * jz[t] : 0.0;
+      for (int bq = a; bq < nm; bq++) {
+        const int pb = F.mem_pos[k0 + bq];
+        if (pb < 0) continue;
+        const double cb = bq == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + bq]);
+        const double cab = ca * cb;
+        const bool diag = bq == a;
+#pragma unroll
+        for (int tb = 0; tb < P; tb++) {
+#pragma unroll
+          for (int ta = 0; ta < P; ta++) {
+            if (!diag || ta <= tb) st[(js + pk(pa + ta, pb + tb)) * ld] = 0.0 + cab * j[tb * P + ta];
+          }
+        }
+      }
+    }
+    st[gs * ld] = 0.0 + gv;
   }
 };
 
@@ -508,6 +608,7 @@ struct DevTables {
   // families
   int32_t *node_cluster = nullptr, *mem_off = nullptr, *mem_pos = nullptr, *mem_color = nullptr,
           *node_datarow = nullptr, *clu_off = nullptr, *clu_node = nullptr;
+  uint8_t* clu_fast = nullptr;
   double *mem_length = nullptr, *mem_gamma = nullptr;
   // parameter / data staging
   double* theta = nullptr;
@@ -559,6 +660,7 @@ static int get_tables(pgbp_batch* b, DevTables** out) {
     PGBP_TRY(upload(b, dt.get(), &dt->clu_node, F.clu_node));
     PGBP_TRY(upload(b, dt.get(), &dt->mem_length, F.mem_length));
     PGBP_TRY(upload(b, dt.get(), &dt->mem_gamma, F.mem_gamma));
+    PGBP_TRY(upload(b, dt.get(), &dt->clu_fast, F.clu_fast));
   }
   PGBP_TRY(stream_sync(b->stream));
   b->d_fam = dt.release();
@@ -639,16 +741,15 @@ static int factored_energy_launch(pgbp_batch* b, double* d_out_soa, int64_t ldo)
 
 extern "C" {
 
-int32_t pgbp_assign_factors(pgbp_batch* b, int32_t ncolors, const double* params, int64_t nparamsets,
-                            const double* tipdata, int64_t ndatasets, int32_t pairing) {
-  if (!b || !params) PGBP_FAIL(PGBP_EINVAL, "null argument");
+// shared argument checks + table / staging setup of the two assign_factors entry points
+static int assign_prepare(pgbp_batch* b, int32_t ncolors, int64_t nparamsets, int64_t ndatasets, int32_t pairing,
+                          pgbp::DevTables** dt_out) {
   const pgbp_plan* p = b->plan;
   if (!p->has_families) PGBP_FAIL(PGBP_ESTATE, "the plan has no node-family table");
   const FamilyTable& F = p->fam;
   const int pt = p->ntraits;
   if (pt > PGBP_MAX_TRAITS) PGBP_FAIL(PGBP_EINVAL, "ntraits %d > %d", pt, PGBP_MAX_TRAITS);
   if (ncolors < F.ncolors_min) PGBP_FAIL(PGBP_EINVAL, "ncolors %d but the family table uses colour %d", ncolors, F.ncolors_min - 1);
-  if (F.ntips > 0 && !tipdata) PGBP_FAIL(PGBP_EINVAL, "null tip data");
   const int64_t B = b->B;
   if (pairing == PGBP_PAIR_PRODUCT) {
     if (nparamsets * ndatasets != B) PGBP_FAIL(PGBP_EINVAL, "product pairing needs nparamsets*ndatasets == B");
@@ -660,23 +761,27 @@ int32_t pgbp_assign_factors(pgbp_batch* b, int32_t ncolors, const double* params
   DevTables* dt;
   PGBP_TRY(get_tables(b, &dt));
   ThetaRows tr{pt, ncolors};
-  // parameters: upload AoS, prepare per-set tables
-  const int64_t plen = (int64_t)ncolors * pt * pt + pt + (int64_t)pt * pt;
   PGBP_TRY(ensure_rows(b, &dt->theta, &dt->theta_rows, &dt->ldp, tr.nrows(), nparamsets));
   const int64_t tiprows = (int64_t)F.ntips * pt;
   PGBP_TRY(ensure_rows(b, &dt->tip, &dt->tip_rows, &dt->ldd, std::max<int64_t>(1, tiprows), ndatasets));
-  const size_t need = sizeof(double) * (size_t)std::max(plen * nparamsets, tiprows * ndatasets);
-  PGBP_TRY(batch_need_scratch(b, need));
-  PGBP_TRY(h2d(b->scratch, params, sizeof(double) * (size_t)(plen * nparamsets), b->stream));
-  ThetaPrep prep{b->scratch, dt->theta, dt->ldp, tr};
+  *dt_out = dt;
+  return 0;
+}
+
+// K1 proper, everything on the device, enqueue only: d_params / d_tip are the AoS records of the header
+static int assign_enqueue(pgbp_batch* b, pgbp::DevTables* dt, int32_t ncolors, const double* d_params, int64_t nparamsets,
+                          const double* d_tip, int64_t ndatasets, int32_t pairing) {
+  const pgbp_plan* p = b->plan;
+  const FamilyTable& F = p->fam;
+  const int pt = p->ntraits;
+  ThetaRows tr{pt, ncolors};
+  ThetaPrep prep{d_params, dt->theta, dt->ldp, tr};
   PGBP_TRY(launch_generic(b, "k_theta_prep", nparamsets, 1, prep));
-  if (tiprows > 0) {
-    // tip data AoS [nd][ntips*p] -> SoA [ntips*p][ldd]
-    PGBP_TRY(stream_sync(b->stream));
-    PGBP_TRY(h2d(b->scratch, tipdata, sizeof(double) * (size_t)(tiprows * ndatasets), b->stream));
+  const int64_t tiprows = (int64_t)F.ntips * pt;
+  if (tiprows > 0) {  // tip data AoS [nd][ntips*p] -> SoA [ntips*p][ldd]
     const int64_t saveB = b->B;
     b->B = ndatasets;  // transpose over the data-set axis
-    int rc = aos_to_soa(b, b->scratch, (int)tiprows, nullptr, dt->tip, dt->ldd);
+    int rc = aos_to_soa(b, d_tip, (int)tiprows, nullptr, dt->tip, dt->ldd);
     b->B = saveB;
     PGBP_TRY(rc);
   }
@@ -684,11 +789,45 @@ int32_t pgbp_assign_factors(pgbp_batch* b, int32_t ncolors, const double* params
             dt->node_datarow, dt->clu_off, dt->clu_node, dt->jslot, dt->hslot, dt->gslot, dt->dim,
             pt, ncolors, F.root_fixed};
   AssignBody body{fd, dt->theta, dt->ldp, dt->tip, dt->ldd, b->state, b->status, b->ld, nparamsets, ndatasets, pairing, tr};
-  PGBP_TRY(launch_generic(b, "k_assign_factors", B, p->nclusters, body));
+  switch (pt) {
+#define PGBP_FAST_CASE(P_) \
+  case P_: PGBP_TRY(launch_generic(b, "k_assign_factors", b->B, p->nclusters, AssignFast<P_>{body, dt->clu_fast})); break;
+    PGBP_FAST_CASE(1) PGBP_FAST_CASE(2) PGBP_FAST_CASE(3) PGBP_FAST_CASE(4) PGBP_FAST_CASE(5) PGBP_FAST_CASE(6)
+    PGBP_FAST_CASE(7) PGBP_FAST_CASE(8)
+#undef PGBP_FAST_CASE
+    default: PGBP_TRY(launch_generic(b, "k_assign_factors", b->B, p->nclusters, body));
+  }
   // sepsets <- 0 (src/beliefs.jl:796), factor snapshot (src/clustergraphbeliefs.jl:106)
   PGBP_TRY(dev_memset(b->state + (size_t)p->nslots_factor * (size_t)b->ld, 0,
                       sizeof(double) * (size_t)(p->nslots_state - p->nslots_factor) * (size_t)b->ld, b->stream));
   if (b->factor) PGBP_TRY(d2d(b->factor, b->state, sizeof(double) * (size_t)p->nslots_factor * (size_t)b->ld, b->stream));
+  return 0;
+}
+
+int32_t pgbp_assign_factors_device(pgbp_batch* b, int32_t ncolors, const double* d_params, int64_t nparamsets,
+                                   const double* d_tipdata, int64_t ndatasets, int32_t pairing) {
+  if (!b || !d_params) PGBP_FAIL(PGBP_EINVAL, "null argument");
+  if (b->plan->has_families && b->plan->fam.ntips > 0 && !d_tipdata) PGBP_FAIL(PGBP_EINVAL, "null tip data");
+  pgbp::DevTables* dt;
+  PGBP_TRY(assign_prepare(b, ncolors, nparamsets, ndatasets, pairing, &dt));
+  return assign_enqueue(b, dt, ncolors, d_params, nparamsets, d_tipdata, ndatasets, pairing);
+}
+
+int32_t pgbp_assign_factors(pgbp_batch* b, int32_t ncolors, const double* params, int64_t nparamsets,
+                            const double* tipdata, int64_t ndatasets, int32_t pairing) {
+  if (!b || !params) PGBP_FAIL(PGBP_EINVAL, "null argument");
+  if (b->plan->has_families && b->plan->fam.ntips > 0 && !tipdata) PGBP_FAIL(PGBP_EINVAL, "null tip data");
+  pgbp::DevTables* dt;
+  PGBP_TRY(assign_prepare(b, ncolors, nparamsets, ndatasets, pairing, &dt));
+  const pgbp_plan* p = b->plan;
+  const int pt = p->ntraits;
+  const int64_t plen = (int64_t)ncolors * pt * pt + pt + (int64_t)pt * pt;
+  const int64_t tiprows = (int64_t)p->fam.ntips * pt;
+  const size_t nparam = (size_t)(plen * nparamsets), ntip = (size_t)(tiprows * ndatasets);
+  PGBP_TRY(batch_need_scratch(b, sizeof(double) * (nparam + ntip)));
+  PGBP_TRY(h2d(b->scratch, params, sizeof(double) * nparam, b->stream));
+  if (ntip) PGBP_TRY(h2d(b->scratch + nparam, tipdata, sizeof(double) * ntip, b->stream));
+  PGBP_TRY(assign_enqueue(b, dt, ncolors, b->scratch, nparamsets, b->scratch + nparam, ndatasets, pairing));
   return stream_sync(b->stream);
 }
 

@@ -57,6 +57,8 @@ struct FamilyTable {
   std::vector<double> mem_length, mem_gamma;
   // derived: nodes of each cluster, ascending (order of the loop at src/beliefs.jl:798)
   std::vector<int32_t> clu_off, clu_node;
+  // derived: cluster takes the write-once path of K1 (one family, one colour, members tile the scope)
+  std::vector<uint8_t> clu_fast;
   int32_t ncolors_min = 1;
 };
 
@@ -115,6 +117,7 @@ struct pgbp_batch {
   int64_t launches = 0;
   bool want_info = false;
   int32_t walk_mode = -1;  // -1 auto, 0 never, 1 always (when walkable)
+  int32_t coop_mode = -1;  // medium shapes: -1 auto (cooperative), 0 thread-local generic, 4 / 8 lanes for m <= 16
   int32_t* d_slot = nullptr;  // device scratch for transpose slot tables
   size_t d_slot_len = 0;
 };

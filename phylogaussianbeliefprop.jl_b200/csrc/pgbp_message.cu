@@ -1,4 +1,5 @@
 // K2 (message passing), K3 (integrate) and the calibrate! driver.
+#include "pgbp_coop.cuh"
 #include "pgbp_kernels.cuh"
 #include "pgbp_launch.h"
 #include "pgbp_shapes.h"
@@ -101,6 +102,49 @@ static int launch_message(pgbp_batch* b, const MsgArgs& a, int nmsg) {
   return check_launch("k_message");
 }
 
+template <int MAXM, int G>
+static int launch_coop(pgbp_batch* b, const MsgArgs& a, int nmsg) {
+#ifdef PGBP_HOST_EMUL
+  // host emulation: the generic body gives bit-identical results (same per-entry update order)
+  for (int m = 0; m < nmsg; m++)
+    for (int64_t e = 0; e < a.B; e++) message_thread_rt<MAXM>(a, m, e);
+#else
+  constexpr int RPB = 128 / G;
+  dim3 grid((unsigned)((a.B + RPB - 1) / RPB), (unsigned)nmsg);
+  k_message_coop<MAXM, G><<<grid, 128, 0, b->stream>>>(a);
+#endif
+  b->launches++;
+  return check_launch("k_message_coop");
+}
+
+#define PGBP_SMEM_LIMIT (200 * 1024)
+// EXACT: I is the compile-time integrated dimension (k_message_smem<I>), else an upper bound
+// (k_message_smem_rt<MAXI>)
+template <int MAXI, bool EXACT>
+static int launch_smem(pgbp_batch* b, const MsgArgs& a, int nmsg, int I, int S) {
+#ifdef PGBP_HOST_EMUL
+  (void)I; (void)S;
+  for (int m = 0; m < nmsg; m++)
+    for (int64_t e = 0; e < a.B; e++) message_thread_rt<PGBP_MAX_DIM>(a, m, e);
+#else
+  static bool attr_done = false;  // per instantiation
+  const void* fn;
+  if constexpr (EXACT) fn = (const void*)k_message_smem<MAXI>;
+  else fn = (const void*)k_message_smem_rt<MAXI>;
+  if (!attr_done) {
+    PGBP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_LIMIT));
+    attr_done = true;
+  }
+  if (a.ld * 8 >= ((int64_t)1 << 32)) PGBP_FAIL(PGBP_ESTATE, "batch too large for 32-bit row pitch");
+  const size_t bytes = sizeof(double) * 32 * (size_t)smem_doubles(I, S);
+  dim3 grid((unsigned)((a.B + 31) / 32), (unsigned)nmsg);
+  if constexpr (EXACT) k_message_smem<MAXI><<<grid, 32, bytes, b->stream>>>(a);
+  else k_message_smem_rt<MAXI><<<grid, 32, bytes, b->stream>>>(a);
+#endif
+  b->launches++;
+  return check_launch("k_message_smem");
+}
+
 static int launch_copy(pgbp_batch* b, const MsgArgs& a, int nmsg) {
 #ifdef PGBP_HOST_EMUL
   for (int m = 0; m < nmsg; m++)
@@ -133,12 +177,28 @@ int launch_group(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGr
       PGBP_T0_SHAPES(X)
 #undef X
       if (!hit) PGBP_FAIL(PGBP_ESTATE, "no specialised kernel for shape (%d,%d)", g.ci, g.cs);
-    } else if (g.maxm <= 16) {
-      rc = launch_message<-1, -1, 16>(b, a, n);
-    } else if (g.maxm <= 32) {
-      rc = launch_message<-1, -1, 32>(b, a, n);
-    } else {
-      rc = launch_message<-1, -1, 64>(b, a, n);
+    } else {  // medium / large class: the group is uniform in (I, S) = (g.maxm, g.cs)
+      const int I = g.maxm, S = g.cs, M = I + S;
+      const int mode = b->coop_mode;
+      const bool fits = I <= 32 && sizeof(double) * 32 * (size_t)(I * (I + 1) / 2 + I * S + I) <= PGBP_SMEM_LIMIT;
+      if ((mode == -1 || mode == 1) && fits) {
+        switch (I) {
+#define PGBP_SMEM_CASE(I_) case I_: rc = launch_smem<I_, true>(b, a, n, I, S); break;
+          PGBP_SMEM_CASE(1) PGBP_SMEM_CASE(2) PGBP_SMEM_CASE(3) PGBP_SMEM_CASE(4) PGBP_SMEM_CASE(5) PGBP_SMEM_CASE(6)
+          PGBP_SMEM_CASE(7) PGBP_SMEM_CASE(8) PGBP_SMEM_CASE(9) PGBP_SMEM_CASE(10) PGBP_SMEM_CASE(11)
+          PGBP_SMEM_CASE(12) PGBP_SMEM_CASE(13) PGBP_SMEM_CASE(14) PGBP_SMEM_CASE(15) PGBP_SMEM_CASE(16)
+#undef PGBP_SMEM_CASE
+          default: rc = (I <= 24) ? launch_smem<24, false>(b, a, n, I, S) : launch_smem<32, false>(b, a, n, I, S);
+        }
+      } else if (mode != 0 && M <= PGBP_COOP_MAX) {
+        if (M <= 16) rc = (mode == 4) ? launch_coop<16, 4>(b, a, n) : launch_coop<16, 8>(b, a, n);
+        else if (M <= 24) rc = launch_coop<24, 8>(b, a, n);
+        else rc = launch_coop<32, 8>(b, a, n);
+      } else if (M <= 32) {
+        rc = launch_message<-1, -1, 32>(b, a, n);
+      } else {
+        rc = launch_message<-1, -1, 64>(b, a, n);
+      }
     }
     PGBP_TRY(rc);
     done += n;
@@ -347,6 +407,12 @@ int32_t pgbp_calibrate(pgbp_batch* b, const int32_t* tree_ids, int32_t ntrees, i
 int32_t pgbp_batch_set_walk_mode(pgbp_batch* b, int32_t mode) {
   if (!b || mode < -1 || mode > 1) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
   b->walk_mode = mode;
+  return 0;
+}
+
+int32_t pgbp_batch_set_coop_mode(pgbp_batch* b, int32_t mode) {
+  if (!b || (mode != -1 && mode != 0 && mode != 1 && mode != 4 && mode != 8)) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
+  b->coop_mode = mode;
   return 0;
 }
 

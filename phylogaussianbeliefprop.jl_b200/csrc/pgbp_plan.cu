@@ -275,9 +275,19 @@ int32_t pgbp_plan_create(const pgbp_plan_desc* d, pgbp_plan** out) {
       c2n[c].push_back(v);
     }
     F.clu_off.assign(1, 0);
-    for (auto& v : c2n) {
+    F.clu_fast.assign(p->nclusters, 0);
+    for (int c = 0; c < p->nclusters; c++) {
+      auto& v = c2n[c];
       F.clu_node.insert(F.clu_node.end(), v.begin(), v.end());
       F.clu_off.push_back((int32_t)F.clu_node.size());
+      if (v.size() != 1) continue;
+      const int o0 = F.mem_off[v[0]], o1 = F.mem_off[v[0] + 1];
+      if (o1 - o0 < 2) continue;  // root family
+      bool same = true;
+      int covered = 0;
+      for (int k = o0 + 1; k < o1; k++) same = same && F.mem_color[k] == F.mem_color[o0 + 1];
+      for (int k = o0; k < o1; k++) if (F.mem_pos[k] >= 0) covered += pt;
+      F.clu_fast[c] = same && covered == p->dim[c];
     }
     p->has_families = true;
   }

@@ -1,23 +1,26 @@
 // Shape classes of the message kernel (K2).
 //  T0  register-resident, fully unrolled: i >= 1 variables integrated out, i + s <= PGBP_T0_MAX
 //  COPY  i == 0 (nothing to integrate): streaming, any s
-//  T1  generic runtime dimensions, matrix in thread-local memory, sender dimension
-//      bucketed to 16 / 32 / 64
+//  MEDIUM  i + s > PGBP_T0_MAX, class id ci = -2, launch groups uniform in (i, s) = (maxm, cs):
+//      T0S  one thread per element, chol(J_II) / Z / w in shared memory (k_message_smem), used
+//           whenever 32 * 8 * (tri(i) + i*s + i) bytes fit the SM's shared memory and i <= 32;
+//      COOP G lanes of a warp per element, sender belief column-cyclic in registers
+//           (k_message_coop), i + s <= 32;
+//      T1   generic runtime dimensions, matrix in thread-local memory (what is left).
 // The X-macro below is generated (see the bottom of this file for the recipe).
 #pragma once
 #define PGBP_MAX_DIM 64
 #define PGBP_MAX_FAMILY 8
 #define PGBP_MAX_TRAITS 16
 #define PGBP_T0_MAX 12
+#define PGBP_COOP_MAX 32
 #define PGBP_WALK_MAXP 4
 
 namespace pgbp {
 inline void shape_class(int i, int s, int* ci, int* cs, int* maxm) {
   if (i == 0) { *ci = 0; *cs = -1; *maxm = 0; return; }
   if (i + s <= PGBP_T0_MAX) { *ci = i; *cs = s; *maxm = 0; return; }
-  *ci = -1; *cs = -1;
-  const int m = i + s;
-  *maxm = m <= 16 ? 16 : (m <= 32 ? 32 : 64);
+  *ci = -2; *cs = s; *maxm = i;
 }
 // "Walk" family for ntraits = P: a message whose integrated / kept dimensions are
 // a*P and b*P (a <= 3, b <= 3, whole nodes in scope) gets id 4a+b; anything else -1

@@ -58,9 +58,9 @@ class Case:
     """One network + cluster graph + model scope, oracle side and product side."""
 
     def __init__(self, netstr, method, tbl, taxa, model, lib, schedule="spanningtrees", with_families=True,
-                 edge_color=None, **kw):
+                 edge_color=None, cg=None, **kw):
         self.net = readnewick(netstr) if isinstance(netstr, str) else netstr
-        self.cg = CG.clustergraph(self.net, method, **kw)
+        self.cg = cg if cg is not None else CG.clustergraph(self.net, method, **kw)
         self.tbl = np.asarray(tbl, dtype=float)
         self.taxa = list(taxa)
         self.model = model
@@ -95,6 +95,40 @@ class Case:
             h = np.stack([c.belief[j].h for c in cgbs]) if m else np.zeros((len(cgbs), 0))
             g = np.array([c.belief[j].g for c in cgbs])
             batch.set_belief(j + 1, J, h, g)
+
+
+def synth_oracle_objects(net_tab, plan):
+    """Oracle-side Network + cluster graph (MetaGraph) + schedule of a network / clique tree made by
+    workloads/synth.py, so that the whole reference-following oracle pipeline (allocatebeliefs,
+    assignfactors!, calibrate!, ...) can run on it.  Node names are n<preorder index>."""
+    from oracle.network import Edge, Network, Node
+    n = net_tab["nnodes"]
+    net = Network()
+    nodes = [Node(name=f"n{v}", leaf=bool(net_tab["leaf"][v]), hybrid=len(net_tab["parents"][v]) > 1) for v in range(n)]
+    for v in range(n):
+        for (q, L, g, eno) in net_tab["parents"][v]:
+            e = Edge(number=eno, length=L, gamma=g, hybrid=len(net_tab["parents"][v]) > 1, child=nodes[v], parent=nodes[q])
+            net.edges.append(e)
+    # edge lists: children first (in child order), then parent edges, like the Newick reader
+    for e in net.edges:
+        e.parent.edges.append(e)
+    for e in net.edges:
+        e.child.edges.append(e)
+    net.nodes = list(nodes)
+    net.root = nodes[0]
+    net.vec_node = list(nodes)
+    cg = CG.MetaGraph("cliquetree")
+    labs = []
+    for nodes_c in plan["cluster_nodes"]:
+        lab = "".join(f"n{v}" for v in nodes_c)
+        labs.append(lab)
+        cg.add_vertex(lab, ([f"n{v}" for v in nodes_c], [v + 1 for v in nodes_c]))
+    for (a, b), sn in zip(plan["sepset_clusters"], plan["sepset_nodes"]):
+        cg.add_edge(labs[a], labs[b], [v + 1 for v in sn])
+    tp, tc = plan["trees"][0]
+    sched = [([labs[a] for a in tp], [labs[b] for b in tc], [a + 1 for a in tp], [b + 1 for b in tc])]
+    taxa = [f"n{v}" for v in plan["tip_nodes"]]
+    return net, cg, sched, taxa
 
 
 def relerr(a, b):

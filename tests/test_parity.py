@@ -511,3 +511,73 @@ def test_walk_kernel_matches_level_parallel_and_oracle(backend, p):
         for j, (J1, h1, g1) in enumerate(out[1]["beliefs"]):
             ob = cgb.belief[j]
             assert max(relerr(J1[e], ob.J), relerr(h1[e], ob.h), relerr(g1[e], ob.g)) <= TOL
+
+
+# ------------------------------------------------------------------ cooperative (G lanes / element) kernel
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("p", [4, 5, 6, 7, 8])
+def test_cooperative_kernel_matches_generic_and_oracle(backend, p):
+    # medium shapes (sender dimension 13..32: lazaridis 3- and 4-node cliques at p = 4..8) run in
+    # the cooperative kernel; it must agree BIT FOR BIT with the one-thread-per-element generic
+    # kernel (same per-entry update order, explicit FMAs) in beliefs, residuals, flags and status,
+    # and with the oracle to 1e-10.  B is not a multiple of the elements per warp / block.
+    lib = get_lib(backend)
+    rng = np.random.default_rng(300 + p)
+    A = rng.normal(size=(p, p))
+    R = A @ A.T / p + 0.1 * np.eye(p)
+    mu = rng.normal(size=p)
+    taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
+    B = 37
+    data = rng.normal(size=(B, 7, p))
+    model = M.MvFullBrownianMotion(R, mu)
+    case = Case(GOLD["lazaridis"], "cliquetree", data[0], taxa, model, lib, order_hint=GOLD["lazaridis_cluster_labels"])
+    big = [j for j in range(1, case.nclusters + 1) if case.b[j - 1].dimension() > 12]
+    assert big
+    out = {}
+    for mode in (0, -1, 4, 8):
+        bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+        bt.set_coop_mode(mode)
+        bt.assignfactors(pgbp_b200.bm_params([R], mu), data)
+        # element 5: indefinite precision in a large cluster -> Cholesky failure in its first message;
+        # element 7: a large cluster identically zero -> the "missing data" shortcut (message unchanged)
+        J, h, g = bt.get_belief(big[0])
+        J[5] = -np.eye(J.shape[1])
+        bt.set_belief(big[0], J, h, g)
+        J, h, g = bt.get_belief(big[-1])
+        J[7] = 0.0
+        h[7] = 0.0
+        bt.set_belief(big[-1], J, h, g)
+        succ, iscal = bt.calibrate(case.sched)
+        succ2, iscal2 = bt.calibrate(case.sched)
+        out[mode] = dict(succ=succ, iscal2=iscal2, st=bt.status(),
+                         beliefs=[bt.get_belief(j) for j in range(1, len(case.b) + 1)],
+                         res=[bt.get_residual(case.nclusters + 1 + j, case.plan.sepset_clusters[j][s] + 1)
+                              for j in range(case.plan.nsepsets) for s in (0, 1)])
+    ok = ~np.isin(np.arange(B), [5, 7])
+    okz = np.arange(B) != 5
+    for mode in (-1, 4, 8):
+        assert np.array_equal(out[0]["st"], out[mode]["st"]) and out[0]["st"][5] != 0
+        assert np.array_equal(out[0]["succ"], out[mode]["succ"]) and np.array_equal(out[0]["iscal2"], out[mode]["iscal2"])
+        for (J0, h0, g0), (J1, h1, g1) in zip(out[0]["beliefs"], out[mode]["beliefs"]):
+            assert np.array_equal(J0[okz], J1[okz], equal_nan=True) and np.array_equal(h0[okz], h1[okz], equal_nan=True)
+            assert np.array_equal(g0[okz], g1[okz], equal_nan=True)
+        for r0, r1 in zip(out[0]["res"], out[mode]["res"]):
+            for x0, x1 in zip(r0[:3], r1[:3]):
+                assert np.array_equal(x0[okz], x1[okz], equal_nan=True)
+    assert out[-1]["succ"][ok].all() and out[-1]["iscal2"][ok].all()
+    for e in (0, 6, B - 1):
+        cgb = case.oracle_cgb(tbl=data[e])
+        OBP.calibrate(cgb, case.sched)
+        OBP.calibrate(cgb, case.sched)
+        for j, (J1, h1, g1) in enumerate(out[-1]["beliefs"]):
+            ob = cgb.belief[j]
+            assert max(relerr(J1[e], ob.J), relerr(h1[e], ob.h), relerr(g1[e], ob.g)) <= 1e-9
+    # element 7 against the oracle with the same zeroed cluster
+    cgb = case.oracle_cgb(tbl=data[7])
+    cgb.belief[big[-1] - 1].J[:] = 0.0
+    cgb.belief[big[-1] - 1].h[:] = 0.0
+    OBP.calibrate(cgb, case.sched, verbose=False)
+    for j, (J1, h1, g1) in enumerate(out[-1]["beliefs"]):
+        ob = cgb.belief[j]
+        if np.all(np.isfinite(ob.J)) and np.all(np.isfinite(J1[7])):
+            assert max(relerr(J1[7], ob.J), relerr(h1[7], ob.h)) <= 1e-9
