@@ -246,6 +246,11 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // doubles of shared memory per element
 inline __host__ __device__ int smem_doubles(int I, int S) { return I * (I + 1) / 2 + I * S + I; }
+// bytes of shared memory per block (one warp) of k_message_smem<I>: element data + index tables
+inline __host__ __device__ size_t smem_block_bytes(int I, int S) {
+  const int M = I + S;
+  return sizeof(double) * 32 * (size_t)smem_doubles(I, S) + sizeof(uint16_t) * (size_t)(M * (M + 1) / 2 + M + S * (S + 1) / 2 + S + 4);
+}
 
 template <int MAXI>
 __global__ void __launch_bounds__(32) k_message_smem_rt(MsgArgs a) {
@@ -433,23 +438,43 @@ __device__ __forceinline__ double* gaddr(char* base, uint32_t slot, uint32_t ld8
   return (double*)(base + (uint64_t)slot * (uint64_t)ld8);  // IMAD.WIDE.U32
 }
 
-template <int I>
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
+// MS = 0: kept dimension S is a runtime value (loops over kept columns stay loops);
+// MS > 0: S <= MS and every loop over kept columns / rows is fully unrolled with uniform early exits --
+// straight-line code whose table offsets and shared-memory offsets are immediates and whose loads the
+// scheduler can hoist across columns.
+template <int I, int MS>
 __global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
-  const int64_t e = (int64_t)blockIdx.x * 32 + tid;
-  if (e >= a.B) return;
-  if (a.status[e] != 0) return;
-  if (a.done && a.done[e]) return;
+  const int64_t e0 = (int64_t)blockIdx.x * 32 + tid;
   const MsgDesc md = a.msgs[blockIdx.y];
   const int S = md.s, M = md.mF;
+  constexpr int TI = I * (I + 1) / 2;
+  const int SMM = tri(M), SS = tri(S);
+  // index tables of the message -> shared memory, one coalesced pass per warp (they are the same
+  // for all elements): afterwards every lookup is a broadcast LDS instead of a dependent LDG
+  const int ngat = SMM + M, nsca = SS + S;
+  // (16-bit entries: slot offsets inside one belief are < tri(64) + 64; keeps 8 blocks per SM at (8,8))
+  uint16_t* tgat = (uint16_t*)(sm + 32 * (TI + I * (S + 1)));
+  uint16_t* tsca = tgat + ngat;
+  {
+    const int32_t* __restrict__ g0 = a.tab + md.gat;
+    const int32_t* __restrict__ s0 = a.tab + md.sca;
+    for (int q = tid; q < ngat; q += 32) tgat[q] = (uint16_t)g0[q];
+    for (int q = tid; q < nsca; q += 32) tsca[q] = (uint16_t)s0[q];
+  }
+  __syncwarp();
+  const int64_t e = e0;
+  if (e >= a.B) return;  // (no warp-level synchronisation below this point)
+  if (a.status[e] != 0) return;
+  if (a.done && a.done[e]) return;
   const uint32_t ld8 = (uint32_t)(a.ld * 8);
   char* stb = (char*)(a.state + e);
   char* rsb = a.resid ? (char*)(a.resid + e) : nullptr;
-  const int32_t* __restrict__ gat = a.tab + md.gat;
-  const int32_t* __restrict__ sca = a.tab + md.sca;
-  constexpr int TI = I * (I + 1) / 2;
-  const int SMM = tri(M), SS = tri(S);
+  const uint16_t* gat = tgat;
+  const uint16_t* sca = tsca;
   const uint32_t fJ = (uint32_t)md.fJ, fh = (uint32_t)md.fh, sJ = (uint32_t)md.sJ, sh = (uint32_t)md.sh,
                  tJ = (uint32_t)md.tJ, th = (uint32_t)md.th, rJ = (uint32_t)md.rJ, rh = (uint32_t)md.rh;
   double* smt = sm + tid;             // entry n of this thread: smt[n * 32]
@@ -461,8 +486,10 @@ __global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
 #pragma unroll
     for (int k = 0; k <= c; k++) cp_async8(smt + pk(k, c) * 32, gaddr(stb, fJ + gat[pk(k, c)], ld8));
   }
-  for (int cc = 0; cc < S; cc++) {
-    const int32_t* gc = gat + tri(I + cc);
+#pragma unroll(MS > 0 ? MS : 1)
+  for (int cc = 0; cc < (MS > 0 ? MS : S); cc++) {
+    if (MS > 0 && cc >= S) break;
+    const uint16_t* gc = gat + tri(I + cc);
     double* zc = Z + cc * I * 32;
 #pragma unroll
     for (int k = 0; k < I; k++) cp_async8(zc + k * 32, gaddr(stb, fJ + gc[k], ld8));
@@ -474,6 +501,23 @@ __global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
   }
   double g = *gaddr(stb, (uint32_t)md.fg, ld8);
   const double sg_old = *gaddr(stb, (uint32_t)md.sg, ld8), tg_old = *gaddr(stb, (uint32_t)md.tg, ld8);
+  // ---- L2 prefetch of everything phase C will read (kept block of the sender, old sepset, old
+  //      receiver): the HBM -> L2 transfers overlap phases A and B, phase C then waits on L2 only
+#pragma unroll(MS > 0 ? MS : 1)
+  for (int cc = 0; cc < (MS > 0 ? MS : S); cc++) {
+    if (MS > 0 && cc >= S) break;
+    const uint16_t* gc = gat + tri(I + cc) + I;
+    const int qc = tri(cc);
+#pragma unroll(MS > 0 ? MS : 1)
+    for (int rr = 0; rr <= cc; rr++) {
+      prefetch_l2(gaddr(stb, fJ + gc[rr], ld8));
+      prefetch_l2(gaddr(stb, sJ + qc + rr, ld8));
+      prefetch_l2(gaddr(stb, tJ + sca[qc + rr], ld8));
+    }
+    prefetch_l2(gaddr(stb, fh + gat[SMM + I + cc], ld8));
+    prefetch_l2(gaddr(stb, sh + cc, ld8));
+    prefetch_l2(gaddr(stb, th + sca[SS + cc], ld8));
+  }
   cp_async_wait_all();
 
   // ---- B1: U'U = J_II, left-looking, fully unrolled ------------------------------------------
@@ -552,11 +596,72 @@ __global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
 
   // ---- C: stream the kept block ---------------------------------------------------------------
   double maxJ = 0.0, maxh = 0.0;
+  if constexpr (MS > 0) {
+#pragma unroll
+    for (int cc = 0; cc < MS; cc++) {
+      if (cc >= S) break;
+      const uint16_t* gc = gat + tri(I + cc) + I;  // sender slots of (I+rr, I+cc), rr = 0..cc
+      const int qc = tri(cc);
+      double jo[MS], so[MS], to[MS];
+      double* ta[MS];
+#pragma unroll
+      for (int rr = 0; rr <= cc; rr++) {
+        ta[rr] = gaddr(stb, tJ + sca[qc + rr], ld8);
+        jo[rr] = *gaddr(stb, fJ + gc[rr], ld8);
+        so[rr] = *gaddr(stb, sJ + qc + rr, ld8);
+        to[rr] = *ta[rr];
+      }
+      double zc[I];
+#pragma unroll
+      for (int i = 0; i < I; i++) zc[i] = Z[(cc * I + i) * 32];
+#pragma unroll
+      for (int rr = 0; rr <= cc; rr++) {
+        double nv = jo[rr];
+#pragma unroll
+        for (int i = 0; i < I; i++) nv = nfma(rr == cc ? zc[i] : Z[(rr * I + i) * 32], zc[i], nv);
+        const double d = nv - so[rr];
+        *gaddr(stb, sJ + qc + rr, ld8) = nv;
+        *ta[rr] = to[rr] + d;
+        if (rsb) *gaddr(rsb, rJ + qc + rr, ld8) = d;
+        absmax(maxJ, d);
+      }
+    }
+    {
+      double w[I];
+#pragma unroll
+      for (int i = 0; i < I; i++) w[i] = Z[(S * I + i) * 32];
+      const uint16_t* gh = gat + SMM + I;
+      double ho[MS], so[MS], to[MS];
+      double* ta[MS];
+#pragma unroll
+      for (int k = 0; k < MS; k++) {
+        if (k < S) {
+          ta[k] = gaddr(stb, th + sca[SS + k], ld8);
+          ho[k] = *gaddr(stb, fh + gh[k], ld8);
+          so[k] = *gaddr(stb, sh + k, ld8);
+          to[k] = *ta[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < MS; k++) {
+        if (k < S) {
+          double nv = ho[k];
+#pragma unroll
+          for (int i = 0; i < I; i++) nv = nfma(Z[(k * I + i) * 32], w[i], nv);
+          const double d = nv - so[k];
+          *gaddr(stb, sh + k, ld8) = nv;
+          *ta[k] = to[k] + d;
+          if (rsb) *gaddr(rsb, rh + k, ld8) = d;
+          absmax(maxh, d);
+        }
+      }
+    }
+  } else {
   for (int cc = 0; cc < S; cc++) {
     double zc[I];
 #pragma unroll
     for (int i = 0; i < I; i++) zc[i] = Z[(cc * I + i) * 32];
-    const int32_t* gc = gat + tri(I + cc) + I;  // sender slots of (I+rr, I+cc), rr = 0..cc
+    const uint16_t* gc = gat + tri(I + cc) + I;  // sender slots of (I+rr, I+cc), rr = 0..cc
     const int qc = tri(cc);
     for (int r0 = 0; r0 <= cc; r0 += PGBP_CHUNK) {
       double jo[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
@@ -592,7 +697,7 @@ __global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
     double w[I];
 #pragma unroll
     for (int i = 0; i < I; i++) w[i] = Z[(S * I + i) * 32];
-    const int32_t* gh = gat + SMM + I;
+    const uint16_t* gh = gat + SMM + I;
     for (int k0 = 0; k0 < S; k0 += PGBP_CHUNK) {
       double ho[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
       double* ta[PGBP_CHUNK];
@@ -622,6 +727,7 @@ __global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
         }
       }
     }
+  }
   }
   *gaddr(stb, (uint32_t)md.sg, ld8) = g;
   *gaddr(stb, (uint32_t)md.tg, ld8) = tg_old + (g - sg_old);

@@ -20,9 +20,16 @@ __global__ void __launch_bounds__(128) k_generic(F f, int64_t B) {
   if (e >= B) return;
   f(e, (int)blockIdx.y);
 }
+// same, at least MINB blocks of 128 threads per SM (caps registers; for K1)
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_generic_occ(F f, int64_t B) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B) return;
+  f(e, (int)blockIdx.y);
+}
 #endif
 
-template <class F>
+template <class F, int MINB = 0>
 static int launch_generic(pgbp_batch* b, const char* name, int64_t n, int ny, F f) {
   if (ny <= 0 || n <= 0) return 0;
 #ifdef PGBP_HOST_EMUL
@@ -35,7 +42,8 @@ static int launch_generic(pgbp_batch* b, const char* name, int64_t n, int ny, F 
     F g = f;
     g.y0 = y0;
     dim3 grid((unsigned)((n + 127) / 128), (unsigned)cnt);
-    k_generic<<<grid, 128, 0, b->stream>>>(g, n);
+    if constexpr (MINB > 0) k_generic_occ<F, MINB><<<grid, 128, 0, b->stream>>>(g, n);
+    else k_generic<<<grid, 128, 0, b->stream>>>(g, n);
     b->launches++;
   }
 #endif
@@ -228,20 +236,27 @@ struct AssignBody {
   }
 };
 
-// K1 fast path, compile-time trait count P.  A cluster that holds exactly ONE node family, with
-// one rate colour, whose in-scope members tile the whole cluster scope (host flag `fast`) -- every
-// tree-edge cluster of a clique tree -- is written ONCE: the family precision j = P_c / t0 lives in
-// registers, every (J, h, g) slot gets a single direct store (no zero fill, no read-modify-write,
-// no thread-local arrays).  Same arithmetic, operand for operand, as AssignBody::run; other
-// clusters take that generic path.
+// K1 write-once path, compile-time trait count P.  The precision j of one family lives in
+// registers (P*P doubles).  Families of the cluster are applied in node order, like the loop at
+// src/beliefs.jl:798-859; the host has marked, for every family, which of its (member, member)
+// blocks and h segments it is the FIRST to touch inside its cluster (first_J / first_h): those are
+// written with a plain store (0 + x, the value the reference's zero-then-add produces), later
+// families add into them.  Only clusters with scope entries that no family covers are zero-filled
+// first (flag bit 0).  No thread-local arrays except for heterogeneous hybrids whose parent edges
+// differ in colour (a p x p inverse per element, src/evomodels/heterogeneousmodels.jl:135-150).
+PGBP_HD double* kaddr(char* base, uint32_t slot, uint32_t ld8) {
+  return (double*)(base + (uint64_t)slot * (uint64_t)ld8);  // one IMAD.WIDE.U32
+}
+
 template <int P>
 struct AssignFast {
   AssignBody gen;
-  const uint8_t* fast;  // [nclusters]
+  const uint8_t* cflag;       // [nclusters] bit 0: zero-fill first
+  const uint64_t* first_J;    // [nnodes] bit a*8+b: family v is the first writer of block (a, b), a <= b
+  const uint8_t* first_h;     // [nnodes] bit a: first writer of member a's h segment
   int y0 = 0;
   PGBP_HD void operator()(int64_t e, int y) const {
     const int c = y + y0;
-    if (!fast[c]) { gen.run(e, c); return; }
     const FamDev& F = gen.F;
     const ThetaRows& tr = gen.tr;
     const int64_t ldp = gen.ldp, ld = gen.ld, ldd = gen.ldd;
@@ -254,77 +269,149 @@ struct AssignFast {
     const int64_t js = F.cl_jslot[c], hs = F.cl_hslot[c], gs = F.cl_gslot[c];
     const double kind = th[(int64_t)tr.kind() * ldp];
     if (kind < 0.0) { gen.run(e, c); return; }  // invalid parameters: generic path records the status
-    const int v = F.clu_node[F.clu_off[c]];
-    const int k0 = F.mem_off[v], nm = F.mem_off[v + 1] - k0;
-    const int col = F.mem_color[k0 + 1];
-    double t0 = 0.0;
-    if (nm == 2) t0 = F.mem_length[k0 + 1];
-    else for (int k = k0 + 1; k < k0 + nm; k++) t0 += F.mem_gamma[k] * F.mem_gamma[k] * F.mem_length[k];
-    double j[P * P];
-#pragma unroll
-    for (int cc = 0; cc < P; cc++) {
-#pragma unroll
-      for (int r = 0; r <= cc; r++) {
-        const double x = th[(int64_t)(tr.P(col) + cc * P + r) * ldp] / t0;
-        j[cc * P + r] = x;
-        j[r * P + cc] = x;
-      }
+    if (cflag[c] & 1) {
+      const int m = F.cl_dim[c];
+      for (int q = 0; q < tri(m) + m; q++) st[(js + q) * ld] = 0.0;
     }
-    double gv = th[(int64_t)tr.g0(col) * ldp] - 0.5 * P * log(t0);
-    // evidence: z = sum over fixed members of c_a * value_a
-    bool anyfixed = false;
-    double z[P], jz[P];
+    double g = 0.0;
+    for (int iv = F.clu_off[c]; iv < F.clu_off[c + 1]; iv++) {
+      const int v = F.clu_node[iv];
+      const int k0 = F.mem_off[v], nm = F.mem_off[v + 1] - k0;
+      const uint64_t fJ = first_J[v];
+      const unsigned fh = first_h[v];
+      if (nm == 1) {  // root family (src/beliefs.jl:803-807)
+        const int pos = F.mem_pos[k0];
+        if (pos < 0) continue;
+        const bool proper = kind == 1.0;  // fixed root handled by pos < 0; improper prior: factor == 1
 #pragma unroll
-    for (int t = 0; t < P; t++) z[t] = 0.0;
-    for (int a = 0; a < nm; a++) {
-      if (F.mem_pos[k0 + a] >= 0) continue;
-      anyfixed = true;
-      const double ca = a == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + a]);
-      if (a == 0) {
-        const int row = F.node_datarow[v];
+        for (int cc = 0; cc < P; cc++) {
 #pragma unroll
-        for (int t = 0; t < P; t++) z[t] += ca * td[(int64_t)(row * P + t) * ldd];
-      } else {
-#pragma unroll
-        for (int t = 0; t < P; t++) z[t] += ca * th[(int64_t)(tr.mu() + t) * ldp];
+          for (int r = 0; r <= cc; r++) {
+            const double x = proper ? th[(int64_t)(tr.rootP() + cc * P + r) * ldp] : 0.0;
+            double* d = st + (js + pk(pos + r, pos + cc)) * ld;
+            if (fJ & 1) *d = 0.0 + x;
+            else if (proper) *d += x;
+          }
+          const double xh = proper ? th[(int64_t)(tr.rooth() + cc) * ldp] : 0.0;
+          double* dh = st + (hs + pos + cc) * ld;
+          if (fh & 1) *dh = 0.0 + xh;
+          else if (proper) *dh += xh;
+        }
+        if (proper) g += th[(int64_t)tr.rootg() * ldp];
+        continue;
       }
-    }
+      // precision block j (symmetric: upper triangle kept, 36 registers at P = 8) and log-normaliser
+      double ju[P * (P + 1) / 2];
+#define PGBP_JU(r_, c_) ju[(r_) <= (c_) ? pk((r_), (c_)) : pk((c_), (r_))]
+      double gv;
+      bool samecolor = true;
+      for (int k = k0 + 2; k < k0 + nm; k++) if (F.mem_color[k] != F.mem_color[k0 + 1]) samecolor = false;
+      if (samecolor) {
+        const int col = F.mem_color[k0 + 1];
+        double t0 = 0.0;
+        if (nm == 2) t0 = F.mem_length[k0 + 1];
+        else for (int k = k0 + 1; k < k0 + nm; k++) t0 += F.mem_gamma[k] * F.mem_gamma[k] * F.mem_length[k];
+        // x / t0 for 36 values with one divisor: r = RN(1/t0), q0 = x r, q = q0 + r (x - t0 q0)
+        // (Markstein: correctly rounded quotient from a correctly rounded reciprocal), 3 FMA-class
+        // operations per entry instead of a ~20-instruction division sequence
+        const double rt = 1.0 / t0;
 #pragma unroll
-    for (int t = 0; t < P; t++) jz[t] = 0.0;
-    if (anyfixed) {
-      double quad = 0.0;
+        for (int cc = 0; cc < P; cc++) {
 #pragma unroll
-      for (int r = 0; r < P; r++) {
-        double s = 0.0;
+          for (int r = 0; r <= cc; r++) {
+            const double x = th[(int64_t)(tr.P(col) + cc * P + r) * ldp];
+            const double q0 = x * rt;
+            ju[pk(r, cc)] = fma(fma(-t0, q0, x), rt, q0);
+          }
+        }
+        gv = th[(int64_t)tr.g0(col) * ldp] - 0.5 * P * log(t0);
+      } else {  // heterogeneous hybrid: j = (sum gamma^2 t R_c)^-1
+        double w[P * P], jl[P * P];
+        for (int q = 0; q < P * P; q++) w[q] = 0.0;
+        for (int k = k0 + 1; k < k0 + nm; k++) {
+          const double f = F.mem_gamma[k] * F.mem_gamma[k] * F.mem_length[k];
+          const int col = F.mem_color[k];
+          for (int q = 0; q < P * P; q++) w[q] += f * th[(int64_t)(tr.R(col) + q) * ldp];
+        }
+        double ldv;
+        const int info = spd_inverse_logdet(w, jl, P, &ldv);
+        if (info) { status_fail(gen.status, e, PGBP_STATUS(0x7ffffc, info)); st[gs * ld] = NAN; return; }
 #pragma unroll
-        for (int cc = 0; cc < P; cc++) s += j[cc * P + r] * z[cc];
-        jz[r] = s;
-        quad += z[r] * s;
+        for (int cc = 0; cc < P; cc++) {
+#pragma unroll
+          for (int r = 0; r <= cc; r++) ju[pk(r, cc)] = jl[cc * P + r];
+        }
+        gv = -0.5 * (P * PGBP_LOG2PI + ldv);
       }
-      gv -= 0.5 * quad;
-    }
-    for (int a = 0; a < nm; a++) {
-      const int pa = F.mem_pos[k0 + a];
-      if (pa < 0) continue;
-      const double ca = a == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + a]);
+      // evidence: z = sum over fixed members of c_a * value_a
+      bool anyfixed = false;
+      double z[P], jz[P];
 #pragma unroll
-      for (int t = 0; t < P; t++) st[(hs + pa + t) * ld] = anyfixed ? 0.0 - ca * jz[t] : 0.0;
-      for (int bq = a; bq < nm; bq++) {
-        const int pb = F.mem_pos[k0 + bq];
-        if (pb < 0) continue;
-        const double cb = bq == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + bq]);
-        const double cab = ca * cb;
-        const bool diag = bq == a;
+      for (int t = 0; t < P; t++) { z[t] = 0.0; jz[t] = 0.0; }
+      for (int a = 0; a < nm; a++) {
+        if (F.mem_pos[k0 + a] >= 0) continue;
+        anyfixed = true;
+        const double ca = a == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + a]);
+        if (a == 0) {
+          const int row = F.node_datarow[v];
 #pragma unroll
-        for (int tb = 0; tb < P; tb++) {
+          for (int t = 0; t < P; t++) z[t] += ca * td[(int64_t)(row * P + t) * ldd];
+        } else {
 #pragma unroll
-          for (int ta = 0; ta < P; ta++) {
-            if (!diag || ta <= tb) st[(js + pk(pa + ta, pb + tb)) * ld] = 0.0 + cab * j[tb * P + ta];
+          for (int t = 0; t < P; t++) z[t] += ca * th[(int64_t)(tr.mu() + t) * ldp];
+        }
+      }
+      if (anyfixed) {
+        double quad = 0.0;
+#pragma unroll
+        for (int r = 0; r < P; r++) {
+          double s = 0.0;
+#pragma unroll
+          for (int cc = 0; cc < P; cc++) s += PGBP_JU(r, cc) * z[cc];
+          jz[r] = s;
+          quad += z[r] * s;
+        }
+        gv -= 0.5 * quad;
+      }
+      g += gv;
+      const uint32_t ld8 = (uint32_t)(ld * 8);
+      char* stb = (char*)st;
+      for (int a = 0; a < nm; a++) {
+        const int pa = F.mem_pos[k0 + a];
+        if (pa < 0) continue;
+        const double ca = a == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + a]);
+        if ((fh >> a) & 1) {
+#pragma unroll
+          for (int t = 0; t < P; t++) *kaddr(stb, (uint32_t)(hs + pa + t), ld8) = anyfixed ? 0.0 - ca * jz[t] : 0.0;
+        } else if (anyfixed) {
+#pragma unroll
+          for (int t = 0; t < P; t++) *kaddr(stb, (uint32_t)(hs + pa + t), ld8) -= ca * jz[t];
+        }
+        for (int bq = a; bq < nm; bq++) {
+          const int pb = F.mem_pos[k0 + bq];
+          if (pb < 0) continue;
+          const double cb = bq == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + bq]);
+          const double cab = ca * cb;
+          const bool diag = bq == a;
+          const bool first = (fJ >> (a * 8 + bq)) & 1;
+#pragma unroll
+          for (int tb = 0; tb < P; tb++) {
+            const uint32_t colslot = (uint32_t)js + (uint32_t)tri(pb + tb) + (uint32_t)pa;  // pk(pa + ta, pb + tb)
+#pragma unroll
+            for (int ta = 0; ta < P; ta++) {
+              if (!diag || ta <= tb) {
+                double* d = kaddr(stb, colslot + ta, ld8);
+                const double x = cab * PGBP_JU(ta, tb);
+                if (first) *d = x;
+                else *d += x;
+              }
+            }
           }
         }
       }
+#undef PGBP_JU
     }
-    st[gs * ld] = 0.0 + gv;
+    st[gs * ld] = g;
   }
 };
 
@@ -608,7 +695,9 @@ struct DevTables {
   // families
   int32_t *node_cluster = nullptr, *mem_off = nullptr, *mem_pos = nullptr, *mem_color = nullptr,
           *node_datarow = nullptr, *clu_off = nullptr, *clu_node = nullptr;
-  uint8_t* clu_fast = nullptr;
+  uint8_t* clu_flag = nullptr;
+  uint64_t* first_J = nullptr;
+  uint8_t* first_h = nullptr;
   double *mem_length = nullptr, *mem_gamma = nullptr;
   // parameter / data staging
   double* theta = nullptr;
@@ -660,7 +749,9 @@ static int get_tables(pgbp_batch* b, DevTables** out) {
     PGBP_TRY(upload(b, dt.get(), &dt->clu_node, F.clu_node));
     PGBP_TRY(upload(b, dt.get(), &dt->mem_length, F.mem_length));
     PGBP_TRY(upload(b, dt.get(), &dt->mem_gamma, F.mem_gamma));
-    PGBP_TRY(upload(b, dt.get(), &dt->clu_fast, F.clu_fast));
+    PGBP_TRY(upload(b, dt.get(), &dt->clu_flag, F.clu_flag));
+    PGBP_TRY(upload(b, dt.get(), &dt->first_J, F.first_J));
+    PGBP_TRY(upload(b, dt.get(), &dt->first_h, F.first_h));
   }
   PGBP_TRY(stream_sync(b->stream));
   b->d_fam = dt.release();
@@ -791,7 +882,7 @@ static int assign_enqueue(pgbp_batch* b, pgbp::DevTables* dt, int32_t ncolors, c
   AssignBody body{fd, dt->theta, dt->ldp, dt->tip, dt->ldd, b->state, b->status, b->ld, nparamsets, ndatasets, pairing, tr};
   switch (pt) {
 #define PGBP_FAST_CASE(P_) \
-  case P_: PGBP_TRY(launch_generic(b, "k_assign_factors", b->B, p->nclusters, AssignFast<P_>{body, dt->clu_fast})); break;
+  case P_: PGBP_TRY((launch_generic<AssignFast<P_>, 3>(b, "k_assign_factors", b->B, p->nclusters, AssignFast<P_>{body, dt->clu_flag, dt->first_J, dt->first_h}))); break;
     PGBP_FAST_CASE(1) PGBP_FAST_CASE(2) PGBP_FAST_CASE(3) PGBP_FAST_CASE(4) PGBP_FAST_CASE(5) PGBP_FAST_CASE(6)
     PGBP_FAST_CASE(7) PGBP_FAST_CASE(8)
 #undef PGBP_FAST_CASE

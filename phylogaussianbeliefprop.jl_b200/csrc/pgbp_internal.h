@@ -57,8 +57,11 @@ struct FamilyTable {
   std::vector<double> mem_length, mem_gamma;
   // derived: nodes of each cluster, ascending (order of the loop at src/beliefs.jl:798)
   std::vector<int32_t> clu_off, clu_node;
-  // derived: cluster takes the write-once path of K1 (one family, one colour, members tile the scope)
-  std::vector<uint8_t> clu_fast;
+  // derived, for the write-once path of K1: clu_flag bit 0 = some scope entry of the cluster is covered
+  // by no family (zero-fill first); first_J[v] bit a*8+b / first_h[v] bit a = family v is the first
+  // (in node order) to touch block (member a, member b) / member a's h segment of its cluster
+  std::vector<uint8_t> clu_flag, first_h;
+  std::vector<uint64_t> first_J;
   int32_t ncolors_min = 1;
 };
 

@@ -128,18 +128,28 @@ static int launch_smem(pgbp_batch* b, const MsgArgs& a, int nmsg, int I, int S) 
     for (int64_t e = 0; e < a.B; e++) message_thread_rt<PGBP_MAX_DIM>(a, m, e);
 #else
   static bool attr_done = false;  // per instantiation
+  static bool attr8_done = false;
+  const bool s8 = EXACT && S <= 8 && MAXI <= 10;  // fully unrolled kept-block loops (register budget: I <= 10)
   const void* fn;
-  if constexpr (EXACT) fn = (const void*)k_message_smem<MAXI>;
+  if constexpr (EXACT) fn = s8 ? (const void*)k_message_smem<MAXI, 8> : (const void*)k_message_smem<MAXI, 0>;
   else fn = (const void*)k_message_smem_rt<MAXI>;
-  if (!attr_done) {
+  if (s8 && !attr8_done) {
+    PGBP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_LIMIT));
+    attr8_done = true;
+  }
+  if (!s8 && !attr_done) {
     PGBP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_LIMIT));
     attr_done = true;
   }
   if (a.ld * 8 >= ((int64_t)1 << 32)) PGBP_FAIL(PGBP_ESTATE, "batch too large for 32-bit row pitch");
-  const size_t bytes = sizeof(double) * 32 * (size_t)smem_doubles(I, S);
+  const size_t bytes = smem_block_bytes(I, S);
   dim3 grid((unsigned)((a.B + 31) / 32), (unsigned)nmsg);
-  if constexpr (EXACT) k_message_smem<MAXI><<<grid, 32, bytes, b->stream>>>(a);
-  else k_message_smem_rt<MAXI><<<grid, 32, bytes, b->stream>>>(a);
+  if constexpr (EXACT) {
+    if (s8) k_message_smem<MAXI, 8><<<grid, 32, bytes, b->stream>>>(a);
+    else k_message_smem<MAXI, 0><<<grid, 32, bytes, b->stream>>>(a);
+  } else {
+    k_message_smem_rt<MAXI><<<grid, 32, bytes, b->stream>>>(a);
+  }
 #endif
   b->launches++;
   return check_launch("k_message_smem");
@@ -180,7 +190,7 @@ int launch_group(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGr
     } else {  // medium / large class: the group is uniform in (I, S) = (g.maxm, g.cs)
       const int I = g.maxm, S = g.cs, M = I + S;
       const int mode = b->coop_mode;
-      const bool fits = I <= 32 && sizeof(double) * 32 * (size_t)(I * (I + 1) / 2 + I * S + I) <= PGBP_SMEM_LIMIT;
+      const bool fits = I <= 32 && sizeof(double) * 32 * (size_t)(I * (I + 1) / 2 + I * S + I) + 4 * (size_t)(M * (M + 3) / 2 + S * (S + 3) / 2 + 2) <= PGBP_SMEM_LIMIT;
       if ((mode == -1 || mode == 1) && fits) {
         switch (I) {
 #define PGBP_SMEM_CASE(I_) case I_: rc = launch_smem<I_, true>(b, a, n, I, S); break;

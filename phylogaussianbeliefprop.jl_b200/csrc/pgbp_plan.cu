@@ -3,6 +3,7 @@
 // HBM slot layouts, deduplicated gather/scatter tables and launch steps.
 #include <algorithm>
 #include <mutex>
+#include <set>
 
 #include "pgbp_internal.h"
 #include "pgbp_shapes.h"
@@ -275,19 +276,31 @@ int32_t pgbp_plan_create(const pgbp_plan_desc* d, pgbp_plan** out) {
       c2n[c].push_back(v);
     }
     F.clu_off.assign(1, 0);
-    F.clu_fast.assign(p->nclusters, 0);
+    F.clu_flag.assign(p->nclusters, 0);
+    F.first_J.assign(F.nnodes, 0);
+    F.first_h.assign(F.nnodes, 0);
     for (int c = 0; c < p->nclusters; c++) {
       auto& v = c2n[c];
       F.clu_node.insert(F.clu_node.end(), v.begin(), v.end());
       F.clu_off.push_back((int32_t)F.clu_node.size());
-      if (v.size() != 1) continue;
-      const int o0 = F.mem_off[v[0]], o1 = F.mem_off[v[0] + 1];
-      if (o1 - o0 < 2) continue;  // root family
-      bool same = true;
-      int covered = 0;
-      for (int k = o0 + 1; k < o1; k++) same = same && F.mem_color[k] == F.mem_color[o0 + 1];
-      for (int k = o0; k < o1; k++) if (F.mem_pos[k] >= 0) covered += pt;
-      F.clu_fast[c] = same && covered == p->dim[c];
+      std::set<std::pair<int, int>> seenJ;  // (pos_a, pos_b) blocks already written
+      std::set<int> seenh;
+      for (int node : v) {
+        const int o0 = F.mem_off[node], nm = F.mem_off[node + 1] - o0;
+        for (int a = 0; a < nm; a++) {
+          const int pa = F.mem_pos[o0 + a];
+          if (pa < 0) continue;
+          if (seenh.insert(pa).second) F.first_h[node] |= (uint8_t)(1u << a);
+          for (int bq = a; bq < nm; bq++) {
+            const int pb = F.mem_pos[o0 + bq];
+            if (pb < 0) continue;
+            if (pb < pa) PGBP_FAIL(PGBP_EINVAL, "node %d: family members are not in cluster order", node);
+            if (seenJ.insert({pa, pb}).second) F.first_J[node] |= (uint64_t)1 << (a * 8 + bq);
+          }
+        }
+      }
+      const int nn = p->dim[c] / pt;  // full trait scopes: in-scope nodes of the cluster
+      if ((int)seenh.size() != nn || (int)seenJ.size() != nn * (nn + 1) / 2) F.clu_flag[c] |= 1;
     }
     p->has_families = true;
   }
