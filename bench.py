@@ -178,7 +178,9 @@ def run_reference(args):
     w = WORKLOADS[args.workload]()
     B = args.batch or w.default_batch
     params, tips = w.inputs(B, 0)
-    value, cores, n, dt, _ = cpu_port_rate(w, params, tips, 3.0, steps=args.steps, warmup=args.warmup)
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it explicitly)
+    nthr = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    value, cores, n, dt, _ = cpu_port_rate(w, params, tips, 3.0, nthreads=nthr, steps=args.steps, warmup=args.warmup)
     sample = f"{n} of {B} batch elements per step ({w.cpu_text})"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": w.unit, "n_gpus": args.gpus, "steps": args.steps,
@@ -299,14 +301,31 @@ def run_gpu(args):
                                              factors=w.residuals, residuals=w.residuals)
     if args.walk is not None:
         bt.set_walk_mode(args.walk)
+    if args.pipeline is not None:
+        bt.set_pipeline(args.pipeline)
     root = d["root_cluster"] + 1
     bytes_unit, flops_unit = w.cost(plan)
     nmsg = len(d["trees"][0][0]) * (2 if w.key == "c2" else 1)
 
     # ---- device-resident arm: inputs in HBM before the timed region -----------------------
     _, ld, _ = bt.device_view()
-    d_norm = torch.empty(ld, dtype=torch.float64, device=dev)
-    gathered = torch.empty(world * ld, dtype=torch.float64, device=dev) if world > 1 else None
+    # two result buffers: the NCCL gather of step k (on NCCL's stream) overlaps the kernels of step k+1
+    d_norms = [torch.empty(ld, dtype=torch.float64, device=dev) for _ in range(2)]
+    gathered = [torch.empty(world * ld, dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+    pending = [None, None]
+    counter = [0]
+
+    def finish(ev=None):
+        """integratebelief! at the root + (N > 1) asynchronous all-gather of the log-likelihoods."""
+        k = counter[0] % 2
+        counter[0] += 1
+        if pending[k] is not None:
+            pending[k].wait()  # stream-level wait: buffer k is free again
+            pending[k] = None
+        bt.integrate_device(root, d_norms[k].data_ptr())
+        if world > 1:
+            pending[k] = dist.all_gather_into_tensor(gathered[k], d_norms[k], async_op=True)
+        return d_norms[k]
     if w.key == "c2":
         bt.assignfactors(params, tips)  # factors resident in HBM
 
@@ -317,9 +336,7 @@ def run_gpu(args):
             bt.calibrate_async(None, 1, update_residualnorm=True)
             if ev:
                 ev[1].record(stream)
-            bt.integrate_device(root, d_norm.data_ptr())
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, d_norm)
+            finish()
     else:
         d_params = torch.from_numpy(params).to(dev)
         d_tips = torch.from_numpy(tips).to(dev)
@@ -331,11 +348,13 @@ def run_gpu(args):
             bt.calibrate_async(None, 1, update_residualnorm=False, direction=L.CAL_POSTORDER)
             if ev:
                 ev[1].record(stream)
-            bt.integrate_device(root, d_norm.data_ptr())
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, d_norm)
+            finish()
 
     def barrier():
+        for k in range(2):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -366,7 +385,10 @@ def run_gpu(args):
     value = world * B * args.steps / (ms_total * 1e-3)
     st = bt.status()
     assert (st == 0).all(), "numerical failure inside the timed region"
-    loglik_dev = d_norm[:B].cpu().numpy()
+    loglik_dev = d_norms[(counter[0] - 1) % 2][:B].cpu().numpy()
+    if world > 1:  # the gathered vector holds every rank's log-likelihoods; this rank's slice must match
+        mine = gathered[(counter[0] - 1) % 2].view(world, ld)[rank, :B].cpu().numpy()
+        assert np.array_equal(mine, loglik_dev)
 
     # ---- end-to-end arm: public host-buffer API, pinned host inputs, D2H of the result -------
     nbuf = 2
@@ -428,7 +450,8 @@ def run_gpu(args):
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        rate, cores, n, dt, ll_cpu = cpu_port_rate(w, params, tips, args.cpu_seconds)
+        nthr = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        rate, cores, n, dt, ll_cpu = cpu_port_rate(w, params, tips, args.cpu_seconds, nthreads=nthr)
         err = float(np.max(np.abs(ll_cpu / loglik_dev[:n] - 1)))
         cpu = {"value": rate, "unit": w.unit, "cores": cores, "kind": "port",
                "sample": f"{n} of {B} batch elements in {dt:.1f} s ({w.cpu_text}, C/OpenMP restatement of the Julia "
@@ -441,7 +464,8 @@ def run_gpu(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w.workload, "batch_per_gpu": B, "ntraits": p, "messages_per_unit": nmsg,
-                   "step": w.step_text + (" + nccl all_gather(loglik)" if world > 1 else ""),
+                   "step": w.step_text + (" + nccl all_gather(loglik), double-buffered and asynchronous: it overlaps "
+                                          "the next step's kernels" if world > 1 else ""),
                    "l2": "inputs larger than L2 (state %.2f GB per GPU)" % (bt.device_bytes() / 1e9),
                    "parallelism": f"batch sharded over {world} GPU(s), plan replicated"},
         "roofline": roofline,
@@ -467,6 +491,7 @@ def main():
                     "c4 = configs[3] (10k-tip synthetic network, p=8)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=None, help="element chunks of a calibration (-1 auto, 1 off)")
     ap.add_argument("--walk", type=int, default=None, help="kernel strategy override: 0 level-parallel, 1 walk kernel")
     args = ap.parse_args()
     if args.impl == "reference":

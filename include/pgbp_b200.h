@@ -145,6 +145,11 @@ int64_t pgbp_batch_launch_count(pgbp_batch* batch, int32_t reset);
  * replicate; needs every message shape to be whole nodes of ntraits <= 4 traits, else falls
  * back to 0).  Results are bit-identical. */
 int32_t pgbp_batch_set_walk_mode(pgbp_batch* batch, int32_t mode);
+/* Pipelined calibration: the batch is cut into `nchunks` ranges of elements; every range walks the
+ * whole schedule on its own stream (elements are independent), so the ramp-up and tail of the small
+ * launches of one range overlap the other ranges' work.  -1 automatic (default: up to 4 chunks of
+ * >= 8192 elements when one launch cannot fill the GPU), 1 off.  Results are unaffected. */
+int32_t pgbp_batch_set_pipeline(pgbp_batch* batch, int32_t nchunks);
 /* Kernel for medium message shapes (sender dimension > 12): -1 automatic (= 1 where it fits),
  * 1 shared-memory kernel (one thread per element, factor in shared memory), 4 / 8 cooperative
  * kernel (that many lanes per element for sender dimensions <= 16, 8 above; sender dimension

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(HERE, "lib", "libpgbp_b200.so")
+# PGBP_B200_LIB selects another build of the SAME CUDA library (kernel-tuning variants); never a CPU path
+DEFAULT_LIB = os.environ.get("PGBP_B200_LIB") or os.path.join(HERE, "lib", "libpgbp_b200.so")
 
 i32, i64, u32, u8, f64 = C.c_int32, C.c_int64, C.c_uint32, C.c_uint8, C.c_double
 P = C.POINTER
@@ -53,6 +54,7 @@ SIGNATURES = {
     "pgbp_batch_launch_count": (i64, [vp, i32]),
     "pgbp_batch_set_walk_mode": (i32, [vp, i32]),
     "pgbp_batch_set_coop_mode": (i32, [vp, i32]),
+    "pgbp_batch_set_pipeline": (i32, [vp, i32]),
     "pgbp_set_belief": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
     "pgbp_get_belief": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
     "pgbp_get_factor": (i32, [vp, i32, P(f64), P(f64), P(f64)]),

@@ -286,6 +286,10 @@ class BatchedClusterGraphBelief:
         """-1 auto, 0 level-parallel launches, 1 single walk kernel per traversal."""
         self.lib.check(self.lib.pgbp_batch_set_walk_mode(self.handle, int(mode)))
 
+    def set_pipeline(self, nchunks):
+        """-1 auto, 1 off, n > 1: calibrate in n element chunks on n streams (small graphs)."""
+        self.lib.check(self.lib.pgbp_batch_set_pipeline(self.handle, int(nchunks)))
+
     def set_coop_mode(self, mode):
         """-1 auto, 1 shared-memory kernel, 4 / 8 cooperative lanes, 0 thread-local generic kernel."""
         self.lib.check(self.lib.pgbp_batch_set_coop_mode(self.handle, int(mode)))

@@ -38,12 +38,15 @@ def _run(cmd):
     return r.stdout + r.stderr
 
 
-def build(emul=False, verbose=False, force=False):
+def build(emul=False, verbose=False, force=False, defines=(), tag=""):
+    """tag/defines: experimental variants (lib/libpgbp_b200_<tag>.so built with -D<define>), selected at
+    run time with PGBP_B200_LIB=<path>; the default build has neither."""
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj_emul" if emul else "obj")
+    objdir = os.path.join(LIBDIR, ("obj_emul" if emul else "obj") + (("_" + tag) if tag else ""))
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
-    lib = os.path.join(LIBDIR, "libpgbp_emul.so" if emul else "libpgbp_b200.so")
+    lib = os.path.join(LIBDIR, "libpgbp_emul.so" if emul else ("libpgbp_b200_%s.so" % tag if tag else "libpgbp_b200.so"))
+    dflags = ["-D" + d for d in defines]
     objs, jobs = [], []
     for s in SOURCES:
         src = os.path.join(CSRC, s)
@@ -53,7 +56,7 @@ def build(emul=False, verbose=False, force=False):
             if emul:
                 cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-DPGBP_HOST_EMUL", "-x", "c++", "-c", src, "-o", obj]
             else:
-                cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+                cmd = [NVCC] + NVCC_FLAGS + dflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
     if jobs:
         with ThreadPoolExecutor(max_workers=min(4, len(jobs))) as ex:
@@ -69,4 +72,7 @@ def build(emul=False, verbose=False, force=False):
 
 
 if __name__ == "__main__":
-    print(build(emul="--emul" in sys.argv, verbose="-v" in sys.argv, force="--force" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    tags = [a[6:] for a in sys.argv[1:] if a.startswith("--tag=")]
+    print(build(emul="--emul" in sys.argv, verbose="-v" in sys.argv, force="--force" in sys.argv, defines=defs,
+                tag=tags[0] if tags else ""))

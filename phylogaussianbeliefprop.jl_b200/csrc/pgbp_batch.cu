@@ -190,7 +190,9 @@ extern "C" {
 
 int32_t pgbp_batch_create(const pgbp_plan* plan, int64_t B, int32_t device, uint32_t flags, pgbp_batch** out) {
   if (!plan || !out || B <= 0) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
-  if (plan->nslots_state >= (int64_t)1 << 31) PGBP_FAIL(PGBP_EINVAL, "cluster graph too large for int32 slot tables");
+  if (plan->nslots_state >= (int64_t)1 << 31 || plan->nslots_resid >= (int64_t)1 << 31)
+    PGBP_FAIL(PGBP_EINVAL, "cluster graph too large for int32 slot tables");
+  if ((B + 31) / 32 * 32 * 8 >= (int64_t)1 << 32) PGBP_FAIL(PGBP_EINVAL, "batch too large: row pitch must stay below 4 GiB");
   PGBP_TRY(set_device(device));
   std::unique_ptr<pgbp_batch> b(new pgbp_batch);
   b->plan = plan;
@@ -256,6 +258,8 @@ int32_t pgbp_batch_destroy(pgbp_batch* b) {
   for (auto* p : b->d_msgs) dev_free(p);
   for (auto* p : b->d_walk) dev_free(p);
 #ifndef PGBP_HOST_EMUL
+  for (auto s : b->pipe_streams) cudaStreamDestroy(s);
+  for (auto ev : b->pipe_events) cudaEventDestroy((cudaEvent_t)ev);
   if (b->own_stream) cudaStreamDestroy(b->stream);
 #endif
   delete b;

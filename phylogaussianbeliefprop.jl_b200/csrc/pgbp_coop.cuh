@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128) k_message_coop(MsgArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / RPW, rw = lane % RPW;  // lane = g * RPW + rw
   const int rb = warp * RPW + rw;
-  const int64_t e = (int64_t)blockIdx.x * RPB + rb;
+  const int64_t e = a.e0 + (int64_t)blockIdx.x * RPB + rb;
   const MsgDesc md = a.msgs[blockIdx.y];
   const int I = md.mF - md.s, S = md.s, M = md.mF;
   const int64_t ld = a.ld;
@@ -256,7 +256,7 @@ template <int MAXI>
 __global__ void __launch_bounds__(32) k_message_smem_rt(MsgArgs a) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
-  const int64_t e = (int64_t)blockIdx.x * 32 + tid;
+  const int64_t e = a.e0 + (int64_t)blockIdx.x * 32 + tid;
   if (e >= a.B) return;
   if (a.status[e] != 0) return;
   if (a.done && a.done[e]) return;
@@ -448,7 +448,7 @@ template <int I, int MS>
 __global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
-  const int64_t e0 = (int64_t)blockIdx.x * 32 + tid;
+  const int64_t e0 = a.e0 + (int64_t)blockIdx.x * 32 + tid;
   const MsgDesc md = a.msgs[blockIdx.y];
   const int S = md.s, M = md.mF;
   constexpr int TI = I * (I + 1) / 2;

@@ -120,6 +120,13 @@ struct pgbp_batch {
   int64_t launches = 0;
   bool want_info = false;
   int32_t walk_mode = -1;  // -1 auto, 0 never, 1 always (when walkable)
+  // pipelined calibration: the batch is cut into `pipeline` chunks of elements, each walking the whole
+  // schedule on its own stream (elements are independent), so that the ramp-up / tail of one chunk's
+  // small launches overlaps the others' work.  chunk_begin / chunk_end: range being enqueued.
+  int32_t pipeline = -1;  // -1 auto, 1 off, n > 1 chunks
+  int64_t chunk_begin = 0, chunk_end = 0;
+  std::vector<pgbp_stream_t> pipe_streams;
+  std::vector<void*> pipe_events;  // cudaEvent_t: [0] fork, [1..] joins
   int32_t coop_mode = -1;  // medium shapes: -1 auto (cooperative), 0 thread-local generic, 4 / 8 lanes for m <= 16
   int32_t* d_slot = nullptr;  // device scratch for transpose slot tables
   size_t d_slot_len = 0;

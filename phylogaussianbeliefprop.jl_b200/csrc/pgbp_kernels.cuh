@@ -21,9 +21,10 @@ struct MsgArgs {
   uint8_t* calflag;  // may be null
   int32_t* status;
   const uint8_t* done;  // may be null
-  int64_t B, ld;
+  int64_t B, ld;     // elements [e0, B) are processed (e0 > 0: one chunk of a pipelined calibration)
   uint32_t opts;     // PGBP_CAL_RESIDNORM
   int32_t ref_base;
+  int64_t e0;
 };
 
 // NaN-propagating running maximum of |x| (Julia's maximum(abs, x))
@@ -78,17 +79,24 @@ PGBP_HD void store_flag(const MsgArgs& a, int dmsg, int64_t e, int S, double max
 // value and the receiver's old value are all loaded first (3*CHUNK independent
 // loads in flight per thread), then  new = J_KK - z_r.z_c,  delta = new - old,
 // and the three stores.  h and g follow the same pattern.
+// slot k of this element: base + k * (8*ld); 32-bit slot x 32-bit pitch -> one IMAD.WIDE.U32
+PGBP_HD double* slot_ptr(char* base, uint32_t slot, uint32_t ld8) {
+  return (double*)(base + (uint64_t)slot * (uint64_t)ld8);
+}
+
 template <int CI, int CS>
 PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
   constexpr int I = CI, S = CS, M = I + S, SI = I * (I + 1) / 2, SS = S * (S + 1) / 2;
   const MsgDesc md = a.msgs[msg_index];  // by value: lives in registers, never re-read after a store
   if (a.status[e] != 0) return;
   if (a.done && a.done[e]) return;
-  const int64_t ld = a.ld;
-  double* st = a.state + e;
-  double* rs = a.resid ? a.resid + e : nullptr;
+  const uint32_t ld8 = (uint32_t)(a.ld * 8);  // (batches with 8*ld >= 2^32 are refused at creation)
+  char* st = (char*)(a.state + e);
+  char* rs = a.resid ? (char*)(a.resid + e) : nullptr;
   const int32_t* __restrict__ gat = a.tab + md.gat;
   const int32_t* __restrict__ sca = a.tab + md.sca;
+  const uint32_t fJ = (uint32_t)md.fJ, fh = (uint32_t)md.fh, sJ = (uint32_t)md.sJ, sh = (uint32_t)md.sh,
+                 tJ = (uint32_t)md.tJ, th = (uint32_t)md.th, rJ = (uint32_t)md.rJ, rh = (uint32_t)md.rh;
   constexpr int SMM = M * (M + 1) / 2;
   double AI[SI > 0 ? SI : 1];
   double Bm[I * S > 0 ? I * S : 1];  // Bm[k*S + c] = J[I_k, K_c]
@@ -96,18 +104,18 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
 #pragma unroll
   for (int c = 0; c < I; c++) {
 #pragma unroll
-    for (int r = 0; r <= c; r++) AI[pk(r, c)] = st[(md.fJ + gat[pk(r, c)]) * ld];
+    for (int r = 0; r <= c; r++) AI[pk(r, c)] = *slot_ptr(st, fJ + gat[pk(r, c)], ld8);
   }
 #pragma unroll
   for (int c = 0; c < S; c++) {
 #pragma unroll
-    for (int k = 0; k < I; k++) Bm[k * S + c] = st[(md.fJ + gat[pk(k, I + c)]) * ld];
+    for (int k = 0; k < I; k++) Bm[k * S + c] = *slot_ptr(st, fJ + gat[pk(k, I + c)], ld8);
   }
 #pragma unroll
-  for (int k = 0; k < I; k++) hI[k] = st[(md.fh + gat[SMM + k]) * ld];
-  double g = st[md.fg * ld];
-  const double sg_old = st[md.sg * ld];
-  const double tg_old = st[md.tg * ld];
+  for (int k = 0; k < I; k++) hI[k] = *slot_ptr(st, fh + gat[SMM + k], ld8);
+  double g = *slot_ptr(st, (uint32_t)md.fg, ld8);
+  const double sg_old = *slot_ptr(st, (uint32_t)md.sg, ld8);
+  const double tg_old = *slot_ptr(st, (uint32_t)md.tg, ld8);
 
   // "Ji = Jki = hi = 0 if missing data" shortcut, src/beliefupdates.jl:62-66
   bool allzero = true;
@@ -167,13 +175,13 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
     constexpr int q0 = decltype(chc)::value * PGBP_CHUNK;
     constexpr int n = (SS - q0) < PGBP_CHUNK ? (SS - q0) : PGBP_CHUNK;
     double jo[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
-    int64_t ta[PGBP_CHUNK];
+    double* ta[PGBP_CHUNK];
     static_for<n>([&](auto kc) {
       constexpr int k = decltype(kc)::value, q = q0 + k, c = colof(q), r = q - c * (c + 1) / 2;
-      ta[k] = (md.tJ + sca[q]) * ld;
-      jo[k] = st[(md.fJ + gat[pk(I + r, I + c)]) * ld];
-      so[k] = st[(md.sJ + q) * ld];
-      to[k] = st[ta[k]];
+      ta[k] = slot_ptr(st, tJ + sca[q], ld8);
+      jo[k] = *slot_ptr(st, fJ + gat[pk(I + r, I + c)], ld8);
+      so[k] = *slot_ptr(st, sJ + q, ld8);
+      to[k] = *ta[k];
     });
     static_for<n>([&](auto kc) {
       constexpr int k = decltype(kc)::value, q = q0 + k, c = colof(q), r = q - c * (c + 1) / 2;
@@ -181,21 +189,21 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
 #pragma unroll
       for (int i = 0; i < I; i++) nv = nfma(Bm[i * S + r], Bm[i * S + c], nv);
       const double d = nv - so[k];
-      st[(md.sJ + q) * ld] = nv;
-      st[ta[k]] = to[k] + d;
-      if (rs) rs[(md.rJ + q) * ld] = d;
+      *slot_ptr(st, sJ + q, ld8) = nv;
+      *ta[k] = to[k] + d;
+      if (rs) *slot_ptr(rs, rJ + q, ld8) = d;
       absmax(maxJ, d);
     });
   });
   {
     double ho[S > 0 ? S : 1], so[S > 0 ? S : 1], to[S > 0 ? S : 1];
-    int64_t ta[S > 0 ? S : 1];
+    double* ta[S > 0 ? S : 1];
 #pragma unroll
     for (int k = 0; k < S; k++) {
-      ta[k] = (md.th + sca[SS + k]) * ld;
-      ho[k] = st[(md.fh + gat[SMM + I + k]) * ld];
-      so[k] = st[(md.sh + k) * ld];
-      to[k] = st[ta[k]];
+      ta[k] = slot_ptr(st, th + sca[SS + k], ld8);
+      ho[k] = *slot_ptr(st, fh + gat[SMM + I + k], ld8);
+      so[k] = *slot_ptr(st, sh + k, ld8);
+      to[k] = *ta[k];
     }
 #pragma unroll
     for (int k = 0; k < S; k++) {
@@ -203,14 +211,14 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
 #pragma unroll
       for (int i = 0; i < I; i++) nv = nfma(Bm[i * S + k], hI[i], nv);
       const double d = nv - so[k];
-      st[(md.sh + k) * ld] = nv;
-      st[ta[k]] = to[k] + d;
-      if (rs) rs[(md.rh + k) * ld] = d;
+      *slot_ptr(st, sh + k, ld8) = nv;
+      *ta[k] = to[k] + d;
+      if (rs) *slot_ptr(rs, rh + k, ld8) = d;
       absmax(maxh, d);
     }
   }
-  st[md.sg * ld] = g;
-  st[md.tg * ld] = tg_old + (g - sg_old);
+  *slot_ptr(st, (uint32_t)md.sg, ld8) = g;
+  *slot_ptr(st, (uint32_t)md.tg, ld8) = tg_old + (g - sg_old);
   store_flag(a, md.dmsg, e, S, maxJ, maxh);
 }
 

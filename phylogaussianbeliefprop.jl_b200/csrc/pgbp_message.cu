@@ -17,15 +17,18 @@ namespace pgbp {
 #endif
 
 #ifndef PGBP_HOST_EMUL
+#ifndef PGBP_MSG_MINBLOCKS
+#define PGBP_MSG_MINBLOCKS 1  // measured on C2 (B200): 1 -> 0.641 of HBM roofline, 2 -> 0.641, 3 -> 0.594, 4 -> 0.548
+#endif
 template <int CI, int CS, int MAXM>
-__global__ void __launch_bounds__(PGBP_MSG_THREADS) k_message(MsgArgs a) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(PGBP_MSG_THREADS, (CI >= 0 ? PGBP_MSG_MINBLOCKS : 1)) k_message(MsgArgs a) {
+  const int64_t e = a.e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.B) return;
   if constexpr (CI >= 0) message_thread_t0<CI, CS>(a, blockIdx.y, e);
   else message_thread_rt<MAXM>(a, blockIdx.y, e);
 }
 __global__ void __launch_bounds__(256) k_message_copy(MsgArgs a) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e = a.e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.B) return;
   message_copy_thread(a, blockIdx.y, e);
 }
@@ -71,7 +74,7 @@ PGBP_HD void walk_thread(const MsgArgs& a, int nmsg, int64_t e) {
 #ifndef PGBP_HOST_EMUL
 template <int P>
 __global__ void __launch_bounds__(PGBP_WALK_THREADS, PGBP_WALK_MINBLOCKS) k_walk(MsgArgs a, int nmsg) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e = a.e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.B) return;
   walk_thread<P>(a, nmsg, e);
 }
@@ -90,12 +93,12 @@ template <int CI, int CS, int MAXM>
 static int launch_message(pgbp_batch* b, const MsgArgs& a, int nmsg) {
 #ifdef PGBP_HOST_EMUL
   for (int m = 0; m < nmsg; m++)
-    for (int64_t e = 0; e < a.B; e++) {
+    for (int64_t e = a.e0; e < a.B; e++) {
       if constexpr (CI >= 0) message_thread_t0<CI, CS>(a, m, e);
       else message_thread_rt<MAXM>(a, m, e);
     }
 #else
-  dim3 grid((unsigned)((a.B + PGBP_MSG_THREADS - 1) / PGBP_MSG_THREADS), (unsigned)nmsg);
+  dim3 grid((unsigned)((a.B - a.e0 + PGBP_MSG_THREADS - 1) / PGBP_MSG_THREADS), (unsigned)nmsg);
   k_message<CI, CS, MAXM><<<grid, PGBP_MSG_THREADS, 0, b->stream>>>(a);
 #endif
   b->launches++;
@@ -107,10 +110,10 @@ static int launch_coop(pgbp_batch* b, const MsgArgs& a, int nmsg) {
 #ifdef PGBP_HOST_EMUL
   // host emulation: the generic body gives bit-identical results (same per-entry update order)
   for (int m = 0; m < nmsg; m++)
-    for (int64_t e = 0; e < a.B; e++) message_thread_rt<MAXM>(a, m, e);
+    for (int64_t e = a.e0; e < a.B; e++) message_thread_rt<MAXM>(a, m, e);
 #else
   constexpr int RPB = 128 / G;
-  dim3 grid((unsigned)((a.B + RPB - 1) / RPB), (unsigned)nmsg);
+  dim3 grid((unsigned)((a.B - a.e0 + RPB - 1) / RPB), (unsigned)nmsg);
   k_message_coop<MAXM, G><<<grid, 128, 0, b->stream>>>(a);
 #endif
   b->launches++;
@@ -125,7 +128,7 @@ static int launch_smem(pgbp_batch* b, const MsgArgs& a, int nmsg, int I, int S) 
 #ifdef PGBP_HOST_EMUL
   (void)I; (void)S;
   for (int m = 0; m < nmsg; m++)
-    for (int64_t e = 0; e < a.B; e++) message_thread_rt<PGBP_MAX_DIM>(a, m, e);
+    for (int64_t e = a.e0; e < a.B; e++) message_thread_rt<PGBP_MAX_DIM>(a, m, e);
 #else
   static bool attr_done = false;  // per instantiation
   static bool attr8_done = false;
@@ -143,7 +146,7 @@ static int launch_smem(pgbp_batch* b, const MsgArgs& a, int nmsg, int I, int S) 
   }
   if (a.ld * 8 >= ((int64_t)1 << 32)) PGBP_FAIL(PGBP_ESTATE, "batch too large for 32-bit row pitch");
   const size_t bytes = smem_block_bytes(I, S);
-  dim3 grid((unsigned)((a.B + 31) / 32), (unsigned)nmsg);
+  dim3 grid((unsigned)((a.B - a.e0 + 31) / 32), (unsigned)nmsg);
   if constexpr (EXACT) {
     if (s8) k_message_smem<MAXI, 8><<<grid, 32, bytes, b->stream>>>(a);
     else k_message_smem<MAXI, 0><<<grid, 32, bytes, b->stream>>>(a);
@@ -158,9 +161,9 @@ static int launch_smem(pgbp_batch* b, const MsgArgs& a, int nmsg, int I, int S) 
 static int launch_copy(pgbp_batch* b, const MsgArgs& a, int nmsg) {
 #ifdef PGBP_HOST_EMUL
   for (int m = 0; m < nmsg; m++)
-    for (int64_t e = 0; e < a.B; e++) message_copy_thread(a, m, e);
+    for (int64_t e = a.e0; e < a.B; e++) message_copy_thread(a, m, e);
 #else
-  dim3 grid((unsigned)((a.B + 255) / 256), (unsigned)nmsg);
+  dim3 grid((unsigned)((a.B - a.e0 + 255) / 256), (unsigned)nmsg);
   k_message_copy<<<grid, 256, 0, b->stream>>>(a);
 #endif
   b->launches++;
@@ -225,7 +228,8 @@ MsgArgs make_args(pgbp_batch* b, uint32_t opts, int32_t ref_base, bool use_done)
   a.calflag = b->calflag;
   a.status = b->status;
   a.done = use_done ? b->done : nullptr;
-  a.B = b->B;
+  a.B = b->chunk_end > 0 ? b->chunk_end : b->B;
+  a.e0 = b->chunk_begin;
   a.ld = b->ld;
   a.opts = opts;
   a.ref_base = ref_base;
@@ -235,9 +239,9 @@ MsgArgs make_args(pgbp_batch* b, uint32_t opts, int32_t ref_base, bool use_done)
 template <int P>
 static int launch_walk(pgbp_batch* b, const MsgArgs& a, int nmsg) {
 #ifdef PGBP_HOST_EMUL
-  for (int64_t e = 0; e < a.B; e++) walk_thread<P>(a, nmsg, e);
+  for (int64_t e = a.e0; e < a.B; e++) walk_thread<P>(a, nmsg, e);
 #else
-  k_walk<P><<<(unsigned)((a.B + PGBP_WALK_THREADS - 1) / PGBP_WALK_THREADS), PGBP_WALK_THREADS, 0, b->stream>>>(a, nmsg);
+  k_walk<P><<<(unsigned)((a.B - a.e0 + PGBP_WALK_THREADS - 1) / PGBP_WALK_THREADS), PGBP_WALK_THREADS, 0, b->stream>>>(a, nmsg);
 #endif
   b->launches++;
   return check_launch("k_walk");
@@ -291,9 +295,9 @@ PGBP_HD void iscal_thread(const uint8_t* calflag, int nd, int64_t ld, const int3
 }
 
 #ifndef PGBP_HOST_EMUL
-__global__ void k_iscal(const uint8_t* calflag, int nd, int64_t B, int64_t ld, const int32_t* status,
+__global__ void k_iscal(const uint8_t* calflag, int nd, int64_t e0, int64_t B, int64_t ld, const int32_t* status,
                         uint8_t* done, int32_t* iscal, int32_t* itertree, int32_t it, int32_t tr, int autostop) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= B) return;
   iscal_thread(calflag, nd, ld, status, done, iscal, itertree, it, tr, autostop, e);
 }
@@ -301,12 +305,13 @@ __global__ void k_iscal(const uint8_t* calflag, int nd, int64_t B, int64_t ld, c
 
 static int launch_iscal(pgbp_batch* b, int it, int tr, int autostop) {
   const int nd = 2 * b->plan->nsepsets;
+  const int64_t e0 = b->chunk_begin, e1 = b->chunk_end > 0 ? b->chunk_end : b->B;
 #ifdef PGBP_HOST_EMUL
-  for (int64_t e = 0; e < b->B; e++)
+  for (int64_t e = e0; e < e1; e++)
     iscal_thread(b->calflag, nd, b->ld, b->status, b->done, b->iscal, b->itertree, it, tr, autostop, e);
 #else
-  k_iscal<<<(unsigned)((b->B + 255) / 256), 256, 0, b->stream>>>(b->calflag, nd, b->B, b->ld, b->status, b->done,
-                                                                  b->iscal, b->itertree, it, tr, autostop);
+  k_iscal<<<(unsigned)((e1 - e0 + 255) / 256), 256, 0, b->stream>>>(b->calflag, nd, e0, e1, b->ld, b->status, b->done,
+                                                                     b->iscal, b->itertree, it, tr, autostop);
 #endif
   b->launches++;
   return check_launch("k_iscal");
@@ -358,26 +363,85 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
   if (b->itertree) PGBP_TRY(dev_memset(b->itertree, 0, sizeof(int32_t) * 2 * (size_t)b->ld, b->stream));
   if (b->iscal) PGBP_TRY(dev_memset(b->iscal, 0, sizeof(int32_t) * (size_t)b->ld, b->stream));
   const uint32_t opts = flags & PGBP_CAL_RESIDNORM;
-  int32_t ref = 0;
-  for (int it = 1; it <= niter; it++) {
-    for (size_t j = 0; j < ids.size(); j++) {
-      const int t = ids[j];
-      const int n = (int)p->trees[t].parent.size();
-      if (use_walk(b, t)) {
-        const bool po = flags & PGBP_CAL_POSTORDER, pr = flags & PGBP_CAL_PREORDER;
-        const int first = po ? 0 : n, count = (po ? n : 0) + (pr ? n : 0);
-        PGBP_TRY(run_walk(b, t, first, count, opts, ref, autostop));
-        ref += count;
-      } else {
-        if (flags & PGBP_CAL_POSTORDER) { PGBP_TRY(run_traversal(b, t, 0, opts, ref, autostop)); ref += n; }
-        if (flags & PGBP_CAL_PREORDER) { PGBP_TRY(run_traversal(b, t, 1, opts, ref, autostop)); ref += n; }
+  // the whole schedule for the element range [b->chunk_begin, b->chunk_end) on b->stream
+  auto enqueue = [&]() -> int {
+    int32_t ref = 0;
+    for (int it = 1; it <= niter; it++) {
+      for (size_t j = 0; j < ids.size(); j++) {
+        const int t = ids[j];
+        const int n = (int)p->trees[t].parent.size();
+        if (use_walk(b, t)) {
+          const bool po = flags & PGBP_CAL_POSTORDER, pr = flags & PGBP_CAL_PREORDER;
+          const int first = po ? 0 : n, count = (po ? n : 0) + (pr ? n : 0);
+          PGBP_TRY(run_walk(b, t, first, count, opts, ref, autostop));
+          ref += count;
+        } else {
+          if (flags & PGBP_CAL_POSTORDER) { PGBP_TRY(run_traversal(b, t, 0, opts, ref, autostop)); ref += n; }
+          if (flags & PGBP_CAL_PREORDER) { PGBP_TRY(run_traversal(b, t, 1, opts, ref, autostop)); ref += n; }
+        }
+        const bool last = (it == niter && j + 1 == ids.size());
+        if (track && (autostop || last || b->want_info)) PGBP_TRY(launch_iscal(b, it, (int)j + 1, autostop));
+        if (ref > (1 << 22)) ref = 0;  // keep the status word positive
       }
-      const bool last = (it == niter && j + 1 == ids.size());
-      if (track && (autostop || last || b->want_info)) PGBP_TRY(launch_iscal(b, it, (int)j + 1, autostop));
-      if (ref > (1 << 22)) ref = 0;  // keep the status word positive
     }
+    return 0;
+  };
+  // how many element chunks?  auto: cut when one launch of the schedule cannot fill the GPU
+  // (threads per launch ~ B x messages per step) and the chunks stay >= 8192 elements
+  int nchunk = 1;
+#ifndef PGBP_HOST_EMUL
+  if (b->pipeline > 1) nchunk = b->pipeline;
+  else if (b->pipeline < 0) {
+    int64_t nmsg = 0, nlaunch = 0;
+    for (int t : ids)
+      for (int dir = 0; dir < 2; dir++) {
+        nmsg += (int64_t)p->trees[t].trav[dir].msgs.size();
+        nlaunch += (int64_t)p->trees[t].trav[dir].groups.size();
+      }
+    const double per_launch = nlaunch ? (double)b->B * (double)nmsg / (double)nlaunch : 1e30;
+    if (per_launch < 1.5e6) nchunk = (int)std::min<int64_t>(4, b->B / 8192);
   }
-  return 0;
+  if (nchunk < 1) nchunk = 1;
+#endif
+  if (nchunk == 1) {
+    b->chunk_begin = 0; b->chunk_end = 0;
+    return enqueue();
+  }
+#ifndef PGBP_HOST_EMUL
+  while ((int)b->pipe_streams.size() < nchunk) {
+    cudaStream_t s;
+    PGBP_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    b->pipe_streams.push_back(s);
+  }
+  while ((int)b->pipe_events.size() < nchunk + 1) {
+    cudaEvent_t ev;
+    PGBP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    b->pipe_events.push_back((void*)ev);
+  }
+  const int64_t csz = ((b->B + nchunk - 1) / nchunk + 127) / 128 * 128;
+  cudaStream_t main_stream = b->stream;
+  PGBP_CUDA(cudaEventRecord((cudaEvent_t)b->pipe_events[0], main_stream));
+  int rc = 0;
+  int used = 0;
+  for (int c = 0; c < nchunk && !rc; c++) {
+    const int64_t e0 = (int64_t)c * csz, e1 = std::min<int64_t>(b->B, e0 + csz);
+    if (e0 >= e1) break;
+    b->stream = b->pipe_streams[c];
+    b->chunk_begin = e0; b->chunk_end = e1;
+    cudaError_t ce = cudaStreamWaitEvent(b->stream, (cudaEvent_t)b->pipe_events[0], 0);
+    if (ce != cudaSuccess) { rc = PGBP_ECUDA; set_error("cudaStreamWaitEvent failed"); break; }
+    rc = enqueue();
+    if (!rc && cudaEventRecord((cudaEvent_t)b->pipe_events[c + 1], b->stream) != cudaSuccess) { rc = PGBP_ECUDA; set_error("cudaEventRecord failed"); }
+    used = c + 1;
+  }
+  b->stream = main_stream;
+  b->chunk_begin = 0; b->chunk_end = 0;
+  for (int c = 0; c < used; c++)  // join (also on error, so that the main stream stays ordered after the chunks)
+    if (cudaStreamWaitEvent(main_stream, (cudaEvent_t)b->pipe_events[c + 1], 0) != cudaSuccess && !rc) { rc = PGBP_ECUDA; set_error("cudaStreamWaitEvent failed"); }
+  return rc;
+#else
+  return enqueue();
+#endif
 }
 
 int32_t pgbp_calibrate(pgbp_batch* b, const int32_t* tree_ids, int32_t ntrees, int32_t niter, uint32_t flags,
@@ -417,6 +481,12 @@ int32_t pgbp_calibrate(pgbp_batch* b, const int32_t* tree_ids, int32_t ntrees, i
 int32_t pgbp_batch_set_walk_mode(pgbp_batch* b, int32_t mode) {
   if (!b || mode < -1 || mode > 1) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
   b->walk_mode = mode;
+  return 0;
+}
+
+int32_t pgbp_batch_set_pipeline(pgbp_batch* b, int32_t nchunks) {
+  if (!b || nchunks == 0 || nchunks < -1 || nchunks > 64) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
+  b->pipeline = nchunks;
   return 0;
 }
 
