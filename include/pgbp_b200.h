@@ -194,7 +194,8 @@ int32_t pgbp_reset_calibration_flags(pgbp_batch* batch, int32_t reset_kl);
  * params: nparamsets records of  ncolors*p*p (rates R_c, column-major)
  *                                + p (root mean mu) + p*p (root variance v):
  *         v == 0 fixed root, any diag(v) == Inf improper, else proper prior.
- * tipdata: ndatasets records of ntips*p  (data[row][trait]).
+ * tipdata: ndatasets records of ntips*p  (data[row][trait]); a NaN (missing value) gives the
+ *          element the status PGBP_STATUS(0x7ffffa, trait) -- assign such data sets on the host.
  * pairing: element e uses (param, data) = ZIP: (min(e,np-1), min(e,nd-1)) with
  *          np, nd in {1, B};  PRODUCT: (e / nd, e % nd) with np*nd == B. */
 #define PGBP_PAIR_ZIP 0

@@ -346,8 +346,8 @@ class BatchedClusterGraphBelief:
             td = np.asarray(tipdata, dtype=float)
             if td.ndim == 2:
                 td = td[None]
-            if np.isnan(td).any():
-                raise ValueError("device factor assignment does not handle missing data")
+            # (missing data = NaN is not handled by the device path: such elements get a non-zero status from
+            # the kernel, status word PGBP_STATUS(0x7ffffa, trait), instead of a host-side scan of the table)
             td = np.ascontiguousarray(td)
             nd = td.shape[0]
         pr = {"zip": L.PAIR_ZIP, "product": L.PAIR_PRODUCT}[pairing]

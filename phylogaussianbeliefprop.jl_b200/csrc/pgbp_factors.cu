@@ -203,6 +203,9 @@ struct AssignBody {
         }
       }
       if (anyfixed) {
+        // missing tip data (NaN) needs trait-level scopes (src/beliefs.jl:505-559): not handled on the
+        // device -- flag the element instead of propagating NaNs silently
+        for (int t = 0; t < p; t++) if (z[t] != z[t]) status_fail(status, e, PGBP_STATUS(0x7ffffa, t + 1));
         double quad = 0.0;
         for (int r = 0; r < p; r++) {
           double s = 0.0;
@@ -362,6 +365,8 @@ struct AssignFast {
         }
       }
       if (anyfixed) {
+#pragma unroll
+        for (int t = 0; t < P; t++) if (z[t] != z[t]) status_fail(gen.status, e, PGBP_STATUS(0x7ffffa, t + 1));
         double quad = 0.0;
 #pragma unroll
         for (int r = 0; r < P; r++) {

@@ -581,3 +581,25 @@ def test_cooperative_kernel_matches_generic_and_oracle(backend, p):
         ob = cgb.belief[j]
         if np.all(np.isfinite(ob.J)) and np.all(np.isfinite(J1[7])):
             assert max(relerr(J1[7], ob.J), relerr(h1[7], ob.h)) <= 1e-9
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_assignfactors_nan_tip_data_sets_status(backend):
+    # device factor assignment needs complete tip data: an element whose table holds a NaN is flagged
+    # (status PGBP_STATUS(0x7ffffa, trait)), the others are unaffected
+    lib = get_lib(backend)
+    p = 2
+    R = np.array([[1.0, 0.3], [0.3, 2.0]])
+    taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
+    rng = np.random.default_rng(9)
+    data = rng.normal(size=(6, 7, p))
+    data[4, 2, 1] = np.nan
+    model = M.MvFullBrownianMotion(R, np.zeros(p))
+    case = Case(GOLD["lazaridis"], "cliquetree", data[0], taxa, model, lib, order_hint=GOLD["lazaridis_cluster_labels"])
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, 6)
+    bt.assignfactors(pgbp_b200.bm_params([R], np.zeros(p)), data)
+    st = bt.status()
+    assert st[4] != 0 and (st[4] >> 8) - 1 == 0x7ffffa and (st[4] & 0xff) == 2
+    assert (np.delete(st, 4) == 0).all()
+    succ, _ = bt.calibrate(case.sched)
+    assert not succ[4] and np.delete(succ, 4).all()
