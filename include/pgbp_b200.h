@@ -150,6 +150,9 @@ int32_t pgbp_batch_set_walk_mode(pgbp_batch* batch, int32_t mode);
  * launches of one range overlap the other ranges' work.  -1 automatic (default: up to 4 chunks of
  * >= 8192 elements when one launch cannot fill the GPU), 1 off.  Results are unaffected. */
 int32_t pgbp_batch_set_pipeline(pgbp_batch* batch, int32_t nchunks);
+/* CUDA-graph replay of calibrate calls: -1 automatic (default: calls of >= 24 launches are captured at
+ * their second occurrence and replayed afterwards), 0 off, 1 always.  Results are unaffected. */
+int32_t pgbp_batch_set_graph_mode(pgbp_batch* batch, int32_t mode);
 /* Kernel for medium message shapes (sender dimension > 12): -1 automatic (= 1 where it fits),
  * 1 shared-memory kernel (one thread per element, factor in shared memory), 4 / 8 cooperative
  * kernel (that many lanes per element for sender dimensions <= 16, 8 above; sender dimension

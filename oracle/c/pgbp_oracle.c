@@ -308,6 +308,60 @@ int pgbpo_factored_energy(const og_graph* G, const double* state, const double* 
 }
 
 /* small SPD inverse + logdet (Cholesky), n <= 16 */
+/* regularizebeliefs_bycluster! (src/clustergraphbeliefs.jl:235-249) with
+ * regularizebeliefs_1clustersepset! (:264-275): clusters in index order; eps_c = max(eps, max|J_c|)
+ * taken once before the neighbour loop; neighbours in increasing cluster index (neighbor_labels).
+ * nbr_off / nbr_sep: CSR list of the sepsets incident to each cluster in that order (pgbpo_neighbours). */
+void pgbpo_neighbours(const og_graph* G, int32_t* nbr_off, int32_t* nbr_sep) {
+  const int nc = G->nclusters, ns = G->nsepsets;
+  int32_t* cnt = (int32_t*)calloc((size_t)nc + 1, sizeof(int32_t));
+  for (int j = 0; j < ns; j++) { cnt[G->sep_a[j]]++; cnt[G->sep_b[j]]++; }
+  nbr_off[0] = 0;
+  for (int c = 0; c < nc; c++) nbr_off[c + 1] = nbr_off[c] + cnt[c];
+  memset(cnt, 0, sizeof(int32_t) * (size_t)nc);
+  for (int j = 0; j < ns; j++) {
+    nbr_sep[nbr_off[G->sep_a[j]] + cnt[G->sep_a[j]]++] = j;
+    nbr_sep[nbr_off[G->sep_b[j]] + cnt[G->sep_b[j]]++] = j;
+  }
+  for (int c = 0; c < nc; c++) {  /* insertion sort by the other end's cluster index */
+    for (int x = nbr_off[c] + 1; x < nbr_off[c + 1]; x++) {
+      const int j = nbr_sep[x];
+      const int key = (G->sep_a[j] == c) ? G->sep_b[j] : G->sep_a[j];
+      int y = x - 1;
+      while (y >= nbr_off[c]) {
+        const int jj = nbr_sep[y];
+        const int k2 = (G->sep_a[jj] == c) ? G->sep_b[jj] : G->sep_a[jj];
+        if (k2 <= key) break;
+        nbr_sep[y + 1] = jj;
+        y--;
+      }
+      nbr_sep[y + 1] = j;
+    }
+  }
+  free(cnt);
+}
+void pgbpo_regularize_bycluster(const og_graph* G, double* state, const int32_t* nbr_off, const int32_t* nbr_sep) {
+  const int nc = G->nclusters;
+  for (int c = 0; c < nc; c++) {
+    const int m = G->dim[c];
+    double* J = state + G->off[c];
+    double eps = EPS;
+    for (int q = 0; q < m * m; q++) { const double a = fabs(J[q]); if (a > eps || a != a) eps = a; }
+    for (int x = nbr_off[c]; x < nbr_off[c + 1]; x++) {
+      const int j = nbr_sep[x];
+      const int s = G->dim[nc + j];
+      if (s == 0) continue;
+      const int side = (G->sep_a[j] == c) ? 0 : 1;
+      const int32_t* up = G->up + G->up_off[2 * j + side];
+      double* Js = state + G->off[nc + j];
+      for (int k = 0; k < s; k++) {
+        J[(size_t)up[k] * m + up[k]] += eps;
+        Js[(size_t)k * s + k] += eps;
+      }
+    }
+  }
+}
+
 static int spd_inv(const double* A, int n, double* inv, double* logdet) {
   double U[16 * 16], e[16];
   memcpy(U, A, sizeof(double) * n * n);
@@ -443,7 +497,7 @@ int pgbpo_run_batch(const og_graph* G, const og_families* F, int ncolors, const 
                     const double* tip, int64_t nd, int pairing, int ntrees, const int32_t* tree_off,
                     const int32_t* tsep, const int32_t* tpar, const int32_t* tchi, int niter, int do_post, int do_pre,
                     int upd, int autostop, int root_belief, int64_t B, double* loglik, int32_t* status, double* fe,
-                    double* state_out, int32_t* iscal_out, int nthreads) {
+                    double* state_out, int32_t* iscal_out, int nthreads, int reg_bycluster) {
   const int nb = G->nclusters + G->nsepsets;
   const int64_t ssize = G->off[nb], rsize = G->roff[2 * G->nsepsets];
   const int p = G->ntraits;
@@ -451,6 +505,12 @@ int pgbpo_run_batch(const og_graph* G, const og_families* F, int ncolors, const 
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
+  int32_t* nbr_off = NULL; int32_t* nbr_sep = NULL;
+  if (reg_bycluster) {
+    nbr_off = (int32_t*)malloc(sizeof(int32_t) * ((size_t)G->nclusters + 1));
+    nbr_sep = (int32_t*)malloc(sizeof(int32_t) * (2 * (size_t)G->nsepsets + 1));
+    pgbpo_neighbours(G, nbr_off, nbr_sep);
+  }
 #pragma omp parallel
   {
     double* state = (double*)malloc(sizeof(double) * (size_t)(ssize > 0 ? ssize : 1));
@@ -465,6 +525,7 @@ int pgbpo_run_batch(const og_graph* G, const og_families* F, int ncolors, const 
       int st = pgbpo_assign_bm(G, F, ncolors, params + ip * plen, tip + id * tlen, state);
       if (st) { status[e] = (0x7ffffd << 8) | (st & 0xff); loglik[e] = NAN; continue; }
       if (factor) memcpy(factor, state, sizeof(double) * (size_t)ssize);
+      if (reg_bycluster) pgbpo_regularize_bycluster(G, state, nbr_off, nbr_sep);
       for (int j = 0; j < G->nsepsets; j++) flags[2 * j] = flags[2 * j + 1] = (G->dim[G->nclusters + j] == 0);
       int32_t isc = 0;
       st = pgbpo_calibrate(G, state, resid, flags, ntrees, tree_off, tsep, tpar, tchi, niter, do_post, do_pre, upd,
@@ -478,5 +539,6 @@ int pgbpo_run_batch(const og_graph* G, const og_families* F, int ncolors, const 
     }
     free(state); free(factor); free(resid); free(flags);
   }
+  free(nbr_off); free(nbr_sep);
   return 0;
 }

@@ -110,7 +110,7 @@ class COracle:
         self.state_size = int(self.off[-1])
 
     def run_batch(self, params, tipdata, ncolors=1, pairing="zip", niter=1, post=True, pre=True, residnorm=True,
-                  auto=False, root_belief=0, want_fe=False, want_state=False, nthreads=0, B=None):
+                  auto=False, root_belief=0, want_fe=False, want_state=False, nthreads=0, B=None, reg_bycluster=False):
         params = np.ascontiguousarray(np.atleast_2d(np.asarray(params, dtype=float)))
         tip = np.ascontiguousarray(np.asarray(tipdata, dtype=float))
         if tip.ndim == 2:
@@ -126,7 +126,7 @@ class COracle:
                                    _p(self.tree_off, i32), _p(self.tsep, i32), _p(self.tpar, i32), _p(self.tchi, i32),
                                    i32(niter), i32(post), i32(pre), i32(residnorm), i32(auto), i32(root_belief), i64(B),
                                    _p(ll, f64), _p(st, i32), None if fe is None else _p(fe, f64),
-                                   None if so is None else _p(so, f64), _p(isc, i32), i32(nthreads))
+                                   None if so is None else _p(so, f64), _p(isc, i32), i32(nthreads), i32(int(reg_bycluster)))
         assert rc == 0
         out = dict(loglik=ll, status=st, iscal=isc.astype(bool))
         if want_fe:

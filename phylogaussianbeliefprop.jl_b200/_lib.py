@@ -55,6 +55,7 @@ SIGNATURES = {
     "pgbp_batch_set_walk_mode": (i32, [vp, i32]),
     "pgbp_batch_set_coop_mode": (i32, [vp, i32]),
     "pgbp_batch_set_pipeline": (i32, [vp, i32]),
+    "pgbp_batch_set_graph_mode": (i32, [vp, i32]),
     "pgbp_set_belief": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
     "pgbp_get_belief": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
     "pgbp_get_factor": (i32, [vp, i32, P(f64), P(f64), P(f64)]),

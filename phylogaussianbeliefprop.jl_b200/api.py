@@ -290,6 +290,10 @@ class BatchedClusterGraphBelief:
         """-1 auto, 1 off, n > 1: calibrate in n element chunks on n streams (small graphs)."""
         self.lib.check(self.lib.pgbp_batch_set_pipeline(self.handle, int(nchunks)))
 
+    def set_graph_mode(self, mode):
+        """-1 auto, 0 off, 1 on: CUDA-graph capture / replay of calibrate calls."""
+        self.lib.check(self.lib.pgbp_batch_set_graph_mode(self.handle, int(mode)))
+
     def set_coop_mode(self, mode):
         """-1 auto, 1 shared-memory kernel, 4 / 8 cooperative lanes, 0 thread-local generic kernel."""
         self.lib.check(self.lib.pgbp_batch_set_coop_mode(self.handle, int(mode)))
@@ -466,6 +470,10 @@ class BatchedClusterGraphBelief:
         base, ld, ns = C.c_void_p(), C.c_int64(), C.c_int64()
         self.lib.check(self.lib.pgbp_device_view(self.handle, C.byref(base), C.byref(ld), C.byref(ns)))
         return base.value, ld.value, ns.value
+
+    def factored_energy_device(self, d_out_ptr):
+        """factored_energy into a device array [3][ld] (energy, entropy, factored energy), enqueue only."""
+        self.lib.check(self.lib.pgbp_factored_energy_device(self.handle, C.c_void_p(int(d_out_ptr))))
 
     def integrate_device(self, j, d_norm_ptr, d_mu_ptr=None):
         self.lib.check(self.lib.pgbp_integrate_device(self.handle, j - 1, C.c_void_p(d_mu_ptr) if d_mu_ptr else None,

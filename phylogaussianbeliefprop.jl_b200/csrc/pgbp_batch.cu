@@ -103,6 +103,23 @@ __global__ void k_soa_to_aos(const double* __restrict__ soa, int64_t ld, const i
 }
 #endif
 
+#ifndef PGBP_HOST_EMUL
+__global__ void k_fill(double* p, int64_t n, double v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+#endif
+static int fill(pgbp_batch* b, double* p, int64_t n, double v) {
+  if (n <= 0) return 0;
+#ifdef PGBP_HOST_EMUL
+  for (int64_t i = 0; i < n; i++) p[i] = v;
+#else
+  k_fill<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(p, n, v);
+#endif
+  b->launches++;
+  return check_launch("k_fill");
+}
+
 int aos_to_soa(pgbp_batch* b, const double* d_aos, int K, const int32_t* d_slot, double* d_soa, int64_t ld) {
   if (K <= 0) return 0;
 #ifdef PGBP_HOST_EMUL
@@ -258,6 +275,7 @@ int32_t pgbp_batch_destroy(pgbp_batch* b) {
   for (auto* p : b->d_msgs) dev_free(p);
   for (auto* p : b->d_walk) dev_free(p);
 #ifndef PGBP_HOST_EMUL
+  for (auto& kv : b->graphs) if (kv.second.exec) cudaGraphExecDestroy((cudaGraphExec_t)kv.second.exec);
   for (auto s : b->pipe_streams) cudaStreamDestroy(s);
   for (auto ev : b->pipe_events) cudaEventDestroy((cudaEvent_t)ev);
   if (b->own_stream) cudaStreamDestroy(b->stream);
@@ -364,7 +382,11 @@ int32_t pgbp_reset_calibration_flags(pgbp_batch* b, int32_t reset_kl) {
   for (int j = 0; j < p->nsepsets; j++)
     if (p->dim[p->nclusters + j] == 0)
       PGBP_TRY(dev_memset(b->calflag + (int64_t)2 * j * b->ld, 1, 2 * (size_t)b->ld, b->stream));
-  (void)reset_kl;
+  if (reset_kl && b->kldiv) {  // kldiv <- -1, 0 for empty messages (src/beliefs.jl:908-922, 975)
+    PGBP_TRY(fill(b, b->kldiv, (int64_t)2 * p->nsepsets * b->ld, -1.0));
+    for (int j = 0; j < p->nsepsets; j++)
+      if (p->dim[p->nclusters + j] == 0) PGBP_TRY(fill(b, b->kldiv + (int64_t)2 * j * b->ld, 2 * b->ld, 0.0));
+  }
   return 0;
 }
 

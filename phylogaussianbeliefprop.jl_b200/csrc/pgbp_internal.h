@@ -2,6 +2,7 @@
 // the batch (device state).  See DESIGN.md for the HBM layout.
 #pragma once
 #include <map>
+#include <string>
 #include <memory>
 #include <vector>
 
@@ -124,6 +125,10 @@ struct pgbp_batch {
   // schedule on its own stream (elements are independent), so that the ramp-up / tail of one chunk's
   // small launches overlaps the others' work.  chunk_begin / chunk_end: range being enqueued.
   int32_t pipeline = -1;  // -1 auto, 1 off, n > 1 chunks
+  // CUDA-graph cache of calibrate! calls, keyed by (schedule, niter, flags, strategy, stream)
+  struct GraphEntry { void* exec = nullptr; int64_t launches = 0; bool failed = false; };
+  std::map<std::string, GraphEntry> graphs;
+  int32_t graph_mode = -1;  // -1 auto (calls with >= 24 launches), 0 off, 1 on
   int64_t chunk_begin = 0, chunk_end = 0;
   std::vector<pgbp_stream_t> pipe_streams;
   std::vector<void*> pipe_events;  // cudaEvent_t: [0] fork, [1..] joins

@@ -378,6 +378,87 @@ PGBP_HD void message_copy_thread(const MsgArgs& a, int msg_index, int64_t e) {
   divide_mult_store(a, md, e, S, GatherJ{st, gat, md.fJ, ld}, GatherH{st, gat + SS, md.fh, ld}, g);
 }
 
+// residual_kldiv! (src/beliefs.jl:1060-1075): KL divergence between the message just sent (the new
+// sepset belief, J0 = J_s) and the sepset belief before the update (J1 = J_s - dJ, h1 = h_s - dh):
+//   ( -tr(J0^-1 dJ) + (mu1-mu0)' J1 (mu1-mu0) + logdet J0 - logdet J1 ) / 2.
+// If either matrix is not positive definite nothing is updated (the reference returns false silently).
+template <int MAXM>
+PGBP_HD void kldiv_thread(const MsgArgs& a, double* kldiv, int msg_index, int64_t e) {
+  constexpr int NA = MAXM * (MAXM + 1) / 2;
+  const MsgDesc md = a.msgs[msg_index];
+  if (a.status[e] != 0) return;
+  if (a.done && a.done[e]) return;
+  const int S = md.s;
+  if (S == 0) return;  // empty sepsets are born calibrated (kldiv = 0, src/beliefs.jl:919-922)
+  const int64_t ld = a.ld;
+  const double* st = a.state + e;
+  const double* rs = a.resid + e;
+  double U0[NA], U1[NA], D[NA], m0[MAXM], m1[MAXM];
+  const int SS = tri(S);
+  for (int q = 0; q < SS; q++) {
+    const double j0 = st[(md.sJ + q) * ld], dj = rs[(md.rJ + q) * ld];
+    U0[q] = j0; D[q] = dj; U1[q] = j0 - dj;
+  }
+  for (int k = 0; k < S; k++) {
+    const double h0 = st[(md.sh + k) * ld];
+    m0[k] = h0; m1[k] = h0 - rs[(md.rh + k) * ld];
+  }
+  double ld0 = 0.0, ld1 = 0.0;
+  for (int pass = 0; pass < 2; pass++) {  // U'U factorisation + mean of both beliefs
+    double* A = pass ? U1 : U0;
+    double* hv = pass ? m1 : m0;
+    double lg = 0.0;
+    for (int k = 0; k < S; k++) {
+      const double d = A[pk(k, k)];
+      if (!(d > 0.0)) return;
+      lg += log(d);
+      const double rinv = 1.0 / sqrt(d);
+      A[pk(k, k)] = rinv;  // 1 / U_kk
+      for (int c = k + 1; c < S; c++) A[pk(k, c)] *= rinv;
+      hv[k] *= rinv;
+      for (int c = k + 1; c < S; c++) {
+        const double akc = A[pk(k, c)];
+        for (int r = k + 1; r <= c; r++) A[pk(r, c)] = nfma(A[pk(k, r)], akc, A[pk(r, c)]);
+        hv[c] = nfma(akc, hv[k], hv[c]);
+      }
+    }
+    for (int k = S - 1; k >= 0; k--) {  // U mu = w
+      double s = hv[k];
+      for (int c = k + 1; c < S; c++) s = nfma(A[pk(k, c)], hv[c], s);
+      hv[k] = s * A[pk(k, k)];
+    }
+    if (pass) ld1 = lg; else ld0 = lg;
+  }
+  // tr(J0^-1 dJ): column k of dJ solved through U0
+  double trace = 0.0, x[MAXM];
+  for (int k = 0; k < S; k++) {
+    for (int r = 0; r < S; r++) x[r] = D[r <= k ? pk(r, k) : pk(k, r)];
+    for (int r = 0; r < S; r++) {  // U0' y = d_k
+      double s = x[r];
+      for (int q = 0; q < r; q++) s = nfma(U0[pk(q, r)], x[q], s);
+      x[r] = s * U0[pk(r, r)];
+    }
+    for (int r = S - 1; r >= k; r--) {  // U0 z = y, down to row k
+      double s = x[r];
+      for (int q = r + 1; q < S; q++) s = nfma(U0[pk(r, q)], x[q], s);
+      x[r] = s * U0[pk(r, r)];
+    }
+    trace += x[k];
+  }
+  // (mu1-mu0)' J1 (mu1-mu0) with J1 = J0 - dJ rebuilt from the inputs (U1 now holds its factor)
+  double quad = 0.0;
+  for (int r = 0; r < S; r++) {
+    double s = 0.0;
+    for (int c = 0; c < S; c++) {
+      const int q = r <= c ? pk(r, c) : pk(c, r);
+      const double j1 = st[(md.sJ + q) * ld] - D[q];
+      s = fma(j1, m1[c] - m0[c], s);
+    }
+    quad = fma(m1[r] - m0[r], s, quad);
+  }
+  kldiv[(int64_t)md.dmsg * ld + e] = 0.5 * (-trace + quad + ld0 - ld1);
+}
+
 // integratebelief (src/beliefupdates.jl:187-200): mu = J^-1 h,
 // norm = g + (m log2pi - logdet J + h'mu)/2; all-zero (h,J) -> (Inf.., g).
 template <int MAXM>

@@ -80,6 +80,13 @@ __global__ void __launch_bounds__(PGBP_WALK_THREADS, PGBP_WALK_MINBLOCKS) k_walk
 }
 
 template <int MAXM>
+__global__ void __launch_bounds__(128) k_kldiv(MsgArgs a, double* kldiv) {
+  const int64_t e = a.e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.B) return;
+  kldiv_thread<MAXM>(a, kldiv, blockIdx.y, e);
+}
+
+template <int MAXM>
 __global__ void __launch_bounds__(128) k_integrate(const double* state, int32_t* status, int64_t B, int64_t ld,
                                                    int64_t jslot, int64_t hslot, int64_t gslot, int M,
                                                    double* mu_soa, double* norm, int64_t ld_out) {
@@ -219,6 +226,35 @@ int launch_group(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGr
   return 0;
 }
 
+// residual_kldiv! for the n messages of a launch group (after their propagate_belief!)
+template <int MAXM>
+static int launch_kldiv_t(pgbp_batch* b, const MsgArgs& a, int n) {
+#ifdef PGBP_HOST_EMUL
+  for (int m = 0; m < n; m++)
+    for (int64_t e = a.e0; e < a.B; e++) kldiv_thread<MAXM>(a, b->kldiv, m, e);
+#else
+  dim3 grid((unsigned)((a.B - a.e0 + 127) / 128), (unsigned)n);
+  k_kldiv<MAXM><<<grid, 128, 0, b->stream>>>(a, b->kldiv);
+#endif
+  b->launches++;
+  return check_launch("k_kldiv");
+}
+static int launch_kldiv(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGroup& g) {
+  int maxs = g.ci == 0 ? PGBP_MAX_DIM : g.cs;  // copy groups mix sepset dimensions
+  if (g.ci > 0) maxs = g.cs;
+  int done = 0;
+  while (done < g.count) {
+    const int n = std::min(g.count - done, 65535);
+    a.msgs = d_msgs + g.first + done;
+    if (maxs <= 4) PGBP_TRY(launch_kldiv_t<4>(b, a, n));
+    else if (maxs <= 12) PGBP_TRY(launch_kldiv_t<12>(b, a, n));
+    else if (maxs <= 32) PGBP_TRY(launch_kldiv_t<32>(b, a, n));
+    else PGBP_TRY(launch_kldiv_t<PGBP_MAX_DIM>(b, a, n));
+    done += n;
+  }
+  return 0;
+}
+
 MsgArgs make_args(pgbp_batch* b, uint32_t opts, int32_t ref_base, bool use_done) {
   MsgArgs a;
   a.msgs = nullptr;
@@ -273,7 +309,10 @@ int run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_t ref_b
   const Traversal& tv = b->plan->trees[tree].trav[dir];
   MsgArgs a = make_args(b, opts, ref_base, use_done);
   const MsgDesc* d = b->d_msgs[2 * tree + dir];
-  for (const LaunchGroup& g : tv.groups) PGBP_TRY(launch_group(b, a, d, g));
+  for (const LaunchGroup& g : tv.groups) {
+    PGBP_TRY(launch_group(b, a, d, g));
+    if (opts & PGBP_CAL_RESIDKLDIV) PGBP_TRY(launch_kldiv(b, a, d, g));
+  }
   return 0;
 }
 
@@ -343,6 +382,14 @@ int integrate_launch(pgbp_batch* b, int belief, double* d_mu_soa, double* d_norm
 
 extern "C" {
 
+}  // extern "C"
+
+// Enqueue one calibrate! call (validated arguments) on b->stream, eagerly.  *nlaunch_est: launches of
+// ONE element chunk.
+static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int32_t niter, uint32_t flags);
+
+extern "C" {
+
 int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntrees, int32_t niter, uint32_t flags) {
   if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
   const pgbp_plan* p = b->plan;
@@ -350,19 +397,76 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
   if (niter < 1) PGBP_FAIL(PGBP_EINVAL, "niter < 1");
   if ((flags & (PGBP_CAL_RESIDNORM | PGBP_CAL_AUTO)) && !b->calflag)
     PGBP_FAIL(PGBP_ESTATE, "residual tracking requested but the batch was created without PGBP_BATCH_RESIDUALS");
-  if (flags & PGBP_CAL_RESIDKLDIV) PGBP_FAIL(PGBP_EINVAL, "update_residualkldiv is not implemented yet");
+  if ((flags & PGBP_CAL_RESIDKLDIV) && !b->kldiv)
+    PGBP_FAIL(PGBP_ESTATE, "update_residualkldiv requested but the batch was created without PGBP_BATCH_RESIDUALS");
   std::vector<int32_t> ids;
   if (tree_ids) ids.assign(tree_ids, tree_ids + ntrees);
   else for (int t = 0; t < (int)p->trees.size(); t++) ids.push_back(t);
   if (ids.empty()) PGBP_FAIL(PGBP_EINVAL, "empty schedule");
   for (int t : ids) if (t < 0 || t >= (int)p->trees.size()) PGBP_FAIL(PGBP_EINVAL, "tree id %d out of range", t);
   PGBP_TRY(set_device(b->device));
+#ifndef PGBP_HOST_EMUL
+  // CUDA graph replay: a calibrate! call is a fixed sequence of launches for fixed (schedule, niter,
+  // flags, kernel strategy); the second call with the same key captures it, later calls replay it
+  // (one cudaGraphLaunch instead of up to tens of thousands of launches for loopy schedules).
+  int64_t nl = 0;
+  for (int t : ids) nl += (int64_t)p->trees[t].trav[0].groups.size() + (int64_t)p->trees[t].trav[1].groups.size();
+  nl *= niter;
+  const bool want_graph = b->graph_mode == 1 || (b->graph_mode < 0 && nl >= 24);
+  if (want_graph) {
+    std::string key;
+    for (int t : ids) key += std::to_string(t) + ",";
+    key += "|" + std::to_string(niter) + "|" + std::to_string(flags) + "|" + std::to_string(b->walk_mode) + "|" +
+           std::to_string(b->coop_mode) + "|" + std::to_string(b->pipeline) + "|" + std::to_string((int)b->want_info) +
+           "|" + std::to_string((uintptr_t)b->stream);
+    auto it = b->graphs.find(key);
+    if (it == b->graphs.end()) {  // first sight: run eagerly (also performs one-time cudaFuncSetAttribute calls)
+      b->graphs[key] = pgbp_batch::GraphEntry{};
+      return calibrate_enqueue(b, ids, niter, flags);
+    }
+    pgbp_batch::GraphEntry& ge = it->second;
+    if (!ge.exec && !ge.failed) {
+      const int64_t l0 = b->launches;
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal);
+      int rc = 0;
+      if (ce == cudaSuccess) {
+        rc = calibrate_enqueue(b, ids, niter, flags);
+        ce = cudaStreamEndCapture(b->stream, &graph);
+      }
+      if (ce == cudaSuccess && !rc && graph) {
+        cudaGraphExec_t ex = nullptr;
+        ce = cudaGraphInstantiate(&ex, graph, 0);
+        if (ce == cudaSuccess) { ge.exec = (void*)ex; ge.launches = b->launches - l0; }
+      }
+      if (graph) cudaGraphDestroy(graph);
+      b->launches = l0;
+      if (!ge.exec) {  // capture not possible (e.g. the caller's stream is already capturing): stay eager
+        ge.failed = true;
+        cudaGetLastError();
+        return calibrate_enqueue(b, ids, niter, flags);
+      }
+    }
+    if (ge.exec) {
+      PGBP_CUDA(cudaGraphLaunch((cudaGraphExec_t)ge.exec, b->stream));
+      b->launches += ge.launches;
+      return 0;
+    }
+  }
+#endif
+  return calibrate_enqueue(b, ids, niter, flags);
+}
+
+}  // extern "C"
+
+static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int32_t niter, uint32_t flags) {
+  const pgbp_plan* p = b->plan;
   const bool autostop = (flags & PGBP_CAL_AUTO) != 0;
   const bool track = (flags & PGBP_CAL_RESIDNORM) != 0;
   if (b->done) PGBP_TRY(dev_memset(b->done, 0, (size_t)b->ld, b->stream));
   if (b->itertree) PGBP_TRY(dev_memset(b->itertree, 0, sizeof(int32_t) * 2 * (size_t)b->ld, b->stream));
   if (b->iscal) PGBP_TRY(dev_memset(b->iscal, 0, sizeof(int32_t) * (size_t)b->ld, b->stream));
-  const uint32_t opts = flags & PGBP_CAL_RESIDNORM;
+  const uint32_t opts = flags & (PGBP_CAL_RESIDNORM | PGBP_CAL_RESIDKLDIV);
   // the whole schedule for the element range [b->chunk_begin, b->chunk_end) on b->stream
   auto enqueue = [&]() -> int {
     int32_t ref = 0;
@@ -370,7 +474,7 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
       for (size_t j = 0; j < ids.size(); j++) {
         const int t = ids[j];
         const int n = (int)p->trees[t].parent.size();
-        if (use_walk(b, t)) {
+        if (use_walk(b, t) && !(opts & PGBP_CAL_RESIDKLDIV)) {
           const bool po = flags & PGBP_CAL_POSTORDER, pr = flags & PGBP_CAL_PREORDER;
           const int first = po ? 0 : n, count = (po ? n : 0) + (pr ? n : 0);
           PGBP_TRY(run_walk(b, t, first, count, opts, ref, autostop));
@@ -399,7 +503,8 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
         nlaunch += (int64_t)p->trees[t].trav[dir].groups.size();
       }
     const double per_launch = nlaunch ? (double)b->B * (double)nmsg / (double)nlaunch : 1e30;
-    if (per_launch < 1.5e6) nchunk = (int)std::min<int64_t>(4, b->B / 8192);
+    // (deep loopy schedules are launch-bound already: more launches would not help them)
+    if (per_launch < 1.5e6 && nlaunch * niter <= 512) nchunk = (int)std::min<int64_t>(4, b->B / 8192);
   }
   if (nchunk < 1) nchunk = 1;
 #endif
@@ -444,6 +549,8 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
 #endif
 }
 
+extern "C" {
+
 int32_t pgbp_calibrate(pgbp_batch* b, const int32_t* tree_ids, int32_t ntrees, int32_t niter, uint32_t flags,
                        int32_t* succ, int32_t* iscal, int32_t* iter_tree) {
   if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
@@ -487,6 +594,12 @@ int32_t pgbp_batch_set_walk_mode(pgbp_batch* b, int32_t mode) {
 int32_t pgbp_batch_set_pipeline(pgbp_batch* b, int32_t nchunks) {
   if (!b || nchunks == 0 || nchunks < -1 || nchunks > 64) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
   b->pipeline = nchunks;
+  return 0;
+}
+
+int32_t pgbp_batch_set_graph_mode(pgbp_batch* b, int32_t mode) {
+  if (!b || mode < -1 || mode > 1) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
+  b->graph_mode = mode;
   return 0;
 }
 

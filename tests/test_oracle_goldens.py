@@ -345,3 +345,23 @@ def test_fixed_theta_optimiser_endpoints():
     net, ct, b, ctb = setup(NETSTR_NAMED, "cliquetree", tbl, taxa, m)
     bp.propagate_1traversal_postorder(ctb, *spt)
     assert bp.integratebelief_cgb(ctb, spt[2][0])[1] == pytest.approx(-14.39029465611705, rel=1e-9)
+
+
+def test_muller_2022_structure_goldens():
+    # docs/src/man/clustergraphs.md:40-41 (network), :52-56 (clique tree), :101-117 (Bethe):
+    # pins the Newick reader / preorder / moralisation / min-fill / Bethe construction at 801 nodes
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "muller_2022.json")))
+    net = readnewick(g["newick"])
+    assert len(net.nodes) == g["nnodes"] and len(net.edges) == g["nedges"]
+    assert sum(n.leaf for n in net.nodes) == g["ntips"] and sum(n.hybrid for n in net.nodes) == g["nhybrids"]
+    fg = CG.clustergraph(net, "bethe")
+    assert len(fg.labels) == g["bethe"]["nclusters"] and fg.ne() == g["bethe"]["nsepsets"]
+    sizes = [len(fg.vdata[l][1]) for l in fg.labels]
+    assert max(sizes) == g["bethe"]["max_cluster_size"] and abs(np.mean(sizes) - g["bethe"]["mean_cluster_size"]) < 1e-6
+    ct = CG.clustergraph(net, "cliquetree")
+    assert len(ct.labels) == g["cliquetree"]["nclusters"] and ct.ne() == g["cliquetree"]["nsepsets"]
+    sizes = [len(ct.vdata[l][1]) for l in ct.labels]
+    assert min(sizes) == 2 and max(sizes) == 54  # docs/src/man/clustergraphs.md:73-89
+    sched = CG.spanningtrees_clusterlist(fg, net.vec_node)
+    covered = {frozenset((a, b)) for spt in sched for a, b in zip(spt[2], spt[3])}
+    assert len(covered) == fg.ne()  # every edge of the loopy graph is on some spanning tree

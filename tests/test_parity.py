@@ -603,3 +603,44 @@ def test_assignfactors_nan_tip_data_sets_status(backend):
     assert (np.delete(st, 4) == 0).all()
     succ, _ = bt.calibrate(case.sched)
     assert not succ[4] and np.delete(succ, 4).all()
+
+
+# ------------------------------------------------------------------ residual KL divergence (update_residualkldiv)
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("p", [1, 3])
+def test_residual_kldiv_matches_oracle(backend, p):
+    # residual_kldiv! (src/beliefs.jl:1060-1075; oracle pinned by the golden 1.215973 of
+    # test/test_calibration.jl:13-33): KL divergence of every directed message after 1 and 2
+    # calibrations; -1 where a sepset belief is not yet proper (left untouched), 0 for empty sepsets
+    lib = get_lib(backend)
+    rng = np.random.default_rng(400 + p)
+    A = rng.normal(size=(p, p))
+    R = A @ A.T / p + 0.1 * np.eye(p)
+    taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
+    B = 4
+    data = rng.normal(size=(B, 7, p))
+    model = M.MvFullBrownianMotion(R, np.zeros(p))
+    case = Case(GOLD["lazaridis"], "cliquetree", data[0], taxa, model, lib, order_hint=GOLD["lazaridis_cluster_labels"])
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+    bt.assignfactors(pgbp_b200.bm_params([R], np.zeros(p)), data)
+    cgbs = [case.oracle_cgb(tbl=data[e]) for e in range(B)]
+    labs = case.cg.labels
+    for rnd in range(2):
+        succ, _ = bt.calibrate(case.sched, update_residualkldiv=True)
+        assert succ.all()
+        for c in cgbs:
+            OBP.calibrate(c, case.sched, update_residualkldiv=True)
+        for j in range(case.plan.nsepsets):
+            a, b_ = case.plan.sepset_clusters[j]
+            for to, frm in ((a, b_), (b_, a)):
+                kl = bt.get_residual(case.nclusters + 1 + j, to + 1)[3]
+                for e in range(B):
+                    ref = cgbs[e].messageresidual[(labs[to], labs[frm])].kldiv
+                    if ref in (-1.0, 0.0) or abs(ref) < 1e-12:
+                        assert abs(kl[e] - ref) <= 1e-9, (rnd, j, to, e, kl[e], ref)
+                    else:
+                        assert abs(kl[e] / ref - 1) <= 1e-7, (rnd, j, to, e, kl[e], ref)
+    # second calibration of a clique tree changes nothing: all KL divergences ~ 0
+    kls = np.array([bt.get_residual(case.nclusters + 1 + j, case.plan.sepset_clusters[j][0] + 1)[3]
+                    for j in range(case.plan.nsepsets)])
+    assert np.all(np.abs(kls) <= 1e-5)

@@ -42,7 +42,7 @@ def dump(name, netstr, method, p, taxa, order_hint=None, **kw):
         a, b_ = lab2idx[s.metadata[0]], lab2idx[s.metadata[1]]
         sc.append([a, b_])
         up.append([[int(x) for x in OB.scopeindex(s, b[a])], [int(x) for x in OB.scopeindex(s, b[b_])]])
-    out = dict(name=name, network=netstr, method=method, ntraits=p, taxa=taxa, nclusters=nc,
+    out = dict(name=name, network=netstr if len(netstr) < 2000 else "(see tests/golden)", method=method, ntraits=p, taxa=taxa, nclusters=nc,
                cluster_labels=cg.labels, belief_dim=[x.dimension() for x in b], sepset_clusters=sc, upind=up,
                trees=[[[j - 1 for j in t[2]], [j - 1 for j in t[3]]] for t in sched], families=fam,
                root_cluster=sched[0][2][0] - 1,
@@ -59,3 +59,7 @@ if __name__ == "__main__":
     dump("lazaridis_cliquetree_p3", GOLD["lazaridis"], "cliquetree", 3,
          ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"],
          order_hint=GOLD["lazaridis_cluster_labels"])
+    # BASELINE configs[2]: muller_2022 (801 nodes, 40 tips, 361 hybrids), Bethe cluster graph
+    # (1557 clusters / 1914 sepsets), univariate, spanningtrees_clusterlist schedule (2 trees)
+    MULLER = json.load(open(os.path.join(ROOT, "tests", "golden", "muller_2022.json")))
+    dump("muller_bethe_p1", MULLER["newick"], "bethe", 1, None)
