@@ -351,6 +351,8 @@ def run_gpu(args):
         bt.set_pipeline(args.pipeline)
     if args.graph is not None:
         bt.set_graph_mode(args.graph)
+    if args.tilewalk is not None:
+        bt.set_tilewalk_mode(args.tilewalk)
     root = d["root_cluster"] + 1
     bytes_unit, flops_unit = w.cost(plan)
     nmsg = {"c2": 2 * len(d["trees"][0][0]), "c4": len(d["trees"][0][0])}.get(w.key) or 4 * len(d["trees"][0][0]) * w.niter
@@ -602,6 +604,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--pipeline", type=int, default=None, help="element chunks of a calibration (-1 auto, 1 off)")
+    ap.add_argument("--tilewalk", type=int, default=None, help="tile-walk kernel (-1 auto, 0 off, 1 on)")
     ap.add_argument("--graph", type=int, default=None, help="CUDA-graph replay of calibrate (-1 auto, 0 off, 1 on)")
     ap.add_argument("--walk", type=int, default=None, help="kernel strategy override: 0 level-parallel, 1 walk kernel")
     args = ap.parse_args()

@@ -150,6 +150,11 @@ int32_t pgbp_batch_set_walk_mode(pgbp_batch* batch, int32_t mode);
  * launches of one range overlap the other ranges' work.  -1 automatic (default: up to 4 chunks of
  * >= 8192 elements when one launch cannot fill the GPU), 1 off.  Results are unaffected. */
 int32_t pgbp_batch_set_pipeline(pgbp_batch* batch, int32_t nchunks);
+/* Tile-walk kernel for deep schedules of tiny messages (sender dimension <= 4; loopy BP on Bethe-type
+ * graphs): one launch per traversal, a block walks all steps for its 32 elements with a block barrier
+ * between steps.  -1 automatic (default; currently = off: slower than per-step launches when some
+ * steps are wide), 0 off, 1 on wherever applicable.  Results are unaffected. */
+int32_t pgbp_batch_set_tilewalk_mode(pgbp_batch* batch, int32_t mode);
 /* CUDA-graph replay of calibrate calls: -1 automatic (default: calls of >= 24 launches are captured at
  * their second occurrence and replayed afterwards), 0 off, 1 always.  Results are unaffected. */
 int32_t pgbp_batch_set_graph_mode(pgbp_batch* batch, int32_t mode);
@@ -239,6 +244,9 @@ int32_t pgbp_propagate(pgbp_batch* batch, int32_t from_cluster, int32_t sepset, 
  * mu [B][m] (may be NULL), norm [B].  Elements whose Cholesky fails get NaN and a status. */
 int32_t pgbp_integrate(pgbp_batch* batch, int32_t belief, double* mu, double* norm);
 int32_t pgbp_integrate_device(pgbp_batch* batch, int32_t belief, double* d_mu_soa, double* d_norm);
+/* same + the conditional covariance inv(J): cov [B][m][m] -- the moments calibrate_exact_cliquetree!
+ * takes from every cluster (integratebelief! + inv(b.J), src/calibration.jl:462-463) */
+int32_t pgbp_integrate_cov(pgbp_batch* batch, int32_t belief, double* mu, double* cov, double* norm);
 
 /* factored_energy (src/score.jl:151-154,162-182): out [B][3] =
  * (average energy, approximate entropy, factored energy) */

@@ -279,6 +279,15 @@ function PGBP.integratebelief!(b::BatchedClusterGraphBelief, j::Integer)
     return μ, nrm
 end
 
+"`integratebelief!` + `inv(J)`: `(μ (m,B), cov (m,m,B), norm (B))`, the conditional moments of calibrate_exact_cliquetree!"
+function integratebelief_cov!(b::BatchedClusterGraphBelief, j::Integer)
+    m = dimension(b, j)
+    μ = Matrix{Float64}(undef, m, b.B); cov = Array{Float64}(undef, m, m, b.B); nrm = Vector{Float64}(undef, b.B)
+    GC.@preserve μ cov nrm check(ccall((:pgbp_integrate_cov, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                                       b.handle, j - 1, μ, cov, nrm))
+    return μ, cov, nrm
+end
+
 "`factored_energy(beliefs)` -> (3,B) matrix: average energy, approximate entropy, factored energy (src/score.jl:151)"
 function PGBP.factored_energy(b::BatchedClusterGraphBelief)
     out = Matrix{Float64}(undef, 3, b.B)

@@ -56,6 +56,7 @@ SIGNATURES = {
     "pgbp_batch_set_coop_mode": (i32, [vp, i32]),
     "pgbp_batch_set_pipeline": (i32, [vp, i32]),
     "pgbp_batch_set_graph_mode": (i32, [vp, i32]),
+    "pgbp_batch_set_tilewalk_mode": (i32, [vp, i32]),
     "pgbp_set_belief": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
     "pgbp_get_belief": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
     "pgbp_get_factor": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
@@ -73,6 +74,7 @@ SIGNATURES = {
     "pgbp_propagate": (i32, [vp, i32, i32, i32, u32]),
     "pgbp_integrate": (i32, [vp, i32, P(f64), P(f64)]),
     "pgbp_integrate_device": (i32, [vp, i32, vp, vp]),
+    "pgbp_integrate_cov": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
     "pgbp_factored_energy": (i32, [vp, P(f64)]),
     "pgbp_factored_energy_device": (i32, [vp, vp]),
     "pgbp_regularize_bycluster": (i32, [vp]),

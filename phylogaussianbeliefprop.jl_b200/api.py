@@ -290,6 +290,10 @@ class BatchedClusterGraphBelief:
         """-1 auto, 1 off, n > 1: calibrate in n element chunks on n streams (small graphs)."""
         self.lib.check(self.lib.pgbp_batch_set_pipeline(self.handle, int(nchunks)))
 
+    def set_tilewalk_mode(self, mode):
+        """-1 auto, 0 off, 1 on: one launch per traversal for deep schedules of tiny messages."""
+        self.lib.check(self.lib.pgbp_batch_set_tilewalk_mode(self.handle, int(mode)))
+
     def set_graph_mode(self, mode):
         """-1 auto, 0 off, 1 on: CUDA-graph capture / replay of calibrate calls."""
         self.lib.check(self.lib.pgbp_batch_set_graph_mode(self.handle, int(mode)))
@@ -432,6 +436,14 @@ class BatchedClusterGraphBelief:
         norm = np.empty(self.B)
         self.lib.check(self.lib.pgbp_integrate(self.handle, j - 1, _fptr(mu), _fptr(norm)))
         return mu, norm
+
+    def integratebelief_cov(self, j):
+        """integratebelief!(beliefs, j) + inv(J) -> (mu[B,m], cov[B,m,m], norm[B]): the conditional moments
+        used by calibrate_exact_cliquetree! (src/calibration.jl:462-463)."""
+        m = self.dimension(j)
+        mu = np.empty((self.B, m)); cov = np.empty((self.B, m, m)); norm = np.empty(self.B)
+        self.lib.check(self.lib.pgbp_integrate_cov(self.handle, j - 1, _fptr(mu), _fptr(cov), _fptr(norm)))
+        return mu, cov, norm
 
     def factored_energy(self):
         """-> [B,3] = (average energy, approximate entropy, factored energy)."""

@@ -253,6 +253,13 @@ int32_t pgbp_batch_create(const pgbp_plan* plan, int64_t B, int32_t device, uint
       PGBP_TRY(alloc(b.get(), &b->d_msgs[2 * t + dir], std::max<size_t>(1, tv.msgs.size())));
       PGBP_TRY(h2d(b->d_msgs[2 * t + dir], tv.msgs.data(), tv.msgs.size() * sizeof(MsgDesc), b->stream));
     }
+  b->d_step_off.assign(2 * plan->trees.size(), nullptr);
+  for (size_t t = 0; t < plan->trees.size(); t++)
+    for (int dir = 0; dir < 2; dir++) {
+      const auto& so = plan->trees[t].trav[dir].step_off;
+      PGBP_TRY(alloc(b.get(), &b->d_step_off[2 * t + dir], std::max<size_t>(1, so.size())));
+      PGBP_TRY(h2d(b->d_step_off[2 * t + dir], so.data(), so.size() * sizeof(int32_t), b->stream));
+    }
   b->d_walk.assign(plan->trees.size(), nullptr);
   for (size_t t = 0; t < plan->trees.size(); t++) {
     const auto& w = plan->trees[t].walk;
@@ -274,6 +281,7 @@ int32_t pgbp_batch_destroy(pgbp_batch* b) {
   dev_free(b->d_tab); dev_free(b->d_one); dev_free(b->scratch); dev_free(b->d_slot); free_tables(b);
   for (auto* p : b->d_msgs) dev_free(p);
   for (auto* p : b->d_walk) dev_free(p);
+  for (auto* p : b->d_step_off) dev_free(p);
 #ifndef PGBP_HOST_EMUL
   for (auto& kv : b->graphs) if (kv.second.exec) cudaGraphExecDestroy((cudaGraphExec_t)kv.second.exec);
   for (auto s : b->pipe_streams) cudaStreamDestroy(s);

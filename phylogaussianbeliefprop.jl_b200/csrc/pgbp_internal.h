@@ -41,6 +41,8 @@ struct Traversal {
   std::vector<MsgDesc> msgs;          // execution order
   std::vector<int32_t> step_of_msg;   // step of msgs[i]
   std::vector<LaunchGroup> groups;    // launch order
+  std::vector<int32_t> step_off;      // [nsteps+1] range of msgs of each step (msgs are sorted by step)
+  int32_t max_mF = 0;                 // largest sender dimension
   int32_t nsteps = 0;
   double bytes_noresid = 0, bytes_resid = 0, flops = 0;  // algorithmic, per element
 };
@@ -112,6 +114,8 @@ struct pgbp_batch {
   // per-tree, per-direction descriptor arrays on the device
   std::vector<pgbp::MsgDesc*> d_msgs;  // index 2*tree+dir
   std::vector<pgbp::MsgDesc*> d_walk;  // per tree, reference order (walk kernel)
+  std::vector<int32_t*> d_step_off;    // index 2*tree+dir (tile-walk kernel)
+  int32_t tilewalk_mode = -1;          // -1 auto, 0 off, 1 on (where applicable)
   pgbp::MsgDesc* d_one = nullptr;      // scratch descriptor for pgbp_propagate
   double* scratch = nullptr;           // staging for host<->device transposes / outputs
   size_t scratch_bytes = 0;

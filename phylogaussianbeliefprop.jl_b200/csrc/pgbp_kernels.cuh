@@ -463,7 +463,8 @@ PGBP_HD void kldiv_thread(const MsgArgs& a, double* kldiv, int msg_index, int64_
 // norm = g + (m log2pi - logdet J + h'mu)/2; all-zero (h,J) -> (Inf.., g).
 template <int MAXM>
 PGBP_HD void integrate_thread(const double* state, int32_t* status, int64_t ld, int64_t e, int64_t jslot,
-                              int64_t hslot, int64_t gslot, int M, double* mu_soa, double* norm, int64_t ld_out) {
+                              int64_t hslot, int64_t gslot, int M, double* mu_soa, double* norm, int64_t ld_out,
+                              double* cov_soa = nullptr) {
   constexpr int NA = MAXM * (MAXM + 1) / 2;
   double A[NA > 0 ? NA : 1];
   double hv[MAXM > 0 ? MAXM : 1];
@@ -516,6 +517,24 @@ PGBP_HD void integrate_thread(const double* state, int32_t* status, int64_t ld, 
       hv[k] = s * A[pk(k, k)];
       mu_soa[k * ld_out + e] = hv[k];
     }
+  }
+  if (cov_soa) {
+    // inv(J) = V V' with V = U^-1 (the conditional covariance that calibrate_exact_cliquetree! reads with
+    // inv(b.J), src/calibration.jl:463).  In place: A holds U with 1/U_kk on the diagonal; columns
+    // descending, rows descending, so column c only reads U entries of columns < c and V of column c.
+    for (int c = M - 1; c >= 0; c--) {
+      for (int r = c - 1; r >= 0; r--) {
+        double s = A[pk(r, c)] * A[pk(c, c)];
+        for (int k = r + 1; k < c; k++) s = fma(A[pk(r, k)], A[pk(k, c)], s);
+        A[pk(r, c)] = -s * A[pk(r, r)];
+      }
+    }
+    for (int j = 0; j < M; j++)
+      for (int i = 0; i <= j; i++) {
+        double s = 0.0;
+        for (int k = j; k < M; k++) s = fma(A[pk(i, k)], A[pk(j, k)], s);
+        cov_soa[(int64_t)pk(i, j) * ld_out + e] = s;
+      }
   }
 }
 

@@ -11,7 +11,7 @@ int batch_need_scratch(pgbp_batch* b, size_t bytes);
 // means identity; slot[k] < 0 skips column k.  d_slot is a DEVICE table.
 int aos_to_soa(pgbp_batch* b, const double* d_aos, int K, const int32_t* d_slot, double* d_soa, int64_t ld);
 int soa_to_aos(pgbp_batch* b, const double* d_soa, int64_t ld, double* d_aos, int K, const int32_t* d_slot = nullptr);
-int integrate_launch(pgbp_batch* b, int belief, double* d_mu_soa, double* d_norm, int64_t ld_out);
+int integrate_launch(pgbp_batch* b, int belief, double* d_mu_soa, double* d_norm, int64_t ld_out, double* d_cov_soa = nullptr);
 int launch_group(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGroup& g);
 void free_tables(pgbp_batch* b);
 MsgArgs make_args(pgbp_batch* b, uint32_t opts, int32_t ref_base, bool use_done);

@@ -137,6 +137,11 @@ static int build_traversal(pgbp_plan* p, const std::vector<int32_t>& from, const
     tv->groups.back().count++;
   }
   tv->nsteps = nsteps;
+  tv->step_off.assign(nsteps + 1, 0);
+  for (int k = 0; k < n; k++) tv->step_off[tv->step_of_msg[k] + 1]++;
+  for (int st = 0; st < nsteps; st++) tv->step_off[st + 1] += tv->step_off[st];
+  tv->max_mF = 0;
+  for (int k = 0; k < n; k++) tv->max_mF = std::max(tv->max_mF, tv->msgs[k].mF);
   return 0;
 }
 

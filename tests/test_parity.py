@@ -644,3 +644,72 @@ def test_residual_kldiv_matches_oracle(backend, p):
     kls = np.array([bt.get_residual(case.nclusters + 1 + j, case.plan.sepset_clusters[j][0] + 1)[3]
                     for j in range(case.plan.nsepsets)])
     assert np.all(np.abs(kls) <= 1e-5)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_tilewalk_kernel_matches_level_parallel(backend):
+    # one launch per traversal (block barrier between steps) == one launch per step and shape, bit for bit,
+    # on a loopy Bethe graph with univariate traits (sender dimension <= 3), incl. auto-stop and a failure
+    lib = get_lib(backend)
+    taxa = ["A", "B", "C", "D"]
+    rng = np.random.default_rng(3)
+    B = 45
+    data = rng.normal(size=(B, 4, 1))
+    model = M.UnivariateBrownianMotion(1.0, 0.0)
+    case = Case(GOLD["netstr_unnamed"], "bethe", data[0], taxa, model, lib)
+    out = {}
+    for mode in (0, 1):
+        bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+        bt.set_tilewalk_mode(mode)
+        bt.assignfactors(pgbp_b200.bm_params([1.0], [0.0]), data)
+        bt.regularizebeliefs_bycluster()
+        jbig = next(j for j in range(1, case.nclusters + 1) if case.b[j - 1].dimension() >= 2)
+        J, h, g = bt.get_belief(jbig)
+        J[5] = -np.eye(J.shape[1])  # element 5: indefinite cluster -> failure status
+        bt.set_belief(jbig, J, h, g)
+        bt.launch_count(reset=True)
+        succ, iscal, info = bt.calibrate(case.sched, 20, auto=True, info=True)
+        nl = bt.launch_count()
+        out[mode] = (succ, iscal, info, bt.status(), [bt.get_belief(j) for j in range(1, len(case.b) + 1)], nl,
+                     bt.factored_energy())
+    assert out[1][5] < out[0][5]
+    for k in range(4):
+        assert np.array_equal(out[0][k], out[1][k])
+    ok = np.arange(B) != 5
+    assert out[0][3][5] != 0 and out[0][0][ok].all() and out[0][1][ok].all()
+    for (J0, h0, g0), (J1, h1, g1) in zip(out[0][4], out[1][4]):
+        assert np.array_equal(J0[ok], J1[ok]) and np.array_equal(h0[ok], h1[ok]) and np.array_equal(g0[ok], g1[ok])
+    assert np.array_equal(out[0][6][ok], out[1][6][ok])
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_integratebelief_with_covariance(backend):
+    # conditional moments of every belief after calibration: mean, inv(J), norm (the inputs of
+    # calibrate_exact_cliquetree!, src/calibration.jl:462-463; test/test_exactBM.jl:26-52 checks them
+    # against PhylogeneticEM through the same two calls)
+    lib = get_lib(backend)
+    p = 2
+    R = np.array([[2.0, 0.5], [0.5, 1.0]])
+    taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
+    rng = np.random.default_rng(11)
+    B = 3
+    data = rng.normal(size=(B, 7, p))
+    model = M.MvFullBrownianMotion(R, np.zeros(p), np.diag([np.inf, np.inf]))
+    case = Case(GOLD["lazaridis"], "cliquetree", data[0], taxa, model, lib, order_hint=GOLD["lazaridis_cluster_labels"])
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+    bt.assignfactors(pgbp_b200.bm_params([R], np.zeros(p), np.diag([np.inf, np.inf])), data)
+    assert bt.calibrate(case.sched)[0].all()
+    cgbs = [case.oracle_cgb(tbl=data[e]) for e in range(B)]
+    for c in cgbs:
+        OBP.calibrate(c, case.sched)
+    for j in range(1, len(case.b) + 1):
+        if bt.dimension(j) == 0:
+            continue
+        mu, cov, norm = bt.integratebelief_cov(j)
+        mu2, norm2 = bt.integratebelief(j)
+        assert np.array_equal(mu, mu2) and np.array_equal(norm, norm2)
+        for e in range(B):
+            ob = cgbs[e].belief[j - 1]
+            assert relerr(cov[e], np.linalg.inv(ob.J)) <= 1e-9
+            assert relerr(mu[e], np.linalg.solve(ob.J, ob.h)) <= 1e-9
+            assert np.allclose(cov[e], cov[e].T, rtol=0, atol=0)
