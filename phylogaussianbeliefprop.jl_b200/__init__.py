@@ -15,6 +15,8 @@ from .api import (BatchedClusterGraphBelief, ClusterGraphPlan, assignfactors, bm
                   propagate_belief, regularizebeliefs_bycluster, regularizebeliefs_bynodesubtree,
                   regularizebeliefs_onschedule, scopeindex)
 
+from .drivers import calibrate_exact_cliquetree, calibrate_optimize_cliquetree
+
 # spellings used by the reference revision named in BASELINE.json's north_star
 init_beliefs_allocate = ClusterGraphPlan.from_beliefs
 __all__ = [n for n in dir() if not n.startswith("_")]

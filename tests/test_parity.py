@@ -713,3 +713,56 @@ def test_integratebelief_with_covariance(backend):
             assert relerr(cov[e], np.linalg.inv(ob.J)) <= 1e-9
             assert relerr(mu[e], np.linalg.solve(ob.J, ob.h)) <= 1e-9
             assert np.allclose(cov[e], cov[e].T, rtol=0, atol=0)
+
+
+# ------------------------------------------------------------------ exact REML driver (calibrate_exact_cliquetree!)
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_calibrate_exact_cliquetree_goldens(backend):
+    # test/test_exactBM.jl:168-226: level-1 network, 4 taxa; univariate y and bivariate (x, y)
+    lib = get_lib(backend)
+    netstr = "(((A:4.0,((B1:1.0,B2:1.0)i6:0.6)#H5:1.1::0.9)i4:0.5,(#H5:2.0::0.1,C:0.1)i2:1.0)i1:3.0);"
+    taxa = ["A", "B1", "B2", "C"]
+    x = np.array([10.0, 10.0, 2.0, 0.0])
+    y = np.array([1.0, 0.9, 1.0, -1.0])
+
+    def plans(p):
+        tbl = np.zeros((4, p))
+        m_imp = M.MvFullBrownianMotion(np.eye(p), np.zeros(p), np.diag([np.inf] * p))
+        m_fix = M.MvFullBrownianMotion(np.eye(p), np.zeros(p))
+        c1 = Case(netstr, "cliquetree", tbl, taxa, m_imp, lib, schedule="spanningtree")
+        c2 = Case(netstr, "cliquetree", tbl, taxa, m_fix, lib, schedule="spanningtree")
+        return c1, c2
+
+    c1, c2 = plans(1)
+    data = np.stack([y[:, None], (2 * y + 1)[:, None]])  # second data set: affine image of the first
+    s2, mu, ll = pgbp_b200.calibrate_exact_cliquetree(c1.plan, c2.plan, c1.sched[0], c2.sched[0], data)
+    assert abs(ll[0] / -5.250084678427689 - 1) <= 1e-9
+    assert abs(mu[0, 0] / -0.260008715071627 - 1) <= 1e-9
+    assert abs(s2[0, 0, 0] / 0.4714735834478194 - 1) <= 1e-9
+    # equivariance: y -> 2y + 1 gives mu -> 2 mu + 1, sigma2 -> 4 sigma2, loglik -> loglik - n log 2 (n = 4 tips)
+    assert abs(mu[1, 0] - (2 * mu[0, 0] + 1)) <= 1e-9 and abs(s2[1, 0, 0] / (4 * s2[0, 0, 0]) - 1) <= 1e-9
+    assert abs((ll[1] - ll[0]) / (-4 * np.log(2)) - 1) <= 1e-8
+    c1, c2 = plans(2)
+    s2, mu, ll = pgbp_b200.calibrate_exact_cliquetree(c1.plan, c2.plan, c1.sched[0], c2.sched[0], np.stack([x, y], axis=1)[None])
+    assert np.allclose(mu[0], [2.791001688545128, -0.260008715071627], rtol=1e-9)
+    assert np.allclose(s2[0], [[17.93326111121198, 1.6089749098736517], [1.6089749098736517, 0.4714735834478195]], rtol=1e-9)
+    assert np.isfinite(ll[0])
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_calibrate_optimize_cliquetree_goldens(backend):
+    # ML fit of UnivariateBrownianMotion by L-BFGS with a batched finite-difference stencil per iteration:
+    # test/test_calibration.jl:242-244 (4-taxon level-1 network) and test/test_optimization.jl:16-18 (mateescu)
+    lib = get_lib(backend)
+    netstr = "(((A:4.0,((B1:1.0,B2:1.0)i6:0.6)#H5:1.1::0.9)i4:0.5,(#H5:2.0::0.1,C:0.1)i2:1.0)i1:3.0);"
+    taxa = ["A", "B1", "B2", "C"]
+    y = np.array([1.0, 0.9, 1.0, -1.0])[:, None]
+    c = Case(netstr, "cliquetree", y, taxa, M.UnivariateBrownianMotion(1.0, -2.0), lib, schedule="spanningtree")
+    theta, ll, res = pgbp_b200.calibrate_optimize_cliquetree(c.plan, c.sched[0], y, start=(1.0, -2.0))
+    assert abs(ll / -5.174720533524127 - 1) <= 1e-9
+    assert abs(theta[1] / -0.26000871507162693 - 1) <= 1e-5 and abs(theta[0] / 0.35360518758586457 - 1) <= 1e-5
+    yd = np.array([1.0, -1.0])[:, None]  # tips d, g
+    c = Case(GOLD["mateescu"], "cliquetree", yd, ["d", "g"], M.UnivariateBrownianMotion(1.0, 0.0), lib, schedule="spanningtree")
+    theta, ll, res = pgbp_b200.calibrate_optimize_cliquetree(c.plan, c.sched[0], yd, start=(1.0, 0.0), maxiter=60)
+    assert abs(ll / -3.2763180687070053 - 1) <= 1e-9
+    assert abs(theta[0] / 0.5932930079336234 - 1) <= 1e-4 and abs(theta[1] / -0.07534357691418593 - 1) <= 1e-4
