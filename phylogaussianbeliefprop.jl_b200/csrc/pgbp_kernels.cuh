@@ -79,6 +79,15 @@ PGBP_HD void store_flag(const MsgArgs& a, int dmsg, int64_t e, int S, double max
 // value and the receiver's old value are all loaded first (3*CHUNK independent
 // loads in flight per thread), then  new = J_KK - z_r.z_c,  delta = new - old,
 // and the three stores.  h and g follow the same pattern.
+// L2 prefetch hint (device only): starts the HBM -> L2 transfer of a line that is read later
+PGBP_HD void l2_prefetch(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 // slot k of this element: base + k * (8*ld); 32-bit slot x 32-bit pitch -> one IMAD.WIDE.U32
 PGBP_HD double* slot_ptr(char* base, uint32_t slot, uint32_t ld8) {
   return (double*)(base + (uint64_t)slot * (uint64_t)ld8);
@@ -116,6 +125,23 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
   double g = *slot_ptr(st, (uint32_t)md.fg, ld8);
   const double sg_old = *slot_ptr(st, (uint32_t)md.sg, ld8);
   const double tg_old = *slot_ptr(st, (uint32_t)md.tg, ld8);
+#ifdef PGBP_T0_PREFETCH
+  // everything the streaming phase will read (kept block of the sender, old sepset, old receiver):
+  // the HBM -> L2 transfers overlap the factorisation, the chunk loop then waits on L2 only
+#pragma unroll
+  for (int q = 0; q < SS; q++) {
+    const int c = colof(q), r = q - c * (c + 1) / 2;
+    l2_prefetch(slot_ptr(st, fJ + gat[pk(I + r, I + c)], ld8));
+    l2_prefetch(slot_ptr(st, sJ + q, ld8));
+    l2_prefetch(slot_ptr(st, tJ + sca[q], ld8));
+  }
+#pragma unroll
+  for (int k = 0; k < S; k++) {
+    l2_prefetch(slot_ptr(st, fh + gat[SMM + I + k], ld8));
+    l2_prefetch(slot_ptr(st, sh + k, ld8));
+    l2_prefetch(slot_ptr(st, th + sca[SS + k], ld8));
+  }
+#endif
 
   // "Ji = Jki = hi = 0 if missing data" shortcut, src/beliefupdates.jl:62-66
   bool allzero = true;
