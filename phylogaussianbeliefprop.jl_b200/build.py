@@ -12,9 +12,15 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-SOURCES = ["pgbp_plan.cu", "pgbp_batch.cu", "pgbp_message.cu", "pgbp_factors.cu"]
-HEADERS = ["pgbp_backend.h", "pgbp_internal.h", "pgbp_kernels.cuh", "pgbp_launch.h", "pgbp_shapes.h",
-           "pgbp_factors.cuh", os.path.join("..", "..", "include", "pgbp_b200.h")]
+# (source, extra defines, object name): the 78 register-resident message shapes are compiled as three
+# translation units in parallel (pgbp_message_t0.cu with -DPGBP_T0_PART=0,1,2)
+SOURCES = [("pgbp_plan.cu", [], "pgbp_plan"), ("pgbp_batch.cu", [], "pgbp_batch"), ("pgbp_message.cu", [], "pgbp_message"),
+           ("pgbp_message_medium.cu", [], "pgbp_message_medium"), ("pgbp_factors.cu", [], "pgbp_factors"),
+           ("pgbp_message_t0.cu", ["PGBP_T0_PART=0"], "pgbp_message_t0_0"),
+           ("pgbp_message_t0.cu", ["PGBP_T0_PART=1"], "pgbp_message_t0_1"),
+           ("pgbp_message_t0.cu", ["PGBP_T0_PART=2"], "pgbp_message_t0_2")]
+HEADERS = ["pgbp_backend.h", "pgbp_internal.h", "pgbp_kernels.cuh", "pgbp_launch.h", "pgbp_shapes.h", "pgbp_msg_t0.cuh",
+           "pgbp_coop.cuh", "pgbp_factors.cuh", os.path.join("..", "..", "include", "pgbp_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -48,18 +54,19 @@ def build(emul=False, verbose=False, force=False, defines=(), tag=""):
     lib = os.path.join(LIBDIR, "libpgbp_emul.so" if emul else ("libpgbp_b200_%s.so" % tag if tag else "libpgbp_b200.so"))
     dflags = ["-D" + d for d in defines]
     objs, jobs = [], []
-    for s in SOURCES:
+    for s, sdefs, oname in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(objdir, s + ".o")
+        obj = os.path.join(objdir, oname + ".o")
         objs.append(obj)
+        sd = ["-D" + d for d in sdefs]
         if force or _stale(obj, [src] + hdrs):
             if emul:
-                cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-DPGBP_HOST_EMUL", "-x", "c++", "-c", src, "-o", obj]
+                cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-DPGBP_HOST_EMUL"] + sd + ["-x", "c++", "-c", src, "-o", obj]
             else:
-                cmd = [NVCC] + NVCC_FLAGS + dflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+                cmd = [NVCC] + NVCC_FLAGS + dflags + sd + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
     if jobs:
-        with ThreadPoolExecutor(max_workers=min(4, len(jobs))) as ex:
+        with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 4, len(jobs))) as ex:
             for out in ex.map(_run, jobs):
                 if verbose:
                     print(out)

@@ -1,14 +1,10 @@
 // K2 (message passing), K3 (integrate) and the calibrate! driver.
-#include "pgbp_coop.cuh"
-#include "pgbp_kernels.cuh"
-#include "pgbp_launch.h"
-#include "pgbp_shapes.h"
+#include "pgbp_msg_t0.cuh"
 
 using namespace pgbp;
 
 namespace pgbp {
 
-#define PGBP_MSG_THREADS 128
 #ifndef PGBP_WALK_THREADS
 #define PGBP_WALK_THREADS 128
 #endif
@@ -17,16 +13,6 @@ namespace pgbp {
 #endif
 
 #ifndef PGBP_HOST_EMUL
-#ifndef PGBP_MSG_MINBLOCKS
-#define PGBP_MSG_MINBLOCKS 1  // measured on C2 (B200): 1 -> 0.641 of HBM roofline, 2 -> 0.641, 3 -> 0.594, 4 -> 0.548
-#endif
-template <int CI, int CS, int MAXM>
-__global__ void __launch_bounds__(PGBP_MSG_THREADS, (CI >= 0 ? PGBP_MSG_MINBLOCKS : 1)) k_message(MsgArgs a) {
-  const int64_t e = a.e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= a.B) return;
-  if constexpr (CI >= 0) message_thread_t0<CI, CS>(a, blockIdx.y, e);
-  else message_thread_rt<MAXM>(a, blockIdx.y, e);
-}
 __global__ void __launch_bounds__(256) k_message_copy(MsgArgs a) {
   const int64_t e = a.e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.B) return;
@@ -120,75 +106,6 @@ __global__ void __launch_bounds__(128) k_integrate(const double* state, int32_t*
 }
 #endif
 
-template <int CI, int CS, int MAXM>
-static int launch_message(pgbp_batch* b, const MsgArgs& a, int nmsg) {
-#ifdef PGBP_HOST_EMUL
-  for (int m = 0; m < nmsg; m++)
-    for (int64_t e = a.e0; e < a.B; e++) {
-      if constexpr (CI >= 0) message_thread_t0<CI, CS>(a, m, e);
-      else message_thread_rt<MAXM>(a, m, e);
-    }
-#else
-  dim3 grid((unsigned)((a.B - a.e0 + PGBP_MSG_THREADS - 1) / PGBP_MSG_THREADS), (unsigned)nmsg);
-  k_message<CI, CS, MAXM><<<grid, PGBP_MSG_THREADS, 0, b->stream>>>(a);
-#endif
-  b->launches++;
-  return check_launch("k_message");
-}
-
-template <int MAXM, int G>
-static int launch_coop(pgbp_batch* b, const MsgArgs& a, int nmsg) {
-#ifdef PGBP_HOST_EMUL
-  // host emulation: the generic body gives bit-identical results (same per-entry update order)
-  for (int m = 0; m < nmsg; m++)
-    for (int64_t e = a.e0; e < a.B; e++) message_thread_rt<MAXM>(a, m, e);
-#else
-  constexpr int RPB = 128 / G;
-  dim3 grid((unsigned)((a.B - a.e0 + RPB - 1) / RPB), (unsigned)nmsg);
-  k_message_coop<MAXM, G><<<grid, 128, 0, b->stream>>>(a);
-#endif
-  b->launches++;
-  return check_launch("k_message_coop");
-}
-
-#define PGBP_SMEM_LIMIT (200 * 1024)
-// EXACT: I is the compile-time integrated dimension (k_message_smem<I>), else an upper bound
-// (k_message_smem_rt<MAXI>)
-template <int MAXI, bool EXACT>
-static int launch_smem(pgbp_batch* b, const MsgArgs& a, int nmsg, int I, int S) {
-#ifdef PGBP_HOST_EMUL
-  (void)I; (void)S;
-  for (int m = 0; m < nmsg; m++)
-    for (int64_t e = a.e0; e < a.B; e++) message_thread_rt<PGBP_MAX_DIM>(a, m, e);
-#else
-  static bool attr_done = false;  // per instantiation
-  static bool attr8_done = false;
-  const bool s8 = EXACT && S <= 8 && MAXI <= 10;  // fully unrolled kept-block loops (register budget: I <= 10)
-  const void* fn;
-  if constexpr (EXACT) fn = s8 ? (const void*)k_message_smem<MAXI, 8> : (const void*)k_message_smem<MAXI, 0>;
-  else fn = (const void*)k_message_smem_rt<MAXI>;
-  if (s8 && !attr8_done) {
-    PGBP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_LIMIT));
-    attr8_done = true;
-  }
-  if (!s8 && !attr_done) {
-    PGBP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_LIMIT));
-    attr_done = true;
-  }
-  if (a.ld * 8 >= ((int64_t)1 << 32)) PGBP_FAIL(PGBP_ESTATE, "batch too large for 32-bit row pitch");
-  const size_t bytes = smem_block_bytes(I, S);
-  dim3 grid((unsigned)((a.B - a.e0 + 31) / 32), (unsigned)nmsg);
-  if constexpr (EXACT) {
-    if (s8) k_message_smem<MAXI, 8><<<grid, 32, bytes, b->stream>>>(a);
-    else k_message_smem<MAXI, 0><<<grid, 32, bytes, b->stream>>>(a);
-  } else {
-    k_message_smem_rt<MAXI><<<grid, 32, bytes, b->stream>>>(a);
-  }
-#endif
-  b->launches++;
-  return check_launch("k_message_smem");
-}
-
 static int launch_copy(pgbp_batch* b, const MsgArgs& a, int nmsg) {
 #ifdef PGBP_HOST_EMUL
   for (int m = 0; m < nmsg; m++)
@@ -212,37 +129,12 @@ int launch_group(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGr
     if (g.ci == 0) {
       rc = launch_copy(b, a, n);
     } else if (g.ci > 0) {
-      bool hit = false;
-#define X(I_, S_)                                   \
-  if (!hit && g.ci == I_ && g.cs == S_) {           \
-    rc = launch_message<I_, S_, 0>(b, a, n);        \
-    hit = true;                                     \
-  }
-      PGBP_T0_SHAPES(X)
-#undef X
-      if (!hit) PGBP_FAIL(PGBP_ESTATE, "no specialised kernel for shape (%d,%d)", g.ci, g.cs);
+      rc = launch_t0_part0(b, a, n, g.ci, g.cs);
+      if (rc == PGBP_NOT_MINE) rc = launch_t0_part1(b, a, n, g.ci, g.cs);
+      if (rc == PGBP_NOT_MINE) rc = launch_t0_part2(b, a, n, g.ci, g.cs);
+      if (rc == PGBP_NOT_MINE) PGBP_FAIL(PGBP_ESTATE, "no specialised kernel for shape (%d,%d)", g.ci, g.cs);
     } else {  // medium / large class: the group is uniform in (I, S) = (g.maxm, g.cs)
-      const int I = g.maxm, S = g.cs, M = I + S;
-      const int mode = b->coop_mode;
-      const bool fits = I <= 32 && sizeof(double) * 32 * (size_t)(I * (I + 1) / 2 + I * S + I) + 4 * (size_t)(M * (M + 3) / 2 + S * (S + 3) / 2 + 2) <= PGBP_SMEM_LIMIT;
-      if ((mode == -1 || mode == 1) && fits) {
-        switch (I) {
-#define PGBP_SMEM_CASE(I_) case I_: rc = launch_smem<I_, true>(b, a, n, I, S); break;
-          PGBP_SMEM_CASE(1) PGBP_SMEM_CASE(2) PGBP_SMEM_CASE(3) PGBP_SMEM_CASE(4) PGBP_SMEM_CASE(5) PGBP_SMEM_CASE(6)
-          PGBP_SMEM_CASE(7) PGBP_SMEM_CASE(8) PGBP_SMEM_CASE(9) PGBP_SMEM_CASE(10) PGBP_SMEM_CASE(11)
-          PGBP_SMEM_CASE(12) PGBP_SMEM_CASE(13) PGBP_SMEM_CASE(14) PGBP_SMEM_CASE(15) PGBP_SMEM_CASE(16)
-#undef PGBP_SMEM_CASE
-          default: rc = (I <= 24) ? launch_smem<24, false>(b, a, n, I, S) : launch_smem<32, false>(b, a, n, I, S);
-        }
-      } else if (mode != 0 && M <= PGBP_COOP_MAX) {
-        if (M <= 16) rc = (mode == 4) ? launch_coop<16, 4>(b, a, n) : launch_coop<16, 8>(b, a, n);
-        else if (M <= 24) rc = launch_coop<24, 8>(b, a, n);
-        else rc = launch_coop<32, 8>(b, a, n);
-      } else if (M <= 32) {
-        rc = launch_message<-1, -1, 32>(b, a, n);
-      } else {
-        rc = launch_message<-1, -1, 64>(b, a, n);
-      }
+      rc = launch_medium(b, a, n, g.maxm, g.cs);
     }
     PGBP_TRY(rc);
     done += n;
