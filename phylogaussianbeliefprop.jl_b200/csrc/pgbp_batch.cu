@@ -47,6 +47,18 @@ static int need_slot_table(pgbp_batch* b, size_t n) {
   return 0;
 }
 
+int batch_zero_sepsets(pgbp_batch* b, bool lazy) {
+  const pgbp_plan* p = b->plan;
+  if (lazy) { b->sepsets_lazy_zero = true; return 0; }
+  b->sepsets_lazy_zero = false;
+  return dev_memset(b->state + (size_t)p->nslots_factor * (size_t)b->ld, 0,
+                    sizeof(double) * (size_t)(p->nslots_state - p->nslots_factor) * (size_t)b->ld, b->stream);
+}
+int batch_materialize_sepsets(pgbp_batch* b) {
+  if (!b->sepsets_lazy_zero) return 0;
+  return batch_zero_sepsets(b, false);
+}
+
 int batch_upload_tables(pgbp_batch* b) {
   const pgbp_plan* p = b->plan;
   PGBP_TRY(stream_sync(b->stream));
@@ -183,6 +195,7 @@ static void square_slots(int m, int64_t base, bool upper_only, std::vector<int32
 static int access_hJg(pgbp_batch* b, bool put, double* d_arr, int m, int64_t js, int64_t hs, int64_t gs,
                       double* J, double* h, double* g) {
   PGBP_TRY(set_device(b->device));
+  if (d_arr == b->state) PGBP_TRY(batch_materialize_sepsets(b));
   std::vector<int32_t> sl;
   if (J && m > 0) {
     square_slots(m, js, put, &sl);
@@ -362,6 +375,7 @@ int32_t pgbp_clear_status(pgbp_batch* b) {
 int32_t pgbp_reset_beliefs(pgbp_batch* b) {
   if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
   PGBP_TRY(set_device(b->device));
+  b->sepsets_lazy_zero = false;
   return dev_memset(b->state, 0, sizeof(double) * (size_t)b->plan->nslots_state * (size_t)b->ld, b->stream);
 }
 int32_t pgbp_factors_from_beliefs(pgbp_batch* b) {
@@ -377,8 +391,7 @@ int32_t pgbp_reset_from_factors(pgbp_batch* b) {
   const pgbp_plan* p = b->plan;
   const size_t ld = (size_t)b->ld;
   PGBP_TRY(d2d(b->state, b->factor, sizeof(double) * (size_t)p->nslots_factor * ld, b->stream));
-  return dev_memset(b->state + (size_t)p->nslots_factor * ld, 0,
-                    sizeof(double) * (size_t)(p->nslots_state - p->nslots_factor) * ld, b->stream);
+  return batch_zero_sepsets(b, true);
 }
 int32_t pgbp_reset_calibration_flags(pgbp_batch* b, int32_t reset_kl) {
   if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
@@ -400,6 +413,8 @@ int32_t pgbp_reset_calibration_flags(pgbp_batch* b, int32_t reset_kl) {
 
 int32_t pgbp_device_view(pgbp_batch* b, double** base, int64_t* ld, int64_t* nslots) {
   if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
+  PGBP_TRY(set_device(b->device));
+  PGBP_TRY(batch_materialize_sepsets(b));  // the caller may read any row
   if (base) *base = b->state;
   if (ld) *ld = b->ld;
   if (nslots) *nslots = b->plan->nslots_state;

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(128) k_message_coop(MsgArgs a) {
   if (!skip) gnew += 0.5 * ((double)I * PGBP_LOG2PI - logdet + ww);
 
   // ---- divide! / mult! / residual for my kept columns -----------------------------------------
+  const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;
   double maxJ = 0.0, maxh = 0.0;
 #pragma unroll
   for (int j = 0; j < NJ; j++) {
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(128) k_message_coop(MsgArgs a) {
           const int q = v ? pk(r - I, cc) : 0;
           sa[u] = (md.sJ + q) * ld;
           ta[u] = (md.tJ + (v ? sca[q] : 0)) * ld;
-          so[u] = v ? st[sa[u]] : 0.0;
+          so[u] = (v && !sz) ? st[sa[u]] : 0.0;
           to[u] = v ? st[ta[u]] : 0.0;
         }
       }
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(128) k_message_coop(MsgArgs a) {
     }
     if (cv) {
       const int64_t sa = (md.sh + cc) * ld, ta = (md.th + sca[SS + cc]) * ld;
-      const double so = st[sa], to = st[ta];
+      const double so = sz ? 0.0 : st[sa], to = st[ta];
       const double nv = hc[j];
       const double d = nv - so;
       st[sa] = nv;
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(128) k_message_coop(MsgArgs a) {
     if (oh > maxh || oh != oh) maxh = (maxh != maxh) ? maxh : oh;
   }
   if (active && g == 0) {
-    const double sg_old = st[md.sg * ld], tg_old = st[md.tg * ld];
+    const double sg_old = sz ? 0.0 : st[md.sg * ld], tg_old = st[md.tg * ld];
     st[md.sg * ld] = gnew;
     st[md.tg * ld] = tg_old + (gnew - sg_old);
     store_flag(a, md.dmsg, e, S, maxJ, maxh);
@@ -282,7 +283,8 @@ __global__ void __launch_bounds__(32) k_message_smem_rt(MsgArgs a) {
 #pragma unroll 4
   for (int k = 0; k < I; k++) cp_async8(&PGBP_SM(WB + k), st + (md.fh + gat[SMM + k]) * ld);
   double g = st[md.fg * ld];
-  const double sg_old = st[md.sg * ld], tg_old = st[md.tg * ld];
+  const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;
+  const double sg_old = sz ? 0.0 : st[md.sg * ld], tg_old = st[md.tg * ld];
   cp_async_wait_all();
 
   // "Ji = Jki = hi = 0 if missing data" shortcut (src/beliefupdates.jl:62-66)
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(32) k_message_smem_rt(MsgArgs a) {
         if (rr <= cc) {
           ta[u] = (md.tJ + sca[qc + rr]) * ld;
           jo[u] = st[(md.fJ + gc[rr]) * ld];
-          so[u] = st[(md.sJ + qc + rr) * ld];
+          so[u] = sz ? 0.0 : st[(md.sJ + qc + rr) * ld];
           to[u] = st[ta[u]];
         }
       }
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(32) k_message_smem_rt(MsgArgs a) {
         if (k < S) {
           ta[u] = (md.th + sca[SS + k]) * ld;
           ho[u] = st[(md.fh + gh[k]) * ld];
-          so[u] = st[(md.sh + k) * ld];
+          so[u] = sz ? 0.0 : st[(md.sh + k) * ld];
           to[u] = st[ta[u]];
         }
       }
@@ -500,7 +502,8 @@ __global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
     for (int k = 0; k < I; k++) cp_async8(zc + k * 32, gaddr(stb, fh + gat[SMM + k], ld8));
   }
   double g = *gaddr(stb, (uint32_t)md.fg, ld8);
-  const double sg_old = *gaddr(stb, (uint32_t)md.sg, ld8), tg_old = *gaddr(stb, (uint32_t)md.tg, ld8);
+  const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;
+  const double sg_old = sz ? 0.0 : *gaddr(stb, (uint32_t)md.sg, ld8), tg_old = *gaddr(stb, (uint32_t)md.tg, ld8);
   // ---- L2 prefetch of everything phase C will read (kept block of the sender, old sepset, old
   //      receiver): the HBM -> L2 transfers overlap phases A and B, phase C then waits on L2 only
 #pragma unroll(MS > 0 ? MS : 1)
@@ -511,11 +514,11 @@ __global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
 #pragma unroll(MS > 0 ? MS : 1)
     for (int rr = 0; rr <= cc; rr++) {
       prefetch_l2(gaddr(stb, fJ + gc[rr], ld8));
-      prefetch_l2(gaddr(stb, sJ + qc + rr, ld8));
+      if (!sz) prefetch_l2(gaddr(stb, sJ + qc + rr, ld8));
       prefetch_l2(gaddr(stb, tJ + sca[qc + rr], ld8));
     }
     prefetch_l2(gaddr(stb, fh + gat[SMM + I + cc], ld8));
-    prefetch_l2(gaddr(stb, sh + cc, ld8));
+    if (!sz) prefetch_l2(gaddr(stb, sh + cc, ld8));
     prefetch_l2(gaddr(stb, th + sca[SS + cc], ld8));
   }
   cp_async_wait_all();
@@ -608,7 +611,7 @@ __global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
       for (int rr = 0; rr <= cc; rr++) {
         ta[rr] = gaddr(stb, tJ + sca[qc + rr], ld8);
         jo[rr] = *gaddr(stb, fJ + gc[rr], ld8);
-        so[rr] = *gaddr(stb, sJ + qc + rr, ld8);
+        so[rr] = sz ? 0.0 : *gaddr(stb, sJ + qc + rr, ld8);
         to[rr] = *ta[rr];
       }
       double zc[I];
@@ -638,7 +641,7 @@ __global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
         if (k < S) {
           ta[k] = gaddr(stb, th + sca[SS + k], ld8);
           ho[k] = *gaddr(stb, fh + gh[k], ld8);
-          so[k] = *gaddr(stb, sh + k, ld8);
+          so[k] = sz ? 0.0 : *gaddr(stb, sh + k, ld8);
           to[k] = *ta[k];
         }
       }
@@ -672,7 +675,7 @@ __global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
         if (rr <= cc) {
           ta[u] = gaddr(stb, tJ + sca[qc + rr], ld8);
           jo[u] = *gaddr(stb, fJ + gc[rr], ld8);
-          so[u] = *gaddr(stb, sJ + qc + rr, ld8);
+          so[u] = sz ? 0.0 : *gaddr(stb, sJ + qc + rr, ld8);
           to[u] = *ta[u];
         }
       }
@@ -707,7 +710,7 @@ __global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
         if (k < S) {
           ta[u] = gaddr(stb, th + sca[SS + k], ld8);
           ho[u] = *gaddr(stb, fh + gh[k], ld8);
-          so[u] = *gaddr(stb, sh + k, ld8);
+          so[u] = sz ? 0.0 : *gaddr(stb, sh + k, ld8);
           to[u] = *ta[u];
         }
       }

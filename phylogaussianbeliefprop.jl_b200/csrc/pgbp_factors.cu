@@ -808,6 +808,7 @@ static int launch_energy_bucket(pgbp_batch* b, DevTables* dt, const std::vector<
 
 static int factored_energy_launch(pgbp_batch* b, double* d_out_soa, int64_t ldo) {
   const pgbp_plan* p = b->plan;
+  PGBP_TRY(batch_materialize_sepsets(b));
   if (!b->factor) PGBP_FAIL(PGBP_ESTATE, "batch was created without PGBP_BATCH_FACTORS");
   DevTables* dt;
   PGBP_TRY(get_tables(b, &dt));
@@ -893,9 +894,8 @@ static int assign_enqueue(pgbp_batch* b, pgbp::DevTables* dt, int32_t ncolors, c
 #undef PGBP_FAST_CASE
     default: PGBP_TRY(launch_generic(b, "k_assign_factors", b->B, p->nclusters, body));
   }
-  // sepsets <- 0 (src/beliefs.jl:796), factor snapshot (src/clustergraphbeliefs.jl:106)
-  PGBP_TRY(dev_memset(b->state + (size_t)p->nslots_factor * (size_t)b->ld, 0,
-                      sizeof(double) * (size_t)(p->nslots_state - p->nslots_factor) * (size_t)b->ld, b->stream));
+  // sepsets <- 0 (src/beliefs.jl:796), lazily; factor snapshot (src/clustergraphbeliefs.jl:106)
+  PGBP_TRY(batch_zero_sepsets(b, true));
   if (b->factor) PGBP_TRY(d2d(b->factor, b->state, sizeof(double) * (size_t)p->nslots_factor * (size_t)b->ld, b->stream));
   return 0;
 }
@@ -954,6 +954,7 @@ int32_t pgbp_factored_energy(pgbp_batch* b, double* out) {
 int32_t pgbp_regularize_bycluster(pgbp_batch* b) {
   if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
   PGBP_TRY(set_device(b->device));
+  PGBP_TRY(batch_materialize_sepsets(b));
   const pgbp_plan* p = b->plan;
   DevTables* dt;
   PGBP_TRY(get_tables(b, &dt));
@@ -967,6 +968,7 @@ int32_t pgbp_regularize_bycluster(pgbp_batch* b) {
 int32_t pgbp_regularize_onschedule(pgbp_batch* b) {
   if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
   PGBP_TRY(set_device(b->device));
+  PGBP_TRY(batch_materialize_sepsets(b));
   pgbp_plan* p = const_cast<pgbp_plan*>(b->plan);
   DevTables* dt;
   PGBP_TRY(get_tables(b, &dt));
@@ -1042,6 +1044,7 @@ int32_t pgbp_regularize_bynodesubtree(pgbp_batch* b, int32_t nnodes, const int32
                                       const int32_t* idx_off, const int32_t* idx_cluster, const int32_t* idx_sepset) {
   if (!b || nnodes < 0 || !eps_off || !step_off) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
   PGBP_TRY(set_device(b->device));
+  PGBP_TRY(batch_materialize_sepsets(b));
   const pgbp_plan* p = b->plan;
   DevTables* dt;
   PGBP_TRY(get_tables(b, &dt));

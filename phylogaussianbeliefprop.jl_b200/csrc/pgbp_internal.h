@@ -136,6 +136,11 @@ struct pgbp_batch {
   int64_t chunk_begin = 0, chunk_end = 0;
   std::vector<pgbp_stream_t> pipe_streams;
   std::vector<void*> pipe_events;  // cudaEvent_t: [0] fork, [1..] joins
+  // Lazy zero of the sepsets: assignfactors! / reset leave the sepset rows unwritten and set this flag; the
+  // first postorder traversal of a tree that covers every sepset treats their old value as 0 and writes
+  // them (saves one write and one read of every sepset); anything else that looks at the state calls
+  // batch_materialize_sepsets() first.
+  bool sepsets_lazy_zero = false;
   int32_t coop_mode = -1;  // medium shapes: -1 auto (cooperative), 0 thread-local generic, 4 / 8 lanes for m <= 16
   int32_t* d_slot = nullptr;  // device scratch for transpose slot tables
   size_t d_slot_len = 0;

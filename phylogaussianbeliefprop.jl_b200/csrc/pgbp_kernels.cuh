@@ -22,7 +22,7 @@ struct MsgArgs {
   int32_t* status;
   const uint8_t* done;  // may be null
   int64_t B, ld;     // elements [e0, B) are processed (e0 > 0: one chunk of a pipelined calibration)
-  uint32_t opts;     // PGBP_CAL_RESIDNORM
+  uint32_t opts;     // PGBP_CAL_RESIDNORM | PGBP_CAL_RESIDKLDIV | PGBP_OPT_SEPZERO
   int32_t ref_base;
   int64_t e0;
 };
@@ -56,6 +56,10 @@ PGBP_HD constexpr int colof(int q) {
 }
 
 #define PGBP_CHUNK 8
+// internal option bit: every sepset written by this traversal is known to be identically zero (first
+// postorder traversal after factor assignment / reset): the old sepset value is not loaded, and the
+// zero-fill of the sepsets is skipped by the caller.  x - 0.0 == x, so results are unchanged.
+#define PGBP_OPT_SEPZERO 0x100u
 
 // calibration flag of one residual (src/beliefs.jl:994-1003):
 // max|dh|/sqrt(s) <= 1e-5 && max|dJ|/sqrt(s^2) <= 1e-5.  max_i(|x_i|/c) == (max_i|x_i|)/c
@@ -123,7 +127,8 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
 #pragma unroll
   for (int k = 0; k < I; k++) hI[k] = *slot_ptr(st, fh + gat[SMM + k], ld8);
   double g = *slot_ptr(st, (uint32_t)md.fg, ld8);
-  const double sg_old = *slot_ptr(st, (uint32_t)md.sg, ld8);
+  const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;
+  const double sg_old = sz ? 0.0 : *slot_ptr(st, (uint32_t)md.sg, ld8);
   const double tg_old = *slot_ptr(st, (uint32_t)md.tg, ld8);
 #ifdef PGBP_T0_PREFETCH
   // everything the streaming phase will read (kept block of the sender, old sepset, old receiver):
@@ -206,7 +211,7 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
       constexpr int k = decltype(kc)::value, q = q0 + k, c = colof(q), r = q - c * (c + 1) / 2;
       ta[k] = slot_ptr(st, tJ + sca[q], ld8);
       jo[k] = *slot_ptr(st, fJ + gat[pk(I + r, I + c)], ld8);
-      so[k] = *slot_ptr(st, sJ + q, ld8);
+      so[k] = sz ? 0.0 : *slot_ptr(st, sJ + q, ld8);
       to[k] = *ta[k];
     });
     static_for<n>([&](auto kc) {
@@ -228,7 +233,7 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
     for (int k = 0; k < S; k++) {
       ta[k] = slot_ptr(st, th + sca[SS + k], ld8);
       ho[k] = *slot_ptr(st, fh + gat[SMM + I + k], ld8);
-      so[k] = *slot_ptr(st, sh + k, ld8);
+      so[k] = sz ? 0.0 : *slot_ptr(st, sh + k, ld8);
       to[k] = *ta[k];
     }
 #pragma unroll
@@ -258,7 +263,8 @@ PGBP_HD void divide_mult_store(const MsgArgs& a, const MsgDesc& md, int64_t e, i
   double* rs = a.resid ? a.resid + e : nullptr;
   const int32_t* __restrict__ sca = a.tab + md.sca;
   const int SS = tri(S);
-  const double sg_old = st[md.sg * ld], tg_old = st[md.tg * ld];
+  const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;
+  const double sg_old = sz ? 0.0 : st[md.sg * ld], tg_old = st[md.tg * ld];
   double maxJ = 0.0, maxh = 0.0;
   int r = 0, c = 0;  // (r,c) of packed index q, advanced incrementally
   for (int q0 = 0; q0 < SS; q0 += PGBP_CHUNK) {
@@ -270,7 +276,7 @@ PGBP_HD void divide_mult_store(const MsgArgs& a, const MsgDesc& md, int64_t e, i
       if (q < SS) {
         ta[k] = (md.tJ + sca[q]) * ld;
         nv[k] = newJ(r, c, q);
-        so[k] = st[(md.sJ + q) * ld];
+        so[k] = sz ? 0.0 : st[(md.sJ + q) * ld];
         to[k] = st[ta[k]];
         if (++r > c) { r = 0; c++; }
       }
@@ -295,7 +301,7 @@ PGBP_HD void divide_mult_store(const MsgArgs& a, const MsgDesc& md, int64_t e, i
       if (k0 + k < S) {
         ta[k] = (md.th + sca[SS + k0 + k]) * ld;
         nv[k] = newh(k0 + k);
-        so[k] = st[(md.sh + k0 + k) * ld];
+        so[k] = sz ? 0.0 : st[(md.sh + k0 + k) * ld];
         to[k] = st[ta[k]];
       }
 #pragma unroll

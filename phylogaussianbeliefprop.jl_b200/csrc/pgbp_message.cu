@@ -300,6 +300,7 @@ static int launch_iscal(pgbp_batch* b, int it, int tr, int autostop) {
 
 int integrate_launch(pgbp_batch* b, int belief, double* d_mu_soa, double* d_norm, int64_t ld_out, double* d_cov_soa) {
   const pgbp_plan* p = b->plan;
+  if (belief >= p->nclusters) PGBP_TRY(batch_materialize_sepsets(b));
   const int M = p->dim[belief];
   const int64_t js = p->jslot[belief], hs = p->hslot[belief], gs = p->gslot[belief];
 #ifdef PGBP_HOST_EMUL
@@ -328,7 +329,7 @@ extern "C" {
 
 // Enqueue one calibrate! call (validated arguments) on b->stream, eagerly.  *nlaunch_est: launches of
 // ONE element chunk.
-static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int32_t niter, uint32_t flags);
+static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int32_t niter, uint32_t flags, bool lazy);
 
 extern "C" {
 
@@ -347,6 +348,16 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
   if (ids.empty()) PGBP_FAIL(PGBP_EINVAL, "empty schedule");
   for (int t : ids) if (t < 0 || t >= (int)p->trees.size()) PGBP_FAIL(PGBP_EINVAL, "tree id %d out of range", t);
   PGBP_TRY(set_device(b->device));
+  // lazy sepset zero: usable iff the call starts with the postorder traversal of a tree that writes every
+  // sepset (a spanning tree of a clique tree), through the per-step launches
+  if (b->sepsets_lazy_zero) {
+    const pgbp::Tree& t0 = p->trees[ids[0]];
+    const bool ok = (flags & PGBP_CAL_POSTORDER) && (int)t0.parent.size() == p->nsepsets && !use_walk(b, ids[0]) &&
+                    !(flags & PGBP_CAL_RESIDKLDIV) && b->tilewalk_mode != 1;
+    if (!ok) PGBP_TRY(batch_materialize_sepsets(b));
+  }
+  const bool lazy = b->sepsets_lazy_zero;
+  b->sepsets_lazy_zero = false;  // after this call every sepset holds a real value
 #ifndef PGBP_HOST_EMUL
   // CUDA graph replay: a calibrate! call is a fixed sequence of launches for fixed (schedule, niter,
   // flags, kernel strategy); the second call with the same key captures it, later calls replay it
@@ -360,12 +371,12 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
     for (int t : ids) key += std::to_string(t) + ",";
     key += "|" + std::to_string(niter) + "|" + std::to_string(flags) + "|" + std::to_string(b->walk_mode) + "|" +
            std::to_string(b->coop_mode) + "|" + std::to_string(b->pipeline) + "|" + std::to_string((int)b->want_info) +
-           "|" + std::to_string(b->tilewalk_mode) +
+           "|" + std::to_string(b->tilewalk_mode) + "|" + std::to_string((int)lazy) +
            "|" + std::to_string((uintptr_t)b->stream);
     auto it = b->graphs.find(key);
     if (it == b->graphs.end()) {  // first sight: run eagerly (also performs one-time cudaFuncSetAttribute calls)
       b->graphs[key] = pgbp_batch::GraphEntry{};
-      return calibrate_enqueue(b, ids, niter, flags);
+      return calibrate_enqueue(b, ids, niter, flags, lazy);
     }
     pgbp_batch::GraphEntry& ge = it->second;
     if (!ge.exec && !ge.failed) {
@@ -374,7 +385,7 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
       cudaError_t ce = cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal);
       int rc = 0;
       if (ce == cudaSuccess) {
-        rc = calibrate_enqueue(b, ids, niter, flags);
+        rc = calibrate_enqueue(b, ids, niter, flags, lazy);
         ce = cudaStreamEndCapture(b->stream, &graph);
       }
       if (ce == cudaSuccess && !rc && graph) {
@@ -387,7 +398,7 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
       if (!ge.exec) {  // capture not possible (e.g. the caller's stream is already capturing): stay eager
         ge.failed = true;
         cudaGetLastError();
-        return calibrate_enqueue(b, ids, niter, flags);
+        return calibrate_enqueue(b, ids, niter, flags, lazy);
       }
     }
     if (ge.exec) {
@@ -397,12 +408,12 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
     }
   }
 #endif
-  return calibrate_enqueue(b, ids, niter, flags);
+  return calibrate_enqueue(b, ids, niter, flags, lazy);
 }
 
 }  // extern "C"
 
-static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int32_t niter, uint32_t flags) {
+static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int32_t niter, uint32_t flags, bool lazy) {
   const pgbp_plan* p = b->plan;
   const bool autostop = (flags & PGBP_CAL_AUTO) != 0;
   const bool track = (flags & PGBP_CAL_RESIDNORM) != 0;
@@ -415,6 +426,7 @@ static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int
     int32_t ref = 0;
     for (int it = 1; it <= niter; it++) {
       for (size_t j = 0; j < ids.size(); j++) {
+        const uint32_t sepzero = (lazy && it == 1 && j == 0) ? PGBP_OPT_SEPZERO : 0u;
         const int t = ids[j];
         const int n = (int)p->trees[t].parent.size();
         if (use_walk(b, t) && !(opts & PGBP_CAL_RESIDKLDIV)) {
@@ -423,7 +435,7 @@ static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int
           PGBP_TRY(run_walk(b, t, first, count, opts, ref, autostop));
           ref += count;
         } else {
-          if (flags & PGBP_CAL_POSTORDER) { PGBP_TRY(run_traversal(b, t, 0, opts, ref, autostop)); ref += n; }
+          if (flags & PGBP_CAL_POSTORDER) { PGBP_TRY(run_traversal(b, t, 0, opts | sepzero, ref, autostop)); ref += n; }
           if (flags & PGBP_CAL_PREORDER) { PGBP_TRY(run_traversal(b, t, 1, opts, ref, autostop)); ref += n; }
         }
         const bool last = (it == niter && j + 1 == ids.size());
@@ -568,6 +580,7 @@ int32_t pgbp_propagate(pgbp_batch* b, int32_t from_cluster, int32_t sepset, int3
   const size_t tab_before = p->tab.size();
   PGBP_TRY(p->make_msg(from_cluster, j, to_cluster, &md));
   PGBP_TRY(set_device(b->device));
+  PGBP_TRY(batch_materialize_sepsets(b));
   if (p->tab.size() != tab_before) PGBP_TRY(batch_upload_tables(b));
   PGBP_TRY(h2d(b->d_one, &md, sizeof md, b->stream));
   PGBP_TRY(stream_sync(b->stream));  // md is a stack object
