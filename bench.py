@@ -85,6 +85,31 @@ class C2:
     cpu_kw = dict(post=True, pre=True, residnorm=True)
 
 
+class C2S(C2):
+    """C2 with the shared-precision path: the 65,536 elements are trait replicates under ONE
+    parameter vector, so every J is stored and updated once; per message and element only h and g move.
+    Reported separately, with its own algorithmic-bytes formula (never against the full-J byte count)."""
+    key = "c2s"
+    shared = True
+    workload = ("lazaridis_2014 admixture graph, MvFullBrownianMotion p=3, 65,536 synthetic trait replicates per GPU under "
+                "ONE parameter vector, clique tree, SHARED-PRECISION batch (J stored once per group, h and g per element), "
+                "calibrate! (post+pre order, residual tracking) + integratebelief! [BASELINE configs[1], shared-J variant "
+                "of SURVEY 8f-1: own byte count 8*(m_F + 1 + 4*(s+1) + s) per message]")
+    kernel_text = "k_message<i,s> family, shared-precision mode (32 messages of a calibration)"
+
+    def cost(self, plan):
+        d = self.d
+        dims = d["belief_dim"]
+        by = 0.0
+        for dr in (0, 1):
+            lv = plan.levels(0, dr)
+            for f, sp in zip(lv["frm"], lv["sepset"]):
+                mF, s_ = dims[f], dims[sp]
+                by += 8.0 * (mF + 1 + 4 * (s_ + 1) + s_)
+        fl = plan.traversal_cost(0, 0, True)[1] + plan.traversal_cost(0, 1, True)[1]
+        return by, fl
+
+
 class C4(C2):
     """BASELINE configs[3]: synthetic 10k-tip level-1 network, HeterogeneousBM p=8, grid of 4,096 theta."""
     key = "c4"
@@ -185,7 +210,7 @@ class C3(C2):
     cpu_kw = dict(post=True, pre=True, residnorm=True, niter=10, reg_bycluster=True)
 
 
-WORKLOADS = {"c2": C2, "c3": C3, "c4": C4}
+WORKLOADS = {"c2": C2, "c2s": C2S, "c3": C3, "c4": C4}
 
 
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
@@ -343,8 +368,9 @@ def run_gpu(args):
     plan = pgbp_b200.ClusterGraphPlan(d["nclusters"], d["belief_dim"], d["sepset_clusters"], d["upind"], d["trees"], p,
                                       d["families"], lib)
     stream = torch.cuda.current_stream()
+    group = B if getattr(w, "shared", False) else 0
     bt = pgbp_b200.BatchedClusterGraphBelief(plan, B, device=local, stream=stream.cuda_stream,
-                                             factors=w.residuals, residuals=w.residuals)
+                                             factors=w.residuals, residuals=w.residuals, shared_precision_group=group)
     if args.walk is not None:
         bt.set_walk_mode(args.walk)
     if args.pipeline is not None:
@@ -355,7 +381,8 @@ def run_gpu(args):
         bt.set_tilewalk_mode(args.tilewalk)
     root = d["root_cluster"] + 1
     bytes_unit, flops_unit = w.cost(plan)
-    nmsg = {"c2": 2 * len(d["trees"][0][0]), "c4": len(d["trees"][0][0])}.get(w.key) or 4 * len(d["trees"][0][0]) * w.niter
+    nmsg = ({"c2": 2 * len(d["trees"][0][0]), "c2s": 2 * len(d["trees"][0][0]), "c4": len(d["trees"][0][0])}.get(w.key)
+            or 4 * len(d["trees"][0][0]) * w.niter)
     upe = getattr(w, "niter", 1)  # metric units per element per step
 
     # ---- device-resident arm: inputs in HBM before the timed region -----------------------
@@ -377,7 +404,7 @@ def run_gpu(args):
         if world > 1:
             pending[k] = dist.all_gather_into_tensor(gathered[k], d_norms[k], async_op=True)
         return d_norms[k]
-    if w.key == "c2":
+    if w.key in ("c2", "c2s"):
         bt.assignfactors(params, tips)  # factors resident in HBM
 
         def step(ev=None):
@@ -472,12 +499,13 @@ def run_gpu(args):
     # fit in HBM the steps alternate between two batches driven by two host threads (the ABI allows
     # distinct batches on distinct threads): the H2D / D2H of one step overlaps the kernels of the other.
     big = params if w.key == "c4" else tips
-    e2e_steps = args.steps if w.key == "c2" else min(args.steps, 5)
+    e2e_steps = args.steps if w.key in ("c2", "c2s") else min(args.steps, 5)
     free_b, total_b = torch.cuda.mem_get_info()
     two = bt.device_bytes() * 1.1 < free_b
     bts = [bt]
     if two:
-        bts.append(pgbp_b200.BatchedClusterGraphBelief(plan, B, device=local, factors=w.residuals, residuals=w.residuals))
+        bts.append(pgbp_b200.BatchedClusterGraphBelief(plan, B, device=local, factors=w.residuals, residuals=w.residuals,
+                                                       shared_precision_group=group))
         if args.pipeline is not None:
             bts[1].set_pipeline(args.pipeline)
     pin_np = [torch.from_numpy(big.copy()).pin_memory().numpy() for _ in bts]
@@ -485,7 +513,7 @@ def run_gpu(args):
 
     def e2e_step(i):
         b_ = bts[i]
-        if w.key == "c2":
+        if w.key in ("c2", "c2s"):
             b_.assignfactors(params, pin_np[i])                 # H2D of this step's inputs + K1
             succ, iscal = b_.calibrate(None, 1)                 # D2H of succ / iscal
         elif w.key == "c3":

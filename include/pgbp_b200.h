@@ -130,6 +130,15 @@ int32_t pgbp_plan_traversal_cost(const pgbp_plan* plan, int32_t tree, int32_t di
 
 int32_t pgbp_batch_create(const pgbp_plan* plan, int64_t B, int32_t device, uint32_t flags,
                           pgbp_batch** out);
+/* Shared-precision batch: the `group_size` consecutive elements of a group use ONE parameter vector
+ * (trait replicates under one theta), so every J of the group is the same matrix: it is stored and
+ * updated once (in the group's first element), read by all -- per message and element only h and g
+ * move through HBM.  Same calls, same results as an ordinary batch given the same inputs;
+ * restrictions: pgbp_assign_factors needs one parameter set per group, calibrate has no auto-stop
+ * (it is per element), pgbp_set_belief takes J from each group's first element.
+ * group_size 0 or 1 = ordinary batch (every element its own J). */
+int32_t pgbp_batch_create_shared(const pgbp_plan* plan, int64_t B, int64_t group_size, int32_t device,
+                                 uint32_t flags, pgbp_batch** out);
 int32_t pgbp_batch_destroy(pgbp_batch* batch);
 /* run on an externally owned cudaStream_t (e.g. the caller's current stream) */
 int32_t pgbp_batch_set_stream(pgbp_batch* batch, void* cuda_stream);

@@ -46,6 +46,7 @@ SIGNATURES = {
     "pgbp_plan_get_levels": (i32, [vp, i32, i32, P(i32), P(i32), P(i32), P(i32), P(i32), P(i32), P(i32)]),
     "pgbp_plan_traversal_cost": (i32, [vp, i32, i32, i32, P(f64), P(f64)]),
     "pgbp_batch_create": (i32, [vp, i64, i32, u32, P(vp)]),
+    "pgbp_batch_create_shared": (i32, [vp, i64, i64, i32, u32, P(vp)]),
     "pgbp_batch_destroy": (i32, [vp]),
     "pgbp_batch_set_stream": (i32, [vp, vp]),
     "pgbp_batch_synchronize": (i32, [vp]),

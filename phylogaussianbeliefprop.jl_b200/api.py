@@ -253,11 +253,15 @@ class BatchedClusterGraphBelief:
     """B replicas of a ClusterGraphBelief (src/clustergraphbeliefs.jl:26-53) on
     one GPU: beliefs, factors, message residuals and per-element status."""
 
-    def __init__(self, plan: ClusterGraphPlan, B: int, device: int = 0, factors=True, residuals=True, stream=None):
+    def __init__(self, plan: ClusterGraphPlan, B: int, device: int = 0, factors=True, residuals=True, stream=None,
+                 shared_precision_group: int = 0):
+        """shared_precision_group = g > 1: the g consecutive elements of a group are trait replicates under
+        ONE parameter vector; their (identical) precisions J are stored and updated once per group."""
         self.plan, self.lib, self.B = plan, plan.lib, int(B)
         flags = (L.BATCH_FACTORS if factors else 0) | (L.BATCH_RESIDUALS if residuals else 0)
         h = C.c_void_p()
-        self.lib.check(self.lib.pgbp_batch_create(plan.handle, self.B, int(device), flags, C.byref(h)))
+        self.lib.check(self.lib.pgbp_batch_create_shared(plan.handle, self.B, int(shared_precision_group), int(device),
+                                                         flags, C.byref(h)))
         self.handle = h
         if stream is not None:
             self.lib.check(self.lib.pgbp_batch_set_stream(h, C.c_void_p(int(stream))))

@@ -73,8 +73,10 @@ int batch_upload_tables(pgbp_batch* b) {
 
 // ---- AoS <-> SoA transposes (32 x 32 shared-memory tiles) -----------------
 #ifndef PGBP_HOST_EMUL
+// gs > 1: the columns are J rows of a shared-precision batch -- they live in the group leader's column:
+// the upload keeps the leader's values, the download broadcasts them to the whole group
 __global__ void k_aos_to_soa(const double* __restrict__ aos, int K, const int32_t* __restrict__ slot,
-                             double* __restrict__ soa, int64_t ld, int64_t B) {
+                             double* __restrict__ soa, int64_t ld, int64_t B, int64_t gs) {
   __shared__ double tile[32][33];
   const int64_t e0 = (int64_t)blockIdx.x * 32;
   const int k0 = blockIdx.y * 32;
@@ -89,12 +91,12 @@ __global__ void k_aos_to_soa(const double* __restrict__ aos, int K, const int32_
     const int64_t e = e0 + threadIdx.x;
     if (e < B && k < K) {
       const int sl = slot ? slot[k] : k;
-      if (sl >= 0) soa[(int64_t)sl * ld + e] = tile[threadIdx.x][r];
+      if (sl >= 0 && (gs <= 1 || e % gs == 0)) soa[(int64_t)sl * ld + e] = tile[threadIdx.x][r];
     }
   }
 }
 __global__ void k_soa_to_aos(const double* __restrict__ soa, int64_t ld, const int32_t* __restrict__ slot,
-                             double* __restrict__ aos, int K, int64_t B) {
+                             double* __restrict__ aos, int K, int64_t B, int64_t gs) {
   __shared__ double tile[32][33];
   const int64_t e0 = (int64_t)blockIdx.x * 32;
   const int k0 = blockIdx.y * 32;
@@ -103,7 +105,7 @@ __global__ void k_soa_to_aos(const double* __restrict__ soa, int64_t ld, const i
     const int64_t e = e0 + threadIdx.x;
     if (e < B && k < K) {
       const int sl = slot ? slot[k] : k;
-      tile[r][threadIdx.x] = soa[(int64_t)sl * ld + e];
+      tile[r][threadIdx.x] = soa[(int64_t)sl * ld + (gs > 1 ? e - e % gs : e)];
     }
   }
   __syncthreads();
@@ -132,51 +134,53 @@ static int fill(pgbp_batch* b, double* p, int64_t n, double v) {
   return check_launch("k_fill");
 }
 
-int aos_to_soa(pgbp_batch* b, const double* d_aos, int K, const int32_t* d_slot, double* d_soa, int64_t ld) {
+int aos_to_soa(pgbp_batch* b, const double* d_aos, int K, const int32_t* d_slot, double* d_soa, int64_t ld, int64_t gs) {
   if (K <= 0) return 0;
 #ifdef PGBP_HOST_EMUL
   for (int64_t e = 0; e < b->B; e++)
     for (int k = 0; k < K; k++) {
       const int sl = d_slot ? d_slot[k] : k;
-      if (sl >= 0) d_soa[(int64_t)sl * ld + e] = d_aos[e * K + k];
+      if (sl >= 0 && (gs <= 1 || e % gs == 0)) d_soa[(int64_t)sl * ld + e] = d_aos[e * K + k];
     }
 #else
   dim3 grid((unsigned)((b->B + 31) / 32), (unsigned)((K + 31) / 32));
-  k_aos_to_soa<<<grid, dim3(32, 8), 0, b->stream>>>(d_aos, K, d_slot, d_soa, ld, b->B);
+  k_aos_to_soa<<<grid, dim3(32, 8), 0, b->stream>>>(d_aos, K, d_slot, d_soa, ld, b->B, gs);
 #endif
   b->launches++;
   return check_launch("k_aos_to_soa");
 }
 
-int soa_to_aos(pgbp_batch* b, const double* d_soa, int64_t ld, double* d_aos, int K, const int32_t* d_slot) {
+int soa_to_aos(pgbp_batch* b, const double* d_soa, int64_t ld, double* d_aos, int K, const int32_t* d_slot, int64_t gs) {
   if (K <= 0) return 0;
 #ifdef PGBP_HOST_EMUL
   for (int64_t e = 0; e < b->B; e++)
-    for (int k = 0; k < K; k++) d_aos[e * K + k] = d_soa[(int64_t)(d_slot ? d_slot[k] : k) * ld + e];
+    for (int k = 0; k < K; k++) d_aos[e * K + k] = d_soa[(int64_t)(d_slot ? d_slot[k] : k) * ld + (gs > 1 ? e - e % gs : e)];
 #else
   dim3 grid((unsigned)((b->B + 31) / 32), (unsigned)((K + 31) / 32));
-  k_soa_to_aos<<<grid, dim3(32, 8), 0, b->stream>>>(d_soa, ld, d_slot, d_aos, K, b->B);
+  k_soa_to_aos<<<grid, dim3(32, 8), 0, b->stream>>>(d_soa, ld, d_slot, d_aos, K, b->B, gs);
 #endif
   b->launches++;
   return check_launch("k_soa_to_aos");
 }
 
 // copy K host columns <-> device rows given by `slots` (host table)
-static int put_columns(pgbp_batch* b, const double* host, int K, const std::vector<int32_t>& slots, double* d_soa) {
+static int put_columns(pgbp_batch* b, const double* host, int K, const std::vector<int32_t>& slots, double* d_soa,
+                       int64_t gs = 0) {
   if (K <= 0) return 0;
   PGBP_TRY(batch_need_scratch(b, sizeof(double) * (size_t)b->B * K));
   PGBP_TRY(need_slot_table(b, K));
   PGBP_TRY(h2d(b->scratch, host, sizeof(double) * (size_t)b->B * K, b->stream));
   PGBP_TRY(h2d(b->d_slot, slots.data(), sizeof(int32_t) * K, b->stream));
-  PGBP_TRY(aos_to_soa(b, b->scratch, K, b->d_slot, d_soa, b->ld));
+  PGBP_TRY(aos_to_soa(b, b->scratch, K, b->d_slot, d_soa, b->ld, gs));
   return stream_sync(b->stream);  // `slots` may be a temporary
 }
-static int get_columns(pgbp_batch* b, double* host, int K, const std::vector<int32_t>& slots, const double* d_soa) {
+static int get_columns(pgbp_batch* b, double* host, int K, const std::vector<int32_t>& slots, const double* d_soa,
+                       int64_t gs = 0) {
   if (K <= 0) return 0;
   PGBP_TRY(batch_need_scratch(b, sizeof(double) * (size_t)b->B * K));
   PGBP_TRY(need_slot_table(b, K));
   PGBP_TRY(h2d(b->d_slot, slots.data(), sizeof(int32_t) * K, b->stream));
-  PGBP_TRY(soa_to_aos(b, d_soa, b->ld, b->scratch, K, b->d_slot));
+  PGBP_TRY(soa_to_aos(b, d_soa, b->ld, b->scratch, K, b->d_slot, gs));
   PGBP_TRY(d2h(host, b->scratch, sizeof(double) * (size_t)b->B * K, b->stream));
   return stream_sync(b->stream);
 }
@@ -199,7 +203,7 @@ static int access_hJg(pgbp_batch* b, bool put, double* d_arr, int m, int64_t js,
   std::vector<int32_t> sl;
   if (J && m > 0) {
     square_slots(m, js, put, &sl);
-    PGBP_TRY(put ? put_columns(b, J, m * m, sl, d_arr) : get_columns(b, J, m * m, sl, d_arr));
+    PGBP_TRY(put ? put_columns(b, J, m * m, sl, d_arr, b->group_size) : get_columns(b, J, m * m, sl, d_arr, b->group_size));
   }
   if (h && m > 0) {
     sl.resize(m);
@@ -219,7 +223,14 @@ static int access_hJg(pgbp_batch* b, bool put, double* d_arr, int m, int64_t js,
 extern "C" {
 
 int32_t pgbp_batch_create(const pgbp_plan* plan, int64_t B, int32_t device, uint32_t flags, pgbp_batch** out) {
+  return pgbp_batch_create_shared(plan, B, 0, device, flags, out);
+}
+
+int32_t pgbp_batch_create_shared(const pgbp_plan* plan, int64_t B, int64_t group_size, int32_t device, uint32_t flags,
+                                 pgbp_batch** out) {
   if (!plan || !out || B <= 0) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
+  if (group_size < 0 || (group_size > 1 && B % group_size != 0))
+    PGBP_FAIL(PGBP_EINVAL, "group size must divide the batch size");
   if (plan->nslots_state >= (int64_t)1 << 31 || plan->nslots_resid >= (int64_t)1 << 31)
     PGBP_FAIL(PGBP_EINVAL, "cluster graph too large for int32 slot tables");
   if ((B + 31) / 32 * 32 * 8 >= (int64_t)1 << 32) PGBP_FAIL(PGBP_EINVAL, "batch too large: row pitch must stay below 4 GiB");
@@ -230,6 +241,7 @@ int32_t pgbp_batch_create(const pgbp_plan* plan, int64_t B, int32_t device, uint
   b->ld = (B + 31) / 32 * 32;
   b->device = device;
   b->flags = flags;
+  b->group_size = group_size > 1 ? group_size : 0;
 #ifndef PGBP_HOST_EMUL
   PGBP_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   b->own_stream = true;
@@ -247,6 +259,7 @@ int32_t pgbp_batch_create(const pgbp_plan* plan, int64_t B, int32_t device, uint
     PGBP_TRY(dev_memset(b->resid, 0, sizeof(double) * std::max<size_t>(1, (size_t)plan->nslots_resid) * ld, b->stream));
     PGBP_TRY(alloc(b.get(), &b->kldiv, std::max<size_t>(1, nd) * ld));
     PGBP_TRY(alloc(b.get(), &b->calflag, std::max<size_t>(1, nd) * ld));
+    if (b->group_size > 1) PGBP_TRY(alloc(b.get(), &b->calflagJ, std::max<size_t>(1, nd) * ld));
     PGBP_TRY(alloc(b.get(), &b->done, ld));
     PGBP_TRY(alloc(b.get(), &b->iscal, ld));
     PGBP_TRY(alloc(b.get(), &b->itertree, 2 * ld));
@@ -290,7 +303,7 @@ int32_t pgbp_batch_destroy(pgbp_batch* b) {
   set_device(b->device);
   stream_sync(b->stream);
   dev_free(b->state); dev_free(b->factor); dev_free(b->resid); dev_free(b->kldiv);
-  dev_free(b->calflag); dev_free(b->done); dev_free(b->status); dev_free(b->iscal); dev_free(b->itertree);
+  dev_free(b->calflag); dev_free(b->calflagJ); dev_free(b->done); dev_free(b->status); dev_free(b->iscal); dev_free(b->itertree);
   dev_free(b->d_tab); dev_free(b->d_one); dev_free(b->scratch); dev_free(b->d_slot); free_tables(b);
   for (auto* p : b->d_msgs) dev_free(p);
   for (auto* p : b->d_walk) dev_free(p);
@@ -400,9 +413,12 @@ int32_t pgbp_reset_calibration_flags(pgbp_batch* b, int32_t reset_kl) {
   // empty messages are born calibrated and are never reset (src/beliefs.jl:919-922, 973-974)
   const pgbp_plan* p = b->plan;
   PGBP_TRY(dev_memset(b->calflag, 0, 2 * (size_t)p->nsepsets * (size_t)b->ld, b->stream));
+  if (b->calflagJ) PGBP_TRY(dev_memset(b->calflagJ, 0, 2 * (size_t)p->nsepsets * (size_t)b->ld, b->stream));
   for (int j = 0; j < p->nsepsets; j++)
-    if (p->dim[p->nclusters + j] == 0)
+    if (p->dim[p->nclusters + j] == 0) {
       PGBP_TRY(dev_memset(b->calflag + (int64_t)2 * j * b->ld, 1, 2 * (size_t)b->ld, b->stream));
+      if (b->calflagJ) PGBP_TRY(dev_memset(b->calflagJ + (int64_t)2 * j * b->ld, 1, 2 * (size_t)b->ld, b->stream));
+    }
   if (reset_kl && b->kldiv) {  // kldiv <- -1, 0 for empty messages (src/beliefs.jl:908-922, 975)
     PGBP_TRY(fill(b, b->kldiv, (int64_t)2 * p->nsepsets * b->ld, -1.0));
     for (int j = 0; j < p->nsepsets; j++)

@@ -130,6 +130,7 @@ struct AssignBody {
   int64_t np, nd;
   int pairing;
   ThetaRows tr;
+  int64_t gs = 0;  // shared-precision mode: J rows live in (and are written by) the group leader's column
   int y0 = 0;
   PGBP_HD void operator()(int64_t e, int y) const { run(e, y + y0); }
   PGBP_HD void run(int64_t e, int c) const {
@@ -140,9 +141,12 @@ struct AssignBody {
     const double* th = theta + ip;
     const double* td = tip + id;
     double* st = state + e;
+    const int64_t ej = this->gs > 1 ? e - e % this->gs : e;
+    const bool lead = ej == e;
     const int64_t js = F.cl_jslot[c], hs = F.cl_hslot[c], gs = F.cl_gslot[c];
     const int m = F.cl_dim[c];
-    for (int q = 0; q < tri(m) + m; q++) st[(js + q) * ld] = 0.0;  // J then h are contiguous
+    if (lead) for (int q = 0; q < tri(m); q++) st[(js + q) * ld] = 0.0;
+    for (int q = 0; q < m; q++) st[(hs + q) * ld] = 0.0;
     double g = 0.0;
     const double kind = th[(int64_t)tr.kind() * ldp];
     if (kind < 0.0) {
@@ -159,7 +163,7 @@ struct AssignBody {
         const int pos = F.mem_pos[k0];
         if (pos < 0 || kind != 1.0) continue;  // fixed root, or improper prior: factor == 1
         for (int cc = 0; cc < p; cc++) {
-          for (int r = 0; r <= cc; r++) st[(js + pk(pos + r, pos + cc)) * ld] += th[(int64_t)(tr.rootP() + cc * p + r) * ldp];
+          if (lead) for (int r = 0; r <= cc; r++) st[(js + pk(pos + r, pos + cc)) * ld] += th[(int64_t)(tr.rootP() + cc * p + r) * ldp];
           st[(hs + pos + cc) * ld] += th[(int64_t)(tr.rooth() + cc) * ldp];
         }
         g += th[(int64_t)tr.rootg() * ldp];
@@ -222,7 +226,7 @@ struct AssignBody {
         const double ca = a == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + a]);
         if (anyfixed)
           for (int t = 0; t < p; t++) st[(hs + pa + t) * ld] -= ca * jz[t];
-        for (int bq = a; bq < nm; bq++) {
+        for (int bq = a; lead && bq < nm; bq++) {
           const int pb = F.mem_pos[k0 + bq];
           if (pb < 0) continue;
           const double cb = bq == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + bq]);
@@ -251,7 +255,7 @@ PGBP_HD double* kaddr(char* base, uint32_t slot, uint32_t ld8) {
   return (double*)(base + (uint64_t)slot * (uint64_t)ld8);  // one IMAD.WIDE.U32
 }
 
-template <int P>
+template <int P, bool SH = false>
 struct AssignFast {
   AssignBody gen;
   const uint8_t* cflag;       // [nclusters] bit 0: zero-fill first
@@ -269,12 +273,14 @@ struct AssignFast {
     const double* th = gen.theta + ip;
     const double* td = gen.tip + id;
     double* st = gen.state + e;
+    const bool lead = SH ? (e % gen.gs == 0) : true;  // shared-precision mode: J rows are the leader's
     const int64_t js = F.cl_jslot[c], hs = F.cl_hslot[c], gs = F.cl_gslot[c];
     const double kind = th[(int64_t)tr.kind() * ldp];
     if (kind < 0.0) { gen.run(e, c); return; }  // invalid parameters: generic path records the status
     if (cflag[c] & 1) {
       const int m = F.cl_dim[c];
-      for (int q = 0; q < tri(m) + m; q++) st[(js + q) * ld] = 0.0;
+      if (lead) for (int q = 0; q < tri(m); q++) st[(js + q) * ld] = 0.0;
+      for (int q = 0; q < m; q++) st[(hs + q) * ld] = 0.0;
     }
     double g = 0.0;
     for (int iv = F.clu_off[c]; iv < F.clu_off[c + 1]; iv++) {
@@ -289,7 +295,7 @@ struct AssignFast {
 #pragma unroll
         for (int cc = 0; cc < P; cc++) {
 #pragma unroll
-          for (int r = 0; r <= cc; r++) {
+          for (int r = 0; lead && r <= cc; r++) {
             const double x = proper ? th[(int64_t)(tr.rootP() + cc * P + r) * ldp] : 0.0;
             double* d = st + (js + pk(pos + r, pos + cc)) * ld;
             if (fJ & 1) *d = 0.0 + x;
@@ -392,7 +398,7 @@ struct AssignFast {
 #pragma unroll
           for (int t = 0; t < P; t++) *kaddr(stb, (uint32_t)(hs + pa + t), ld8) -= ca * jz[t];
         }
-        for (int bq = a; bq < nm; bq++) {
+        for (int bq = a; lead && bq < nm; bq++) {
           const int pb = F.mem_pos[k0 + bq];
           if (pb < 0) continue;
           const double cb = bq == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + bq]);
@@ -436,12 +442,16 @@ struct EnergyClusterBody {
   double* part;         // [2*nclusters + nsepsets][ld]: energy_c, entropy_c, entropy_s
   int nclusters;
   int64_t ld;
+  int64_t gs = 0;       // shared-precision mode: J rows (belief and factor) from the group leader's column
   int y0 = 0;
   PGBP_HD void operator()(int64_t e, int y) const {
     const int c = list[y + y0];
     const int M = cl_dim[c];
+    const int64_t ej = gs > 1 ? e - e % gs : e;
     const double* st = state + e;
     const double* fa = factor + e;
+    const double* stj = state + ej;
+    const double* faj = factor + ej;
     const int64_t js = cl_jslot[c], hs = cl_hslot[c], gs = cl_gslot[c];
     const double gf = fa[gs * ld];
     if (M == 0) {  // src/score.jl:170-171
@@ -452,7 +462,7 @@ struct EnergyClusterBody {
     constexpr int NA = MAXM * (MAXM + 1) / 2;
     double A[NA], mu[MAXM], x[MAXM];
     const int SM = tri(M);
-    for (int q = 0; q < SM; q++) A[q] = st[(js + q) * ld];
+    for (int q = 0; q < SM; q++) A[q] = stj[(js + q) * ld];
     for (int k = 0; k < M; k++) mu[k] = st[(hs + k) * ld];
     double logdet = 0.0;
     for (int k = 0; k < M; k++) {  // U'U = J_b; forward solve w = U^-T h
@@ -485,7 +495,7 @@ struct EnergyClusterBody {
     for (int k = 0; k < M; k++) {
       double fk_mu = 0.0;
       for (int r = 0; r < M; r++) {
-        const double f = fa[(js + (r <= k ? pk(r, k) : pk(k, r))) * ld];
+        const double f = faj[(js + (r <= k ? pk(r, k) : pk(k, r))) * ld];
         x[r] = f;
         fk_mu = fma(f, mu[r], fk_mu);
       }
@@ -517,6 +527,7 @@ struct EntropySepsetBody {
   double* part;
   int nclusters;
   int64_t ld;
+  int64_t gs = 0;
   int y0 = 0;
   PGBP_HD void operator()(int64_t e, int y) const {
     const int j = list[y + y0];
@@ -525,7 +536,7 @@ struct EntropySepsetBody {
     if (M == 0) { *out = 0.0; return; }
     constexpr int NA = MAXM * (MAXM + 1) / 2;
     double A[NA];
-    const double* st = state + e;
+    const double* st = state + (gs > 1 ? e - e % gs : e);
     const int64_t js = jslot[nclusters + j];
     for (int q = 0; q < tri(M); q++) A[q] = st[(js + q) * ld];
     double logdet = 0.0;
@@ -584,8 +595,10 @@ struct RegClusterBody {
   const int32_t* reg_pos;
   int64_t ld;
   double floor_eps;
+  int64_t gs = 0;  // shared-precision mode: only group leaders own J rows
   int y0 = 0;
   PGBP_HD void operator()(int64_t e, int y) const {
+    if (gs > 1 && e % gs) return;
     const int c = y + y0;
     double* st = state + e;
     const int64_t js = jslot[c];
@@ -608,8 +621,10 @@ struct RegSepsetBody {
   const int32_t* sep_b;
   int nclusters;
   int64_t ld;
+  int64_t gs = 0;  // shared-precision mode: only group leaders own J rows
   int y0 = 0;
   PGBP_HD void operator()(int64_t e, int y) const {
+    if (gs > 1 && e % gs) return;
     const int j = y + y0;
     const int M = dim[nclusters + j];
     if (M == 0) return;
@@ -632,8 +647,10 @@ struct EpsOneBody {
   int64_t js, ld;
   int M;
   double floor_eps;
+  int64_t gs = 0;  // shared-precision mode: only group leaders own J rows
   int y0 = 0;
   PGBP_HD void operator()(int64_t e, int) const {
+    if (gs > 1 && e % gs) return;
     double ep = maxabs_packed(state + e, js, M, ld);
     if (!(ep >= floor_eps)) ep = (ep != ep) ? ep : floor_eps;
     eps[e] = ep;
@@ -646,8 +663,10 @@ struct RegOneBody {
   const int32_t* upind;  // device table: cluster positions of the sepset's variables
   int64_t cjs, sjs, ld;
   int S;
+  int64_t gs = 0;  // shared-precision mode: only group leaders own J rows
   int y0 = 0;
   PGBP_HD void operator()(int64_t e, int) const {
+    if (gs > 1 && e % gs) return;
     double* st = state + e;
     const double ep = eps[e];
     for (int k = 0; k < S; k++) {
@@ -667,8 +686,10 @@ struct RegNodeBody {
   int e0, e1, s0, s1;  // ranges of this node in eps_cluster / steps
   int nclusters;
   int64_t ld;
+  int64_t gs = 0;  // shared-precision mode: only group leaders own J rows
   int y0 = 0;
   PGBP_HD void operator()(int64_t e, int) const {
+    if (gs > 1 && e % gs) return;
     double* st = state + e;
     double ep = PGBP_EPS;
     for (int k = e0; k < e1; k++) {
@@ -794,13 +815,13 @@ static int launch_energy_bucket(pgbp_batch* b, DevTables* dt, const std::vector<
   if (!cl.empty()) {
     PGBP_TRY(h2d(d_list, cl.data(), cl.size() * sizeof(int32_t), b->stream));
     EnergyClusterBody<MAXM> body{b->state, b->factor, b->status, dt->jslot, dt->hslot, dt->gslot, dt->dim, d_list,
-                                 part, p->nclusters, b->ld};
+                                 part, p->nclusters, b->ld, b->group_size};
     PGBP_TRY(launch_generic(b, "k_energy_cluster", b->B, (int)cl.size(), body));
   }
   if (!sp.empty()) {
     int32_t* d_list2 = d_list + p->nclusters;
     PGBP_TRY(h2d(d_list2, sp.data(), sp.size() * sizeof(int32_t), b->stream));
-    EntropySepsetBody<MAXM> body{b->state, dt->jslot, dt->dim, d_list2, part, p->nclusters, b->ld};
+    EntropySepsetBody<MAXM> body{b->state, dt->jslot, dt->dim, d_list2, part, p->nclusters, b->ld, b->group_size};
     PGBP_TRY(launch_generic(b, "k_entropy_sepset", b->B, (int)sp.size(), body));
   }
   return 0;
@@ -854,6 +875,12 @@ static int assign_prepare(pgbp_batch* b, int32_t ncolors, int64_t nparamsets, in
     if ((nparamsets != 1 && nparamsets != B) || (ndatasets != 1 && ndatasets != B))
       PGBP_FAIL(PGBP_EINVAL, "zip pairing needs nparamsets, ndatasets in {1, B}");
   } else PGBP_FAIL(PGBP_EINVAL, "unknown pairing %d", pairing);
+  if (b->group_size > 1) {  // shared-precision mode: the elements of a group must use one parameter vector
+    const bool ok = (pairing == PGBP_PAIR_ZIP && nparamsets == 1) ||
+                    (pairing == PGBP_PAIR_PRODUCT && ndatasets % b->group_size == 0);
+    if (!ok) PGBP_FAIL(PGBP_EINVAL, "shared-precision batch: every group of %lld elements needs a single parameter vector "
+                       "(zip with 1 parameter set, or product with ndatasets a multiple of the group size)", (long long)b->group_size);
+  }
   PGBP_TRY(set_device(b->device));
   DevTables* dt;
   PGBP_TRY(get_tables(b, &dt));
@@ -886,9 +913,13 @@ static int assign_enqueue(pgbp_batch* b, pgbp::DevTables* dt, int32_t ncolors, c
             dt->node_datarow, dt->clu_off, dt->clu_node, dt->jslot, dt->hslot, dt->gslot, dt->dim,
             pt, ncolors, F.root_fixed};
   AssignBody body{fd, dt->theta, dt->ldp, dt->tip, dt->ldd, b->state, b->status, b->ld, nparamsets, ndatasets, pairing, tr};
+  body.gs = b->group_size;
   switch (pt) {
 #define PGBP_FAST_CASE(P_) \
-  case P_: PGBP_TRY((launch_generic<AssignFast<P_>, 3>(b, "k_assign_factors", b->B, p->nclusters, AssignFast<P_>{body, dt->clu_flag, dt->first_J, dt->first_h}))); break;
+  case P_: \
+    if (b->group_size > 1) PGBP_TRY((launch_generic<AssignFast<P_, true>, 3>(b, "k_assign_factors", b->B, p->nclusters, AssignFast<P_, true>{body, dt->clu_flag, dt->first_J, dt->first_h}))); \
+    else PGBP_TRY((launch_generic<AssignFast<P_>, 3>(b, "k_assign_factors", b->B, p->nclusters, AssignFast<P_>{body, dt->clu_flag, dt->first_J, dt->first_h}))); \
+    break;
     PGBP_FAST_CASE(1) PGBP_FAST_CASE(2) PGBP_FAST_CASE(3) PGBP_FAST_CASE(4) PGBP_FAST_CASE(5) PGBP_FAST_CASE(6)
     PGBP_FAST_CASE(7) PGBP_FAST_CASE(8)
 #undef PGBP_FAST_CASE
@@ -960,8 +991,10 @@ int32_t pgbp_regularize_bycluster(pgbp_batch* b) {
   PGBP_TRY(get_tables(b, &dt));
   PGBP_TRY(batch_need_scratch(b, sizeof(double) * (size_t)p->nclusters * (size_t)b->ld));
   RegClusterBody a{b->state, b->scratch, dt->jslot, dt->dim, dt->reg_off, dt->reg_pos, b->ld, PGBP_EPS};
+  a.gs = b->group_size;
   PGBP_TRY(launch_generic(b, "k_reg_cluster", b->B, p->nclusters, a));
   RegSepsetBody s{b->state, b->scratch, dt->jslot, dt->dim, dt->sep_a, dt->sep_b, p->nclusters, b->ld};
+  s.gs = b->group_size;
   return launch_generic(b, "k_reg_sepset", b->B, p->nsepsets, s);
 }
 
@@ -1018,11 +1051,13 @@ int32_t pgbp_regularize_onschedule(pgbp_batch* b) {
     const Op& o = ops[k];
     if (o.kind == 0) {
       EpsOneBody body{b->state, b->scratch, p->jslot[o.c], b->ld, p->dim[o.c], eps0};
+      body.gs = b->group_size;
       rc = launch_generic(b, "k_eps_one", b->B, 1, body);
     } else if (o.kind == 1) {
       const int S = p->dim[p->nclusters + o.j];
       if (S == 0) continue;  // isempty(upind) && return
       RegOneBody body{b->state, b->scratch, d_up + upoff[o.nb], p->jslot[o.c], p->jslot[p->nclusters + o.j], b->ld, S};
+      body.gs = b->group_size;
       rc = launch_generic(b, "k_reg_one", b->B, 1, body);
     } else {
       const MsgDesc& md = msgs[o.nb];
@@ -1074,6 +1109,7 @@ int32_t pgbp_regularize_bynodesubtree(pgbp_batch* b, int32_t nnodes, const int32
     if (step_off[n + 1] == step_off[n]) continue;
     RegNodeBody body{b->state, dt->jslot, dt->dim, d, nullptr, d + o_sc, d + o_ss, d + o_io, d + o_ic, d + o_is,
                      eps_off[n], eps_off[n + 1], step_off[n], step_off[n + 1], p->nclusters, b->ld};
+    body.gs = b->group_size;
     rc = launch_generic(b, "k_reg_node", b->B, 1, body);
   }
   if (!rc) rc = stream_sync(b->stream);

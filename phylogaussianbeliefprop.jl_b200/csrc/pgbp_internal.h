@@ -106,6 +106,8 @@ struct pgbp_batch {
   double* resid = nullptr;
   double* kldiv = nullptr;
   uint8_t* calflag = nullptr;  // [2*nsepsets][ld]
+  uint8_t* calflagJ = nullptr; // [2*nsepsets][ld], shared-precision mode: J part of the flags (leader columns)
+  int64_t group_size = 0;      // > 1: shared-precision mode, elements [k*gs, (k+1)*gs) share every J
   uint8_t* done = nullptr;     // [ld] (auto-stop mask)
   int32_t* status = nullptr;   // [ld]
   int32_t* iscal = nullptr;    // [ld]

@@ -25,7 +25,16 @@ struct MsgArgs {
   uint32_t opts;     // PGBP_CAL_RESIDNORM | PGBP_CAL_RESIDKLDIV | PGBP_OPT_SEPZERO
   int32_t ref_base;
   int64_t e0;
+  // Shared-precision mode (gs > 1): the gs consecutive elements of a group share every J (same parameter
+  // vector, different data).  J rows are valid in the group LEADER's column only; all threads read them
+  // from there (a warp-wide broadcast instead of 256 bytes), only the leader's thread writes J, the J
+  // part of the residual and the J part of the calibration flag (calflagJ).  h and g stay per element.
+  int64_t gs;
+  uint8_t* calflagJ;
 };
+
+// column holding the J rows of element e, and whether e owns them
+PGBP_HD int64_t jcol(const MsgArgs& a, int64_t e) { return a.gs > 1 ? e - e % a.gs : e; }
 
 // NaN-propagating running maximum of |x| (Julia's maximum(abs, x))
 PGBP_HD void absmax(double& m, double x) {
@@ -66,9 +75,14 @@ PGBP_HD constexpr int colof(int q) {
 // exactly (division by c > 0 is monotone, so is rounding).
 PGBP_HD void store_flag(const MsgArgs& a, int dmsg, int64_t e, int S, double maxJ, double maxh) {
   if ((a.opts & PGBP_CAL_RESIDNORM) && a.calflag) {
-    bool ok = true;
-    if (S > 0) ok = (maxh / sqrt((double)S) <= 1e-5) && (maxJ / (double)S <= 1e-5);
-    a.calflag[(int64_t)dmsg * a.ld + e] = ok ? 1 : 0;
+    const bool okh = S > 0 ? (maxh / sqrt((double)S) <= 1e-5) : true;
+    const bool okJ = S > 0 ? (maxJ / (double)S <= 1e-5) : true;
+    if (a.gs > 1) {  // J part kept apart: it is the group's, not the element's
+      a.calflag[(int64_t)dmsg * a.ld + e] = okh ? 1 : 0;
+      if (e % a.gs == 0) a.calflagJ[(int64_t)dmsg * a.ld + e] = okJ ? 1 : 0;
+    } else {
+      a.calflag[(int64_t)dmsg * a.ld + e] = (okh && okJ) ? 1 : 0;
+    }
   }
 }
 
@@ -97,7 +111,9 @@ PGBP_HD double* slot_ptr(char* base, uint32_t slot, uint32_t ld8) {
   return (double*)(base + (uint64_t)slot * (uint64_t)ld8);
 }
 
-template <int CI, int CS>
+// SH: shared-precision mode compiled in (J rows read from / written by the group leader's column);
+// the ordinary instantiation (SH = false) carries none of that logic.
+template <int CI, int CS, bool SH = false>
 PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
   constexpr int I = CI, S = CS, M = I + S, SI = I * (I + 1) / 2, SS = S * (S + 1) / 2;
   const MsgDesc md = a.msgs[msg_index];  // by value: lives in registers, never re-read after a store
@@ -106,6 +122,9 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
   const uint32_t ld8 = (uint32_t)(a.ld * 8);  // (batches with 8*ld >= 2^32 are refused at creation)
   char* st = (char*)(a.state + e);
   char* rs = a.resid ? (char*)(a.resid + e) : nullptr;
+  const int64_t ej = SH ? jcol(a, e) : e;
+  const bool lead = SH ? ej == e : true;  // this thread owns (writes) the J rows
+  char* stj = SH ? (char*)(a.state + ej) : st;  // J rows are read from the leader's column
   const int32_t* __restrict__ gat = a.tab + md.gat;
   const int32_t* __restrict__ sca = a.tab + md.sca;
   const uint32_t fJ = (uint32_t)md.fJ, fh = (uint32_t)md.fh, sJ = (uint32_t)md.sJ, sh = (uint32_t)md.sh,
@@ -117,12 +136,12 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
 #pragma unroll
   for (int c = 0; c < I; c++) {
 #pragma unroll
-    for (int r = 0; r <= c; r++) AI[pk(r, c)] = *slot_ptr(st, fJ + gat[pk(r, c)], ld8);
+    for (int r = 0; r <= c; r++) AI[pk(r, c)] = *slot_ptr(stj, fJ + gat[pk(r, c)], ld8);
   }
 #pragma unroll
   for (int c = 0; c < S; c++) {
 #pragma unroll
-    for (int k = 0; k < I; k++) Bm[k * S + c] = *slot_ptr(st, fJ + gat[pk(k, I + c)], ld8);
+    for (int k = 0; k < I; k++) Bm[k * S + c] = *slot_ptr(stj, fJ + gat[pk(k, I + c)], ld8);
   }
 #pragma unroll
   for (int k = 0; k < I; k++) hI[k] = *slot_ptr(st, fh + gat[SMM + k], ld8);
@@ -202,7 +221,7 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
 
   double maxJ = 0.0, maxh = 0.0;
   constexpr int NCH = (SS + PGBP_CHUNK - 1) / PGBP_CHUNK;
-  static_for<NCH>([&](auto chc) {
+  if (lead) static_for<NCH>([&](auto chc) {
     constexpr int q0 = decltype(chc)::value * PGBP_CHUNK;
     constexpr int n = (SS - q0) < PGBP_CHUNK ? (SS - q0) : PGBP_CHUNK;
     double jo[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
@@ -255,7 +274,7 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
 
 // Runtime-shape variants share this tail: divide / multiply / residual / flag with
 // chunked prefetch.  newJ(r,c,q), newh(k) give the outgoing message.
-template <class FJ, class FH>
+template <bool SH = false, class FJ, class FH>
 PGBP_HD void divide_mult_store(const MsgArgs& a, const MsgDesc& md, int64_t e, int S, FJ newJ, FH newh,
                                double newg) {
   const int64_t ld = a.ld;
@@ -267,7 +286,8 @@ PGBP_HD void divide_mult_store(const MsgArgs& a, const MsgDesc& md, int64_t e, i
   const double sg_old = sz ? 0.0 : st[md.sg * ld], tg_old = st[md.tg * ld];
   double maxJ = 0.0, maxh = 0.0;
   int r = 0, c = 0;  // (r,c) of packed index q, advanced incrementally
-  for (int q0 = 0; q0 < SS; q0 += PGBP_CHUNK) {
+  const bool lead = SH ? jcol(a, e) == e : true;  // shared-precision mode: only the group leader updates J rows
+  for (int q0 = 0; lead && q0 < SS; q0 += PGBP_CHUNK) {
     double nv[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
     int64_t ta[PGBP_CHUNK];
 #pragma unroll
@@ -345,7 +365,7 @@ struct GatherH {
 // Generic message kernel body: runtime shape, the whole sender belief gathered in
 // [I;K] order into thread-local memory sized for MAXM, right-looking partial
 // Cholesky over the first i pivots; the trailing block is the outgoing message.
-template <int MAXM>
+template <int MAXM, bool SH = false>
 PGBP_HD void message_thread_rt(const MsgArgs& a, int msg_index, int64_t e) {
   constexpr int NA = MAXM * (MAXM + 1) / 2;
   const MsgDesc md = a.msgs[msg_index];
@@ -354,12 +374,13 @@ PGBP_HD void message_thread_rt(const MsgArgs& a, int msg_index, int64_t e) {
   const int I = md.mF - md.s, S = md.s, M = md.mF;
   const int64_t ld = a.ld;
   const double* st = a.state + e;
+  const double* stj = SH ? a.state + jcol(a, e) : st;
   const int32_t* __restrict__ gat = a.tab + md.gat;
   double A[NA];
   double hv[MAXM];
   const int SM = tri(M);
 #pragma unroll 8
-  for (int q = 0; q < SM; q++) A[q] = st[(md.fJ + gat[q]) * ld];
+  for (int q = 0; q < SM; q++) A[q] = stj[(md.fJ + gat[q]) * ld];
 #pragma unroll 8
   for (int k = 0; k < M; k++) hv[k] = st[(md.fh + gat[SM + k]) * ld];
   double g = st[md.fg * ld];
@@ -392,11 +413,12 @@ PGBP_HD void message_thread_rt(const MsgArgs& a, int msg_index, int64_t e) {
     }
     g += 0.5 * ((double)I * PGBP_LOG2PI - logdet + ww);
   }
-  divide_mult_store(a, md, e, S, TrailJ{A, I}, TrailH{hv, I}, g);
+  divide_mult_store<SH>(a, md, e, S, TrailJ{A, I}, TrailH{hv, I}, g);
 }
 
 // Message with nothing to integrate out (src/beliefupdates.jl:56): the outgoing
 // message is the sender's belief re-ordered; streamed, no local storage.
+template <bool SH = false>
 PGBP_HD void message_copy_thread(const MsgArgs& a, int msg_index, int64_t e) {
   const MsgDesc md = a.msgs[msg_index];
   if (a.status[e] != 0) return;
@@ -407,7 +429,7 @@ PGBP_HD void message_copy_thread(const MsgArgs& a, int msg_index, int64_t e) {
   const int32_t* __restrict__ gat = a.tab + md.gat;
   const int SS = tri(S);
   const double g = st[md.fg * ld];
-  divide_mult_store(a, md, e, S, GatherJ{st, gat, md.fJ, ld}, GatherH{st, gat + SS, md.fh, ld}, g);
+  divide_mult_store<SH>(a, md, e, S, GatherJ{SH ? a.state + jcol(a, e) : st, gat, md.fJ, ld}, GatherH{st, gat + SS, md.fh, ld}, g);
 }
 
 // residual_kldiv! (src/beliefs.jl:1060-1075): KL divergence between the message just sent (the new
@@ -425,10 +447,12 @@ PGBP_HD void kldiv_thread(const MsgArgs& a, double* kldiv, int msg_index, int64_
   const int64_t ld = a.ld;
   const double* st = a.state + e;
   const double* rs = a.resid + e;
+  const double* stj = a.state + jcol(a, e);
+  const double* rsj = a.resid + jcol(a, e);
   double U0[NA], U1[NA], D[NA], m0[MAXM], m1[MAXM];
   const int SS = tri(S);
   for (int q = 0; q < SS; q++) {
-    const double j0 = st[(md.sJ + q) * ld], dj = rs[(md.rJ + q) * ld];
+    const double j0 = stj[(md.sJ + q) * ld], dj = rsj[(md.rJ + q) * ld];
     U0[q] = j0; D[q] = dj; U1[q] = j0 - dj;
   }
   for (int k = 0; k < S; k++) {
@@ -483,7 +507,7 @@ PGBP_HD void kldiv_thread(const MsgArgs& a, double* kldiv, int msg_index, int64_
     double s = 0.0;
     for (int c = 0; c < S; c++) {
       const int q = r <= c ? pk(r, c) : pk(c, r);
-      const double j1 = st[(md.sJ + q) * ld] - D[q];
+      const double j1 = stj[(md.sJ + q) * ld] - D[q];
       s = fma(j1, m1[c] - m0[c], s);
     }
     quad = fma(m1[r] - m0[r], s, quad);
@@ -496,15 +520,16 @@ PGBP_HD void kldiv_thread(const MsgArgs& a, double* kldiv, int msg_index, int64_
 template <int MAXM>
 PGBP_HD void integrate_thread(const double* state, int32_t* status, int64_t ld, int64_t e, int64_t jslot,
                               int64_t hslot, int64_t gslot, int M, double* mu_soa, double* norm, int64_t ld_out,
-                              double* cov_soa = nullptr) {
+                              double* cov_soa = nullptr, int64_t gs = 0) {
   constexpr int NA = MAXM * (MAXM + 1) / 2;
   double A[NA > 0 ? NA : 1];
   double hv[MAXM > 0 ? MAXM : 1];
   const double* st = state + e;
+  const double* stj = state + (gs > 1 ? e - e % gs : e);  // shared-precision mode: J from the group leader
   const int SM = tri(M);
   bool zero = true;
   for (int q = 0; q < SM; q++) {
-    A[q] = st[(jslot + q) * ld];
+    A[q] = stj[(jslot + q) * ld];
     if (A[q] != 0.0) zero = false;
   }
   for (int k = 0; k < M; k++) {

@@ -9,8 +9,8 @@ int batch_upload_tables(pgbp_batch* b);
 int batch_need_scratch(pgbp_batch* b, size_t bytes);
 // AoS (host layout: src[e*K + k]) <-> SoA (dst[slot[k]*ld + e]); slot == nullptr
 // means identity; slot[k] < 0 skips column k.  d_slot is a DEVICE table.
-int aos_to_soa(pgbp_batch* b, const double* d_aos, int K, const int32_t* d_slot, double* d_soa, int64_t ld);
-int soa_to_aos(pgbp_batch* b, const double* d_soa, int64_t ld, double* d_aos, int K, const int32_t* d_slot = nullptr);
+int aos_to_soa(pgbp_batch* b, const double* d_aos, int K, const int32_t* d_slot, double* d_soa, int64_t ld, int64_t gs = 0);
+int soa_to_aos(pgbp_batch* b, const double* d_soa, int64_t ld, double* d_aos, int K, const int32_t* d_slot = nullptr, int64_t gs = 0);
 int integrate_launch(pgbp_batch* b, int belief, double* d_mu_soa, double* d_norm, int64_t ld_out, double* d_cov_soa = nullptr);
 int launch_group(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGroup& g);
 void free_tables(pgbp_batch* b);

@@ -13,10 +13,11 @@ namespace pgbp {
 #endif
 
 #ifndef PGBP_HOST_EMUL
+template <bool SH>
 __global__ void __launch_bounds__(256) k_message_copy(MsgArgs a) {
   const int64_t e = a.e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.B) return;
-  message_copy_thread(a, blockIdx.y, e);
+  message_copy_thread<SH>(a, blockIdx.y, e);
 }
 #endif
 
@@ -29,7 +30,7 @@ __global__ void __launch_bounds__(256) k_message_copy(MsgArgs a) {
 // every message still runs the register-resident specialised body.
 template <int P, int A_, int B_>
 PGBP_HD void walk_case(const MsgArgs& a, int m, int64_t e) {
-  if constexpr (A_ == 0) message_copy_thread(a, m, e);
+  if constexpr (A_ == 0) message_copy_thread<false>(a, m, e);
   else if constexpr ((A_ + B_) * P <= PGBP_T0_MAX) message_thread_t0<A_ * P, B_ * P>(a, m, e);
 }
 template <int P>
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(32 * PGBP_TW_LANES) k_tilewalk(MsgArgs a, cons
     const int m1 = step_off[st + 1];
     if (live) {
       for (int m = step_off[st] + threadIdx.y; m < m1; m += PGBP_TW_LANES) {
-        if (a.msgs[m].mF == a.msgs[m].s) message_copy_thread(a, m, e);
+        if (a.msgs[m].mF == a.msgs[m].s) message_copy_thread<false>(a, m, e);
         else message_thread_rt<MAXM>(a, m, e);
       }
     }
@@ -99,20 +100,25 @@ __global__ void __launch_bounds__(128) k_kldiv(MsgArgs a, double* kldiv) {
 template <int MAXM>
 __global__ void __launch_bounds__(128) k_integrate(const double* state, int32_t* status, int64_t B, int64_t ld,
                                                    int64_t jslot, int64_t hslot, int64_t gslot, int M,
-                                                   double* mu_soa, double* norm, int64_t ld_out, double* cov_soa) {
+                                                   double* mu_soa, double* norm, int64_t ld_out, double* cov_soa,
+                                                   int64_t gsz) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= B) return;
-  integrate_thread<MAXM>(state, status, ld, e, jslot, hslot, gslot, M, mu_soa, norm, ld_out, cov_soa);
+  integrate_thread<MAXM>(state, status, ld, e, jslot, hslot, gslot, M, mu_soa, norm, ld_out, cov_soa, gsz);
 }
 #endif
 
 static int launch_copy(pgbp_batch* b, const MsgArgs& a, int nmsg) {
 #ifdef PGBP_HOST_EMUL
   for (int m = 0; m < nmsg; m++)
-    for (int64_t e = a.e0; e < a.B; e++) message_copy_thread(a, m, e);
+    for (int64_t e = a.e0; e < a.B; e++) {
+      if (a.gs > 1) message_copy_thread<true>(a, m, e);
+      else message_copy_thread<false>(a, m, e);
+    }
 #else
   dim3 grid((unsigned)((a.B - a.e0 + 255) / 256), (unsigned)nmsg);
-  k_message_copy<<<grid, 256, 0, b->stream>>>(a);
+  if (a.gs > 1) k_message_copy<true><<<grid, 256, 0, b->stream>>>(a);
+  else k_message_copy<false><<<grid, 256, 0, b->stream>>>(a);
 #endif
   b->launches++;
   return check_launch("k_message_copy");
@@ -129,9 +135,15 @@ int launch_group(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGr
     if (g.ci == 0) {
       rc = launch_copy(b, a, n);
     } else if (g.ci > 0) {
-      rc = launch_t0_part0(b, a, n, g.ci, g.cs);
-      if (rc == PGBP_NOT_MINE) rc = launch_t0_part1(b, a, n, g.ci, g.cs);
-      if (rc == PGBP_NOT_MINE) rc = launch_t0_part2(b, a, n, g.ci, g.cs);
+      if (b->group_size > 1) {
+        rc = launch_t0s_part0(b, a, n, g.ci, g.cs);
+        if (rc == PGBP_NOT_MINE) rc = launch_t0s_part1(b, a, n, g.ci, g.cs);
+        if (rc == PGBP_NOT_MINE) rc = launch_t0s_part2(b, a, n, g.ci, g.cs);
+      } else {
+        rc = launch_t0_part0(b, a, n, g.ci, g.cs);
+        if (rc == PGBP_NOT_MINE) rc = launch_t0_part1(b, a, n, g.ci, g.cs);
+        if (rc == PGBP_NOT_MINE) rc = launch_t0_part2(b, a, n, g.ci, g.cs);
+      }
       if (rc == PGBP_NOT_MINE) PGBP_FAIL(PGBP_ESTATE, "no specialised kernel for shape (%d,%d)", g.ci, g.cs);
     } else {  // medium / large class: the group is uniform in (I, S) = (g.maxm, g.cs)
       rc = launch_medium(b, a, n, g.maxm, g.cs);
@@ -182,6 +194,8 @@ MsgArgs make_args(pgbp_batch* b, uint32_t opts, int32_t ref_base, bool use_done)
   a.done = use_done ? b->done : nullptr;
   a.B = b->chunk_end > 0 ? b->chunk_end : b->B;
   a.e0 = b->chunk_begin;
+  a.gs = b->group_size;
+  a.calflagJ = b->calflagJ;
   a.ld = b->ld;
   a.opts = opts;
   a.ref_base = ref_base;
@@ -215,7 +229,7 @@ int run_walk(pgbp_batch* b, int tree, int first, int count, uint32_t opts, int32
 
 bool use_walk(const pgbp_batch* b, int tree) {
   const Tree& tr = b->plan->trees[tree];
-  if (!tr.walkable || b->plan->ntraits > PGBP_WALK_MAXP) return false;
+  if (!tr.walkable || b->plan->ntraits > PGBP_WALK_MAXP || b->group_size > 1) return false;
   // measured on B200 (lazaridis p=3, B=65536): level-parallel 70.3M calibrations/s, walk 46.5M
   // (8 warps/SM at 255 registers cannot hide HBM latency) => the walk kernel is opt-in only
   return b->walk_mode == 1;
@@ -224,7 +238,7 @@ bool use_walk(const pgbp_batch* b, int tree) {
 // tile-walk applies to: tiny messages (sender dimension <= 4), no KL update, and a schedule deep
 // enough that per-step launches are latency-bound (>= 24 steps averaging < 64 messages)
 static bool use_tilewalk(const pgbp_batch* b, const Traversal& tv, uint32_t opts) {
-  if (b->tilewalk_mode == 0 || (opts & PGBP_CAL_RESIDKLDIV) || tv.max_mF > 4 || tv.msgs.empty()) return false;
+  if (b->tilewalk_mode == 0 || (opts & PGBP_CAL_RESIDKLDIV) || tv.max_mF > 4 || tv.msgs.empty() || b->group_size > 1) return false;
   // Measured on B200 (muller_2022 Bethe, B = 16,384): 309.7 ms per 10 iterations against 105.2 ms for the
   // level-parallel launches -- the first steps of a postorder traversal hold hundreds of messages that 8
   // lanes serialise.  Opt-in only until wide steps are split off into ordinary launches.
@@ -241,7 +255,7 @@ int run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_t ref_b
     for (int st = 0; st < tv.nsteps; st++)
       for (int m = tv.step_off[st]; m < tv.step_off[st + 1]; m++)
         for (int64_t e = a.e0; e < a.B; e++) {
-          if (tv.msgs[m].mF == tv.msgs[m].s) message_copy_thread(a, m, e);
+          if (tv.msgs[m].mF == tv.msgs[m].s) message_copy_thread<false>(a, m, e);
           else message_thread_rt<4>(a, m, e);
         }
 #else
@@ -261,10 +275,15 @@ int run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_t ref_b
 // iscalibrated_residnorm(beliefs) = AND over all directed messages
 // (src/clustergraphbeliefs.jl:168-169); with auto, freeze calibrated elements.
 PGBP_HD void iscal_thread(const uint8_t* calflag, int nd, int64_t ld, const int32_t* status, uint8_t* done,
-                          int32_t* iscal, int32_t* itertree, int32_t it, int32_t tr, int autostop, int64_t e) {
+                          int32_t* iscal, int32_t* itertree, int32_t it, int32_t tr, int autostop, int64_t e,
+                          const uint8_t* calflagJ, int64_t gs) {
   if (done && done[e]) return;  // frozen: keeps its (true) result
   int ok = status[e] == 0;
   for (int d = 0; d < nd && ok; d++) ok = calflag[(int64_t)d * ld + e] != 0;
+  if (gs > 1) {  // shared-precision mode: the J part of every flag lives in the group leader's column
+    const int64_t ej = e - e % gs;
+    for (int d = 0; d < nd && ok; d++) ok = calflagJ[(int64_t)d * ld + ej] != 0;
+  }
   iscal[e] = ok;
   if (ok) {
     if (itertree && itertree[e] == 0) {
@@ -277,10 +296,11 @@ PGBP_HD void iscal_thread(const uint8_t* calflag, int nd, int64_t ld, const int3
 
 #ifndef PGBP_HOST_EMUL
 __global__ void k_iscal(const uint8_t* calflag, int nd, int64_t e0, int64_t B, int64_t ld, const int32_t* status,
-                        uint8_t* done, int32_t* iscal, int32_t* itertree, int32_t it, int32_t tr, int autostop) {
+                        uint8_t* done, int32_t* iscal, int32_t* itertree, int32_t it, int32_t tr, int autostop,
+                        const uint8_t* calflagJ, int64_t gs) {
   const int64_t e = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= B) return;
-  iscal_thread(calflag, nd, ld, status, done, iscal, itertree, it, tr, autostop, e);
+  iscal_thread(calflag, nd, ld, status, done, iscal, itertree, it, tr, autostop, e, calflagJ, gs);
 }
 #endif
 
@@ -289,10 +309,11 @@ static int launch_iscal(pgbp_batch* b, int it, int tr, int autostop) {
   const int64_t e0 = b->chunk_begin, e1 = b->chunk_end > 0 ? b->chunk_end : b->B;
 #ifdef PGBP_HOST_EMUL
   for (int64_t e = e0; e < e1; e++)
-    iscal_thread(b->calflag, nd, b->ld, b->status, b->done, b->iscal, b->itertree, it, tr, autostop, e);
+    iscal_thread(b->calflag, nd, b->ld, b->status, b->done, b->iscal, b->itertree, it, tr, autostop, e, b->calflagJ, b->group_size);
 #else
   k_iscal<<<(unsigned)((e1 - e0 + 255) / 256), 256, 0, b->stream>>>(b->calflag, nd, e0, e1, b->ld, b->status, b->done,
-                                                                     b->iscal, b->itertree, it, tr, autostop);
+                                                                     b->iscal, b->itertree, it, tr, autostop, b->calflagJ,
+                                                                     b->group_size);
 #endif
   b->launches++;
   return check_launch("k_iscal");
@@ -305,17 +326,17 @@ int integrate_launch(pgbp_batch* b, int belief, double* d_mu_soa, double* d_norm
   const int64_t js = p->jslot[belief], hs = p->hslot[belief], gs = p->gslot[belief];
 #ifdef PGBP_HOST_EMUL
   for (int64_t e = 0; e < b->B; e++)
-    integrate_thread<PGBP_MAX_DIM>(b->state, b->status, b->ld, e, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa);
+    integrate_thread<PGBP_MAX_DIM>(b->state, b->status, b->ld, e, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, b->group_size);
 #else
   const unsigned grid = (unsigned)((b->B + 127) / 128);
   if (M <= 4)
-    k_integrate<4><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa);
+    k_integrate<4><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, b->group_size);
   else if (M <= 12)
-    k_integrate<12><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa);
+    k_integrate<12><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, b->group_size);
   else if (M <= 32)
-    k_integrate<32><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa);
+    k_integrate<32><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, b->group_size);
   else
-    k_integrate<PGBP_MAX_DIM><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa);
+    k_integrate<PGBP_MAX_DIM><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, b->group_size);
 #endif
   b->launches++;
   return check_launch("k_integrate");
@@ -340,6 +361,8 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
   if (niter < 1) PGBP_FAIL(PGBP_EINVAL, "niter < 1");
   if ((flags & (PGBP_CAL_RESIDNORM | PGBP_CAL_AUTO)) && !b->calflag)
     PGBP_FAIL(PGBP_ESTATE, "residual tracking requested but the batch was created without PGBP_BATCH_RESIDUALS");
+  if (b->group_size > 1 && (flags & PGBP_CAL_AUTO))
+    PGBP_FAIL(PGBP_EINVAL, "auto-stop is per element: not available in shared-precision mode (the group's J keeps moving)");
   if ((flags & PGBP_CAL_RESIDKLDIV) && !b->kldiv)
     PGBP_FAIL(PGBP_ESTATE, "update_residualkldiv requested but the batch was created without PGBP_BATCH_RESIDUALS");
   std::vector<int32_t> ids;
@@ -449,7 +472,8 @@ static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int
   // (threads per launch ~ B x messages per step) and the chunks stay >= 8192 elements
   int nchunk = 1;
 #ifndef PGBP_HOST_EMUL
-  if (b->pipeline > 1) nchunk = b->pipeline;
+  if (b->group_size > 1) nchunk = 1;  // chunks on different streams would race on the shared J rows
+  else if (b->pipeline > 1) nchunk = b->pipeline;
   else if (b->pipeline < 0) {
     int64_t nmsg = 0, nlaunch = 0;
     for (int t : ids)

@@ -62,7 +62,8 @@ static int launch_smem(pgbp_batch* b, const MsgArgs& a, int nmsg, int I, int S) 
 int launch_medium(pgbp_batch* b, const MsgArgs& a, int n, int I, int S) {
       const int M = I + S;
       int rc = 0;
-      const int mode = b->coop_mode;
+      // shared-precision mode: only the register / generic / copy bodies know about group leaders
+      const int mode = b->group_size > 1 ? 0 : b->coop_mode;
       const bool fits = I <= 32 && sizeof(double) * 32 * (size_t)(I * (I + 1) / 2 + I * S + I) + 4 * (size_t)(M * (M + 3) / 2 + S * (S + 3) / 2 + 2) <= PGBP_SMEM_LIMIT;
       if ((mode == -1 || mode == 1) && fits) {
         switch (I) {
@@ -77,6 +78,8 @@ int launch_medium(pgbp_batch* b, const MsgArgs& a, int n, int I, int S) {
         if (M <= 16) rc = (mode == 4) ? launch_coop<16, 4>(b, a, n) : launch_coop<16, 8>(b, a, n);
         else if (M <= 24) rc = launch_coop<24, 8>(b, a, n);
         else rc = launch_coop<32, 8>(b, a, n);
+      } else if (b->group_size > 1) {
+        rc = (M <= 32) ? launch_message<-1, -1, 32, true>(b, a, n) : launch_message<-1, -1, 64, true>(b, a, n);
       } else if (M <= 32) {
         rc = launch_message<-1, -1, 32>(b, a, n);
       } else {

@@ -766,3 +766,64 @@ def test_calibrate_optimize_cliquetree_goldens(backend):
     theta, ll, res = pgbp_b200.calibrate_optimize_cliquetree(c.plan, c.sched[0], yd, start=(1.0, 0.0), maxiter=60)
     assert abs(ll / -3.2763180687070053 - 1) <= 1e-9
     assert abs(theta[0] / 0.5932930079336234 - 1) <= 1e-4 and abs(theta[1] / -0.07534357691418593 - 1) <= 1e-4
+
+
+# ------------------------------------------------------------------ shared-precision batches (trait replicates under one theta)
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("p,method", [(3, "cliquetree"), (1, "bethe"), (6, "cliquetree")])
+def test_shared_precision_batch_is_bit_identical(backend, p, method):
+    # groups of elements that share a parameter vector store / update their J once (pgbp_batch_create_shared);
+    # every result must equal the ordinary batch (each element its own J) bit for bit: beliefs, residuals,
+    # flags, log-likelihood, factored energy, KL divergences, with and without regularisation
+    lib = get_lib(backend)
+    rng = np.random.default_rng(500 + p)
+    taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
+    ntheta, nd = 3, 8
+    B = ntheta * nd
+    Rs = []
+    for _ in range(ntheta):
+        A = rng.normal(size=(p, p))
+        Rs.append(A @ A.T / p + 0.1 * np.eye(p))
+    mu = rng.normal(size=p)
+    data = rng.normal(size=(nd, 7, p))
+    model = M.MvFullBrownianMotion(Rs[0], mu)
+    kw = dict(order_hint=GOLD["lazaridis_cluster_labels"]) if method == "cliquetree" else {}
+    case = Case(GOLD["lazaridis"], method, data[0], taxa, model, lib, **kw)
+    params = np.stack([pgbp_b200.bm_params([R], mu) for R in Rs])
+    out = {}
+    for name, group in (("own", 0), ("shared", nd)):
+        bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B, shared_precision_group=group)
+        bt.assignfactors(params, data, pairing="product")  # element e = (theta e // nd, data set e % nd)
+        rec = {"assigned": [bt.get_belief(j) for j in range(1, len(case.b) + 1)]}
+        if method == "bethe":
+            bt.regularizebeliefs_bycluster()
+        succ, iscal = bt.calibrate(case.sched, 2, update_residualkldiv=True)
+        rec.update(succ=succ, iscal=iscal, st=bt.status(),
+                   beliefs=[bt.get_belief(j) for j in range(1, len(case.b) + 1)],
+                   res=[bt.get_residual(case.nclusters + 1 + j, case.plan.sepset_clusters[j][s] + 1)
+                        for j in range(case.plan.nsepsets) for s in (0, 1)],
+                   ll=bt.integratebelief(case.sched[0][2][0])[1], fe=bt.factored_energy(),
+                   cov=bt.integratebelief_cov(case.sched[0][2][0]))
+        out[name] = rec
+    a, b_ = out["own"], out["shared"]
+    assert a["succ"].all() and np.array_equal(a["succ"], b_["succ"]) and np.array_equal(a["iscal"], b_["iscal"])
+    assert np.array_equal(a["st"], b_["st"])
+    for key in ("assigned", "beliefs"):
+        for x, y in zip(a[key], b_[key]):
+            for u, v in zip(x, y):
+                assert np.array_equal(u, v), key
+    for x, y in zip(a["res"], b_["res"]):
+        for u, v in zip(x, y):
+            assert np.array_equal(u, v)
+    assert np.array_equal(a["ll"], b_["ll"]) and np.array_equal(a["fe"], b_["fe"])
+    for u, v in zip(a["cov"], b_["cov"]):
+        assert np.array_equal(u, v)
+    # API restrictions of the shared mode
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B, shared_precision_group=nd)
+    with pytest.raises(pgbp_b200.PgbpError):
+        bt.assignfactors(params[:1].repeat(B, axis=0), data[:1].repeat(B, axis=0))  # zip with B parameter sets
+    bt.assignfactors(params, data, pairing="product")
+    with pytest.raises(pgbp_b200.PgbpError):
+        bt.calibrate(case.sched, 2, auto=True)
+    with pytest.raises(pgbp_b200.PgbpError):
+        pgbp_b200.BatchedClusterGraphBelief(case.plan, B, shared_precision_group=5)
