@@ -179,11 +179,14 @@ mutable struct BatchedClusterGraphBelief
     plan::Plan
     B::Int
     schedule::Vector            # the spanning trees the plan was built with (for tree ids)
-    function BatchedClusterGraphBelief(plan::Plan, B::Integer, schedule; device::Integer=0, factors=true, residuals=true)
+    # sharedgroup = g > 1: the g consecutive elements of a group are trait replicates under one parameter
+    # vector; their (identical) precisions J are stored and updated once per group
+    function BatchedClusterGraphBelief(plan::Plan, B::Integer, schedule; device::Integer=0, factors=true, residuals=true,
+                                       sharedgroup::Integer=0)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         fl = (factors ? BATCH_FACTORS : UInt32(0)) | (residuals ? BATCH_RESIDUALS : UInt32(0))
-        check(ccall((:pgbp_batch_create, LIB), Int32, (Ptr{Cvoid}, Int64, Int32, UInt32, Ref{Ptr{Cvoid}}),
-                    plan.handle, B, device, fl, h))
+        check(ccall((:pgbp_batch_create_shared, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int32, UInt32, Ref{Ptr{Cvoid}}),
+                    plan.handle, B, sharedgroup, device, fl, h))
         b = new(h[], plan, B, collect(schedule))
         finalizer(x -> ccall((:pgbp_batch_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle), b)
     end
