@@ -210,7 +210,50 @@ class C3(C2):
     cpu_kw = dict(post=True, pre=True, residnorm=True, niter=10, reg_bycluster=True)
 
 
-WORKLOADS = {"c2": C2, "c2s": C2S, "c3": C3, "c4": C4}
+class C5(C4):
+    """BASELINE configs[4]: synthetic 100k-tip network with 10k reticulations, MvFullBrownianMotion p=16, one
+    theta, replicate batch as large as HBM allows per GPU (0.92 GB of state per replicate), sharded by
+    replicate across GPUs."""
+    key = "c5"
+    unit = "calibrations/s"
+    default_batch = 128
+    ncolors = 1
+    residuals = False
+    workload = ("synthetic level-1 network, 100,000 tips + 10,000 reticulations (219,999 nodes; clique tree of 209,998 "
+                "clusters, sender dimensions 16 / 32 / 48), MvFullBrownianMotion p=16, one parameter vector, 128 simulated "
+                "trait replicates per GPU (0.92 GB of state each: 118 GB of the 180 GB), assignfactors! + calibrate! "
+                "(post+pre order) + integratebelief!(root) [BASELINE configs[4]]")
+    step_text = "assign_factors (K1, generic path: p = 16) + calibrate (419,994 messages) + integrate(root)"
+    e2e_text = "pinned host tip data -> assignfactors (H2D + K1) -> calibrate -> integratebelief -> D2H loglik"
+    kernel_text = "k_message* family (419,994 messages of one calibration; (16,16) shared-memory kernel, (32,16) generic)"
+    cpu_text = "assignfactors + calibrate + integratebelief per replicate"
+
+    def __init__(self, ntips=100000, nretic=10000, p=16):
+        from workloads import synth
+        net = synth.level1_network(ntips, nretic, SEED + 5)
+        self.col = None
+        self.d = synth.cliquetree_plan(net, p, True, None, name="synthetic_level1_%d" % ntips)
+        self.synth = synth
+
+    def inputs(self, B, rank):
+        d = self.d
+        p = d["ntraits"]
+        rng = np.random.Generator(np.random.PCG64(SEED + 5 + 1000 * rank))
+        A = rng.normal(size=(p, p))
+        R = A @ A.T / p + 0.1 * np.eye(p)
+        tips = self.synth.simulate_tips(d, lambda v, k: R, B, SEED + 50 + rank)
+        params = np.concatenate([R.reshape(-1), np.zeros(p), np.zeros(p * p)])[None]
+        return params, tips
+
+    def cost(self, plan):
+        by = plan.traversal_cost(0, 0, False)[0] + plan.traversal_cost(0, 1, False)[0]
+        fl = plan.traversal_cost(0, 0, False)[1] + plan.traversal_cost(0, 1, False)[1]
+        return by, fl
+
+    cpu_kw = dict(post=True, pre=True, residnorm=False)
+
+
+WORKLOADS = {"c2": C2, "c2s": C2S, "c3": C3, "c4": C4, "c5": C5}
 
 
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
@@ -381,7 +424,8 @@ def run_gpu(args):
         bt.set_tilewalk_mode(args.tilewalk)
     root = d["root_cluster"] + 1
     bytes_unit, flops_unit = w.cost(plan)
-    nmsg = ({"c2": 2 * len(d["trees"][0][0]), "c2s": 2 * len(d["trees"][0][0]), "c4": len(d["trees"][0][0])}.get(w.key)
+    nmsg = ({"c2": 2 * len(d["trees"][0][0]), "c2s": 2 * len(d["trees"][0][0]), "c4": len(d["trees"][0][0]),
+             "c5": 2 * len(d["trees"][0][0])}.get(w.key)
             or 4 * len(d["trees"][0][0]) * w.niter)
     upe = getattr(w, "niter", 1)  # metric units per element per step
 
@@ -443,12 +487,13 @@ def run_gpu(args):
     else:
         d_params = torch.from_numpy(params).to(dev)
         d_tips = torch.from_numpy(tips).to(dev)
+        direction = L.CAL_BOTH if w.key == "c5" else L.CAL_POSTORDER
 
         def step(ev=None):
             bt.assignfactors_device(d_params.data_ptr(), params.shape[0], d_tips.data_ptr(), tips.shape[0], ncolors=w.ncolors)
             if ev:
                 ev[0].record(stream)
-            bt.calibrate_async(None, 1, update_residualnorm=False, direction=L.CAL_POSTORDER)
+            bt.calibrate_async(None, 1, update_residualnorm=False, direction=direction)
             if ev:
                 ev[1].record(stream)
             finish()
@@ -522,6 +567,9 @@ def run_gpu(args):
             succ, iscal = b_.calibrate(None, w.niter)
             results[i] = b_.factored_energy()[:, 2]
             return
+        elif w.key == "c5":
+            b_.assignfactors(params, pin_np[i])
+            succ, _ = b_.calibrate(None, 1, update_residualnorm=False)
         else:
             b_.assignfactors(pin_np[i], tips, ncolors=w.ncolors)
             succ = b_.propagate_1traversal_postorder(0, update_residualnorm=False)

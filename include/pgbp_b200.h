@@ -226,6 +226,13 @@ int32_t pgbp_assign_factors_device(pgbp_batch* batch, int32_t ncolors, const dou
                                    int64_t nparamsets, const double* d_tipdata, int64_t ndatasets,
                                    int32_t pairing);
 
+/* assignfactors! for the univariate Ornstein-Uhlenbeck model
+ * (src/evomodels/homogeneousornsteinuhlenbeck.jl:18-66; generic linear-Gaussian factors of
+ * src/evomodels/evomodels.jl:208-245, 314-330).  params: nparamsets records (sigma2, alpha, theta, mu, v),
+ * v == 0 fixed root, Inf improper; ntraits must be 1; tipdata / pairing as above. */
+int32_t pgbp_assign_factors_ou(pgbp_batch* batch, const double* params, int64_t nparamsets,
+                               const double* tipdata, int64_t ndatasets, int32_t pairing);
+
 /* ---------------------------------------------------------------- message passing */
 #define PGBP_CAL_POSTORDER 1u       /* propagate_1traversal_postorder! (src/calibration.jl:111-135) */
 #define PGBP_CAL_PREORDER 2u        /* propagate_1traversal_preorder!  (src/calibration.jl:137-161) */

@@ -69,6 +69,7 @@ SIGNATURES = {
     "pgbp_reset_from_factors": (i32, [vp]),
     "pgbp_reset_calibration_flags": (i32, [vp, i32]),
     "pgbp_assign_factors": (i32, [vp, i32, P(f64), i64, P(f64), i64, i32]),
+    "pgbp_assign_factors_ou": (i32, [vp, P(f64), i64, P(f64), i64, i32]),
     "pgbp_assign_factors_device": (i32, [vp, i32, vp, i64, vp, i64, i32]),
     "pgbp_calibrate": (i32, [vp, P(i32), i32, i32, u32, P(i32), P(i32), P(i32)]),
     "pgbp_calibrate_async": (i32, [vp, P(i32), i32, i32, u32]),

@@ -367,6 +367,19 @@ class BatchedClusterGraphBelief:
 
     init_factors_frommodel = assignfactors
 
+    def assignfactors_ou(self, params, tipdata, pairing="zip"):
+        """assignfactors! for UnivariateOrnsteinUhlenbeck on the device.  params: (nparamsets, 5) records
+        (sigma2, alpha, theta, mu, v) with v = 0 fixed root, inf improper; tipdata: (ndatasets, ntips, 1)."""
+        pa = np.ascontiguousarray(np.atleast_2d(np.asarray(params, dtype=float)))
+        if pa.shape[1] != 5:
+            raise ValueError("OU parameter records are (sigma2, alpha, theta, mu, v)")
+        td = np.asarray(tipdata, dtype=float)
+        if td.ndim == 2:
+            td = td[None]
+        td = np.ascontiguousarray(td)
+        pr = {"zip": L.PAIR_ZIP, "product": L.PAIR_PRODUCT}[pairing]
+        self.lib.check(self.lib.pgbp_assign_factors_ou(self.handle, _fptr(pa), pa.shape[0], _fptr(td), td.shape[0], pr))
+
     def assignfactors_device(self, d_params_ptr, nparamsets, d_tip_ptr, ndatasets, ncolors=1, pairing="zip"):
         """assignfactors! with the parameter / tip-data records already on the device (enqueue only)."""
         pr = {"zip": L.PAIR_ZIP, "product": L.PAIR_PRODUCT}[pairing]

@@ -251,6 +251,90 @@ struct AssignBody {
 // families add into them.  Only clusters with scope entries that no family covers are zero-filled
 // first (flag bit 0).  No thread-local arrays except for heterogeneous hybrids whose parent edges
 // differ in colour (a p x p inverse per element, src/evomodels/heterogeneousmodels.jl:135-150).
+// K1 for the univariate Ornstein-Uhlenbeck model (src/evomodels/homogeneousornsteinuhlenbeck.jl:51-66) -- and,
+// through it, the generic linear-Gaussian factor X_v ~ N(sum_k gamma_k (q_k x_k + omega_k), sum_k gamma_k^2 v_k)
+// of src/evomodels/evomodels.jl:208-245, 314-330 for one trait:
+//   q_k = exp(-alpha t_k), v_k = gamma2 (1 - q_k^2), omega_k = (1 - q_k) theta,  gamma2 = sigma2 / (2 alpha).
+// With c = (1, -gamma_1 q_1, ..), z = sum over fixed members c_a y_a - omega:  J_ab += c_a c_b j,
+// h_b -= c_b j z, g += g0 - j z^2 / 2, g0 = -(log 2pi + log v)/2  (the same absorbed form as the BM path).
+// params: AoS records (sigma2, alpha, theta, mu, v);  v == 0 fixed root, v == Inf improper, else proper.
+struct AssignOU {
+  FamDev F;
+  const double* params;  // [np][5]
+  const double* tip;     // SoA [ntips][ldd]
+  int64_t ldd;
+  double* state;
+  int32_t* status;
+  int64_t ld, np, nd;
+  int pairing;
+  int64_t gs = 0;
+  int y0 = 0;
+  PGBP_HD void operator()(int64_t e, int y) const {
+    const int c = y + y0;
+    int64_t ip, id;
+    if (pairing == PGBP_PAIR_PRODUCT) { ip = e / nd; id = e % nd; }
+    else { ip = np == 1 ? 0 : e; id = nd == 1 ? 0 : e; }
+    const double* th = params + 5 * ip;
+    const double sigma2 = th[0], alpha = th[1], theta = th[2], mu = th[3], v = th[4];
+    const double* td = tip + id;
+    double* st = state + e;
+    const bool lead = gs > 1 ? (e % gs == 0) : true;
+    const int64_t js = F.cl_jslot[c], hs = F.cl_hslot[c], gsl = F.cl_gslot[c];
+    const int m = F.cl_dim[c];
+    if (lead) for (int q = 0; q < tri(m); q++) st[(js + q) * ld] = 0.0;
+    for (int q = 0; q < m; q++) st[(hs + q) * ld] = 0.0;
+    if (!(sigma2 > 0.0) || !(alpha > 0.0)) {  // the reference's constructor rejects these
+      if (c == 0) status_fail(status, e, PGBP_STATUS(0x7ffffd, 1));
+      st[gsl * ld] = NAN;
+      return;
+    }
+    const double gamma2 = sigma2 / (2.0 * alpha);
+    double g = 0.0;
+    for (int iv = F.clu_off[c]; iv < F.clu_off[c + 1]; iv++) {
+      const int vtx = F.clu_node[iv];
+      const int k0 = F.mem_off[vtx], nm = F.mem_off[vtx + 1] - k0;
+      if (nm == 1) {  // root prior, as for UnivariateBrownianMotion (src/evomodels/evomodels.jl:377-396)
+        const int pos = F.mem_pos[k0];
+        if (pos < 0 || v == 0.0 || v == INFINITY) continue;
+        const double jr = 1.0 / v;
+        if (lead) st[(js + pk(pos, pos)) * ld] += jr;
+        st[(hs + pos) * ld] += jr * mu;
+        g += 0.5 * (-PGBP_LOG2PI + log(jr) - mu * (jr * mu));
+        continue;
+      }
+      double cf[PGBP_MAX_FAMILY];
+      double var = 0.0, omega = 0.0;
+      cf[0] = 1.0;
+      for (int a = 1; a < nm; a++) {
+        const double t = F.mem_length[k0 + a], gam = nm == 2 ? 1.0 : F.mem_gamma[k0 + a];
+        const double q = exp(-alpha * t);
+        var += gam * gam * (gamma2 * (1.0 - q * q));
+        omega += gam * ((1.0 - q) * theta);
+        cf[a] = -(gam * q);
+      }
+      const double j = 1.0 / var;
+      double z = -omega;
+      for (int a = 0; a < nm; a++) {
+        if (F.mem_pos[k0 + a] >= 0) continue;
+        z += cf[a] * (a == 0 ? td[(int64_t)F.node_datarow[vtx] * ldd] : mu);
+      }
+      if (z != z) status_fail(status, e, PGBP_STATUS(0x7ffffa, 1));  // missing tip value
+      g += -0.5 * (PGBP_LOG2PI + log(var)) - 0.5 * (z * (j * z));
+      for (int a = 0; a < nm; a++) {
+        const int pa = F.mem_pos[k0 + a];
+        if (pa < 0) continue;
+        st[(hs + pa) * ld] -= cf[a] * (j * z);
+        for (int bq = a; lead && bq < nm; bq++) {
+          const int pb = F.mem_pos[k0 + bq];
+          if (pb < 0) continue;
+          st[(js + pk(pa, pb)) * ld] += (cf[a] * cf[bq]) * j;
+        }
+      }
+    }
+    st[gsl * ld] = g;
+  }
+};
+
 PGBP_HD double* kaddr(char* base, uint32_t slot, uint32_t ld8) {
   return (double*)(base + (uint64_t)slot * (uint64_t)ld8);  // one IMAD.WIDE.U32
 }
@@ -929,6 +1013,36 @@ static int assign_enqueue(pgbp_batch* b, pgbp::DevTables* dt, int32_t ncolors, c
   PGBP_TRY(batch_zero_sepsets(b, true));
   if (b->factor) PGBP_TRY(d2d(b->factor, b->state, sizeof(double) * (size_t)p->nslots_factor * (size_t)b->ld, b->stream));
   return 0;
+}
+
+int32_t pgbp_assign_factors_ou(pgbp_batch* b, const double* params, int64_t nparamsets, const double* tipdata,
+                               int64_t ndatasets, int32_t pairing) {
+  if (!b || !params) PGBP_FAIL(PGBP_EINVAL, "null argument");
+  if (b->plan->ntraits != 1) PGBP_FAIL(PGBP_EINVAL, "the Ornstein-Uhlenbeck model of the reference is univariate");
+  if (b->plan->has_families && b->plan->fam.ntips > 0 && !tipdata) PGBP_FAIL(PGBP_EINVAL, "null tip data");
+  pgbp::DevTables* dt;
+  PGBP_TRY(assign_prepare(b, 1, nparamsets, ndatasets, pairing, &dt));
+  const pgbp_plan* p = b->plan;
+  const FamilyTable& F = p->fam;
+  const size_t nparam = (size_t)(5 * nparamsets), ntip = (size_t)((int64_t)F.ntips * ndatasets);
+  PGBP_TRY(batch_need_scratch(b, sizeof(double) * (nparam + ntip + 1)));
+  PGBP_TRY(h2d(b->scratch, params, sizeof(double) * nparam, b->stream));
+  if (ntip) {
+    PGBP_TRY(h2d(b->scratch + nparam, tipdata, sizeof(double) * ntip, b->stream));
+    const int64_t saveB = b->B;
+    b->B = ndatasets;
+    int rc = aos_to_soa(b, b->scratch + nparam, F.ntips, nullptr, dt->tip, dt->ldd);
+    b->B = saveB;
+    PGBP_TRY(rc);
+  }
+  FamDev fd{dt->node_cluster, dt->mem_off, dt->mem_pos, dt->mem_length, dt->mem_gamma, dt->mem_color,
+            dt->node_datarow, dt->clu_off, dt->clu_node, dt->jslot, dt->hslot, dt->gslot, dt->dim, 1, 1, F.root_fixed};
+  AssignOU body{fd, b->scratch, dt->tip, dt->ldd, b->state, b->status, b->ld, nparamsets, ndatasets, pairing};
+  body.gs = b->group_size;
+  PGBP_TRY(launch_generic(b, "k_assign_ou", b->B, p->nclusters, body));
+  PGBP_TRY(batch_zero_sepsets(b, true));
+  if (b->factor) PGBP_TRY(d2d(b->factor, b->state, sizeof(double) * (size_t)p->nslots_factor * (size_t)b->ld, b->stream));
+  return stream_sync(b->stream);
 }
 
 int32_t pgbp_assign_factors_device(pgbp_batch* b, int32_t ncolors, const double* d_params, int64_t nparamsets,

@@ -179,3 +179,28 @@ def test_c3_muller_loopy_bethe_vs_cport():
     assert np.max(np.abs(fes[0][:128, 2] / ref["fe"][:, 2] - 1)) <= 2e-4
     assert np.max(np.abs(fes[0][:128, 0] / ref["fe"][:, 0] - 1)) <= 1e-4
     assert np.max(np.abs(fes[0][:128, 1] / ref["fe"][:, 1] - 1)) <= 1e-4
+
+
+def test_c5_shapes_reduced_network_vs_cport():
+    # BASELINE configs[4] at reduced size (2,000 tips instead of 100,000; the full network is a bench
+    # workload: python bench.py --workload c5): MvFullBM p = 16, sender dimensions 16 / 32 / 48 -- the
+    # (16,16) messages through the shared-memory kernel, (32,16) through the generic kernel --
+    # full calibration, log-likelihood at the root and at distant clusters against the C twin
+    lib = get_lib("cuda")
+    w = bench.C5(ntips=2000, nretic=200)
+    B = 6
+    params, tips = w.inputs(B, 0)
+    plan = plan_of(w, lib)
+    root = w.d["root_cluster"] + 1
+    ref = COracle.from_plan_dict(w.d).run_batch(params, tips, root_belief=w.d["root_cluster"], B=B, **w.cpu_kw)
+    assert (ref["status"] == 0).all()
+    bt = pgbp_b200.BatchedClusterGraphBelief(plan, B, factors=False, residuals=False)
+    bt.assignfactors(params, tips)
+    succ, _ = bt.calibrate(None, 1, update_residualnorm=False)
+    assert succ.all()
+    ll = bt.integratebelief(root, want_mu=False)[1]
+    assert np.max(np.abs(ll / ref["loglik"] - 1)) <= TOL
+    rng = np.random.default_rng(6)
+    for j in rng.choice(plan.nclusters, size=10, replace=False) + 1:
+        if bt.dimension(int(j)) > 0:
+            assert np.max(np.abs(bt.integratebelief(int(j), want_mu=False)[1] / ll - 1)) <= 1e-8, j

@@ -827,3 +827,31 @@ def test_shared_precision_batch_is_bit_identical(backend, p, method):
         bt.calibrate(case.sched, 2, auto=True)
     with pytest.raises(pgbp_b200.PgbpError):
         pgbp_b200.BatchedClusterGraphBelief(case.plan, B, shared_precision_group=5)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_assignfactors_ou_device_vs_oracle_and_golden(backend):
+    # UnivariateOrnsteinUhlenbeck factors assigned on the device (generic linear-Gaussian factor, one trait):
+    # every cluster against the oracle's assignfactors!, log-likelihood against test/test_evomodels.jl:120
+    # (-42.31401134496844 for OU(2, 3, -2, 0.0, 0.4) on trait y), for random, fixed and improper roots
+    lib = get_lib(backend)
+    tbl = TBL[:, [1]]
+    recs = [(2.0, 3.0, -2.0, 0.0, 0.4), (0.7, 0.4, 1.5, -0.3, 0.0), (1.3, 1.1, 0.2, 0.0, math.inf)]
+    for k, (s2, al, th, mu, v) in enumerate(recs):
+        model = M.UnivariateOrnsteinUhlenbeck(s2, al, th, mu, None if v == 0.0 else v)
+        case = Case(GOLD["netstr_named"], "cliquetree", tbl, TAXA, model, lib, schedule="spanningtree")
+        B = 3
+        data = np.stack([tbl, tbl + 0.25, 2 * tbl])
+        bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+        bt.assignfactors_ou([[s2, al, th, mu, v]], data)
+        assert (bt.status() == 0).all()
+        cgbs = [case.oracle_cgb(tbl=data[e]) for e in range(B)]
+        check_all_beliefs(case, bt, cgbs)
+        spt = case.sched[0]
+        assert bt.propagate_1traversal_postorder(spt).all()
+        ll = bt.integratebelief(spt[2][0])[1]
+        for e in range(B):
+            assert OBP.propagate_1traversal_postorder(cgbs[e], *spt)
+            assert abs(ll[e] / OBP.integratebelief_cgb(cgbs[e], spt[2][0])[1] - 1) <= TOL
+        if k == 0:
+            assert abs(ll[0] / -42.31401134496844 - 1) <= 1e-9
