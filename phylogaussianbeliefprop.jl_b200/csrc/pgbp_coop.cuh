@@ -84,10 +84,12 @@ __global__ void __launch_bounds__(128) k_message_coop(MsgArgs a) {
   for (int j = 0; j < NJ; j++) dk[j] = 1.0;
   double ww = 0.0;
   int fail_pivot = 0;
-#pragma unroll
-  for (int k = 0; k < MAXM; k++) {
-    if (k >= I) break;
-    const int jk = k / G, gk = k % G;  // compile-time after unrolling
+  // (static_for: the pivot index must be a compile-time constant for the register arrays, also at MAXM = 48
+  //  where a pragma-unrolled loop is left rolled by the compiler)
+  static_for<MAXM>([&](auto kc_) {
+    constexpr int k = decltype(kc_)::value;
+    if (k < I) {
+    constexpr int jk = k / G, gk = k % G;
     const int src = gk * RPW + rw;
     const double d = __shfl_sync(FULL, A[jk][k], src);
     if (!skip && fail_pivot == 0 && !(d > 0.0)) fail_pivot = k + 1;  // LAPACK potrf info (also NaN)
@@ -126,7 +128,8 @@ __global__ void __launch_bounds__(128) k_message_coop(MsgArgs a) {
         }
       }
     }
-  }
+    }
+  });
   if (fail_pivot) {
     if (active && g == 0) status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, fail_pivot));
     active = false;
@@ -137,11 +140,10 @@ __global__ void __launch_bounds__(128) k_message_coop(MsgArgs a) {
 #pragma unroll
   for (int j = 0; j < NJ; j++) lg[j] = (G * j < MAXM && g + G * j < I) ? log(dk[j]) : 0.0;
   double logdet = 0.0;
-#pragma unroll
-  for (int k = 0; k < MAXM; k++) {
-    if (k >= I) break;
-    logdet += __shfl_sync(FULL, lg[k / G], (k % G) * RPW + rw);
-  }
+  static_for<MAXM>([&](auto kc_) {
+    constexpr int k = decltype(kc_)::value;
+    if (k < I) logdet += __shfl_sync(FULL, lg[k / G], (k % G) * RPW + rw);
+  });
   double gnew = g_old;
   if (!skip) gnew += 0.5 * ((double)I * PGBP_LOG2PI - logdet + ww);
 

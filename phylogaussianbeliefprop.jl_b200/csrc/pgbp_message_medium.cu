@@ -77,7 +77,8 @@ int launch_medium(pgbp_batch* b, const MsgArgs& a, int n, int I, int S) {
       } else if (mode != 0 && M <= PGBP_COOP_MAX) {
         if (M <= 16) rc = (mode == 4) ? launch_coop<16, 4>(b, a, n) : launch_coop<16, 8>(b, a, n);
         else if (M <= 24) rc = launch_coop<24, 8>(b, a, n);
-        else rc = launch_coop<32, 8>(b, a, n);
+        else if (M <= 32) rc = launch_coop<32, 8>(b, a, n);
+        else rc = launch_coop<48, 16>(b, a, n);  // 16 lanes per element: 2 elements per warp (half sectors)
       } else if (b->group_size > 1) {
         rc = (M <= 32) ? launch_message<-1, -1, 32, true>(b, a, n) : launch_message<-1, -1, 64, true>(b, a, n);
       } else if (M <= 32) {

@@ -13,7 +13,7 @@
 #define PGBP_MAX_FAMILY 8
 #define PGBP_MAX_TRAITS 16
 #define PGBP_T0_MAX 12
-#define PGBP_COOP_MAX 32
+#define PGBP_COOP_MAX 48
 #define PGBP_WALK_MAXP 4
 
 namespace pgbp {

@@ -515,7 +515,7 @@ def test_walk_kernel_matches_level_parallel_and_oracle(backend, p):
 
 # ------------------------------------------------------------------ cooperative (G lanes / element) kernel
 @pytest.mark.parametrize("backend", BACKENDS)
-@pytest.mark.parametrize("p", [4, 5, 6, 7, 8])
+@pytest.mark.parametrize("p", [4, 5, 6, 7, 8, 12])
 def test_cooperative_kernel_matches_generic_and_oracle(backend, p):
     # medium shapes (sender dimension 13..32: lazaridis 3- and 4-node cliques at p = 4..8) run in
     # the cooperative kernel; it must agree BIT FOR BIT with the one-thread-per-element generic
