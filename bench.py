@@ -422,6 +422,8 @@ def run_gpu(args):
         bt.set_graph_mode(args.graph)
     if args.tilewalk is not None:
         bt.set_tilewalk_mode(args.tilewalk)
+    if args.tw_lanes or args.tw_wide:
+        bt.set_tilewalk_params(args.tw_lanes, args.tw_wide)
     root = d["root_cluster"] + 1
     bytes_unit, flops_unit = w.cost(plan)
     nmsg = ({"c2": 2 * len(d["trees"][0][0]), "c2s": 2 * len(d["trees"][0][0]), "c4": len(d["trees"][0][0]),
@@ -546,13 +548,14 @@ def run_gpu(args):
     big = params if w.key == "c4" else tips
     e2e_steps = args.steps if w.key in ("c2", "c2s") else min(args.steps, 5)
     free_b, total_b = torch.cuda.mem_get_info()
-    two = bt.device_bytes() * 1.1 < free_b
+    nb_e2e = max(1, min(args.e2e_batches, 1 + int(free_b / (bt.device_bytes() * 1.1))))
+    two = nb_e2e > 1
     bts = [bt]
-    if two:
+    for _ in range(nb_e2e - 1):
         bts.append(pgbp_b200.BatchedClusterGraphBelief(plan, B, device=local, factors=w.residuals, residuals=w.residuals,
                                                        shared_precision_group=group))
         if args.pipeline is not None:
-            bts[1].set_pipeline(args.pipeline)
+            bts[-1].set_pipeline(args.pipeline)
     pin_np = [torch.from_numpy(big.copy()).pin_memory().numpy() for _ in bts]
     results = [None] * len(bts)
 
@@ -584,7 +587,8 @@ def run_gpu(args):
         if len(bts) == 1:
             worker(0, nsteps)
             return
-        ths = [threading.Thread(target=worker, args=(i, nsteps // 2 + (i < nsteps % 2))) for i in range(2)]
+        nb = len(bts)
+        ths = [threading.Thread(target=worker, args=(i, nsteps // nb + (i < nsteps % nb))) for i in range(nb)]
         for t in ths:
             t.start()
         for t in ths:
@@ -658,8 +662,8 @@ def run_gpu(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": w.unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "path": w.e2e_text + (" (2 batches x 2 host threads: copies of one step overlap the "
-                                                         "kernels of the other)" if two else "")},
+                "steps": e2e_steps, "path": w.e2e_text + ((" (%d batches x %d host threads: copies of one step overlap the "
+                                                          "kernels of the others)" % (nb_e2e, nb_e2e)) if two else "")},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -679,8 +683,11 @@ def main():
                     "c4 = configs[3] (10k-tip synthetic network, p=8)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-batches", type=int, default=2, help="batches (= host threads) alternating in the end-to-end arm")
     ap.add_argument("--pipeline", type=int, default=None, help="element chunks of a calibration (-1 auto, 1 off)")
     ap.add_argument("--tilewalk", type=int, default=None, help="tile-walk kernel (-1 auto, 0 off, 1 on)")
+    ap.add_argument("--tw-lanes", type=int, default=0, help="tile-walk message lanes per block (4, 8, 16)")
+    ap.add_argument("--tw-wide", type=int, default=0, help="tile-walk: steps wider than this keep their own launches")
     ap.add_argument("--graph", type=int, default=None, help="CUDA-graph replay of calibrate (-1 auto, 0 off, 1 on)")
     ap.add_argument("--walk", type=int, default=None, help="kernel strategy override: 0 level-parallel, 1 walk kernel")
     args = ap.parse_args()

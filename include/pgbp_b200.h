@@ -160,10 +160,14 @@ int32_t pgbp_batch_set_walk_mode(pgbp_batch* batch, int32_t mode);
  * >= 8192 elements when one launch cannot fill the GPU), 1 off.  Results are unaffected. */
 int32_t pgbp_batch_set_pipeline(pgbp_batch* batch, int32_t nchunks);
 /* Tile-walk kernel for deep schedules of tiny messages (sender dimension <= 4; loopy BP on Bethe-type
- * graphs): one launch per traversal, a block walks all steps for its 32 elements with a block barrier
- * between steps.  -1 automatic (default; currently = off: slower than per-step launches when some
- * steps are wide), 0 off, 1 on wherever applicable.  Results are unaffected. */
+ * graphs): one launch per run of consecutive narrow steps, a block walks the steps for its 32 elements
+ * with a block barrier between steps; steps wider than `wide` messages keep their ordinary launches.
+ * -1 automatic (default: on for traversals of >= 24 steps averaging < 32 messages), 0 off, 1 on wherever
+ * applicable.  Results are unaffected (same per-message arithmetic). */
 int32_t pgbp_batch_set_tilewalk_mode(pgbp_batch* batch, int32_t mode);
+/* Tuning of the tile-walk kernel: message lanes per block (4, 8 or 16; default 8) and the step width above
+ * which a step is launched on its own (default 64).  0 keeps the current value. */
+int32_t pgbp_batch_set_tilewalk_params(pgbp_batch* batch, int32_t lanes, int32_t wide);
 /* CUDA-graph replay of calibrate calls: -1 automatic (default: calls of >= 24 launches are captured at
  * their second occurrence and replayed afterwards), 0 off, 1 always.  Results are unaffected. */
 int32_t pgbp_batch_set_graph_mode(pgbp_batch* batch, int32_t mode);

@@ -58,6 +58,7 @@ SIGNATURES = {
     "pgbp_batch_set_pipeline": (i32, [vp, i32]),
     "pgbp_batch_set_graph_mode": (i32, [vp, i32]),
     "pgbp_batch_set_tilewalk_mode": (i32, [vp, i32]),
+    "pgbp_batch_set_tilewalk_params": (i32, [vp, i32, i32]),
     "pgbp_set_belief": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
     "pgbp_get_belief": (i32, [vp, i32, P(f64), P(f64), P(f64)]),
     "pgbp_get_factor": (i32, [vp, i32, P(f64), P(f64), P(f64)]),

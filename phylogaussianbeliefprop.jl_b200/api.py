@@ -298,6 +298,10 @@ class BatchedClusterGraphBelief:
         """-1 auto, 0 off, 1 on: one launch per traversal for deep schedules of tiny messages."""
         self.lib.check(self.lib.pgbp_batch_set_tilewalk_mode(self.handle, int(mode)))
 
+    def set_tilewalk_params(self, lanes=0, wide=0):
+        """message lanes per block (4 / 8 / 16) and the step width launched on its own; 0 = unchanged."""
+        self.lib.check(self.lib.pgbp_batch_set_tilewalk_params(self.handle, int(lanes), int(wide)))
+
     def set_graph_mode(self, mode):
         """-1 auto, 0 off, 1 on: CUDA-graph capture / replay of calibrate calls."""
         self.lib.check(self.lib.pgbp_batch_set_graph_mode(self.handle, int(mode)))

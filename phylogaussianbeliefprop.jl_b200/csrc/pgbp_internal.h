@@ -118,6 +118,7 @@ struct pgbp_batch {
   std::vector<pgbp::MsgDesc*> d_walk;  // per tree, reference order (walk kernel)
   std::vector<int32_t*> d_step_off;    // index 2*tree+dir (tile-walk kernel)
   int32_t tilewalk_mode = -1;          // -1 auto, 0 off, 1 on (where applicable)
+  int32_t tw_lanes = 8, tw_wide = 64;  // tile-walk tuning: message lanes per block, width of a step launched alone
   pgbp::MsgDesc* d_one = nullptr;      // scratch descriptor for pgbp_propagate
   double* scratch = nullptr;           // staging for host<->device transposes / outputs
   size_t scratch_bytes = 0;

@@ -58,6 +58,38 @@ PGBP_HD void walk_thread(const MsgArgs& a, int nmsg, int64_t e) {
   }
 }
 
+// Tile-walk kernel: ONE launch for a run of consecutive steps of a deep, thin schedule of tiny messages
+// (loopy BP on Bethe-type graphs: hundreds of steps of a few messages each, which per-step launches
+// execute at ~9 us of pure latency apiece).  A block owns 32 elements (threadIdx.x) and LANES message
+// lanes (threadIdx.y); it walks the steps in order, the lanes share the messages of a step,
+// __syncthreads() separates the steps.  All threads that ever touch an element's beliefs are in the same
+// block, so the block barrier (which also orders their global-memory accesses) is the only
+// synchronisation: no launch per step, no grid-wide sync.  The messages run the same register-resident
+// bodies as the level-parallel launches (message_thread_t0<I,S>, I + S <= 4; I = 0 is the streaming
+// copy) => bit-identical results.  Registers are capped (launch bounds) so that every block of the batch
+// is resident at once: the walk is latency-bound per step, a second wave would double its time.
+#define PGBP_TW_MAXM 4
+PGBP_HD void tilewalk_message(const MsgArgs& a, int m, int64_t e) {
+  const int S = a.msgs[m].s, I = a.msgs[m].mF - S;
+  switch (I * 8 + S) {
+    case 0 * 8 + 0: message_thread_t0<0, 0>(a, m, e); break;
+    case 0 * 8 + 1: message_thread_t0<0, 1>(a, m, e); break;
+    case 0 * 8 + 2: message_thread_t0<0, 2>(a, m, e); break;
+    case 0 * 8 + 3: message_thread_t0<0, 3>(a, m, e); break;
+    case 0 * 8 + 4: message_thread_t0<0, 4>(a, m, e); break;
+    case 1 * 8 + 0: message_thread_t0<1, 0>(a, m, e); break;
+    case 1 * 8 + 1: message_thread_t0<1, 1>(a, m, e); break;
+    case 1 * 8 + 2: message_thread_t0<1, 2>(a, m, e); break;
+    case 1 * 8 + 3: message_thread_t0<1, 3>(a, m, e); break;
+    case 2 * 8 + 0: message_thread_t0<2, 0>(a, m, e); break;
+    case 2 * 8 + 1: message_thread_t0<2, 1>(a, m, e); break;
+    case 2 * 8 + 2: message_thread_t0<2, 2>(a, m, e); break;
+    case 3 * 8 + 0: message_thread_t0<3, 0>(a, m, e); break;
+    case 3 * 8 + 1: message_thread_t0<3, 1>(a, m, e); break;
+    case 4 * 8 + 0: message_thread_t0<4, 0>(a, m, e); break;
+    default: break;  // unreachable: use_tilewalk() admits sender dimensions <= 4 only
+  }
+}
 #ifndef PGBP_HOST_EMUL
 template <int P>
 __global__ void __launch_bounds__(PGBP_WALK_THREADS, PGBP_WALK_MINBLOCKS) k_walk(MsgArgs a, int nmsg) {
@@ -66,26 +98,16 @@ __global__ void __launch_bounds__(PGBP_WALK_THREADS, PGBP_WALK_MINBLOCKS) k_walk
   walk_thread<P>(a, nmsg, e);
 }
 
-// Tile-walk kernel: ONE launch per traversal for deep, thin schedules of tiny messages (loopy BP on
-// Bethe-type graphs: hundreds of steps of a few messages each).  A block owns 32 elements
-// (threadIdx.x) and PGBP_TW_LANES message lanes (threadIdx.y); it walks the steps of the traversal in
-// order, the lanes share the messages of a step, __syncthreads() separates the steps.  All threads
-// that ever touch an element's beliefs are in the same block, so the block barrier (which also orders
-// their global-memory accesses) is the only synchronisation: no launch per step, no grid-wide sync.
-// Same thread bodies as the level-parallel launches => bit-identical results.
-#define PGBP_TW_LANES 8
-template <int MAXM>
-__global__ void __launch_bounds__(32 * PGBP_TW_LANES) k_tilewalk(MsgArgs a, const int32_t* __restrict__ step_off, int nsteps) {
+template <int LANES, int MINB>
+__global__ void __launch_bounds__(32 * LANES, MINB) k_tilewalk(MsgArgs a, const int32_t* __restrict__ step_off, int s0, int s1) {
   const int64_t e = a.e0 + (int64_t)blockIdx.x * 32 + threadIdx.x;
   const bool live = e < a.B;
-  for (int st = 0; st < nsteps; st++) {
-    const int m1 = step_off[st + 1];
-    if (live) {
-      for (int m = step_off[st] + threadIdx.y; m < m1; m += PGBP_TW_LANES) {
-        if (a.msgs[m].mF == a.msgs[m].s) message_copy_thread<false>(a, m, e);
-        else message_thread_rt<MAXM>(a, m, e);
-      }
-    }
+  int m1 = step_off[s0];
+  for (int st = s0; st < s1; st++) {
+    const int m0 = m1;
+    m1 = step_off[st + 1];
+    if (live)
+      for (int m = m0 + threadIdx.y; m < m1; m += LANES) tilewalk_message(a, m, e);
     __syncthreads();
   }
 }
@@ -236,13 +258,32 @@ bool use_walk(const pgbp_batch* b, int tree) {
 }
 
 // tile-walk applies to: tiny messages (sender dimension <= 4), no KL update, and a schedule deep
-// enough that per-step launches are latency-bound (>= 24 steps averaging < 64 messages)
+// enough that per-step launches are latency-bound (>= 24 steps averaging < 32 messages).  Steps wider than
+// b->tw_wide messages are split off into ordinary launches (LANES lanes would serialise them); runs of
+// narrower steps in between go to one tile-walk launch each.
 static bool use_tilewalk(const pgbp_batch* b, const Traversal& tv, uint32_t opts) {
-  if (b->tilewalk_mode == 0 || (opts & PGBP_CAL_RESIDKLDIV) || tv.max_mF > 4 || tv.msgs.empty() || b->group_size > 1) return false;
-  // Measured on B200 (muller_2022 Bethe, B = 16,384): 309.7 ms per 10 iterations against 105.2 ms for the
-  // level-parallel launches -- the first steps of a postorder traversal hold hundreds of messages that 8
-  // lanes serialise.  Opt-in only until wide steps are split off into ordinary launches.
-  return b->tilewalk_mode == 1;
+  if (b->tilewalk_mode == 0 || (opts & PGBP_CAL_RESIDKLDIV) || tv.max_mF > PGBP_TW_MAXM || tv.msgs.empty() || b->group_size > 1) return false;
+  if (b->tilewalk_mode == 1) return true;
+  return tv.nsteps >= 24 && (int64_t)tv.msgs.size() < 32 * (int64_t)tv.nsteps;
+}
+
+static int launch_tilewalk(pgbp_batch* b, const MsgArgs& a, const Traversal& tv, const int32_t* d_step_off, int s0, int s1) {
+#ifdef PGBP_HOST_EMUL
+  (void)d_step_off;
+  for (int st = s0; st < s1; st++)
+    for (int m = tv.step_off[st]; m < tv.step_off[st + 1]; m++)
+      for (int64_t e = a.e0; e < a.B; e++) tilewalk_message(a, m, e);
+#else
+  (void)tv;
+  const unsigned grid = (unsigned)((a.B - a.e0 + 31) / 32);
+  switch (b->tw_lanes) {
+    case 4: k_tilewalk<4, 8><<<grid, dim3(32, 4), 0, b->stream>>>(a, d_step_off, s0, s1); break;
+    case 16: k_tilewalk<16, 2><<<grid, dim3(32, 16), 0, b->stream>>>(a, d_step_off, s0, s1); break;
+    default: k_tilewalk<8, 4><<<grid, dim3(32, 8), 0, b->stream>>>(a, d_step_off, s0, s1); break;
+  }
+#endif
+  b->launches++;
+  return check_launch("k_tilewalk");
 }
 
 int run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_t ref_base, bool use_done) {
@@ -250,20 +291,26 @@ int run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_t ref_b
   MsgArgs a = make_args(b, opts, ref_base, use_done);
   const MsgDesc* d = b->d_msgs[2 * tree + dir];
   if (use_tilewalk(b, tv, opts)) {
-    a.msgs = d;
-#ifdef PGBP_HOST_EMUL
-    for (int st = 0; st < tv.nsteps; st++)
-      for (int m = tv.step_off[st]; m < tv.step_off[st + 1]; m++)
-        for (int64_t e = a.e0; e < a.B; e++) {
-          if (tv.msgs[m].mF == tv.msgs[m].s) message_copy_thread<false>(a, m, e);
-          else message_thread_rt<4>(a, m, e);
-        }
-#else
-    dim3 grid((unsigned)((a.B - a.e0 + 31) / 32)), block(32, PGBP_TW_LANES);
-    k_tilewalk<4><<<grid, block, 0, b->stream>>>(a, b->d_step_off[2 * tree + dir], tv.nsteps);
-#endif
-    b->launches++;
-    return check_launch("k_tilewalk");
+    const int wide = b->tw_wide;
+    auto width = [&](int st) { return tv.step_off[st + 1] - tv.step_off[st]; };
+    size_t gi = 0;  // groups are in launch order, i.e. sorted by step
+    int st = 0;
+    while (st < tv.nsteps) {
+      int s1 = st;
+      while (s1 < tv.nsteps && width(s1) <= wide) s1++;
+      if (s1 - st >= 2) {  // a run of narrow steps: one launch
+        a.msgs = d;
+        PGBP_TRY(launch_tilewalk(b, a, tv, b->d_step_off[2 * tree + dir], st, s1));
+        while (gi < tv.groups.size() && tv.groups[gi].step < s1) gi++;
+        st = s1;
+        continue;
+      }
+      // a wide (or isolated) step: its ordinary launch groups
+      while (gi < tv.groups.size() && tv.groups[gi].step < st) gi++;
+      for (; gi < tv.groups.size() && tv.groups[gi].step == st; gi++) PGBP_TRY(launch_group(b, a, d, tv.groups[gi]));
+      st++;
+    }
+    return 0;
   }
   for (const LaunchGroup& g : tv.groups) {
     PGBP_TRY(launch_group(b, a, d, g));
@@ -376,7 +423,7 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
   if (b->sepsets_lazy_zero) {
     const pgbp::Tree& t0 = p->trees[ids[0]];
     const bool ok = (flags & PGBP_CAL_POSTORDER) && (int)t0.parent.size() == p->nsepsets && !use_walk(b, ids[0]) &&
-                    !(flags & PGBP_CAL_RESIDKLDIV) && b->tilewalk_mode != 1;
+                    !(flags & PGBP_CAL_RESIDKLDIV);
     if (!ok) PGBP_TRY(batch_materialize_sepsets(b));
   }
   const bool lazy = b->sepsets_lazy_zero;
@@ -394,7 +441,8 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
     for (int t : ids) key += std::to_string(t) + ",";
     key += "|" + std::to_string(niter) + "|" + std::to_string(flags) + "|" + std::to_string(b->walk_mode) + "|" +
            std::to_string(b->coop_mode) + "|" + std::to_string(b->pipeline) + "|" + std::to_string((int)b->want_info) +
-           "|" + std::to_string(b->tilewalk_mode) + "|" + std::to_string((int)lazy) +
+           "|" + std::to_string(b->tilewalk_mode) + "|" + std::to_string(b->tw_lanes) + "|" + std::to_string(b->tw_wide) +
+           "|" + std::to_string((int)lazy) +
            "|" + std::to_string((uintptr_t)b->stream);
     auto it = b->graphs.find(key);
     if (it == b->graphs.end()) {  // first sight: run eagerly (also performs one-time cudaFuncSetAttribute calls)
@@ -579,6 +627,13 @@ int32_t pgbp_batch_set_pipeline(pgbp_batch* b, int32_t nchunks) {
 int32_t pgbp_batch_set_tilewalk_mode(pgbp_batch* b, int32_t mode) {
   if (!b || mode < -1 || mode > 1) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
   b->tilewalk_mode = mode;
+  return 0;
+}
+
+int32_t pgbp_batch_set_tilewalk_params(pgbp_batch* b, int32_t lanes, int32_t wide) {
+  if (!b || (lanes != 0 && lanes != 4 && lanes != 8 && lanes != 16) || wide < 0) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
+  if (lanes) b->tw_lanes = lanes;
+  if (wide) b->tw_wide = wide;
   return 0;
 }
 

@@ -169,6 +169,21 @@ def test_c3_muller_loopy_bethe_vs_cport():
         fes.append(bt.factored_energy())
         assert np.array_equal(iscal[:128], ref["iscal"])
     assert np.array_equal(fes[0], fes[1]) and np.array_equal(fes[0], fes[2])
+    # the automatic strategy here is the tile-walk kernel (runs of narrow steps in one launch, wide steps on
+    # their own); per-step launches and other lane counts must give the same bits
+    n_auto = bt.launch_count(reset=True)
+    for mode, lanes, wide in ((0, 0, 0), (1, 16, 16), (1, 4, 1000)):
+        bt.set_tilewalk_mode(mode)
+        if lanes:
+            bt.set_tilewalk_params(lanes, wide)
+        bt.init_beliefs_reset_fromfactors()
+        bt.init_messagecalibrationflags_reset()
+        bt.regularizebeliefs_bycluster()
+        succ, iscal = bt.calibrate(None, w.niter)
+        assert succ.all()
+        assert np.array_equal(bt.factored_energy(), fes[0]), (mode, lanes, wide)
+        if mode == 0:
+            assert bt.launch_count(reset=True) > 10 * n_auto / 3
     # Tolerance: this configuration is ILL-CONDITIONED by construction.  regularizebeliefs_bycluster!
     # gives the 800 factor-less variable clusters of the Bethe graph eps = max(eps(Float64), max|J|) =
     # 2.2e-16 (src/clustergraphbeliefs.jl:244), so their messages are differences of O(1) quantities

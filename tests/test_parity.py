@@ -658,9 +658,13 @@ def test_tilewalk_kernel_matches_level_parallel(backend):
     model = M.UnivariateBrownianMotion(1.0, 0.0)
     case = Case(GOLD["netstr_unnamed"], "bethe", data[0], taxa, model, lib)
     out = {}
-    for mode in (0, 1):
+    # modes: 0 = per-step launches; 1 = tile-walk; 2 = tile-walk with steps wider than 1 message split off
+    # into ordinary launches (the hybrid path of deep schedules with a few wide steps), 16 lanes
+    for mode in (0, 1, 2):
         bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
-        bt.set_tilewalk_mode(mode)
+        bt.set_tilewalk_mode(min(mode, 1))
+        if mode == 2:
+            bt.set_tilewalk_params(lanes=16, wide=1)
         bt.assignfactors(pgbp_b200.bm_params([1.0], [0.0]), data)
         bt.regularizebeliefs_bycluster()
         jbig = next(j for j in range(1, case.nclusters + 1) if case.b[j - 1].dimension() >= 2)
@@ -672,14 +676,15 @@ def test_tilewalk_kernel_matches_level_parallel(backend):
         nl = bt.launch_count()
         out[mode] = (succ, iscal, info, bt.status(), [bt.get_belief(j) for j in range(1, len(case.b) + 1)], nl,
                      bt.factored_energy())
-    assert out[1][5] < out[0][5]
-    for k in range(4):
-        assert np.array_equal(out[0][k], out[1][k])
+    assert out[1][5] < out[2][5] < out[0][5]
     ok = np.arange(B) != 5
     assert out[0][3][5] != 0 and out[0][0][ok].all() and out[0][1][ok].all()
-    for (J0, h0, g0), (J1, h1, g1) in zip(out[0][4], out[1][4]):
-        assert np.array_equal(J0[ok], J1[ok]) and np.array_equal(h0[ok], h1[ok]) and np.array_equal(g0[ok], g1[ok])
-    assert np.array_equal(out[0][6][ok], out[1][6][ok])
+    for mode in (1, 2):
+        for k in range(4):
+            assert np.array_equal(out[0][k], out[mode][k])
+        for (J0, h0, g0), (J1, h1, g1) in zip(out[0][4], out[mode][4]):
+            assert np.array_equal(J0[ok], J1[ok]) and np.array_equal(h0[ok], h1[ok]) and np.array_equal(g0[ok], g1[ok])
+        assert np.array_equal(out[0][6][ok], out[mode][6][ok])
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
