@@ -166,7 +166,7 @@ int32_t pgbp_batch_set_pipeline(pgbp_batch* batch, int32_t nchunks);
  * applicable.  Results are unaffected (same per-message arithmetic). */
 int32_t pgbp_batch_set_tilewalk_mode(pgbp_batch* batch, int32_t mode);
 /* Tuning of the tile-walk kernel: message lanes per block (4, 8 or 16; default 8) and the step width above
- * which a step is launched on its own (default 64).  0 keeps the current value. */
+ * which a step is launched on its own (default 512).  0 keeps the current value. */
 int32_t pgbp_batch_set_tilewalk_params(pgbp_batch* batch, int32_t lanes, int32_t wide);
 /* CUDA-graph replay of calibrate calls: -1 automatic (default: calls of >= 24 launches are captured at
  * their second occurrence and replayed afterwards), 0 off, 1 always.  Results are unaffected. */

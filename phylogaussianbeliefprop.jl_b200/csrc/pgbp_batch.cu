@@ -286,6 +286,17 @@ int32_t pgbp_batch_create_shared(const pgbp_plan* plan, int64_t B, int64_t group
       PGBP_TRY(alloc(b.get(), &b->d_step_off[2 * t + dir], std::max<size_t>(1, so.size())));
       PGBP_TRY(h2d(b->d_step_off[2 * t + dir], so.data(), so.size() * sizeof(int32_t), b->stream));
     }
+  b->d_tw.assign(2 * plan->trees.size(), nullptr);
+  b->d_stage_off.assign(2 * plan->trees.size(), nullptr);
+  for (size_t t = 0; t < plan->trees.size(); t++)
+    for (int dir = 0; dir < 2; dir++) {
+      const Traversal& tv = plan->trees[t].trav[dir];
+      if (tv.tw.empty()) continue;
+      PGBP_TRY(alloc(b.get(), &b->d_tw[2 * t + dir], tv.tw.size()));
+      PGBP_TRY(h2d(b->d_tw[2 * t + dir], tv.tw.data(), tv.tw.size() * sizeof(TwDesc), b->stream));
+      PGBP_TRY(alloc(b.get(), &b->d_stage_off[2 * t + dir], tv.stage_off.size()));
+      PGBP_TRY(h2d(b->d_stage_off[2 * t + dir], tv.stage_off.data(), tv.stage_off.size() * sizeof(int32_t), b->stream));
+    }
   b->d_walk.assign(plan->trees.size(), nullptr);
   for (size_t t = 0; t < plan->trees.size(); t++) {
     const auto& w = plan->trees[t].walk;
@@ -308,6 +319,8 @@ int32_t pgbp_batch_destroy(pgbp_batch* b) {
   for (auto* p : b->d_msgs) dev_free(p);
   for (auto* p : b->d_walk) dev_free(p);
   for (auto* p : b->d_step_off) dev_free(p);
+  for (auto* p : b->d_tw) dev_free(p);
+  for (auto* p : b->d_stage_off) dev_free(p);
 #ifndef PGBP_HOST_EMUL
   for (auto& kv : b->graphs) if (kv.second.exec) cudaGraphExecDestroy((cudaGraphExec_t)kv.second.exec);
   for (auto s : b->pipe_streams) cudaStreamDestroy(s);
@@ -356,6 +369,8 @@ int32_t pgbp_get_factor(pgbp_batch* b, int32_t i, double* J, double* h, double* 
   if (!b || i < 0 || i >= b->plan->nclusters) PGBP_FAIL(PGBP_EINVAL, "bad batch / cluster index");
   if (!b->factor) PGBP_FAIL(PGBP_ESTATE, "batch was created without PGBP_BATCH_FACTORS");
   const pgbp_plan* p = b->plan;
+  PGBP_TRY(set_device(b->device));
+  PGBP_TRY(batch_materialize_factors(b));
   return access_hJg(b, false, b->factor, p->dim[i], p->jslot[i], p->hslot[i], p->gslot[i], J, h, g);
 }
 int32_t pgbp_get_residual(pgbp_batch* b, int32_t j, int32_t to_cluster, double* dJ, double* dh, uint8_t* iscal_resid,
@@ -395,6 +410,7 @@ int32_t pgbp_factors_from_beliefs(pgbp_batch* b) {
   if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
   if (!b->factor) PGBP_FAIL(PGBP_ESTATE, "batch was created without PGBP_BATCH_FACTORS");
   PGBP_TRY(set_device(b->device));
+  b->lazy_factors.pending = false;
   return d2d(b->factor, b->state, sizeof(double) * (size_t)b->plan->nslots_factor * (size_t)b->ld, b->stream);
 }
 int32_t pgbp_reset_from_factors(pgbp_batch* b) {
@@ -403,6 +419,7 @@ int32_t pgbp_reset_from_factors(pgbp_batch* b) {
   PGBP_TRY(set_device(b->device));
   const pgbp_plan* p = b->plan;
   const size_t ld = (size_t)b->ld;
+  PGBP_TRY(batch_materialize_factors(b));
   PGBP_TRY(d2d(b->state, b->factor, sizeof(double) * (size_t)p->nslots_factor * ld, b->stream));
   return batch_zero_sepsets(b, true);
 }

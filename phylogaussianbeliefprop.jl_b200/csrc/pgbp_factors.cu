@@ -915,6 +915,7 @@ static int factored_energy_launch(pgbp_batch* b, double* d_out_soa, int64_t ldo)
   const pgbp_plan* p = b->plan;
   PGBP_TRY(batch_materialize_sepsets(b));
   if (!b->factor) PGBP_FAIL(PGBP_ESTATE, "batch was created without PGBP_BATCH_FACTORS");
+  PGBP_TRY(batch_materialize_factors(b));
   DevTables* dt;
   PGBP_TRY(get_tables(b, &dt));
   const size_t nrows = 2 * (size_t)p->nclusters + p->nsepsets;
@@ -966,6 +967,7 @@ static int assign_prepare(pgbp_batch* b, int32_t ncolors, int64_t nparamsets, in
                        "(zip with 1 parameter set, or product with ndatasets a multiple of the group size)", (long long)b->group_size);
   }
   PGBP_TRY(set_device(b->device));
+  b->lazy_factors.pending = false;  // the tables a pending snapshot would be recomputed from are about to change
   DevTables* dt;
   PGBP_TRY(get_tables(b, &dt));
   ThetaRows tr{pt, ncolors};
@@ -975,6 +977,9 @@ static int assign_prepare(pgbp_batch* b, int32_t ncolors, int64_t nparamsets, in
   *dt_out = dt;
   return 0;
 }
+
+static int assign_launch(pgbp_batch* b, pgbp::DevTables* dt, double* out, int32_t ncolors, int64_t nparamsets,
+                         int64_t ndatasets, int32_t pairing);
 
 // K1 proper, everything on the device, enqueue only: d_params / d_tip are the AoS records of the header
 static int assign_enqueue(pgbp_batch* b, pgbp::DevTables* dt, int32_t ncolors, const double* d_params, int64_t nparamsets,
@@ -993,10 +998,25 @@ static int assign_enqueue(pgbp_batch* b, pgbp::DevTables* dt, int32_t ncolors, c
     b->B = saveB;
     PGBP_TRY(rc);
   }
+  PGBP_TRY(assign_launch(b, dt, b->state, ncolors, nparamsets, ndatasets, pairing));
+  // sepsets <- 0 (src/beliefs.jl:796), lazily; factor snapshot (src/clustergraphbeliefs.jl:106), lazily
+  PGBP_TRY(batch_zero_sepsets(b, true));
+  if (b->factor) b->lazy_factors = pgbp_batch::LazyFactors{true, ncolors, nparamsets, ndatasets, pairing};
+  return 0;
+}
+
+// the K1 kernel: cluster beliefs (J, h, g) from the prepared tables dt->theta / dt->tip, written to `out`
+// (the state array, or the factor array when a lazy snapshot is materialised: same layout)
+static int assign_launch(pgbp_batch* b, pgbp::DevTables* dt, double* out, int32_t ncolors, int64_t nparamsets,
+                         int64_t ndatasets, int32_t pairing) {
+  const pgbp_plan* p = b->plan;
+  const FamilyTable& F = p->fam;
+  const int pt = p->ntraits;
+  ThetaRows tr{pt, ncolors};
   FamDev fd{dt->node_cluster, dt->mem_off, dt->mem_pos, dt->mem_length, dt->mem_gamma, dt->mem_color,
             dt->node_datarow, dt->clu_off, dt->clu_node, dt->jslot, dt->hslot, dt->gslot, dt->dim,
             pt, ncolors, F.root_fixed};
-  AssignBody body{fd, dt->theta, dt->ldp, dt->tip, dt->ldd, b->state, b->status, b->ld, nparamsets, ndatasets, pairing, tr};
+  AssignBody body{fd, dt->theta, dt->ldp, dt->tip, dt->ldd, out, b->status, b->ld, nparamsets, ndatasets, pairing, tr};
   body.gs = b->group_size;
   switch (pt) {
 #define PGBP_FAST_CASE(P_) \
@@ -1009,11 +1029,23 @@ static int assign_enqueue(pgbp_batch* b, pgbp::DevTables* dt, int32_t ncolors, c
 #undef PGBP_FAST_CASE
     default: PGBP_TRY(launch_generic(b, "k_assign_factors", b->B, p->nclusters, body));
   }
-  // sepsets <- 0 (src/beliefs.jl:796), lazily; factor snapshot (src/clustergraphbeliefs.jl:106)
-  PGBP_TRY(batch_zero_sepsets(b, true));
-  if (b->factor) PGBP_TRY(d2d(b->factor, b->state, sizeof(double) * (size_t)p->nslots_factor * (size_t)b->ld, b->stream));
   return 0;
 }
+
+}  // extern "C"
+namespace pgbp {
+int batch_materialize_factors(pgbp_batch* b) {
+  if (!b->lazy_factors.pending) return 0;
+  if (!b->factor) { b->lazy_factors.pending = false; return 0; }
+  DevTables* dt;
+  PGBP_TRY(get_tables(b, &dt));
+  const pgbp_batch::LazyFactors lf = b->lazy_factors;
+  PGBP_TRY(assign_launch(b, dt, b->factor, lf.ncolors, lf.nparamsets, lf.ndatasets, lf.pairing));
+  b->lazy_factors.pending = false;
+  return 0;
+}
+}  // namespace pgbp
+extern "C" {
 
 int32_t pgbp_assign_factors_ou(pgbp_batch* b, const double* params, int64_t nparamsets, const double* tipdata,
                                int64_t ndatasets, int32_t pairing) {
@@ -1041,6 +1073,7 @@ int32_t pgbp_assign_factors_ou(pgbp_batch* b, const double* params, int64_t npar
   body.gs = b->group_size;
   PGBP_TRY(launch_generic(b, "k_assign_ou", b->B, p->nclusters, body));
   PGBP_TRY(batch_zero_sepsets(b, true));
+  b->lazy_factors.pending = false;  // (the OU parameters live in scratch memory: eager snapshot)
   if (b->factor) PGBP_TRY(d2d(b->factor, b->state, sizeof(double) * (size_t)p->nslots_factor * (size_t)b->ld, b->stream));
   return stream_sync(b->stream);
 }

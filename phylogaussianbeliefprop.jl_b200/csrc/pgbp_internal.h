@@ -30,6 +30,24 @@ struct MsgDesc {
   int32_t wid;         // walk-kernel shape id (pgbp_shapes.h), -1 if outside the family
 };
 
+// Tile-walk descriptor: one message of sender dimension <= 4 with every slot index resolved (no
+// index-table indirection), 160 bytes = ten 16-byte chunks, staged in shared memory one stage ahead.
+#define PGBP_TW_MAXM 4
+#define PGBP_TW_STAGE 64  // messages per stage (a stage never crosses a step boundary)
+struct alignas(16) TwDesc {
+  uint32_t fJ[10];    // sender J slots, packed upper in [I;K] order
+  uint32_t fh[4];     // sender h slots in [I;K] order
+  uint32_t tJ[10];    // receiver J slots of the sepset scope, packed upper
+  uint32_t th[4];     // receiver h slots of the sepset scope
+  uint32_t fg, sg, tg;
+  uint32_t sJ, sh;    // sepset J / h rows (contiguous)
+  uint32_t rJ, rh;    // residual rows (contiguous)
+  uint32_t dmsg, ref;
+  uint32_t shape;     // I * 8 + S
+  uint32_t pad[2];
+};
+static_assert(sizeof(TwDesc) == 160, "TwDesc must be ten 16-byte chunks");
+
 struct LaunchGroup {
   int32_t step;        // launch step (groups of one step are independent)
   int32_t ci, cs;      // shape class (i, s) if specialised, (-1,-1) generic
@@ -43,6 +61,10 @@ struct Traversal {
   std::vector<LaunchGroup> groups;    // launch order
   std::vector<int32_t> step_off;      // [nsteps+1] range of msgs of each step (msgs are sorted by step)
   int32_t max_mF = 0;                 // largest sender dimension
+  // tile-walk form (only when max_mF <= PGBP_TW_MAXM): resolved descriptors in execution order, stages of
+  // <= PGBP_TW_STAGE messages inside one step, first stage of every step ([nsteps+1])
+  std::vector<TwDesc> tw;
+  std::vector<int32_t> stage_off, step_stage;
   int32_t nsteps = 0;
   double bytes_noresid = 0, bytes_resid = 0, flops = 0;  // algorithmic, per element
 };
@@ -116,9 +138,11 @@ struct pgbp_batch {
   // per-tree, per-direction descriptor arrays on the device
   std::vector<pgbp::MsgDesc*> d_msgs;  // index 2*tree+dir
   std::vector<pgbp::MsgDesc*> d_walk;  // per tree, reference order (walk kernel)
-  std::vector<int32_t*> d_step_off;    // index 2*tree+dir (tile-walk kernel)
+  std::vector<int32_t*> d_step_off;    // index 2*tree+dir
+  std::vector<pgbp::TwDesc*> d_tw;     // index 2*tree+dir (tile-walk kernel; null when not applicable)
+  std::vector<int32_t*> d_stage_off;   // index 2*tree+dir
   int32_t tilewalk_mode = -1;          // -1 auto, 0 off, 1 on (where applicable)
-  int32_t tw_lanes = 8, tw_wide = 64;  // tile-walk tuning: message lanes per block, width of a step launched alone
+  int32_t tw_lanes = 8, tw_wide = 512;  // tile-walk tuning: message lanes per block, width of a step launched alone
   pgbp::MsgDesc* d_one = nullptr;      // scratch descriptor for pgbp_propagate
   double* scratch = nullptr;           // staging for host<->device transposes / outputs
   size_t scratch_bytes = 0;
@@ -144,6 +168,12 @@ struct pgbp_batch {
   // them (saves one write and one read of every sepset); anything else that looks at the state calls
   // batch_materialize_sepsets() first.
   bool sepsets_lazy_zero = false;
+  // Lazy factor snapshot: assignfactors! copies every cluster belief into its ClusterFactor
+  // (src/clustergraphbeliefs.jl:106).  K1 is a pure function of the prepared parameter / tip tables the
+  // batch keeps on the device, so instead of copying (one read + one write of every cluster) the batch
+  // remembers the call; the factors are produced by running K1 again into the factor array the first time
+  // something reads them (factored_energy, reset_from_factors, get_factor).  Bit-identical by construction.
+  struct LazyFactors { bool pending = false; int32_t ncolors = 1; int64_t nparamsets = 0, ndatasets = 0; int32_t pairing = 0; } lazy_factors;
   int32_t coop_mode = -1;  // medium shapes: -1 auto (cooperative), 0 thread-local generic, 4 / 8 lanes for m <= 16
   int32_t* d_slot = nullptr;  // device scratch for transpose slot tables
   size_t d_slot_len = 0;

@@ -18,5 +18,7 @@ void free_tables(pgbp_batch* b);
 int batch_materialize_sepsets(pgbp_batch* b);
 // the sepsets become zero: lazily when `lazy`, else with a memset now
 int batch_zero_sepsets(pgbp_batch* b, bool lazy);
+// run the pending K1 into the factor array (no-op unless lazy_factors.pending)
+int batch_materialize_factors(pgbp_batch* b);
 MsgArgs make_args(pgbp_batch* b, uint32_t opts, int32_t ref_base, bool use_done);
 }  // namespace pgbp

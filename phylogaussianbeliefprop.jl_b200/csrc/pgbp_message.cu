@@ -61,32 +61,155 @@ PGBP_HD void walk_thread(const MsgArgs& a, int nmsg, int64_t e) {
 // Tile-walk kernel: ONE launch for a run of consecutive steps of a deep, thin schedule of tiny messages
 // (loopy BP on Bethe-type graphs: hundreds of steps of a few messages each, which per-step launches
 // execute at ~9 us of pure latency apiece).  A block owns 32 elements (threadIdx.x) and LANES message
-// lanes (threadIdx.y); it walks the steps in order, the lanes share the messages of a step,
-// __syncthreads() separates the steps.  All threads that ever touch an element's beliefs are in the same
-// block, so the block barrier (which also orders their global-memory accesses) is the only
-// synchronisation: no launch per step, no grid-wide sync.  The messages run the same register-resident
-// bodies as the level-parallel launches (message_thread_t0<I,S>, I + S <= 4; I = 0 is the streaming
-// copy) => bit-identical results.  Registers are capped (launch bounds) so that every block of the batch
-// is resident at once: the walk is latency-bound per step, a second wave would double its time.
-#define PGBP_TW_MAXM 4
-PGBP_HD void tilewalk_message(const MsgArgs& a, int m, int64_t e) {
-  const int S = a.msgs[m].s, I = a.msgs[m].mF - S;
-  switch (I * 8 + S) {
-    case 0 * 8 + 0: message_thread_t0<0, 0>(a, m, e); break;
-    case 0 * 8 + 1: message_thread_t0<0, 1>(a, m, e); break;
-    case 0 * 8 + 2: message_thread_t0<0, 2>(a, m, e); break;
-    case 0 * 8 + 3: message_thread_t0<0, 3>(a, m, e); break;
-    case 0 * 8 + 4: message_thread_t0<0, 4>(a, m, e); break;
-    case 1 * 8 + 0: message_thread_t0<1, 0>(a, m, e); break;
-    case 1 * 8 + 1: message_thread_t0<1, 1>(a, m, e); break;
-    case 1 * 8 + 2: message_thread_t0<1, 2>(a, m, e); break;
-    case 1 * 8 + 3: message_thread_t0<1, 3>(a, m, e); break;
-    case 2 * 8 + 0: message_thread_t0<2, 0>(a, m, e); break;
-    case 2 * 8 + 1: message_thread_t0<2, 1>(a, m, e); break;
-    case 2 * 8 + 2: message_thread_t0<2, 2>(a, m, e); break;
-    case 3 * 8 + 0: message_thread_t0<3, 0>(a, m, e); break;
-    case 3 * 8 + 1: message_thread_t0<3, 1>(a, m, e); break;
-    case 4 * 8 + 0: message_thread_t0<4, 0>(a, m, e); break;
+// lanes (threadIdx.y); it walks the steps in order, the lanes share the messages of a step, a block
+// barrier separates the steps.  All threads that ever touch an element's beliefs are in the same block,
+// so the block barrier (which also orders their global-memory accesses) is the only synchronisation: no
+// launch per step, no grid-wide sync.  The walk is latency-bound per step, so everything is arranged to
+// shorten the dependent chain of one message:
+//  * descriptors are pre-resolved (TwDesc: slot numbers, no index-table indirection) and staged in shared
+//    memory with cp.async ONE STAGE AHEAD (a stage = <= 64 messages of one step), double-buffered;
+//  * a message issues ALL its loads (sender, old sepset, old receiver, status) before any arithmetic:
+//    one HBM/L2 round trip per message instead of three;
+//  * registers are capped (launch bounds) so that every block of the batch is resident at once.
+// The arithmetic is statement for statement that of message_thread_t0<I,S> (I = 0 is the streaming copy)
+// => bit-identical results (asserted by tests/test_parity.py and tests/test_fullsize.py).
+template <int CI, int CS>
+PGBP_HD void message_thread_tw(const MsgArgs& a, const TwDesc& d, int64_t e) {
+  constexpr int I = CI, S = CS, SI = I * (I + 1) / 2, SS = S * (S + 1) / 2;
+  const uint32_t ld8 = (uint32_t)(a.ld * 8);
+  char* st = (char*)(a.state + e);
+  char* rs = a.resid ? (char*)(a.resid + e) : nullptr;
+  const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;
+  const int32_t stat = a.status[e];
+  const uint8_t dn = a.done ? a.done[e] : (uint8_t)0;
+  double AI[SI > 0 ? SI : 1], Bm[I * S > 0 ? I * S : 1], hI[I > 0 ? I : 1];
+  double jo[SS > 0 ? SS : 1], sJo[SS > 0 ? SS : 1], tJo[SS > 0 ? SS : 1];
+  double ho[S > 0 ? S : 1], sho[S > 0 ? S : 1], tho[S > 0 ? S : 1];
+#pragma unroll
+  for (int c = 0; c < I; c++) {
+#pragma unroll
+    for (int r = 0; r <= c; r++) AI[pk(r, c)] = *slot_ptr(st, d.fJ[pk(r, c)], ld8);
+  }
+#pragma unroll
+  for (int c = 0; c < S; c++) {
+#pragma unroll
+    for (int k = 0; k < I; k++) Bm[k * S + c] = *slot_ptr(st, d.fJ[pk(k, I + c)], ld8);
+  }
+#pragma unroll
+  for (int k = 0; k < I; k++) hI[k] = *slot_ptr(st, d.fh[k], ld8);
+  double g = *slot_ptr(st, d.fg, ld8);
+  const double sg_old = sz ? 0.0 : *slot_ptr(st, d.sg, ld8);
+  const double tg_old = *slot_ptr(st, d.tg, ld8);
+#pragma unroll
+  for (int q = 0; q < SS; q++) {
+    const int c = colof(q), r = q - c * (c + 1) / 2;
+    jo[q] = *slot_ptr(st, d.fJ[pk(I + r, I + c)], ld8);
+    sJo[q] = sz ? 0.0 : *slot_ptr(st, d.sJ + q, ld8);
+    tJo[q] = *slot_ptr(st, d.tJ[q], ld8);
+  }
+#pragma unroll
+  for (int k = 0; k < S; k++) {
+    ho[k] = *slot_ptr(st, d.fh[I + k], ld8);
+    sho[k] = sz ? 0.0 : *slot_ptr(st, d.sh + k, ld8);
+    tho[k] = *slot_ptr(st, d.th[k], ld8);
+  }
+  if (stat != 0 || dn) return;
+
+  bool allzero = true;  // src/beliefupdates.jl:62-66
+#pragma unroll
+  for (int q = 0; q < SI; q++)
+    if (!(fabs(AI[q]) <= PGBP_EPS)) allzero = false;
+#pragma unroll
+  for (int q = 0; q < I * S; q++)
+    if (!(fabs(Bm[q]) <= PGBP_EPS)) allzero = false;
+#pragma unroll
+  for (int k = 0; k < I; k++)
+    if (!(fabs(hI[k]) <= PGBP_EPS)) allzero = false;
+  if (!allzero) {
+    double logdet = 0.0, ww = 0.0;
+#pragma unroll
+    for (int k = 0; k < I; k++) {
+      const double dd = AI[pk(k, k)];
+      if (!(dd > 0.0)) {
+        status_fail(a.status, e, PGBP_STATUS(a.ref_base + (int32_t)d.ref, k + 1));
+        return;
+      }
+      logdet += log(dd);
+      const double rinv = 1.0 / sqrt(dd);
+#pragma unroll
+      for (int c = k + 1; c < I; c++) AI[pk(k, c)] *= rinv;
+#pragma unroll
+      for (int c = 0; c < S; c++) Bm[k * S + c] *= rinv;
+      const double wk = hI[k] * rinv;
+      hI[k] = wk;
+      ww = fma(wk, wk, ww);
+#pragma unroll
+      for (int c = k + 1; c < I; c++) {
+        const double akc = AI[pk(k, c)];
+#pragma unroll
+        for (int r = k + 1; r <= c; r++) AI[pk(r, c)] = nfma(AI[pk(k, r)], akc, AI[pk(r, c)]);
+        hI[c] = nfma(akc, wk, hI[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < S; c++) {
+        const double bkc = Bm[k * S + c];
+#pragma unroll
+        for (int r = k + 1; r < I; r++) Bm[r * S + c] = nfma(AI[pk(k, r)], bkc, Bm[r * S + c]);
+      }
+    }
+    g += 0.5 * ((double)I * PGBP_LOG2PI - logdet + ww);
+  } else {
+#pragma unroll
+    for (int q = 0; q < I * S; q++) Bm[q] = 0.0;
+#pragma unroll
+    for (int k = 0; k < I; k++) hI[k] = 0.0;
+  }
+  double maxJ = 0.0, maxh = 0.0;
+#pragma unroll
+  for (int q = 0; q < SS; q++) {
+    const int c = colof(q), r = q - c * (c + 1) / 2;
+    double nv = jo[q];
+#pragma unroll
+    for (int i = 0; i < I; i++) nv = nfma(Bm[i * S + r], Bm[i * S + c], nv);
+    const double dl = nv - sJo[q];
+    *slot_ptr(st, d.sJ + q, ld8) = nv;
+    *slot_ptr(st, d.tJ[q], ld8) = tJo[q] + dl;
+    if (rs) *slot_ptr(rs, d.rJ + q, ld8) = dl;
+    absmax(maxJ, dl);
+  }
+#pragma unroll
+  for (int k = 0; k < S; k++) {
+    double nv = ho[k];
+#pragma unroll
+    for (int i = 0; i < I; i++) nv = nfma(Bm[i * S + k], hI[i], nv);
+    const double dl = nv - sho[k];
+    *slot_ptr(st, d.sh + k, ld8) = nv;
+    *slot_ptr(st, d.th[k], ld8) = tho[k] + dl;
+    if (rs) *slot_ptr(rs, d.rh + k, ld8) = dl;
+    absmax(maxh, dl);
+  }
+  *slot_ptr(st, d.sg, ld8) = g;
+  *slot_ptr(st, d.tg, ld8) = tg_old + (g - sg_old);
+  store_flag(a, (int)d.dmsg, e, S, maxJ, maxh);
+}
+
+PGBP_HD void tilewalk_message(const MsgArgs& a, const TwDesc& d, int64_t e) {
+  switch (d.shape) {
+    case 0 * 8 + 0: message_thread_tw<0, 0>(a, d, e); break;
+    case 0 * 8 + 1: message_thread_tw<0, 1>(a, d, e); break;
+    case 0 * 8 + 2: message_thread_tw<0, 2>(a, d, e); break;
+    case 0 * 8 + 3: message_thread_tw<0, 3>(a, d, e); break;
+    case 0 * 8 + 4: message_thread_tw<0, 4>(a, d, e); break;
+    case 1 * 8 + 0: message_thread_tw<1, 0>(a, d, e); break;
+    case 1 * 8 + 1: message_thread_tw<1, 1>(a, d, e); break;
+    case 1 * 8 + 2: message_thread_tw<1, 2>(a, d, e); break;
+    case 1 * 8 + 3: message_thread_tw<1, 3>(a, d, e); break;
+    case 2 * 8 + 0: message_thread_tw<2, 0>(a, d, e); break;
+    case 2 * 8 + 1: message_thread_tw<2, 1>(a, d, e); break;
+    case 2 * 8 + 2: message_thread_tw<2, 2>(a, d, e); break;
+    case 3 * 8 + 0: message_thread_tw<3, 0>(a, d, e); break;
+    case 3 * 8 + 1: message_thread_tw<3, 1>(a, d, e); break;
+    case 4 * 8 + 0: message_thread_tw<4, 0>(a, d, e); break;
     default: break;  // unreachable: use_tilewalk() admits sender dimensions <= 4 only
   }
 }
@@ -98,17 +221,39 @@ __global__ void __launch_bounds__(PGBP_WALK_THREADS, PGBP_WALK_MINBLOCKS) k_walk
   walk_thread<P>(a, nmsg, e);
 }
 
+PGBP_D void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+PGBP_D void cp_async_commit_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+
 template <int LANES, int MINB>
-__global__ void __launch_bounds__(32 * LANES, MINB) k_tilewalk(MsgArgs a, const int32_t* __restrict__ step_off, int s0, int s1) {
+__global__ void __launch_bounds__(32 * LANES, MINB) k_tilewalk(MsgArgs a, const TwDesc* __restrict__ descs,
+                                                              const int32_t* __restrict__ stage_off, int k0, int k1) {
+  __shared__ TwDesc buf[2][PGBP_TW_STAGE];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
   const int64_t e = a.e0 + (int64_t)blockIdx.x * 32 + threadIdx.x;
   const bool live = e < a.B;
-  int m1 = step_off[s0];
-  for (int st = s0; st < s1; st++) {
-    const int m0 = m1;
-    m1 = step_off[st + 1];
-    if (live)
-      for (int m = m0 + threadIdx.y; m < m1; m += LANES) tilewalk_message(a, m, e);
-    __syncthreads();
+  auto stage_load = [&](int m0, int m1, int which) {
+    const uint4* src = reinterpret_cast<const uint4*>(descs + m0);
+    uint4* dst = reinterpret_cast<uint4*>(&buf[which][0]);
+    const int nch = (m1 - m0) * (int)(sizeof(TwDesc) / 16);
+    for (int c = tid; c < nch; c += 32 * LANES) cp_async16(dst + c, src + c);
+  };
+  int m0 = stage_off[k0], m1 = stage_off[k0 + 1];
+  stage_load(m0, m1, 0);
+  for (int k = k0; k < k1; k++) {
+    const int cur = (k - k0) & 1;
+    const int m2 = (k + 1 < k1) ? stage_off[k + 2] : m1;  // end of the next stage
+    cp_async_commit_wait_all();  // this thread's chunks of stage k have landed
+    __syncthreads();             // stage k visible to all; every message of stage k-1 is complete
+    if (k + 1 < k1) stage_load(m1, m2, cur ^ 1);  // overlaps the messages of stage k
+    if (live) {
+      const int n = m1 - m0;
+      for (int j = threadIdx.y; j < n; j += LANES) tilewalk_message(a, buf[cur][j], e);
+    }
+    m0 = m1;
+    m1 = m2;
   }
 }
 
@@ -262,24 +407,26 @@ bool use_walk(const pgbp_batch* b, int tree) {
 // b->tw_wide messages are split off into ordinary launches (LANES lanes would serialise them); runs of
 // narrower steps in between go to one tile-walk launch each.
 static bool use_tilewalk(const pgbp_batch* b, const Traversal& tv, uint32_t opts) {
-  if (b->tilewalk_mode == 0 || (opts & PGBP_CAL_RESIDKLDIV) || tv.max_mF > PGBP_TW_MAXM || tv.msgs.empty() || b->group_size > 1) return false;
+  if (b->tilewalk_mode == 0 || (opts & PGBP_CAL_RESIDKLDIV) || tv.tw.empty() || b->group_size > 1) return false;
   if (b->tilewalk_mode == 1) return true;
   return tv.nsteps >= 24 && (int64_t)tv.msgs.size() < 32 * (int64_t)tv.nsteps;
 }
 
-static int launch_tilewalk(pgbp_batch* b, const MsgArgs& a, const Traversal& tv, const int32_t* d_step_off, int s0, int s1) {
+static int launch_tilewalk(pgbp_batch* b, const MsgArgs& a, const Traversal& tv, int td, int s0, int s1) {
+  const int k0 = tv.step_stage[s0], k1 = tv.step_stage[s1];
 #ifdef PGBP_HOST_EMUL
-  (void)d_step_off;
-  for (int st = s0; st < s1; st++)
-    for (int m = tv.step_off[st]; m < tv.step_off[st + 1]; m++)
-      for (int64_t e = a.e0; e < a.B; e++) tilewalk_message(a, m, e);
+  (void)td;
+  for (int k = k0; k < k1; k++)
+    for (int m = tv.stage_off[k]; m < tv.stage_off[k + 1]; m++)
+      for (int64_t e = a.e0; e < a.B; e++) tilewalk_message(a, tv.tw[m], e);
 #else
-  (void)tv;
   const unsigned grid = (unsigned)((a.B - a.e0 + 31) / 32);
+  const TwDesc* descs = b->d_tw[td];
+  const int32_t* so = b->d_stage_off[td];
   switch (b->tw_lanes) {
-    case 4: k_tilewalk<4, 8><<<grid, dim3(32, 4), 0, b->stream>>>(a, d_step_off, s0, s1); break;
-    case 16: k_tilewalk<16, 2><<<grid, dim3(32, 16), 0, b->stream>>>(a, d_step_off, s0, s1); break;
-    default: k_tilewalk<8, 4><<<grid, dim3(32, 8), 0, b->stream>>>(a, d_step_off, s0, s1); break;
+    case 4: k_tilewalk<4, 8><<<grid, dim3(32, 4), 0, b->stream>>>(a, descs, so, k0, k1); break;
+    case 16: k_tilewalk<16, 2><<<grid, dim3(32, 16), 0, b->stream>>>(a, descs, so, k0, k1); break;
+    default: k_tilewalk<8, 4><<<grid, dim3(32, 8), 0, b->stream>>>(a, descs, so, k0, k1); break;
   }
 #endif
   b->launches++;
@@ -300,7 +447,7 @@ int run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_t ref_b
       while (s1 < tv.nsteps && width(s1) <= wide) s1++;
       if (s1 - st >= 2) {  // a run of narrow steps: one launch
         a.msgs = d;
-        PGBP_TRY(launch_tilewalk(b, a, tv, b->d_step_off[2 * tree + dir], st, s1));
+        PGBP_TRY(launch_tilewalk(b, a, tv, 2 * tree + dir, st, s1));
         while (gi < tv.groups.size() && tv.groups[gi].step < s1) gi++;
         st = s1;
         continue;

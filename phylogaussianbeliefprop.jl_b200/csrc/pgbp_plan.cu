@@ -142,6 +142,36 @@ static int build_traversal(pgbp_plan* p, const std::vector<int32_t>& from, const
   for (int st = 0; st < nsteps; st++) tv->step_off[st + 1] += tv->step_off[st];
   tv->max_mF = 0;
   for (int k = 0; k < n; k++) tv->max_mF = std::max(tv->max_mF, tv->msgs[k].mF);
+  // tile-walk form
+  tv->tw.clear(); tv->stage_off.clear(); tv->step_stage.clear();
+  bool fits32 = p->nslots_state < (int64_t)0xffffffffLL && p->nslots_resid < (int64_t)0xffffffffLL;
+  if (n > 0 && tv->max_mF <= PGBP_TW_MAXM && fits32) {
+    tv->tw.resize(n);
+    for (int k = 0; k < n; k++) {
+      const MsgDesc& m = tv->msgs[k];
+      TwDesc d;
+      memset(&d, 0, sizeof d);
+      const int I = m.mF - m.s, S = m.s, SM = tri(m.mF), SS = tri(S);
+      const int32_t* gat = p->tab.data() + m.gat;
+      const int32_t* sca = p->tab.data() + m.sca;
+      for (int q = 0; q < SM; q++) d.fJ[q] = (uint32_t)(m.fJ + gat[q]);
+      for (int q = 0; q < m.mF; q++) d.fh[q] = (uint32_t)(m.fh + gat[SM + q]);
+      for (int q = 0; q < SS; q++) d.tJ[q] = (uint32_t)(m.tJ + sca[q]);
+      for (int q = 0; q < S; q++) d.th[q] = (uint32_t)(m.th + sca[SS + q]);
+      d.fg = (uint32_t)m.fg; d.sg = (uint32_t)m.sg; d.tg = (uint32_t)m.tg;
+      d.sJ = (uint32_t)m.sJ; d.sh = (uint32_t)m.sh; d.rJ = (uint32_t)m.rJ; d.rh = (uint32_t)m.rh;
+      d.dmsg = (uint32_t)m.dmsg; d.ref = (uint32_t)m.ref; d.shape = (uint32_t)(I * 8 + S);
+      tv->tw[k] = d;
+    }
+    tv->step_stage.assign(nsteps + 1, 0);
+    tv->stage_off.push_back(0);
+    for (int st = 0; st < nsteps; st++) {
+      tv->step_stage[st] = (int32_t)tv->stage_off.size() - 1;
+      for (int m0 = tv->step_off[st]; m0 < tv->step_off[st + 1]; m0 += PGBP_TW_STAGE)
+        tv->stage_off.push_back(std::min(m0 + PGBP_TW_STAGE, tv->step_off[st + 1]));
+    }
+    tv->step_stage[nsteps] = (int32_t)tv->stage_off.size() - 1;
+  }
   return 0;
 }
 

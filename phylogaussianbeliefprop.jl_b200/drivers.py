@@ -149,3 +149,55 @@ def calibrate_optimize_cliquetree(plan: ClusterGraphPlan, spt, tipdata, model="U
 
     res = minimize(fun, theta0, jac=True, method="L-BFGS-B", options=dict(maxiter=maxiter, ftol=1e-14, gtol=1e-9))
     return to_orig(res.x), -float(res.fun), res
+
+
+def calibrate_optimize_clustergraph(plan: ClusterGraphPlan, schedule, tipdata, model="UnivariateBrownianMotion",
+                                    start=(1.0, 0.0), v=None, maxiter=100, regfun="bycluster", optim_iterations=30,
+                                    fd_step=1e-6, device: int = 0):
+    """calibrate_optimize_clustergraph! (src/calibration.jl:309-359): maximise the factored energy (the negative
+    Bethe free energy; the log-likelihood when the cluster graph is a clique tree) over the BM rate(s) and
+    root mean(s) on an arbitrary cluster graph.
+
+    Objective, as in the reference (:323-351): assignfactors! -> factor snapshot -> reset of the message
+    residual flags -> regularisation (`regfun`: "bycluster" | "onschedule" | a node-subtree program for
+    regularizebeliefs_bynodesubtree!) -> calibrate!(schedule, maxiter, auto=true) -> free_energy[3];
+    +Inf when a message fails.  `schedule` = spanningtrees_clusterlist of the graph (reference 4-tuples or
+    tree ids; None = every tree of the plan).  Every L-BFGS iteration evaluates its central-difference
+    stencil (2n+1 parameter vectors) as ONE batch; auto-stop is per batch element.
+    Returns (theta_hat as a bm_params record, factored energy, scipy result)."""
+    from scipy.optimize import minimize
+    td = np.ascontiguousarray(np.asarray(tipdata, dtype=float))
+    if td.ndim == 2:
+        td = td[None]
+    p = td.shape[2]
+    to_opt, to_orig = _bm_transforms(model, p, v)
+    theta0 = to_opt(*start)
+    n = theta0.size
+    bb = BatchedClusterGraphBelief(plan, 2 * n + 1, device=device, factors=True, residuals=True)
+
+    def scores(thetas):
+        bb.clear_status()
+        bb.assignfactors(np.stack([to_orig(t) for t in thetas]), td)  # also snapshots the factors
+        bb.init_messagecalibrationflags_reset(True)
+        if regfun == "bycluster":
+            bb.regularizebeliefs_bycluster()
+        elif regfun == "onschedule":
+            bb.regularizebeliefs_onschedule()
+        elif regfun is not None:
+            bb.regularizebeliefs_bynodesubtree(regfun)
+        succ, _ = bb.calibrate(schedule, maxiter, auto=True)
+        fe = bb.free_energy()[:, 2]
+        out = fe.copy()
+        out[~succ | ~np.isfinite(fe) | (bb.status() != 0)] = np.inf
+        return out
+
+    def fun(theta):
+        st = np.tile(theta, (2 * n + 1, 1))
+        for k in range(n):
+            st[1 + 2 * k, k] += fd_step
+            st[2 + 2 * k, k] -= fd_step
+        f = scores(st)
+        return f[0], (f[1::2] - f[2::2]) / (2 * fd_step)
+
+    res = minimize(fun, theta0, jac=True, method="L-BFGS-B", options=dict(maxiter=optim_iterations, ftol=1e-14, gtol=1e-9))
+    return to_orig(res.x), -float(res.fun), res

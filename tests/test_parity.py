@@ -193,6 +193,49 @@ def test_lazaridis_docs_numbers(backend):
     assert succ.all() and iscal.all()
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_lazy_factor_snapshot_is_the_assigned_belief(backend):
+    # ClusterFactor = copy of the cluster belief right after assignfactors! (src/clustergraphbeliefs.jl:106).
+    # The library takes the snapshot lazily (K1 re-run into the factor array at the first read): a snapshot
+    # read right away, one read after a calibration, and the belief read right after assignment must be
+    # the same bits; a second assignment replaces a pending snapshot; init_factors_frombeliefs overrides it.
+    lib = get_lib(backend)
+    taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
+    rng = np.random.default_rng(5)
+    p, B = 2, 6
+    R = np.array([[2.0, 0.5], [0.5, 1.0]])
+    data = rng.normal(size=(2, B, 7, p))
+    model = M.MvFullBrownianMotion(R, np.zeros(p))
+    case = Case(GOLD["lazaridis"], "cliquetree", data[0, 0], taxa, model, lib, order_hint=GOLD["lazaridis_cluster_labels"])
+    par = pgbp_b200.bm_params([R], np.zeros(p))
+    nc = case.nclusters
+    early = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+    early.assignfactors(par, data[1])
+    fac_early = [early.get_factor(j) for j in range(1, nc + 1)]  # materialised before anything else happens
+    bel = [early.get_belief(j) for j in range(1, nc + 1)]
+    late = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+    late.assignfactors(par, data[0])  # pending snapshot, replaced by the next call
+    late.assignfactors(par, data[1])
+    succ, _ = late.calibrate(case.sched)
+    assert succ.all()
+    early.calibrate(case.sched)
+    fe_late = late.factored_energy()  # first reader of the factors
+    assert np.array_equal(fe_late, early.factored_energy())
+    for j in range(nc):
+        for x, y, z in zip(fac_early[j], late.get_factor(j + 1), bel[j]):
+            assert np.array_equal(x, y) and np.array_equal(x, z)
+    late.init_beliefs_reset_fromfactors()
+    for j in range(nc):
+        for x, y in zip(late.get_belief(j + 1), bel[j]):
+            assert np.array_equal(x, y)
+    late.assignfactors(par, data[0])  # pending again ...
+    late.calibrate(case.sched)
+    late.init_factors_frombeliefs()  # ... and overridden by an explicit snapshot of the calibrated beliefs
+    for j in range(nc):
+        for x, y in zip(late.get_factor(j + 1), late.get_belief(j + 1)):
+            assert np.array_equal(x, y)
+
+
 # ------------------------------------------------------------------ device factor assignment
 ASSIGN_CASES = [
     ("uni_fixed", lambda: M.UnivariateBrownianMotion(2, 3, 0), [1], lambda: ([[[2.0]]], [3.0], None)),
