@@ -422,6 +422,8 @@ def run_gpu(args):
         bt.set_graph_mode(args.graph)
     if args.tilewalk is not None:
         bt.set_tilewalk_mode(args.tilewalk)
+    if args.coop is not None:
+        bt.set_coop_mode(args.coop)
     if args.tw_lanes or args.tw_wide:
         bt.set_tilewalk_params(args.tw_lanes, args.tw_wide)
     root = d["root_cluster"] + 1
@@ -683,11 +685,12 @@ def main():
                     "c4 = configs[3] (10k-tip synthetic network, p=8)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-batches", type=int, default=2, help="batches (= host threads) alternating in the end-to-end arm")
+    ap.add_argument("--e2e-batches", type=int, default=3, help="batches (= host threads) alternating in the end-to-end arm")
     ap.add_argument("--pipeline", type=int, default=None, help="element chunks of a calibration (-1 auto, 1 off)")
     ap.add_argument("--tilewalk", type=int, default=None, help="tile-walk kernel (-1 auto, 0 off, 1 on)")
     ap.add_argument("--tw-lanes", type=int, default=0, help="tile-walk message lanes per block (4, 8, 16)")
     ap.add_argument("--tw-wide", type=int, default=0, help="tile-walk: steps wider than this keep their own launches")
+    ap.add_argument("--coop", type=int, default=None, help="medium-shape kernel: -1 auto, 1 shared-memory, 8 cooperative, 0 generic")
     ap.add_argument("--graph", type=int, default=None, help="CUDA-graph replay of calibrate (-1 auto, 0 off, 1 on)")
     ap.add_argument("--walk", type=int, default=None, help="kernel strategy override: 0 level-parallel, 1 walk kernel")
     args = ap.parse_args()

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define PGBP_ABI_VERSION 1
+#define PGBP_ABI_VERSION 2
 
 typedef struct pgbp_plan pgbp_plan;
 typedef struct pgbp_batch pgbp_batch;
@@ -72,6 +72,15 @@ typedef struct pgbp_family_table {
   const int32_t* node_datarow; /* [nnodes] row of the tip in the data set, -1 for internal nodes */
   int32_t root_fixed;          /* 1 if the plan was allocated for a fixed root (isrootfixed,
                                   src/evomodels/evomodels.jl:41): the root is out of scope */
+  /* Trait-level scopes (missing data; src/beliefs.jl:505-559, 833-857).  Both NULL = every non-fixed
+   * member has all its traits in scope and no tip value is missing (the fast paths). */
+  const int32_t* mem_tpos;     /* [#members * ntraits] position of trait t of the member inside the
+                                  cluster's scope, -1 if that trait is out of scope (all -1 for a
+                                  fixed member); when given, mem_pos only says whether the member is
+                                  fixed (< 0) or not (>= 0) */
+  const uint8_t* tip_missing;  /* [ntips * ntraits] 1 = this trait is missing at this tip in every data
+                                  set (the pattern the beliefs were allocated for); those entries of
+                                  `tipdata` are not read */
 } pgbp_family_table;
 
 /* ---------------------------------------------------------------- plan
@@ -208,15 +217,19 @@ int32_t pgbp_reset_calibration_flags(pgbp_batch* batch, int32_t reset_kl);
  * formulas (src/evomodels/homogeneousbrownianmotion.jl:222-351,
  * src/evomodels/heterogeneousmodels.jl:119-150, src/evomodels/evomodels.jl:377-396)
  * and evidence absorption (src/beliefupdates.jl:210-231), then the factor
- * snapshot (src/clustergraphbeliefs.jl:106).  Requires plan.families and full
- * trait scopes (no missing data); other models / scopes are assigned on the
- * host and uploaded with pgbp_set_belief + pgbp_factors_from_beliefs.
+ * snapshot (src/clustergraphbeliefs.jl:106).  Requires plan.families.  Plans with trait-level
+ * scopes (families->mem_tpos / tip_missing: missing data) go through the reference's own sequence --
+ * full family factor, absorbleaf!, marginalisation of missing tip traits, fixed-root evidence, two-stage
+ * marginalisation of out-of-scope traits (src/beliefs.jl:822-858) -- on the device, one thread per
+ * (cluster, element); family size * ntraits <= 48 there.  Other models are assigned on the host and
+ * uploaded with pgbp_set_belief + pgbp_factors_from_beliefs.
  *
  * params: nparamsets records of  ncolors*p*p (rates R_c, column-major)
  *                                + p (root mean mu) + p*p (root variance v):
  *         v == 0 fixed root, any diag(v) == Inf improper, else proper prior.
- * tipdata: ndatasets records of ntips*p  (data[row][trait]); a NaN (missing value) gives the
- *          element the status PGBP_STATUS(0x7ffffa, trait) -- assign such data sets on the host.
+ * tipdata: ndatasets records of ntips*p  (data[row][trait]); a NaN where the plan expects a value
+ *          (tip_missing == 0) gives the element the status PGBP_STATUS(0x7ffffa, trait); a failed
+ *          marginalisation (src/beliefupdates.jl:68-76) PGBP_STATUS(0x7ffff9, pivot).
  * pairing: element e uses (param, data) = ZIP: (min(e,np-1), min(e,nd-1)) with
  *          np, nd in {1, B};  PRODUCT: (e / nd, e % nd) with np*nd == B. */
 #define PGBP_PAIR_ZIP 0

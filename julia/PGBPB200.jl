@@ -53,6 +53,8 @@ struct FamilyTableC
     mem_color::Ptr{Int32}
     node_datarow::Ptr{Int32}
     root_fixed::Int32
+    mem_tpos::Ptr{Int32}     # trait-level scopes (missing data); C_NULL = full scopes
+    tip_missing::Ptr{UInt8}
 end
 struct PlanDescC
     nclusters::Int32
@@ -109,23 +111,31 @@ function PlanArrays(beliefs::AbstractVector, nclu::Integer, cgraph, schedule::Ab
 end
 
 """
-    familiestable(prenodes, node2cluster, node2family, node2fixed, beliefs, taxa; edgecolor = e -> 0, rootfixed)
+    familiestable(prenodes, node2cluster, node2family, node2fixed, beliefs, taxa; edgecolor = e -> 0, rootfixed, tbl = nothing)
 
-Node-family table for device-side `assignfactors!` (Brownian-motion models, no missing data).
+Node-family table for device-side `assignfactors!` (Brownian-motion models).  With `tbl` (the column
+table the beliefs were allocated from) the missingness pattern of the tips is recorded; whenever a
+value is missing or a belief has a partial trait scope the table carries trait-level scope positions
+and the library runs the reference's absorb / marginalise sequence per node family on the device.
 """
-function familiestable(prenodes, node2cluster, node2family, node2fixed, beliefs, taxa; edgecolor = e -> 0, rootfixed::Bool)
+function familiestable(prenodes, node2cluster, node2family, node2fixed, beliefs, taxa; edgecolor = e -> 0, rootfixed::Bool, tbl = nothing)
     p = beliefs[1].ntraits
     mem_off = Int32[0]; mem_pos = Int32[]; mem_len = Float64[]; mem_gam = Float64[]; mem_col = Int32[]; row = Int32[]
+    mem_tpos = Int32[]; partial = false
     for (v, node) in enumerate(prenodes)
         be = beliefs[node2cluster[v]]
         nd = vec(sum(be.inscope, dims=1)); cs = cumsum(vcat(0, nd))
         for (k, q) in enumerate(node2family[v])
             if node2fixed[q]
-                push!(mem_pos, -1)
+                push!(mem_pos, -1); append!(mem_tpos, fill(Int32(-1), p))
             else
                 jj = findfirst(isequal(q), be.nodelabel)
-                nd[jj] == p || error("device factor assignment needs full trait scopes (no missing data)")
+                nd[jj] == p || (partial = true)
                 push!(mem_pos, cs[jj])
+                run = cs[jj]
+                for t in 1:p
+                    if be.inscope[t, jj]; push!(mem_tpos, run); run += 1 else push!(mem_tpos, -1) end
+                end
             end
             if k == 1
                 push!(mem_len, 0.0); push!(mem_gam, 1.0); push!(mem_col, 0)
@@ -137,9 +147,14 @@ function familiestable(prenodes, node2cluster, node2family, node2fixed, beliefs,
         push!(mem_off, length(mem_pos))
         push!(row, node.leaf ? findfirst(isequal(node.name), taxa) - 1 : -1)
     end
+    # tip_missing[row, trait] (row-major, like a tip-data record)
+    miss = tbl === nothing ? zeros(UInt8, p * length(taxa)) :
+           UInt8[ismissing(col[i]) for i in eachindex(taxa) for col in tbl]
+    scoped = partial || any(!iszero, miss)
     (nnodes = Int32(length(prenodes)), ntips = Int32(length(taxa)), root_fixed = Int32(rootfixed),
      node_cluster = Int32.(node2cluster .- 1), mem_off = mem_off, mem_pos = mem_pos, mem_length = mem_len,
-     mem_gamma = mem_gam, mem_color = mem_col, node_datarow = row)
+     mem_gamma = mem_gam, mem_color = mem_col, node_datarow = row,
+     mem_tpos = scoped ? mem_tpos : Int32[], tip_missing = scoped ? miss : UInt8[])
 end
 
 mutable struct Plan
@@ -154,7 +169,9 @@ mutable struct Plan
             if f !== nothing
                 famref[] = FamilyTableC(f.nnodes, f.ntips, pointer(f.node_cluster), pointer(f.mem_off), pointer(f.mem_pos),
                                         pointer(f.mem_length), pointer(f.mem_gamma), pointer(f.mem_color),
-                                        pointer(f.node_datarow), f.root_fixed)
+                                        pointer(f.node_datarow), f.root_fixed,
+                                        isempty(f.mem_tpos) ? Ptr{Int32}(C_NULL) : pointer(f.mem_tpos),
+                                        isempty(f.tip_missing) ? Ptr{UInt8}(C_NULL) : pointer(f.tip_missing))
                 famptr = Base.unsafe_convert(Ptr{FamilyTableC}, famref)
             end
             d = Ref(PlanDescC(a.nclusters, length(a.belief_dim) - a.nclusters, a.ntraits, pointer(a.belief_dim),

@@ -15,7 +15,7 @@ from .api import (BatchedClusterGraphBelief, ClusterGraphPlan, assignfactors, bm
                   propagate_belief, regularizebeliefs_bycluster, regularizebeliefs_bynodesubtree,
                   regularizebeliefs_onschedule, scopeindex)
 
-from .drivers import calibrate_exact_cliquetree, calibrate_optimize_cliquetree
+from .drivers import calibrate_exact_cliquetree, calibrate_optimize_cliquetree, calibrate_optimize_clustergraph
 
 # spellings used by the reference revision named in BASELINE.json's north_star
 init_beliefs_allocate = ClusterGraphPlan.from_beliefs

@@ -26,7 +26,7 @@ class PgbpError(RuntimeError):
 class FamilyTable(C.Structure):
     _fields_ = [("nnodes", i32), ("ntips", i32), ("node_cluster", P(i32)), ("mem_off", P(i32)),
                 ("mem_pos", P(i32)), ("mem_length", P(f64)), ("mem_gamma", P(f64)), ("mem_color", P(i32)),
-                ("node_datarow", P(i32)), ("root_fixed", i32)]
+                ("node_datarow", P(i32)), ("root_fixed", i32), ("mem_tpos", P(i32)), ("tip_missing", P(u8))]
 
 
 class PlanDesc(C.Structure):
@@ -105,7 +105,7 @@ class Library:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(self.dll, name)
             fn.restype, fn.argtypes = res, args
-        if self.dll.pgbp_abi_version() != 1:
+        if self.dll.pgbp_abi_version() != 2:
             raise ImportError("libpgbp_b200 ABI version mismatch")
 
     def check(self, rc):

@@ -118,6 +118,10 @@ class ClusterGraphPlan:
             a, ft.mem_gamma = _fa(families["mem_gamma"]); keep.append(a)
             a, ft.mem_color = _ia(families["mem_color"]); keep.append(a)
             a, ft.node_datarow = _ia(families["node_datarow"]); keep.append(a)
+            if families.get("mem_tpos") is not None:  # trait-level scopes (missing data)
+                a, ft.mem_tpos = _ia(families["mem_tpos"]); keep.append(a)
+                a = np.ascontiguousarray(np.asarray(families["tip_missing"], dtype=np.uint8)); keep.append(a)
+                ft.tip_missing = a.ctypes.data_as(C.POINTER(C.c_uint8))
             keep.append(ft)
             d.families = C.pointer(ft)
         h = C.c_void_p()
@@ -184,14 +188,18 @@ class ClusterGraphPlan:
 
 
 def families_table(prenodes_info, node2cluster, node2family, node2fixed, beliefs, ntraits, root_fixed,
-                   taxa=None, edge_color=None):
+                   taxa=None, edge_color=None, tip_missing=None):
     """Node-family table for pgbp_assign_factors from the reference's
     allocatebeliefs outputs (node2cluster, node2family, node2fixed; 1-based) and
     per-node parent-edge data: prenodes_info[v] = dict(name, leaf,
-    parents=[(parent_preorder_idx_1based, length, gamma, edge_number)])."""
+    parents=[(parent_preorder_idx_1based, length, gamma, edge_number)]).
+    tip_missing: optional (ntips, ntraits) boolean array, True where the trait is missing at that tip
+    (row order = taxa); with it, or when some belief has a partial trait scope, the table carries the
+    trait-level scope positions (mem_tpos) and the plan uses the scoped factor-assignment path."""
     n = len(node2cluster)
     taxa = list(taxa) if taxa is not None else None
     mem_off, mem_pos, mem_len, mem_gam, mem_col, datarow = [0], [], [], [], [], []
+    mem_tpos, partial = [], False
     for v in range(n):
         ci = node2cluster[v] - 1
         be = beliefs[ci]
@@ -202,11 +210,20 @@ def families_table(prenodes_info, node2cluster, node2family, node2fixed, beliefs
         for k, q in enumerate(nf):
             if node2fixed[q - 1]:
                 mem_pos.append(-1)
+                mem_tpos.extend([-1] * ntraits)
             else:
                 jj = list(be.nodelabel).index(q)
                 if nd[jj] != ntraits:
-                    raise ValueError("device factor assignment needs full trait scopes (no missing data)")
+                    partial = True
                 mem_pos.append(int(cs[jj]))
+                col = np.asarray(be.inscope)[:, jj].astype(bool)
+                run = int(cs[jj])
+                for t in range(ntraits):
+                    if col[t]:
+                        mem_tpos.append(run)
+                        run += 1
+                    else:
+                        mem_tpos.append(-1)
             if k == 0:
                 mem_len.append(0.0); mem_gam.append(1.0); mem_col.append(0)
             else:
@@ -215,9 +232,14 @@ def families_table(prenodes_info, node2cluster, node2family, node2fixed, beliefs
                 mem_col.append(int(edge_color(par[3])) if edge_color else 0)
         mem_off.append(len(mem_pos))
         datarow.append(taxa.index(info["name"]) if (info["leaf"] and taxa is not None) else -1)
-    return dict(nnodes=n, ntips=len(taxa) if taxa is not None else 0, root_fixed=int(bool(root_fixed)),
-                node_cluster=[c - 1 for c in node2cluster], mem_off=mem_off, mem_pos=mem_pos,
-                mem_length=mem_len, mem_gamma=mem_gam, mem_color=mem_col, node_datarow=datarow)
+    out = dict(nnodes=n, ntips=len(taxa) if taxa is not None else 0, root_fixed=int(bool(root_fixed)),
+               node_cluster=[c - 1 for c in node2cluster], mem_off=mem_off, mem_pos=mem_pos,
+               mem_length=mem_len, mem_gamma=mem_gam, mem_color=mem_col, node_datarow=datarow)
+    tm = None if tip_missing is None else np.ascontiguousarray(np.asarray(tip_missing, dtype=bool).reshape(out["ntips"], ntraits))
+    if partial or (tm is not None and tm.any()):
+        out["mem_tpos"] = mem_tpos
+        out["tip_missing"] = (tm if tm is not None else np.zeros((out["ntips"], ntraits), bool)).astype(np.uint8).ravel()
+    return out
 
 
 def bm_params(rates, mu, v=None):

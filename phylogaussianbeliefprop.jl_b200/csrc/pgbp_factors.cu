@@ -243,6 +243,242 @@ struct AssignBody {
   }
 };
 
+// K1 for plans with trait-level scopes (missing data).  One thread = (cluster, element); it follows the
+// reference's own sequence for every node family of the cluster (src/beliefs.jl:798-859):
+//   full factor phi_v over (child, parents) x traits  (homogeneousbrownianmotion.jl:222-351,
+//   heterogeneousmodels.jl:119-150, evomodels.jl:377-396)
+//   -> absorbleaf!: absorb the observed traits of a leaf, marginalise its missing ones (beliefupdates.jl:266-274)
+//   -> absorbevidence! of a fixed root among the parents (beliefs.jl:828-831)
+//   -> marginalise the out-of-scope traits: child first, then parents (beliefs.jl:836-857)
+//   -> mult! into the cluster at the scope positions (beliefs.jl:858).
+// The working factor is a dense packed-upper matrix over the live variables in thread-local memory
+// (<= PGBP_SCOPED_MAXN variables): this path is about coverage, not speed.  marginalize() keeps the
+// reference's shortcuts (beliefupdates.jl:56,62-66) and failure rule (status instead of an exception).
+struct ScopedFactor {
+  double A[PGBP_SCOPED_MAXN * (PGBP_SCOPED_MAXN + 1) / 2];  // packed upper over live variables
+  double Bq[PGBP_SCOPED_MAXN * (PGBP_SCOPED_MAXN + 1) / 2];  // scratch (permuted copy)
+  double h[PGBP_SCOPED_MAXN], hb[PGBP_SCOPED_MAXN];
+  int16_t id[PGBP_SCOPED_MAXN], idb[PGBP_SCOPED_MAXN];  // original variable (member * p + trait) of each live position
+  int n;
+  double g;
+  PGBP_HD double& a(int r, int c) { return r <= c ? A[pk(r, c)] : A[pk(c, r)]; }
+  // absorbevidence! (beliefupdates.jl:210-231) of the live positions flagged in `sel` with values val[pos]
+  PGBP_HD void absorb(const bool* sel, const double* val) {
+    double gl = 0.0, quad = 0.0;
+    for (int i = 0; i < n; i++) if (sel[i]) {
+      gl += h[i] * val[i];
+      double s = 0.0;
+      for (int j = 0; j < n; j++) if (sel[j]) s += a(i, j) * val[j];
+      quad += s * val[i];
+    }
+    g += gl - 0.5 * quad;
+    for (int k = 0; k < n; k++) if (!sel[k]) {
+      double s = 0.0;
+      for (int j = 0; j < n; j++) if (sel[j]) s += a(k, j) * val[j];
+      h[k] -= s;
+    }
+    compact_keep(sel);
+  }
+  // drop the flagged positions (keep the others, order preserved)
+  PGBP_HD void compact_keep(const bool* drop) {
+    int m = 0;
+    for (int c = 0; c < n; c++) {
+      if (drop[c]) continue;
+      int mr = 0;
+      for (int r = 0; r <= c; r++) {
+        if (drop[r]) continue;
+        Bq[pk(mr, m)] = A[pk(r, c)];
+        mr++;
+      }
+      hb[m] = h[c];
+      idb[m] = id[c];
+      m++;
+    }
+    n = m;
+    for (int q = 0; q < tri(n); q++) A[q] = Bq[q];
+    for (int k = 0; k < n; k++) { h[k] = hb[k]; id[k] = idb[k]; }
+  }
+  // marginalize(h, J, g, keep, integrate) (beliefupdates.jl:48-83); returns 0 or the failing pivot
+  PGBP_HD int marginalize(const bool* integ) {
+    int ni = 0;
+    for (int i = 0; i < n; i++) ni += integ[i] ? 1 : 0;
+    if (ni == 0) return 0;
+    bool allzero = true;
+    for (int i = 0; i < n && allzero; i++) if (integ[i]) {
+      if (!(fabs(h[i]) <= PGBP_EPS)) allzero = false;
+      for (int j = 0; j < n; j++) if (!(fabs(a(i, j)) <= PGBP_EPS)) allzero = false;
+    }
+    if (allzero) { compact_keep(integ); return 0; }
+    // permute to [I; K], then right-looking U'U over the first ni pivots (same update order as K2)
+    int perm[PGBP_SCOPED_MAXN];
+    int m = 0;
+    for (int i = 0; i < n; i++) if (integ[i]) perm[m++] = i;
+    for (int i = 0; i < n; i++) if (!integ[i]) perm[m++] = i;
+    for (int c = 0; c < n; c++) {
+      for (int r = 0; r <= c; r++) Bq[pk(r, c)] = a(perm[r], perm[c]);
+      hb[c] = h[perm[c]];
+      idb[c] = id[perm[c]];
+    }
+    double logdet = 0.0, ww = 0.0;
+    for (int k = 0; k < ni; k++) {
+      const double d = Bq[pk(k, k)];
+      if (!(d > 0.0)) return k + 1;
+      logdet += log(d);
+      const double rinv = 1.0 / sqrt(d);
+      for (int c = k + 1; c < n; c++) Bq[pk(k, c)] *= rinv;
+      const double wk = hb[k] * rinv;
+      ww = fma(wk, wk, ww);
+      for (int c = k + 1; c < n; c++) {
+        const double akc = Bq[pk(k, c)];
+        for (int r = k + 1; r <= c; r++) Bq[pk(r, c)] = fma(-Bq[pk(k, r)], akc, Bq[pk(r, c)]);
+        hb[c] = fma(-akc, wk, hb[c]);
+      }
+    }
+    g += 0.5 * ((double)ni * PGBP_LOG2PI - logdet + ww);
+    const int nk = n - ni;
+    for (int c = 0; c < nk; c++) {
+      for (int r = 0; r <= c; r++) A[pk(r, c)] = Bq[pk(ni + r, ni + c)];
+      h[c] = hb[ni + c];
+      id[c] = idb[ni + c];
+    }
+    n = nk;
+    return 0;
+  }
+};
+
+struct AssignScoped {
+  AssignBody gen;
+  const int32_t* mem_tpos;     // [#members * p]
+  const uint8_t* tip_missing;  // [ntips * p]
+  int y0 = 0;
+  PGBP_HD void operator()(int64_t e, int y) const { run(e, y + y0); }
+  PGBP_HD void run(int64_t e, int c) const {
+    const FamDev& F = gen.F;
+    const ThetaRows& tr = gen.tr;
+    const int p = F.p, pp = p * p;
+    const int64_t ld = gen.ld, ldp = gen.ldp, ldd = gen.ldd;
+    int64_t ip, idd;
+    if (gen.pairing == PGBP_PAIR_PRODUCT) { ip = e / gen.nd; idd = e % gen.nd; }
+    else { ip = gen.np == 1 ? 0 : e; idd = gen.nd == 1 ? 0 : e; }
+    const double* th = gen.theta + ip;
+    const double* td = gen.tip + idd;
+    double* st = gen.state + e;
+    const int64_t ej = gen.gs > 1 ? e - e % gen.gs : e;
+    const bool lead = ej == e;
+    const int64_t js = F.cl_jslot[c], hs = F.cl_hslot[c], gsl = F.cl_gslot[c];
+    const int m = F.cl_dim[c];
+    if (lead) for (int q = 0; q < tri(m); q++) st[(js + q) * ld] = 0.0;
+    for (int q = 0; q < m; q++) st[(hs + q) * ld] = 0.0;
+    double g = 0.0;
+    const double kind = th[(int64_t)tr.kind() * ldp];
+    if (kind < 0.0) {
+      if (c == 0) status_fail(gen.status, e, PGBP_STATUS(0x7ffffd, (int)(-kind)));
+      st[gsl * ld] = NAN;
+      return;
+    }
+    double j[PGBP_MAX_TRAITS * PGBP_MAX_TRAITS], w[PGBP_MAX_TRAITS * PGBP_MAX_TRAITS];
+    ScopedFactor f;
+    bool sel[PGBP_SCOPED_MAXN];
+    double val[PGBP_SCOPED_MAXN];
+    for (int iv = F.clu_off[c]; iv < F.clu_off[c + 1]; iv++) {
+      const int v = F.clu_node[iv];
+      const int k0 = F.mem_off[v], nm = F.mem_off[v + 1] - k0;
+      f.n = nm * p;
+      for (int i = 0; i < f.n; i++) { f.h[i] = 0.0; f.id[i] = (int16_t)i; }
+      if (nm == 1) {  // root family (src/beliefs.jl:803-807)
+        if (F.mem_pos[k0] < 0 || kind != 1.0) continue;  // fixed root, or improper prior: factor == 1
+        for (int cc = 0; cc < p; cc++) {
+          for (int r = 0; r <= cc; r++) f.A[pk(r, cc)] = th[(int64_t)(tr.rootP() + cc * p + r) * ldp];
+          f.h[cc] = th[(int64_t)(tr.rooth() + cc) * ldp];
+        }
+        f.g = th[(int64_t)tr.rootg() * ldp];
+      } else {
+        bool samecolor = true;
+        for (int k = k0 + 2; k < k0 + nm; k++) if (F.mem_color[k] != F.mem_color[k0 + 1]) samecolor = false;
+        if (samecolor) {
+          const int col = F.mem_color[k0 + 1];
+          double t0 = 0.0;
+          if (nm == 2) t0 = F.mem_length[k0 + 1];
+          else for (int k = k0 + 1; k < k0 + nm; k++) t0 += F.mem_gamma[k] * F.mem_gamma[k] * F.mem_length[k];
+          for (int q = 0; q < pp; q++) j[q] = th[(int64_t)(tr.P(col) + q) * ldp] / t0;
+          f.g = th[(int64_t)tr.g0(col) * ldp] - 0.5 * p * log(t0);
+        } else {
+          for (int q = 0; q < pp; q++) w[q] = 0.0;
+          for (int k = k0 + 1; k < k0 + nm; k++) {
+            const double fk = F.mem_gamma[k] * F.mem_gamma[k] * F.mem_length[k];
+            const int col = F.mem_color[k];
+            for (int q = 0; q < pp; q++) w[q] += fk * th[(int64_t)(tr.R(col) + q) * ldp];
+          }
+          double ldv;
+          const int info = spd_inverse_logdet(w, j, p, &ldv);
+          if (info) { status_fail(gen.status, e, PGBP_STATUS(0x7ffffc, info)); st[gsl * ld] = NAN; return; }
+          f.g = -0.5 * (p * PGBP_LOG2PI + ldv);
+        }
+        for (int b2 = 0; b2 < nm; b2++) {
+          const double cb = b2 == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + b2]);
+          for (int a2 = 0; a2 <= b2; a2++) {
+            const double ca = a2 == 0 ? 1.0 : (nm == 2 ? -1.0 : -F.mem_gamma[k0 + a2]);
+            const double cab = ca * cb;
+            for (int tb = 0; tb < p; tb++)
+              for (int ta = 0; ta < (a2 == b2 ? tb + 1 : p); ta++) f.A[pk(a2 * p + ta, b2 * p + tb)] = cab * j[tb * p + ta];
+          }
+        }
+        // absorbleaf!: observed traits of the leaf, then its missing traits
+        const int row = F.node_datarow[v];
+        const bool child_fixed = F.mem_pos[k0] < 0;
+        if (child_fixed && row >= 0) {
+          bool anymiss = false;
+          for (int i = 0; i < f.n; i++) { sel[i] = false; val[i] = 0.0; }
+          for (int t = 0; t < p; t++) {
+            if (tip_missing[row * p + t]) { anymiss = true; continue; }
+            sel[t] = true;
+            val[t] = td[(int64_t)(row * p + t) * ldd];
+            if (val[t] != val[t]) status_fail(gen.status, e, PGBP_STATUS(0x7ffffa, t + 1));
+          }
+          f.absorb(sel, val);
+          if (anymiss) {
+            for (int i = 0; i < f.n; i++) sel[i] = f.id[i] < p;
+            const int info = f.marginalize(sel);
+            if (info) { status_fail(gen.status, e, PGBP_STATUS(0x7ffff9, info)); st[gsl * ld] = NAN; return; }
+          }
+        }
+        // a fixed root among the parents: clamp it to the prior mean (src/beliefs.jl:828-831)
+        bool anyroot = false;
+        for (int i = 0; i < f.n; i++) {
+          const int a2 = f.id[i] / p, t = f.id[i] % p;
+          sel[i] = a2 >= 1 && F.mem_pos[k0 + a2] < 0;
+          val[i] = sel[i] ? th[(int64_t)(tr.mu() + t) * ldp] : 0.0;
+          anyroot = anyroot || sel[i];
+        }
+        if (anyroot) f.absorb(sel, val);
+      }
+      // out-of-scope traits (src/beliefs.jl:836-857): child first, then parents
+      for (int stage = 0; stage < 2; stage++) {
+        bool any = false;
+        for (int i = 0; i < f.n; i++) {
+          const int a2 = f.id[i] / p, t = f.id[i] % p;
+          sel[i] = ((stage == 0) == (a2 == 0)) && mem_tpos[(k0 + a2) * p + t] < 0;
+          any = any || sel[i];
+        }
+        if (!any) continue;
+        const int info = f.marginalize(sel);
+        if (info) { status_fail(gen.status, e, PGBP_STATUS(0x7ffff9, info)); st[gsl * ld] = NAN; return; }
+      }
+      // mult! (src/beliefs.jl:858)
+      g += f.g;
+      for (int cc = 0; cc < f.n; cc++) {
+        const int pc = mem_tpos[(k0 + f.id[cc] / p) * p + f.id[cc] % p];
+        st[(hs + pc) * ld] += f.h[cc];
+        if (lead) for (int r = 0; r <= cc; r++) {
+          const int pr = mem_tpos[(k0 + f.id[r] / p) * p + f.id[r] % p];
+          st[(js + (pr <= pc ? pk(pr, pc) : pk(pc, pr))) * ld] += f.A[pk(r, cc)];
+        }
+      }
+    }
+    st[gsl * ld] = g;
+  }
+};
+
 // K1 write-once path, compile-time trait count P.  The precision j of one family lives in
 // registers (P*P doubles).  Families of the cluster are applied in node order, like the loop at
 // src/beliefs.jl:798-859; the host has marked, for every family, which of its (member, member)
@@ -809,6 +1045,8 @@ struct DevTables {
   uint64_t* first_J = nullptr;
   uint8_t* first_h = nullptr;
   double *mem_length = nullptr, *mem_gamma = nullptr;
+  int32_t* mem_tpos = nullptr;    // trait-level scopes (scoped plans only)
+  uint8_t* tip_missing = nullptr;
   // parameter / data staging
   double* theta = nullptr;
   int64_t theta_rows = 0, ldp = 0;
@@ -853,6 +1091,10 @@ static int get_tables(pgbp_batch* b, DevTables** out) {
     PGBP_TRY(upload(b, dt.get(), &dt->node_cluster, F.node_cluster));
     PGBP_TRY(upload(b, dt.get(), &dt->mem_off, F.mem_off));
     PGBP_TRY(upload(b, dt.get(), &dt->mem_pos, F.mem_pos));
+    if (F.scoped) {
+      PGBP_TRY(upload(b, dt.get(), &dt->mem_tpos, F.mem_tpos));
+      PGBP_TRY(upload(b, dt.get(), &dt->tip_missing, F.tip_missing));
+    }
     PGBP_TRY(upload(b, dt.get(), &dt->mem_color, F.mem_color));
     PGBP_TRY(upload(b, dt.get(), &dt->node_datarow, F.node_datarow));
     PGBP_TRY(upload(b, dt.get(), &dt->clu_off, F.clu_off));
@@ -1018,6 +1260,8 @@ static int assign_launch(pgbp_batch* b, pgbp::DevTables* dt, double* out, int32_
             pt, ncolors, F.root_fixed};
   AssignBody body{fd, dt->theta, dt->ldp, dt->tip, dt->ldd, out, b->status, b->ld, nparamsets, ndatasets, pairing, tr};
   body.gs = b->group_size;
+  if (F.scoped)  // trait-level scopes (missing data): the reference's absorb / marginalise sequence
+    return launch_generic(b, "k_assign_scoped", b->B, p->nclusters, AssignScoped{body, dt->mem_tpos, dt->tip_missing});
   switch (pt) {
 #define PGBP_FAST_CASE(P_) \
   case P_: \
@@ -1026,6 +1270,9 @@ static int assign_launch(pgbp_batch* b, pgbp::DevTables* dt, double* out, int32_
     break;
     PGBP_FAST_CASE(1) PGBP_FAST_CASE(2) PGBP_FAST_CASE(3) PGBP_FAST_CASE(4) PGBP_FAST_CASE(5) PGBP_FAST_CASE(6)
     PGBP_FAST_CASE(7) PGBP_FAST_CASE(8)
+    // p = 16 (C5): the family precision (136 doubles) no longer fits the register file and lives in
+    // thread-local memory (L1-resident), which still beats the generic body's global read-modify-write
+    PGBP_FAST_CASE(12) PGBP_FAST_CASE(16)
 #undef PGBP_FAST_CASE
     default: PGBP_TRY(launch_generic(b, "k_assign_factors", b->B, p->nclusters, body));
   }

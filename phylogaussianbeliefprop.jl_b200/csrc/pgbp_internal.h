@@ -88,6 +88,10 @@ struct FamilyTable {
   std::vector<uint8_t> clu_flag, first_h;
   std::vector<uint64_t> first_J;
   int32_t ncolors_min = 1;
+  // trait-level scopes (missing data): scoped == true routes K1 through the generic scoped body
+  bool scoped = false;
+  std::vector<int32_t> mem_tpos;     // [#members * p]
+  std::vector<uint8_t> tip_missing;  // [ntips * p]
 };
 
 }  // namespace pgbp

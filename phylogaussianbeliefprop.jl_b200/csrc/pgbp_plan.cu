@@ -292,6 +292,17 @@ int32_t pgbp_plan_create(const pgbp_plan_desc* d, pgbp_plan** out) {
     F.mem_color.assign(ft->mem_color, ft->mem_color + nm);
     F.node_datarow.assign(ft->node_datarow, ft->node_datarow + F.nnodes);
     const int pt = p->ntraits;
+    F.scoped = ft->mem_tpos != nullptr || ft->tip_missing != nullptr;
+    if (F.scoped) {
+      if (ft->mem_tpos) F.mem_tpos.assign(ft->mem_tpos, ft->mem_tpos + (size_t)nm * pt);
+      else {
+        F.mem_tpos.assign((size_t)nm * pt, -1);
+        for (int k = 0; k < nm; k++)
+          for (int t = 0; t < pt; t++) if (F.mem_pos[k] >= 0) F.mem_tpos[(size_t)k * pt + t] = F.mem_pos[k] + t;
+      }
+      if (ft->tip_missing) F.tip_missing.assign(ft->tip_missing, ft->tip_missing + (size_t)F.ntips * pt);
+      else F.tip_missing.assign((size_t)F.ntips * pt, 0);
+    }
     std::vector<std::vector<int32_t>> c2n(p->nclusters);
     for (int v = 0; v < F.nnodes; v++) {
       const int c = F.node_cluster[v];
@@ -299,7 +310,10 @@ int32_t pgbp_plan_create(const pgbp_plan_desc* d, pgbp_plan** out) {
       const int o0 = F.mem_off[v], o1 = F.mem_off[v + 1];
       if (o1 - o0 < 1 || o1 - o0 > PGBP_MAX_FAMILY) PGBP_FAIL(PGBP_EINVAL, "node %d: family size %d unsupported", v, o1 - o0);
       for (int k = o0; k < o1; k++) {
-        if (F.mem_pos[k] >= 0 && F.mem_pos[k] + pt > p->dim[c])
+        if (F.scoped) {
+          for (int t = 0; t < pt; t++)
+            if (F.mem_tpos[(size_t)k * pt + t] >= p->dim[c]) PGBP_FAIL(PGBP_EINVAL, "node %d: member scope exceeds cluster %d", v, c);
+        } else if (F.mem_pos[k] >= 0 && F.mem_pos[k] + pt > p->dim[c])
           PGBP_FAIL(PGBP_EINVAL, "node %d: member scope exceeds cluster %d", v, c);
         if (k > o0) {
           if (!(F.mem_length[k] >= 0)) PGBP_FAIL(PGBP_EINVAL, "node %d: negative edge length", v);
@@ -308,6 +322,9 @@ int32_t pgbp_plan_create(const pgbp_plan_desc* d, pgbp_plan** out) {
         }
       }
       if (F.node_datarow[v] >= F.ntips) PGBP_FAIL(PGBP_EINVAL, "node %d: data row out of range", v);
+      if (F.scoped && (o1 - o0) * pt > PGBP_SCOPED_MAXN)
+        PGBP_FAIL(PGBP_EINVAL, "node %d: family of %d members x %d traits exceeds the %d variables of the scoped "
+                  "factor-assignment path", v, o1 - o0, pt, PGBP_SCOPED_MAXN);
       c2n[c].push_back(v);
     }
     F.clu_off.assign(1, 0);
@@ -321,6 +338,7 @@ int32_t pgbp_plan_create(const pgbp_plan_desc* d, pgbp_plan** out) {
       std::set<std::pair<int, int>> seenJ;  // (pos_a, pos_b) blocks already written
       std::set<int> seenh;
       for (int node : v) {
+        if (F.scoped) break;  // the scoped body zero-fills and accumulates
         const int o0 = F.mem_off[node], nm = F.mem_off[node + 1] - o0;
         for (int a = 0; a < nm; a++) {
           const int pa = F.mem_pos[o0 + a];

@@ -15,6 +15,7 @@
 #define PGBP_T0_MAX 12
 #define PGBP_COOP_MAX 48
 #define PGBP_WALK_MAXP 4
+#define PGBP_SCOPED_MAXN 48  // variables of one node family in the scoped (missing-data) K1 path
 
 namespace pgbp {
 inline void shape_class(int i, int s, int* ci, int* cs, int* maxm) {

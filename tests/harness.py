@@ -75,8 +75,9 @@ class Case:
             self.sched = schedule(self)
         fam = None
         if with_families:
+            tm = np.isnan(np.atleast_2d(self.tbl).reshape(len(self.taxa), -1)) if np.isnan(self.tbl).any() else None
             fam = pgbp_b200.families_table(prenodes_info(self.net), n2c, n2f, n2x, b, model.ntraits,
-                                           model.isrootfixed(), self.taxa, edge_color)
+                                           model.isrootfixed(), self.taxa, edge_color, tip_missing=tm)
         self.plan = pgbp_b200.ClusterGraphPlan.from_beliefs(b, self.nclusters, self.cg.labels, self.sched, fam, lib)
 
     def oracle_cgb(self, tbl=None, model=None):

@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol(libname):
     for name in declared_symbols():
         assert hasattr(dll, name), name
     dll.pgbp_abi_version.restype = ctypes.c_int32
-    assert dll.pgbp_abi_version() == 1
+    assert dll.pgbp_abi_version() == 2
     lib = pgbp_b200.Library(path)  # binds restype / argtypes of every symbol
     buf = ctypes.create_string_buffer(64)
     assert lib.pgbp_last_error(buf, 64) == 0

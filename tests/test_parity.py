@@ -29,14 +29,23 @@ TAXA = ["A", "B1", "B2", "C"]
 HINT9 = GOLD["canonicalform_beliefnodelabels"][:7]
 
 
-def check_all_beliefs(case, batch, cgbs, tol=TOL, elems=None):
+def check_all_beliefs(case, batch, cgbs, tol=TOL, elems=None, floor=0.0):
+    """floor > 0: quantities that are exact zeros in exact arithmetic (a missing tip trait marginalised out of
+    its edge factor: j - j*j/j) are roundoff of either sign on both sides; differences are then measured
+    against max(|reference|, floor) instead of |reference| alone."""
     elems = range(len(cgbs)) if elems is None else elems
     worst = 0.0
+
+    def rel(a, b):
+        r = relerr(a, b)
+        if floor and np.size(b):
+            r = min(r, float(np.max(np.abs(np.asarray(a, float) - np.asarray(b, float)))) / floor)
+        return r
     for j in range(1, len(case.b) + 1):
         J, h, g = batch.get_belief(j)
         for e in elems:
             ob = cgbs[e].belief[j - 1]
-            worst = max(worst, relerr(J[e], ob.J), relerr(h[e], ob.h), relerr(g[e], ob.g))
+            worst = max(worst, rel(J[e], ob.J), rel(h[e], ob.h), rel(g[e], ob.g))
     assert worst <= tol, worst
     return worst
 
@@ -278,6 +287,86 @@ def test_assignfactors_device_vs_oracle(backend, name, mk, cols, par):
     for e in range(B):
         OBP.propagate_1traversal_postorder(cgbs[e], *spt)
         assert abs(ll[e] / OBP.integratebelief_cgb(cgbs[e], spt[2][0])[1] - 1) <= TOL
+
+
+MISSING_CASES = [c for c in GOLD["evomodels"] if c["traits"] in ("x", "xy") and "BrownianMotion" in c["model"]]
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("case_", MISSING_CASES, ids=lambda c: c["id"])
+def test_assignfactors_device_missing_data_goldens(backend, case_):
+    # trait-level scopes on the device: trait x is missing at tip B2, so the scoped K1 path
+    # runs absorbleaf! + the marginalisations of src/beliefs.jl:833-857 per family.  Beliefs against the
+    # oracle's assignfactors!, log-likelihood against the reference's goldens (test/test_evomodels.jl:107-262);
+    # other replicates of the batch carry different values at the observed entries.
+    lib = get_lib(backend)
+    cols = {"x": [0], "xy": [0, 1]}[case_["traits"]]
+    tbl = TBL[:, cols]
+    args = eval(case_["args"], {"inf": math.inf, "np": np})
+    model = getattr(M, case_["model"])(*args)
+    edge_color = None
+    if case_["model"] == "HeterogeneousBrownianMotion":
+        colors = args[1] or {}
+        edge_color = lambda num: colors.get(num, 1) - 1  # noqa: E731
+        rates, mu, v = [np.array(r) for r in args[0]], args[2], (args[3] if len(args) > 3 else None)
+    elif case_["model"] == "UnivariateBrownianMotion":
+        rates, mu, v = [[[float(args[0])]]], [float(args[1])], [[float(args[2])]]
+    elif case_["model"] == "MvDiagBrownianMotion":
+        rates, mu, v = [np.array(args[0], float)], args[1], np.array(args[2], float)
+    else:
+        rates, mu, v = [np.array(args[0])], args[1], (np.array(args[2]) if len(args) > 2 else None)
+    case = Case(GOLD["netstr_named"], "cliquetree", tbl, TAXA, model, lib, schedule="spanningtree", edge_color=edge_color)
+    assert case.plan.families.get("mem_tpos") is not None
+    B = 4
+    rng = np.random.default_rng(17)
+    data = np.repeat(tbl[None], B, axis=0)
+    data[1:] += rng.normal(size=(B - 1,) + tbl.shape)  # NaN stays NaN
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+    bt.assignfactors(pgbp_b200.bm_params(rates, mu, v), data, ncolors=len(rates))
+    assert (bt.status() == 0).all()
+    cgbs = [case.oracle_cgb(tbl=data[e]) for e in range(B)]
+    check_all_beliefs(case, bt, cgbs, floor=1e-3)
+    spt = case.sched[0]
+    assert bt.propagate_1traversal_postorder(spt).all()
+    _, ll = bt.integratebelief(spt[2][0])
+    assert abs(ll[0] / case_["loglik"] - 1) < 1e-9
+    for e in range(B):
+        OBP.propagate_1traversal_postorder(cgbs[e], *spt)
+        assert abs(ll[e] / OBP.integratebelief_cgb(cgbs[e], spt[2][0])[1] - 1) <= TOL
+    # a NaN where the plan expects a value is a per-element status, not a silent NaN
+    bad = data.copy()
+    bad[2, 0, 0] = NAN
+    bt.assignfactors(pgbp_b200.bm_params(rates, mu, v), bad, ncolors=len(rates))
+    stt = bt.status()
+    assert stt[2] != 0 and (np.delete(stt, 2) == 0).all()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_assignfactors_device_missing_data_tree_and_joingraph(backend):
+    # test/test_calibration.jl:107-129: tree, trait 2 observed at one tip only (internal nodes lose that trait
+    # from their scope); every belief integrates to -7.578343735986344 after calibration.
+    lib = get_lib(backend)
+    tbl = np.array([[1, NAN], [1, NAN], [1, NAN], [1, 1.0]])
+    m = M.MvDiagBrownianMotion([1, 1], [0, 0])
+    case = Case("(((A:1.0, B:1.0)E:1.0, C:2.0)F:1.0, D:3.0)G;", "cliquetree", tbl, ["A", "B", "C", "D"], m, lib,
+                schedule="spanningtree")
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, 3)
+    bt.assignfactors(pgbp_b200.bm_params([np.array([1.0, 1.0])], [0, 0]), tbl[None])
+    cgb = case.oracle_cgb()
+    check_all_beliefs(case, bt, [cgb] * 3, floor=1e-3)
+    succ, _ = bt.calibrate(case.sched)
+    assert succ.all()
+    for j in range(1, len(case.b) + 1):
+        assert np.all(np.abs(bt.integratebelief(j, want_mu=False)[1] / -7.578343735986344 - 1) < 1e-9)
+    # test/test_calibration.jl:131-185: level-3 network, join-graph structuring, improper root, one value missing
+    tbl = np.array([[2.11, 30.0], [2.15, NAN]])
+    R = [[1, 0.5], [0.5, 1]]
+    m = M.MvFullBrownianMotion(R, [0, 0], [[math.inf, 0], [0, math.inf]])
+    case = Case(GOLD["netstr_level3"], "jgs", tbl, ["A", "B"], m, lib, maxclustersize=3)
+    bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, 2)
+    bt.assignfactors(pgbp_b200.bm_params([np.array(R, float)], [0, 0], [[math.inf, 0], [0, math.inf]]), tbl[None])
+    assert (bt.status() == 0).all()
+    check_all_beliefs(case, bt, [case.oracle_cgb()] * 2, floor=1e-3)
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
@@ -814,6 +903,24 @@ def test_calibrate_optimize_cliquetree_goldens(backend):
     theta, ll, res = pgbp_b200.calibrate_optimize_cliquetree(c.plan, c.sched[0], yd, start=(1.0, 0.0), maxiter=60)
     assert abs(ll / -3.2763180687070053 - 1) <= 1e-9
     assert abs(theta[0] / 0.5932930079336234 - 1) <= 1e-4 and abs(theta[1] / -0.07534357691418593 - 1) <= 1e-4
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_calibrate_optimize_clustergraph_goldens(backend):
+    # calibrate_optimize_clustergraph! on a loopy Bethe cluster graph (regularizebeliefs_bycluster!, calibrate!
+    # with auto = true, objective = free energy): test/test_calibration.jl:188-204 (compared there with RxInfer,
+    # rtol 1e-4) and test/test_optimization.jl:38-46 (mateescu_2010, against the exact ML fit)
+    lib = get_lib(backend)
+    y = np.array([11.275034507978296, 10.032494469945764, 11.49586603350308, 11.004447427824012])[:, None]
+    c = Case(GOLD["netstr_unnamed"], "bethe", y, ["A", "B", "C", "D"], M.UnivariateBrownianMotion(1.0, 0.0), lib)
+    theta, fe, res = pgbp_b200.calibrate_optimize_clustergraph(c.plan, c.sched, y, start=(1.0, 0.0), maxiter=100)
+    assert abs(fe / -3.4312133894974126 - 1) <= 1e-4
+    assert abs(theta[1] / 10.931640613828181 - 1) <= 1e-4 and abs(theta[0] / 0.15239159696122745 - 1) <= 1e-4
+    yd = np.array([1.0, -1.0])[:, None]
+    c = Case(GOLD["mateescu"], "bethe", yd, ["d", "g"], M.UnivariateBrownianMotion(1.0, 0.0), lib)
+    theta, fe, res = pgbp_b200.calibrate_optimize_clustergraph(c.plan, c.sched, yd, start=(1.0, 0.0), maxiter=100)
+    assert abs(theta[1] / -0.07534357691418593 - 1) <= 2e-5 and abs(theta[0] / 0.5932930079336234 - 1) <= 2e-6
+    assert abs(fe / -3.2763180687070053 - 1) <= 3e-2
 
 
 # ------------------------------------------------------------------ shared-precision batches (trait replicates under one theta)
