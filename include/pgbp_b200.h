@@ -180,10 +180,12 @@ int32_t pgbp_batch_set_tilewalk_params(pgbp_batch* batch, int32_t lanes, int32_t
 /* CUDA-graph replay of calibrate calls: -1 automatic (default: calls of >= 24 launches are captured at
  * their second occurrence and replayed afterwards), 0 off, 1 always.  Results are unaffected. */
 int32_t pgbp_batch_set_graph_mode(pgbp_batch* batch, int32_t mode);
-/* Kernel for medium message shapes (sender dimension > 12): -1 automatic (= 1 where it fits),
- * 1 shared-memory kernel (one thread per element, factor in shared memory), 4 / 8 cooperative
- * kernel (that many lanes per element for sender dimensions <= 16, 8 above; sender dimension
- * <= 32), 0 one thread per element with thread-local storage.  Results are bit-identical. */
+/* Kernel for medium message shapes (sender dimension > 12): -1 automatic (shared-memory kernel where it
+ * fits; integrated dimensions 12..16 use its multi-warp form: 8 warps share one tile of 32 elements and
+ * split the work by column), 1 single-warp shared-memory kernel (one thread per element, factor in
+ * shared memory), 2 multi-warp form with 4 warps, 4 / 8 cooperative kernel (that many lanes per element
+ * for sender dimensions <= 16, 8 above; sender dimension <= 48), 0 one thread per element with
+ * thread-local storage.  Results are bit-identical. */
 int32_t pgbp_batch_set_coop_mode(pgbp_batch* batch, int32_t mode);
 
 /* Host <-> device belief access (CanonicalBelief fields, src/beliefs.jl:72-132).

@@ -739,6 +739,282 @@ __global__ void __launch_bounds__(32) k_message_smem(MsgArgs a) {
   store_flag(a, md.dmsg, e, S, maxJ, maxh);
 }
 
+// -------------------------------------------------------------------------------------
+// Multi-warp version of k_message_smem for LARGE integrated dimensions (I >= 12: C5's (16,16) and (16,32)
+// messages).  There the factor of 32 elements fills 100-175 KB of shared memory, so only one or two
+// single-warp blocks fit an SM and every phase runs at the latency of its own dependent chain
+// (profiles/r1_c5_launches.txt: 49 % of the C5 step).  Here NW warps share ONE tile of 32 elements (lane =
+// element, as before) and split the work by COLUMN: the asynchronous staging (phase A) by entry, the
+// right-hand sides of Z = U^-T [J_IK | h_I] (phase B2) and the kept columns of the streamed Schur
+// complement (phase C, paired cc / S-1-cc for balance) by warp; only the Cholesky of J_II (phase B1,
+// ~12 % of the flops) stays on warp 0.  Same shared-memory footprint, NW x the warps per SM.
+// NW = 4 (two tiles per SM, full register budget) when two tiles fit the SM's shared memory, else NW = 8
+// (one tile per SM).  Measured on C5 (B200): single-warp tiles 490 ms per calibration step, 8 warps at
+// 128 registers 389 ms, 4 warps at 255 registers 356 ms.
+// Every entry is still produced by one thread with the same operands in the same order: bit-identical.
+// -------------------------------------------------------------------------------------
+// shared memory of one tile: factor rows + 2 scalar rows (x 32 lanes x 8 bytes), per-lane flags, index tables
+inline __host__ __device__ size_t smem_mw_block_bytes(int I, int S, int NW) {
+  const int M = I + S;
+  return sizeof(double) * 32 * (size_t)(smem_doubles(I, S) + 2) + sizeof(int32_t) * 32 * (size_t)(2 + NW) +
+         sizeof(uint16_t) * (size_t)(M * (M + 1) / 2 + M + S * (S + 1) / 2 + S + 4);
+}
+
+template <int I, int NW>
+__global__ void __launch_bounds__(32 * NW, (NW <= 4 ? 2 : 1)) k_message_smem_mw(MsgArgs a) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x, wid = threadIdx.y;
+  const int64_t e = a.e0 + (int64_t)blockIdx.x * 32 + tid;
+  const MsgDesc md = a.msgs[blockIdx.y];
+  const int S = md.s, M = md.mF;
+  constexpr int TI = I * (I + 1) / 2;
+  const int SMM = tri(M), SS = tri(S);
+  const int nrhs = S + 1;
+  const int NE = TI + I * nrhs;            // staged entries per element
+  // shared layout: rows of 32 lanes: [0, NE) factor | ww | logdet; then per-lane int32 flags
+  // ([tid] active, [32 + tid] failed pivot, [64 + 32 w + tid] warp w saw a non-zero), then the index tables.
+  // 1/U_cc is kept in the (otherwise unused) diagonal slot of U; the flag reduction of phase C reuses
+  // rows of U, which is dead by then.
+  double* smt = sm + tid;
+  double* Z = smt + TI * 32;               // Z(k, cc) = Z[(cc * I + k) * 32]; column S holds h_I / w
+  double* s_ww = smt + NE * 32;
+  double* s_logdet = s_ww + 32;
+  double* s_redJ = smt;                    // rows [0, NW) and [NW, 2 NW) of U (2 NW <= TI)
+  double* s_redh = smt + NW * 32;
+  int32_t* s_flag = (int32_t*)(sm + 32 * (NE + 2));
+  uint16_t* tgat = (uint16_t*)(s_flag + 32 * (2 + NW));
+  const int ngat = SMM + M, nsca = SS + S;
+  uint16_t* tsca = tgat + ngat;
+  {
+    const int32_t* __restrict__ g0 = a.tab + md.gat;
+    const int32_t* __restrict__ s0 = a.tab + md.sca;
+    for (int q = wid * 32 + tid; q < ngat; q += 32 * NW) tgat[q] = (uint16_t)g0[q];
+    for (int q = wid * 32 + tid; q < nsca; q += 32 * NW) tsca[q] = (uint16_t)s0[q];
+    if (wid == 0) {
+      int act = e < a.B;
+      if (act && a.status[e] != 0) act = 0;
+      if (act && a.done && a.done[e]) act = 0;
+      s_flag[tid] = act;
+      s_flag[32 + tid] = 0;
+    }
+  }
+  __syncthreads();
+  const bool active = s_flag[tid] != 0;    // same answer in every warp of the tile
+  const int64_t ee = active ? e : a.e0 + (int64_t)blockIdx.x * 32;  // inactive lanes shadow a valid element, never store
+  const uint32_t ld8 = (uint32_t)(a.ld * 8);
+  char* stb = (char*)(a.state + ee);
+  char* rsb = a.resid ? (char*)(a.resid + ee) : nullptr;
+  const uint16_t* gat = tgat;
+  const uint16_t* sca = tsca;
+  const uint32_t fJ = (uint32_t)md.fJ, fh = (uint32_t)md.fh, sJ = (uint32_t)md.sJ, sh = (uint32_t)md.sh,
+                 tJ = (uint32_t)md.tJ, th = (uint32_t)md.th, rJ = (uint32_t)md.rJ, rh = (uint32_t)md.rh;
+  const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;
+
+  // ---- A: staging, entries dealt to the warps round-robin --------------------------------------
+  for (int n = wid; n < NE; n += NW) {
+    uint32_t slot;
+    if (n < TI) slot = fJ + gat[n];
+    else {
+      const int idx = n - TI, cc = idx / I, k = idx - cc * I;
+      slot = cc < S ? fJ + gat[tri(I + cc) + k] : fh + gat[SMM + k];
+    }
+    cp_async8(smt + n * 32, gaddr(stb, slot, ld8));
+  }
+  double g = 0.0, sg_old = 0.0, tg_old = 0.0;
+  if (wid == 0) {
+    g = *gaddr(stb, (uint32_t)md.fg, ld8);
+    sg_old = sz ? 0.0 : *gaddr(stb, (uint32_t)md.sg, ld8);
+    tg_old = *gaddr(stb, (uint32_t)md.tg, ld8);
+  }
+  // L2 prefetch of what phase C reads, by kept column
+  for (int cc = wid; cc < S; cc += NW) {
+    const uint16_t* gc = gat + tri(I + cc) + I;
+    const int qc = tri(cc);
+    for (int rr = 0; rr <= cc; rr++) {
+      prefetch_l2(gaddr(stb, fJ + gc[rr], ld8));
+      if (!sz) prefetch_l2(gaddr(stb, sJ + qc + rr, ld8));
+      prefetch_l2(gaddr(stb, tJ + sca[qc + rr], ld8));
+    }
+    prefetch_l2(gaddr(stb, fh + gat[SMM + I + cc], ld8));
+    if (!sz) prefetch_l2(gaddr(stb, sh + cc, ld8));
+    prefetch_l2(gaddr(stb, th + sca[SS + cc], ld8));
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- B1: U'U = J_II on warp 0 (left-looking, fully unrolled; as k_message_smem) ----------------
+  bool nz = false;
+  if (wid == 0) {
+    double rinv[I];
+    double logdet = 0.0;
+    int fail = 0;
+#pragma unroll
+    for (int c = 0; c < I; c++) {
+      double v[I];
+#pragma unroll
+      for (int k = 0; k <= c; k++) {
+        v[k] = smt[pk(k, c) * 32];
+        if (!(fabs(v[k]) <= PGBP_EPS)) nz = true;
+      }
+#pragma unroll
+      for (int k = 0; k < c; k++) {
+        const double u = v[k] * rinv[k];
+        v[k] = u;
+        smt[pk(k, c) * 32] = u;
+#pragma unroll
+        for (int r = k + 1; r <= c; r++) v[r] = nfma(r == c ? u : smt[pk(k, r) * 32], u, v[r]);
+      }
+      const double d = v[c];
+      if (!(d > 0.0) && fail == 0) fail = c + 1;
+      logdet += log(d);
+      rinv[c] = 1.0 / sqrt(d);
+      smt[pk(c, c) * 32] = rinv[c];
+    }
+    s_logdet[0] = logdet;
+    s_flag[32 + tid] = fail;
+  }
+  __syncthreads();
+
+  // ---- B2: Z = U^-T [J_IK | h_I], right-hand sides dealt to the warps ---------------------------
+  {
+    double rinv[I];
+#pragma unroll
+    for (int k = 0; k < I; k++) rinv[k] = smt[pk(k, k) * 32];
+    for (int c0 = wid; c0 < nrhs; c0 += NW) {
+      double* z0 = Z + c0 * I * 32;
+      double v0[I];
+#pragma unroll
+      for (int k = 0; k < I; k++) {
+        v0[k] = z0[k * 32];
+        if (!(fabs(v0[k]) <= PGBP_EPS)) nz = true;
+      }
+#pragma unroll
+      for (int k = 0; k < I; k++) {
+        const double u0 = v0[k] * rinv[k];
+        v0[k] = u0;
+#pragma unroll
+        for (int r = k + 1; r < I; r++) v0[r] = nfma(smt[pk(k, r) * 32], u0, v0[r]);
+      }
+#pragma unroll
+      for (int k = 0; k < I; k++) z0[k * 32] = v0[k];
+      if (c0 == S) {  // the h column: w = U^-T h_I
+        double ww = 0.0;
+#pragma unroll
+        for (int k = 0; k < I; k++) ww = fma(v0[k], v0[k], ww);
+        s_ww[0] = ww;
+      }
+    }
+  }
+  s_flag[64 + wid * 32 + tid] = nz ? 1 : 0;
+  __syncthreads();
+  bool nzall = false;
+#pragma unroll
+  for (int w = 0; w < NW; w++) nzall = nzall || s_flag[64 + w * 32 + tid] != 0;
+  const int fail = s_flag[32 + tid];
+  const bool dead = !active || (nzall && fail != 0);
+  if (nzall) {
+    if (fail && active && wid == 0) status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, fail));
+    if (wid == 0) g += 0.5 * ((double)I * PGBP_LOG2PI - s_logdet[0] + s_ww[0]);
+  } else {  // "missing data" shortcut: message = (h_K, J_KK, g) unchanged
+    for (int q = wid; q < nrhs * I; q += NW) Z[q * 32] = 0.0;
+  }
+  __syncthreads();
+
+  // ---- C: stream the kept block, kept columns paired (j, S-1-j) and dealt to the warps ------------
+  double maxJ = 0.0, maxh = 0.0;
+  const int half = (S + 1) / 2;
+  for (int j = wid; j < half && !dead; j += NW) {
+    for (int side = 0; side < 2; side++) {
+      const int cc = side == 0 ? j : S - 1 - j;
+      if (side == 1 && cc == j) break;
+      double zc[I];
+#pragma unroll
+      for (int i = 0; i < I; i++) zc[i] = Z[(cc * I + i) * 32];
+      const uint16_t* gc = gat + tri(I + cc) + I;
+      const int qc = tri(cc);
+      for (int r0 = 0; r0 <= cc; r0 += PGBP_CHUNK) {
+        double jo[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
+        double* ta[PGBP_CHUNK];
+#pragma unroll
+        for (int u = 0; u < PGBP_CHUNK; u++) {
+          const int rr = r0 + u;
+          if (rr <= cc) {
+            ta[u] = gaddr(stb, tJ + sca[qc + rr], ld8);
+            jo[u] = *gaddr(stb, fJ + gc[rr], ld8);
+            so[u] = sz ? 0.0 : *gaddr(stb, sJ + qc + rr, ld8);
+            to[u] = *ta[u];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < PGBP_CHUNK; u++) {
+          const int rr = r0 + u;
+          if (rr <= cc) {
+            double nv = jo[u];
+            const double* zr = Z + rr * I * 32;
+#pragma unroll
+            for (int i = 0; i < I; i++) nv = nfma(zr[i * 32], zc[i], nv);
+            const double d = nv - so[u];
+            *gaddr(stb, sJ + qc + rr, ld8) = nv;
+            *ta[u] = to[u] + d;
+            if (rsb) *gaddr(rsb, rJ + qc + rr, ld8) = d;
+            absmax(maxJ, d);
+          }
+        }
+      }
+    }
+  }
+  if (!dead) {  // h part: chunks of kept entries dealt to the warps, last warp first (it has the lightest J share)
+    double w[I];
+#pragma unroll
+    for (int i = 0; i < I; i++) w[i] = Z[(S * I + i) * 32];
+    const uint16_t* gh = gat + SMM + I;
+    for (int k0 = (NW - 1 - wid) * PGBP_CHUNK; k0 < S; k0 += NW * PGBP_CHUNK) {
+      double ho[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
+      double* ta[PGBP_CHUNK];
+#pragma unroll
+      for (int u = 0; u < PGBP_CHUNK; u++) {
+        const int k = k0 + u;
+        if (k < S) {
+          ta[u] = gaddr(stb, th + sca[SS + k], ld8);
+          ho[u] = *gaddr(stb, fh + gh[k], ld8);
+          so[u] = sz ? 0.0 : *gaddr(stb, sh + k, ld8);
+          to[u] = *ta[u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PGBP_CHUNK; u++) {
+        const int k = k0 + u;
+        if (k < S) {
+          double nv = ho[u];
+          const double* zr = Z + k * I * 32;
+#pragma unroll
+          for (int i = 0; i < I; i++) nv = nfma(zr[i * 32], w[i], nv);
+          const double d = nv - so[u];
+          *gaddr(stb, sh + k, ld8) = nv;
+          *ta[u] = to[u] + d;
+          if (rsb) *gaddr(rsb, rh + k, ld8) = d;
+          absmax(maxh, d);
+        }
+      }
+    }
+  }
+  s_redJ[wid * 32] = maxJ;
+  s_redh[wid * 32] = maxh;
+  __syncthreads();
+  if (wid == 0 && !dead) {
+    double mJ = 0.0, mh = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {  // NaN-propagating maximum, like absmax
+      const double xj = s_redJ[w * 32], xh = s_redh[w * 32];
+      if (xj > mJ || xj != xj) mJ = xj;
+      if (xh > mh || xh != xh) mh = xh;
+    }
+    *gaddr(stb, (uint32_t)md.sg, ld8) = g;
+    *gaddr(stb, (uint32_t)md.tg, ld8) = tg_old + (g - sg_old);
+    store_flag(a, md.dmsg, e, S, mJ, mh);
+  }
+}
+
 #endif  // !PGBP_HOST_EMUL
 
 }  // namespace pgbp

@@ -791,7 +791,7 @@ int32_t pgbp_batch_set_graph_mode(pgbp_batch* b, int32_t mode) {
 }
 
 int32_t pgbp_batch_set_coop_mode(pgbp_batch* b, int32_t mode) {
-  if (!b || (mode != -1 && mode != 0 && mode != 1 && mode != 4 && mode != 8)) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
+  if (!b || (mode != -1 && mode != 0 && mode != 1 && mode != 2 && mode != 4 && mode != 8)) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
   b->coop_mode = mode;
   return 0;
 }

@@ -59,13 +59,50 @@ static int launch_smem(pgbp_batch* b, const MsgArgs& a, int nmsg, int I, int S) 
 }
 
 
+// multi-warp shared-memory kernel (large I): NW warps per tile of 32 elements
+#define PGBP_SMEM_MW_LIMIT (225 * 1024)
+static size_t mw_bytes(int I, int S, int NW) {  // == smem_mw_block_bytes (pgbp_coop.cuh, device build only)
+  const int M = I + S;
+  return sizeof(double) * 32 * (size_t)(I * (I + 1) / 2 + I * S + I + 2) + sizeof(int32_t) * 32 * (size_t)(2 + NW) +
+         sizeof(uint16_t) * (size_t)(M * (M + 1) / 2 + M + S * (S + 1) / 2 + S + 4);
+}
+template <int I, int NW>
+static int launch_smem_mw(pgbp_batch* b, const MsgArgs& a, int nmsg, int S) {
+#ifdef PGBP_HOST_EMUL
+  (void)S;
+  for (int m = 0; m < nmsg; m++)
+    for (int64_t e = a.e0; e < a.B; e++) message_thread_rt<PGBP_MAX_DIM>(a, m, e);
+#else
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    PGBP_CUDA(cudaFuncSetAttribute((const void*)k_message_smem_mw<I, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_MW_LIMIT));
+    attr_done = true;
+  }
+  if (a.ld * 8 >= ((int64_t)1 << 32)) PGBP_FAIL(PGBP_ESTATE, "batch too large for 32-bit row pitch");
+  dim3 grid((unsigned)((a.B - a.e0 + 31) / 32), (unsigned)nmsg), block(32, NW);
+  k_message_smem_mw<I, NW><<<grid, block, mw_bytes(I, S, NW), b->stream>>>(a);
+#endif
+  b->launches++;
+  return check_launch("k_message_smem_mw");
+}
+
 int launch_medium(pgbp_batch* b, const MsgArgs& a, int n, int I, int S) {
       const int M = I + S;
       int rc = 0;
       // shared-precision mode: only the register / generic / copy bodies know about group leaders
       const int mode = b->group_size > 1 ? 0 : b->coop_mode;
       const bool fits = I <= 32 && sizeof(double) * 32 * (size_t)(I * (I + 1) / 2 + I * S + I) + 4 * (size_t)(M * (M + 3) / 2 + S * (S + 3) / 2 + 2) <= PGBP_SMEM_LIMIT;
-      if ((mode == -1 || mode == 1) && fits) {
+      // large I (C5: p = 16): one or two single-warp tiles per SM are latency-bound; share the tile among warps
+      const bool fits_mw = I >= 12 && I <= 16 && mw_bytes(I, S, 8) <= PGBP_SMEM_MW_LIMIT;
+      if ((mode == -1 || mode == 2) && fits_mw) {
+        switch (I) {
+        // two tiles per SM with 4 warps each when they fit (233,472 bytes per SM, 1 KB reserved per block), else
+        // one tile with 8 warps
+#define PGBP_MW_CASE(I_) case I_: rc = (mode == 2 || 2 * (mw_bytes(I, S, 4) + 1024) <= 233472) ? launch_smem_mw<I_, 4>(b, a, n, S) : launch_smem_mw<I_, 8>(b, a, n, S); break;
+          PGBP_MW_CASE(12) PGBP_MW_CASE(13) PGBP_MW_CASE(14) PGBP_MW_CASE(15) PGBP_MW_CASE(16)
+#undef PGBP_MW_CASE
+        }
+      } else if ((mode == -1 || mode == 1 || mode == 2) && fits) {
         switch (I) {
 #define PGBP_SMEM_CASE(I_) case I_: rc = launch_smem<I_, true>(b, a, n, I, S); break;
           PGBP_SMEM_CASE(1) PGBP_SMEM_CASE(2) PGBP_SMEM_CASE(3) PGBP_SMEM_CASE(4) PGBP_SMEM_CASE(5) PGBP_SMEM_CASE(6)

@@ -647,7 +647,7 @@ def test_walk_kernel_matches_level_parallel_and_oracle(backend, p):
 
 # ------------------------------------------------------------------ cooperative (G lanes / element) kernel
 @pytest.mark.parametrize("backend", BACKENDS)
-@pytest.mark.parametrize("p", [4, 5, 6, 7, 8, 12])
+@pytest.mark.parametrize("p", [4, 5, 6, 7, 8, 12, 16])
 def test_cooperative_kernel_matches_generic_and_oracle(backend, p):
     # medium shapes (sender dimension 13..32: lazaridis 3- and 4-node cliques at p = 4..8) run in
     # the cooperative kernel; it must agree BIT FOR BIT with the one-thread-per-element generic
@@ -666,7 +666,9 @@ def test_cooperative_kernel_matches_generic_and_oracle(backend, p):
     big = [j for j in range(1, case.nclusters + 1) if case.b[j - 1].dimension() > 12]
     assert big
     out = {}
-    for mode in (0, -1, 4, 8):
+    # modes: 0 generic, -1 automatic (shared-memory kernel; its multi-warp form for integrated dimensions
+    # 12..16), 1 single-warp shared-memory kernel, 2 multi-warp form with 4 warps, 4 / 8 cooperative lanes
+    for mode in (0, -1, 1, 2, 4, 8):
         bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
         bt.set_coop_mode(mode)
         bt.assignfactors(pgbp_b200.bm_params([R], mu), data)
@@ -687,7 +689,7 @@ def test_cooperative_kernel_matches_generic_and_oracle(backend, p):
                               for j in range(case.plan.nsepsets) for s in (0, 1)])
     ok = ~np.isin(np.arange(B), [5, 7])
     okz = np.arange(B) != 5
-    for mode in (-1, 4, 8):
+    for mode in (-1, 1, 2, 4, 8):
         assert np.array_equal(out[0]["st"], out[mode]["st"]) and out[0]["st"][5] != 0
         assert np.array_equal(out[0]["succ"], out[mode]["succ"]) and np.array_equal(out[0]["iscal2"], out[mode]["iscal2"])
         for (J0, h0, g0), (J1, h1, g1) in zip(out[0]["beliefs"], out[mode]["beliefs"]):
