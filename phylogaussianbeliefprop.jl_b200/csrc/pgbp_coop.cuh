@@ -760,8 +760,8 @@ inline __host__ __device__ size_t smem_mw_block_bytes(int I, int S, int NW) {
          sizeof(uint16_t) * (size_t)(M * (M + 1) / 2 + M + S * (S + 1) / 2 + S + 4);
 }
 
-template <int I, int NW>
-__global__ void __launch_bounds__(32 * NW, (NW <= 4 ? 2 : 1)) k_message_smem_mw(MsgArgs a) {
+template <int I, int NW, int MINB = (NW <= 4 ? 2 : 1)>
+__global__ void __launch_bounds__(32 * NW, MINB) k_message_smem_mw(MsgArgs a) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x, wid = threadIdx.y;
   const int64_t e = a.e0 + (int64_t)blockIdx.x * 32 + tid;

@@ -66,7 +66,7 @@ static size_t mw_bytes(int I, int S, int NW) {  // == smem_mw_block_bytes (pgbp_
   return sizeof(double) * 32 * (size_t)(I * (I + 1) / 2 + I * S + I + 2) + sizeof(int32_t) * 32 * (size_t)(2 + NW) +
          sizeof(uint16_t) * (size_t)(M * (M + 1) / 2 + M + S * (S + 1) / 2 + S + 4);
 }
-template <int I, int NW>
+template <int I, int NW, int MINB = (NW <= 4 ? 2 : 1)>
 static int launch_smem_mw(pgbp_batch* b, const MsgArgs& a, int nmsg, int S) {
 #ifdef PGBP_HOST_EMUL
   (void)S;
@@ -75,12 +75,12 @@ static int launch_smem_mw(pgbp_batch* b, const MsgArgs& a, int nmsg, int S) {
 #else
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
-    PGBP_CUDA(cudaFuncSetAttribute((const void*)k_message_smem_mw<I, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_MW_LIMIT));
+    PGBP_CUDA(cudaFuncSetAttribute((const void*)k_message_smem_mw<I, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_MW_LIMIT));
     attr_done = true;
   }
   if (a.ld * 8 >= ((int64_t)1 << 32)) PGBP_FAIL(PGBP_ESTATE, "batch too large for 32-bit row pitch");
   dim3 grid((unsigned)((a.B - a.e0 + 31) / 32), (unsigned)nmsg), block(32, NW);
-  k_message_smem_mw<I, NW><<<grid, block, mw_bytes(I, S, NW), b->stream>>>(a);
+  k_message_smem_mw<I, NW, MINB><<<grid, block, mw_bytes(I, S, NW), b->stream>>>(a);
 #endif
   b->launches++;
   return check_launch("k_message_smem_mw");
@@ -94,6 +94,9 @@ int launch_medium(pgbp_batch* b, const MsgArgs& a, int n, int I, int S) {
       const bool fits = I <= 32 && sizeof(double) * 32 * (size_t)(I * (I + 1) / 2 + I * S + I) + 4 * (size_t)(M * (M + 3) / 2 + S * (S + 3) / 2 + 2) <= PGBP_SMEM_LIMIT;
       // large I (C5: p = 16): one or two single-warp tiles per SM are latency-bound; share the tile among warps
       const bool fits_mw = I >= 12 && I <= 16 && mw_bytes(I, S, 8) <= PGBP_SMEM_MW_LIMIT;
+      // (measured on C4: the multi-warp form for I = 8 -- 4 warps x 4 tiles or 2 warps x 8 tiles per SM at 128
+      // registers -- is SLOWER than the single-warp kernel with its unrolled S <= 8 variant: 70.6 / 68.5 ms per
+      // step against 60.3 ms; it stays reserved for I >= 12.)
       if ((mode == -1 || mode == 2) && fits_mw) {
         switch (I) {
         // two tiles per SM with 4 warps each when they fit (233,472 bytes per SM, 1 KB reserved per block), else
