@@ -411,6 +411,7 @@ int32_t pgbp_factors_from_beliefs(pgbp_batch* b) {
   if (!b->factor) PGBP_FAIL(PGBP_ESTATE, "batch was created without PGBP_BATCH_FACTORS");
   PGBP_TRY(set_device(b->device));
   b->lazy_factors.pending = false;
+  b->lazy_factors.valid = false;
   return d2d(b->factor, b->state, sizeof(double) * (size_t)b->plan->nslots_factor * (size_t)b->ld, b->stream);
 }
 int32_t pgbp_reset_from_factors(pgbp_batch* b) {
@@ -419,6 +420,11 @@ int32_t pgbp_reset_from_factors(pgbp_batch* b) {
   PGBP_TRY(set_device(b->device));
   const pgbp_plan* p = b->plan;
   const size_t ld = (size_t)b->ld;
+  {  // factors that are still K1's output: re-run K1 into the beliefs (write only) instead of copying
+    const int r = batch_reset_by_assign(b);
+    if (r < 0) return r;
+    if (r == 1) return batch_zero_sepsets(b, true);
+  }
   PGBP_TRY(batch_materialize_factors(b));
   PGBP_TRY(d2d(b->state, b->factor, sizeof(double) * (size_t)p->nslots_factor * ld, b->stream));
   return batch_zero_sepsets(b, true);

@@ -1210,6 +1210,7 @@ static int assign_prepare(pgbp_batch* b, int32_t ncolors, int64_t nparamsets, in
   }
   PGBP_TRY(set_device(b->device));
   b->lazy_factors.pending = false;  // the tables a pending snapshot would be recomputed from are about to change
+  b->lazy_factors.valid = false;
   DevTables* dt;
   PGBP_TRY(get_tables(b, &dt));
   ThetaRows tr{pt, ncolors};
@@ -1243,7 +1244,7 @@ static int assign_enqueue(pgbp_batch* b, pgbp::DevTables* dt, int32_t ncolors, c
   PGBP_TRY(assign_launch(b, dt, b->state, ncolors, nparamsets, ndatasets, pairing));
   // sepsets <- 0 (src/beliefs.jl:796), lazily; factor snapshot (src/clustergraphbeliefs.jl:106), lazily
   PGBP_TRY(batch_zero_sepsets(b, true));
-  if (b->factor) b->lazy_factors = pgbp_batch::LazyFactors{true, ncolors, nparamsets, ndatasets, pairing};
+  if (b->factor) b->lazy_factors = pgbp_batch::LazyFactors{true, true, ncolors, nparamsets, ndatasets, pairing};
   return 0;
 }
 
@@ -1291,6 +1292,15 @@ int batch_materialize_factors(pgbp_batch* b) {
   b->lazy_factors.pending = false;
   return 0;
 }
+int batch_reset_by_assign(pgbp_batch* b) {
+  if (!b->lazy_factors.valid) return 0;
+  if (b->plan->fam.scoped) return 0;  // the scoped (missing-data) K1 is a slow thread-local path: copy instead
+  DevTables* dt;
+  PGBP_TRY(get_tables(b, &dt));
+  const pgbp_batch::LazyFactors lf = b->lazy_factors;
+  int rc = assign_launch(b, dt, b->state, lf.ncolors, lf.nparamsets, lf.ndatasets, lf.pairing);
+  return rc ? rc : 1;
+}
 }  // namespace pgbp
 extern "C" {
 
@@ -1321,6 +1331,7 @@ int32_t pgbp_assign_factors_ou(pgbp_batch* b, const double* params, int64_t npar
   PGBP_TRY(launch_generic(b, "k_assign_ou", b->B, p->nclusters, body));
   PGBP_TRY(batch_zero_sepsets(b, true));
   b->lazy_factors.pending = false;  // (the OU parameters live in scratch memory: eager snapshot)
+  b->lazy_factors.valid = false;
   if (b->factor) PGBP_TRY(d2d(b->factor, b->state, sizeof(double) * (size_t)p->nslots_factor * (size_t)b->ld, b->stream));
   return stream_sync(b->stream);
 }

@@ -176,8 +176,10 @@ struct pgbp_batch {
   // (src/clustergraphbeliefs.jl:106).  K1 is a pure function of the prepared parameter / tip tables the
   // batch keeps on the device, so instead of copying (one read + one write of every cluster) the batch
   // remembers the call; the factors are produced by running K1 again into the factor array the first time
-  // something reads them (factored_energy, reset_from_factors, get_factor).  Bit-identical by construction.
-  struct LazyFactors { bool pending = false; int32_t ncolors = 1; int64_t nparamsets = 0, ndatasets = 0; int32_t pairing = 0; } lazy_factors;
+  // something reads them (factored_energy, get_factor).  Bit-identical by construction.  `valid` = the factors
+  // (materialised or not) still equal K1's output for the remembered call: init_beliefs_reset_fromfactors! then
+  // re-runs K1 straight into the beliefs (one write of every cluster) instead of copying (one read + one write).
+  struct LazyFactors { bool pending = false; bool valid = false; int32_t ncolors = 1; int64_t nparamsets = 0, ndatasets = 0; int32_t pairing = 0; } lazy_factors;
   int32_t coop_mode = -1;  // medium shapes: -1 auto (cooperative), 0 thread-local generic, 4 / 8 lanes for m <= 16
   int32_t* d_slot = nullptr;  // device scratch for transpose slot tables
   size_t d_slot_len = 0;

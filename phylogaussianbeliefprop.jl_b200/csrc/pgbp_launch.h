@@ -20,5 +20,8 @@ int batch_materialize_sepsets(pgbp_batch* b);
 int batch_zero_sepsets(pgbp_batch* b, bool lazy);
 // run the pending K1 into the factor array (no-op unless lazy_factors.pending)
 int batch_materialize_factors(pgbp_batch* b);
+// beliefs <- factors by re-running K1 into the state array; returns 1 if done, 0 if the factors are not K1's
+// output any more (caller copies), < 0 on error
+int batch_reset_by_assign(pgbp_batch* b);
 MsgArgs make_args(pgbp_batch* b, uint32_t opts, int32_t ref_base, bool use_done);
 }  // namespace pgbp
