@@ -255,11 +255,15 @@ inline __host__ __device__ size_t smem_block_bytes(int I, int S) {
   return sizeof(double) * 32 * (size_t)smem_doubles(I, S) + sizeof(uint16_t) * (size_t)(M * (M + 1) / 2 + M + S * (S + 1) / 2 + S + 4);
 }
 
-template <int MAXI>
+// TILE < 32: narrow tiles for shapes whose 32-element factor exceeds the SM's shared memory (C5's (32,16)
+// messages: 274 KB at 32 lanes, 206 KB at 24): lanes >= TILE idle, rows of TILE doubles (whole 32-byte sectors
+// for TILE = 16, 24).  No warp-level synchronisation anywhere in this kernel.
+template <int MAXI, int TILE = 32>
 __global__ void __launch_bounds__(32) k_message_smem_rt(MsgArgs a) {
   extern __shared__ double sm[];
   const int tid = threadIdx.x;
-  const int64_t e = a.e0 + (int64_t)blockIdx.x * 32 + tid;
+  if (TILE < 32 && tid >= TILE) return;
+  const int64_t e = a.e0 + (int64_t)blockIdx.x * TILE + tid;
   if (e >= a.B) return;
   if (a.status[e] != 0) return;
   if (a.done && a.done[e]) return;
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(32) k_message_smem_rt(MsgArgs a) {
   const int32_t* __restrict__ sca = a.tab + md.sca;
   const int TI = tri(I), SMM = tri(M), SS = tri(S);
   const int ZB = TI, WB = TI + I * S;  // region bases: Z(k, cc) = ZB + cc*I + k, w(k) = WB + k
-#define PGBP_SM(ent) sm[(ent) * 32 + tid]
+#define PGBP_SM(ent) sm[(ent) * TILE + tid]
 
   // ---- A: I-rows of the sender -> shared (asynchronous) ---------------------------------
   for (int c = 0; c < M; c++) {
@@ -1006,6 +1010,302 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_message_smem_mw(MsgArgs a) {
 #pragma unroll
     for (int w = 0; w < NW; w++) {  // NaN-propagating maximum, like absmax
       const double xj = s_redJ[w * 32], xh = s_redh[w * 32];
+      if (xj > mJ || xj != xj) mJ = xj;
+      if (xh > mh || xh != xh) mh = xh;
+    }
+    *gaddr(stb, (uint32_t)md.sg, ld8) = g;
+    *gaddr(stb, (uint32_t)md.tg, ld8) = tg_old + (g - sg_old);
+    store_flag(a, md.dmsg, e, S, mJ, mh);
+  }
+}
+
+// -------------------------------------------------------------------------------------
+// Multi-warp kernel for integrated dimension 32 (C5's (32,16) messages: sender dimension 48).  The factor of
+// 32 elements needs 274 KB of shared memory, so the tile is TILE = 24 elements (lanes 24..31 idle; rows of
+// 24 doubles = six whole 32-byte sectors) and ONE tile of 206 KB occupies the SM: all the parallelism has to
+// come from inside the tile.  NW = 8 warps split every phase by column -- including the Cholesky of J_II,
+// which at I = 32 is 29 % of the flops and would otherwise serialise the tile on one warp:
+//   B1  right-looking, one block barrier per pivot: the owner of column c (c mod NW) applies pivot k to its
+//       column, A[r,c] -= u_kr u_kc with u_k. = A[k,.] / sqrt(A[k,k]) formed on the fly (row k is not
+//       written during step k); rows are scaled in place afterwards.  Per entry the updates arrive in
+//       ascending k with the same operands as in the left-looking form: bit-identical to every other kernel.
+//   B2 / C  as in k_message_smem_mw.
+// -------------------------------------------------------------------------------------
+template <int I, int NW, int TILE>
+__global__ void __launch_bounds__(32 * NW, 1) k_message_smem_mwp(MsgArgs a) {
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x, wid = threadIdx.y;
+  const bool lane_ok = tid < TILE;
+  const int lane = lane_ok ? tid : 0;      // idle lanes never touch shared memory (all accesses are guarded)
+  const int64_t e = a.e0 + (int64_t)blockIdx.x * TILE + lane;
+  const MsgDesc md = a.msgs[blockIdx.y];
+  const int S = md.s, M = md.mF;
+  constexpr int TI = I * (I + 1) / 2;
+  const int SMM = tri(M), SS = tri(S);
+  const int nrhs = S + 1;
+  const int NE = TI + I * nrhs;
+  double* smt = sm + lane;                 // entry n of this lane: smt[n * TILE]
+  double* Z = smt + TI * TILE;             // Z(k, cc) = Z[(cc * I + k) * TILE]; column S holds h_I / w
+  double* s_ww = smt + NE * TILE;
+  double* s_logdet = s_ww + TILE;
+  double* s_redJ = smt;                    // rows [0, NW) / [NW, 2 NW) of U, dead by the end of phase C
+  double* s_redh = smt + NW * TILE;
+  int32_t* s_flag = (int32_t*)(sm + TILE * (NE + 2));  // [lane] active, [TILE + lane] failed pivot, [(2 + w) TILE + lane] nz
+  uint16_t* tgat = (uint16_t*)(s_flag + TILE * (2 + NW));
+  const int ngat = SMM + M, nsca = SS + S;
+  uint16_t* tsca = tgat + ngat;
+  {
+    const int32_t* __restrict__ g0 = a.tab + md.gat;
+    const int32_t* __restrict__ s0 = a.tab + md.sca;
+    for (int q = wid * 32 + tid; q < ngat; q += 32 * NW) tgat[q] = (uint16_t)g0[q];
+    for (int q = wid * 32 + tid; q < nsca; q += 32 * NW) tsca[q] = (uint16_t)s0[q];
+    if (wid == 0 && lane_ok) {
+      int act = e < a.B;
+      if (act && a.status[e] != 0) act = 0;
+      if (act && a.done && a.done[e]) act = 0;
+      s_flag[tid] = act;
+      s_flag[TILE + tid] = 0;
+    }
+  }
+  __syncthreads();
+  const bool active = lane_ok && s_flag[lane] != 0;
+  const int64_t ee = active ? e : a.e0 + (int64_t)blockIdx.x * TILE;  // inactive lanes shadow a valid element, never store
+  const uint32_t ld8 = (uint32_t)(a.ld * 8);
+  char* stb = (char*)(a.state + ee);
+  char* rsb = a.resid ? (char*)(a.resid + ee) : nullptr;
+  const uint16_t* gat = tgat;
+  const uint16_t* sca = tsca;
+  const uint32_t fJ = (uint32_t)md.fJ, fh = (uint32_t)md.fh, sJ = (uint32_t)md.sJ, sh = (uint32_t)md.sh,
+                 tJ = (uint32_t)md.tJ, th = (uint32_t)md.th, rJ = (uint32_t)md.rJ, rh = (uint32_t)md.rh;
+  const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;
+
+  // ---- A: staging, entries dealt to the warps round-robin --------------------------------------
+  double g = 0.0, sg_old = 0.0, tg_old = 0.0;
+  if (lane_ok) {
+    for (int n = wid; n < NE; n += NW) {
+      uint32_t slot;
+      if (n < TI) slot = fJ + gat[n];
+      else {
+        const int idx = n - TI, cc = idx / I, k = idx - cc * I;
+        slot = cc < S ? fJ + gat[tri(I + cc) + k] : fh + gat[SMM + k];
+      }
+      cp_async8(smt + n * TILE, gaddr(stb, slot, ld8));
+    }
+    if (wid == 0) {
+      g = *gaddr(stb, (uint32_t)md.fg, ld8);
+      sg_old = sz ? 0.0 : *gaddr(stb, (uint32_t)md.sg, ld8);
+      tg_old = *gaddr(stb, (uint32_t)md.tg, ld8);
+    }
+    for (int cc = wid; cc < S; cc += NW) {  // L2 prefetch of what phase C reads
+      const uint16_t* gc = gat + tri(I + cc) + I;
+      const int qc = tri(cc);
+      for (int rr = 0; rr <= cc; rr++) {
+        prefetch_l2(gaddr(stb, fJ + gc[rr], ld8));
+        if (!sz) prefetch_l2(gaddr(stb, sJ + qc + rr, ld8));
+        prefetch_l2(gaddr(stb, tJ + sca[qc + rr], ld8));
+      }
+      prefetch_l2(gaddr(stb, fh + gat[SMM + I + cc], ld8));
+      if (!sz) prefetch_l2(gaddr(stb, sh + cc, ld8));
+      prefetch_l2(gaddr(stb, th + sca[SS + cc], ld8));
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- B1: U'U = J_II, right-looking, columns dealt to the warps, one barrier per pivot ----------
+  bool nz = false;
+  double rinv[I];
+  double logdet = 0.0;
+  int fail = 0;
+  if (lane_ok)  // "all zero" test on the original entries of this warp's columns (src/beliefupdates.jl:62-66)
+    for (int c = wid; c < I; c += NW)
+      for (int k = 0; k <= c; k++)
+        if (!(fabs(smt[(tri(c) + k) * TILE]) <= PGBP_EPS)) nz = true;
+#pragma unroll
+  for (int k = 0; k < I; k++) {
+    double d = 1.0;
+    if (lane_ok) d = smt[pk(k, k) * TILE];  // final: every update of steps < k is behind the barrier
+    if (!(d > 0.0) && fail == 0) fail = k + 1;  // LAPACK potrf info (also NaN); reported below
+    if (wid == 0) logdet += log(d);
+    const double ri = 1.0 / sqrt(d);
+    rinv[k] = ri;
+    if (lane_ok) {
+      const int c0 = k + 1 + ((wid - (k + 1)) % NW + NW) % NW;  // first column > k owned by this warp
+      for (int c = c0; c < I; c += NW) {
+        const int tc = tri(c);
+        const double ukc = smt[(tc + k) * TILE] * ri;
+        // operands of 8 rows loaded before the first store: the compiler cannot move a shared-memory load above
+        // a store it cannot disambiguate, and one row per iteration exposed the full LDS latency every time
+        for (int r0 = k + 1; r0 <= c; r0 += 8) {
+          double ur[8], av[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int r = r0 + u;
+            if (r <= c) {
+              ur[u] = smt[(tri(r) + k) * TILE];
+              av[u] = smt[(tc + r) * TILE];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int r = r0 + u;
+            if (r <= c) smt[(tc + r) * TILE] = nfma(ur[u] * ri, ukc, av[u]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (lane_ok) {  // scale the rows in place: U(k,c) = A(k,c) / sqrt(A(k,k)) (every warp keeps 1/U_kk in registers)
+    for (int c = wid; c < I; c += NW) {
+      const int tc = tri(c);
+#pragma unroll
+      for (int k = 0; k < I; k++)
+        if (k < c) smt[(tc + k) * TILE] *= rinv[k];
+    }
+    if (wid == 0) {
+      s_logdet[0] = logdet;
+      s_flag[TILE + tid] = fail;
+    }
+  }
+  __syncthreads();
+
+  // ---- B2: Z = U^-T [J_IK | h_I], right-hand sides dealt to the warps ---------------------------
+  if (lane_ok) {
+    for (int c0 = wid; c0 < nrhs; c0 += NW) {
+      double* z0 = Z + c0 * I * TILE;
+      double v0[I];
+#pragma unroll
+      for (int k = 0; k < I; k++) {
+        v0[k] = z0[k * TILE];
+        if (!(fabs(v0[k]) <= PGBP_EPS)) nz = true;
+      }
+#pragma unroll
+      for (int k = 0; k < I; k++) {
+        const double u0 = v0[k] * rinv[k];
+        v0[k] = u0;
+#pragma unroll
+        for (int r = k + 1; r < I; r++) v0[r] = nfma(smt[pk(k, r) * TILE], u0, v0[r]);
+      }
+#pragma unroll
+      for (int k = 0; k < I; k++) z0[k * TILE] = v0[k];
+      if (c0 == S) {  // the h column: w = U^-T h_I
+        double ww = 0.0;
+#pragma unroll
+        for (int k = 0; k < I; k++) ww = fma(v0[k], v0[k], ww);
+        s_ww[0] = ww;
+      }
+    }
+    s_flag[(2 + wid) * TILE + tid] = nz ? 1 : 0;
+  }
+  __syncthreads();
+  bool nzall = false;
+  int failp = 0;
+  if (lane_ok) {
+#pragma unroll
+    for (int w = 0; w < NW; w++) nzall = nzall || s_flag[(2 + w) * TILE + tid] != 0;
+    failp = s_flag[TILE + tid];
+  }
+  const bool dead = !active || (nzall && failp != 0);
+  if (lane_ok) {
+    if (nzall) {
+      if (failp && active && wid == 0) status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, failp));
+      if (wid == 0) g += 0.5 * ((double)I * PGBP_LOG2PI - s_logdet[0] + s_ww[0]);
+    } else {  // "missing data" shortcut: message = (h_K, J_KK, g) unchanged
+      for (int q = wid; q < nrhs * I; q += NW) Z[q * TILE] = 0.0;
+    }
+  }
+  __syncthreads();
+
+  // ---- C: stream the kept block, kept columns paired (j, S-1-j) and dealt to the warps ------------
+  double maxJ = 0.0, maxh = 0.0;
+  const int half = (S + 1) / 2;
+  for (int j = wid; j < half && !dead; j += NW) {
+    for (int side = 0; side < 2; side++) {
+      const int cc = side == 0 ? j : S - 1 - j;
+      if (side == 1 && cc == j) break;
+      double zc[I];
+#pragma unroll
+      for (int i = 0; i < I; i++) zc[i] = Z[(cc * I + i) * TILE];
+      const uint16_t* gc = gat + tri(I + cc) + I;
+      const int qc = tri(cc);
+      for (int r0 = 0; r0 <= cc; r0 += PGBP_CHUNK) {
+        double jo[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
+        double* ta[PGBP_CHUNK];
+#pragma unroll
+        for (int u = 0; u < PGBP_CHUNK; u++) {
+          const int rr = r0 + u;
+          if (rr <= cc) {
+            ta[u] = gaddr(stb, tJ + sca[qc + rr], ld8);
+            jo[u] = *gaddr(stb, fJ + gc[rr], ld8);
+            so[u] = sz ? 0.0 : *gaddr(stb, sJ + qc + rr, ld8);
+            to[u] = *ta[u];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < PGBP_CHUNK; u++) {
+          const int rr = r0 + u;
+          if (rr <= cc) {
+            double nv = jo[u];
+            const double* zr = Z + rr * I * TILE;
+#pragma unroll
+            for (int i = 0; i < I; i++) nv = nfma(zr[i * TILE], zc[i], nv);
+            const double d = nv - so[u];
+            *gaddr(stb, sJ + qc + rr, ld8) = nv;
+            *ta[u] = to[u] + d;
+            if (rsb) *gaddr(rsb, rJ + qc + rr, ld8) = d;
+            absmax(maxJ, d);
+          }
+        }
+      }
+    }
+  }
+  if (!dead) {  // h part: chunks of kept entries dealt to the warps, last warp first
+    double w[I];
+#pragma unroll
+    for (int i = 0; i < I; i++) w[i] = Z[(S * I + i) * TILE];
+    const uint16_t* gh = gat + SMM + I;
+    for (int k0 = (NW - 1 - wid) * PGBP_CHUNK; k0 < S; k0 += NW * PGBP_CHUNK) {
+      double ho[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
+      double* ta[PGBP_CHUNK];
+#pragma unroll
+      for (int u = 0; u < PGBP_CHUNK; u++) {
+        const int k = k0 + u;
+        if (k < S) {
+          ta[u] = gaddr(stb, th + sca[SS + k], ld8);
+          ho[u] = *gaddr(stb, fh + gh[k], ld8);
+          so[u] = sz ? 0.0 : *gaddr(stb, sh + k, ld8);
+          to[u] = *ta[u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PGBP_CHUNK; u++) {
+        const int k = k0 + u;
+        if (k < S) {
+          double nv = ho[u];
+          const double* zr = Z + k * I * TILE;
+#pragma unroll
+          for (int i = 0; i < I; i++) nv = nfma(zr[i * TILE], w[i], nv);
+          const double d = nv - so[u];
+          *gaddr(stb, sh + k, ld8) = nv;
+          *ta[u] = to[u] + d;
+          if (rsb) *gaddr(rsb, rh + k, ld8) = d;
+          absmax(maxh, d);
+        }
+      }
+    }
+  }
+  __syncthreads();  // phase C of every warp is done with Z ... and nobody reads U any more: reuse its rows
+  if (lane_ok) {
+    s_redJ[wid * TILE] = maxJ;
+    s_redh[wid * TILE] = maxh;
+  }
+  __syncthreads();
+  if (wid == 0 && !dead) {
+    double mJ = 0.0, mh = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {  // NaN-propagating maximum, like absmax
+      const double xj = s_redJ[w * TILE], xh = s_redh[w * TILE];
       if (xj > mJ || xj != xj) mJ = xj;
       if (xh > mh || xh != xh) mh = xh;
     }

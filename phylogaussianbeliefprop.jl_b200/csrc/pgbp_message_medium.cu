@@ -86,6 +86,53 @@ static int launch_smem_mw(pgbp_batch* b, const MsgArgs& a, int nmsg, int S) {
   return check_launch("k_message_smem_mw");
 }
 
+// multi-warp kernel with the column-parallel Cholesky, tiles of TILE <= 32 elements (C5's (32,16) messages)
+static size_t mwp_bytes(int I, int S, int NW, int TILE) {
+  const int M = I + S;
+  return sizeof(double) * TILE * (size_t)(I * (I + 1) / 2 + I * S + I + 2) + sizeof(int32_t) * TILE * (size_t)(2 + NW) +
+         sizeof(uint16_t) * (size_t)(M * (M + 1) / 2 + M + S * (S + 1) / 2 + S + 4) + 16;
+}
+template <int I, int NW, int TILE>
+static int launch_smem_mwp(pgbp_batch* b, const MsgArgs& a, int nmsg, int S) {
+#ifdef PGBP_HOST_EMUL
+  (void)S;
+  for (int m = 0; m < nmsg; m++)
+    for (int64_t e = a.e0; e < a.B; e++) message_thread_rt<PGBP_MAX_DIM>(a, m, e);
+#else
+  static bool attr_done = false;
+  if (!attr_done) {
+    PGBP_CUDA(cudaFuncSetAttribute((const void*)k_message_smem_mwp<I, NW, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_MW_LIMIT));
+    attr_done = true;
+  }
+  if (a.ld * 8 >= ((int64_t)1 << 32)) PGBP_FAIL(PGBP_ESTATE, "batch too large for 32-bit row pitch");
+  dim3 grid((unsigned)((a.B - a.e0 + TILE - 1) / TILE), (unsigned)nmsg), block(32, NW);
+  k_message_smem_mwp<I, NW, TILE><<<grid, block, mwp_bytes(I, S, NW, TILE), b->stream>>>(a);
+#endif
+  b->launches++;
+  return check_launch("k_message_smem_mwp");
+}
+
+// narrow tiles (TILE = 24 or 16 elements per single-warp block) for I <= 32 when the 32-lane factor does not fit
+template <int TILE>
+static int launch_smem_tile(pgbp_batch* b, const MsgArgs& a, int nmsg, int I, int S) {
+#ifdef PGBP_HOST_EMUL
+  (void)I; (void)S;
+  for (int m = 0; m < nmsg; m++)
+    for (int64_t e = a.e0; e < a.B; e++) message_thread_rt<PGBP_MAX_DIM>(a, m, e);
+#else
+  static bool attr_done = false;
+  if (!attr_done) {
+    PGBP_CUDA(cudaFuncSetAttribute((const void*)k_message_smem_rt<32, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_MW_LIMIT));
+    attr_done = true;
+  }
+  const size_t bytes = sizeof(double) * TILE * (size_t)(I * (I + 1) / 2 + I * S + I);
+  dim3 grid((unsigned)((a.B - a.e0 + TILE - 1) / TILE), (unsigned)nmsg);
+  k_message_smem_rt<32, TILE><<<grid, 32, bytes, b->stream>>>(a);
+#endif
+  b->launches++;
+  return check_launch("k_message_smem_rt");
+}
+
 int launch_medium(pgbp_batch* b, const MsgArgs& a, int n, int I, int S) {
       const int M = I + S;
       int rc = 0;
@@ -113,6 +160,20 @@ int launch_medium(pgbp_batch* b, const MsgArgs& a, int n, int I, int S) {
           PGBP_SMEM_CASE(12) PGBP_SMEM_CASE(13) PGBP_SMEM_CASE(14) PGBP_SMEM_CASE(15) PGBP_SMEM_CASE(16)
 #undef PGBP_SMEM_CASE
           default: rc = (I <= 24) ? launch_smem<24, false>(b, a, n, I, S) : launch_smem<32, false>(b, a, n, I, S);
+        }
+      } else if ((mode == -1 || mode == 1 || mode == 2) && I <= 32 &&
+                 sizeof(double) * 16 * (size_t)(I * (I + 1) / 2 + I * S + I) <= PGBP_SMEM_MW_LIMIT) {
+        // the 32-element factor does not fit (C5's (32,16)): tiles of 24 or 16 elements.  Measured on C5: the
+        // 16-lane cooperative kernel needs ~0.5 ms per launch of these messages (serial pivots with broadcasts)
+        if (mode == 1) {  // single-warp narrow tiles: measured 880 ms per C5 step (one warp per SM), kept for comparison
+          if (sizeof(double) * 24 * (size_t)(I * (I + 1) / 2 + I * S + I) <= PGBP_SMEM_MW_LIMIT) rc = launch_smem_tile<24>(b, a, n, I, S);
+          else rc = launch_smem_tile<16>(b, a, n, I, S);
+        } else if (I == 32 && mwp_bytes(I, S, 8, 24) <= PGBP_SMEM_MW_LIMIT) {
+          rc = launch_smem_mwp<32, 8, 24>(b, a, n, S);
+        } else if (M <= PGBP_COOP_MAX) {
+          rc = launch_coop<48, 16>(b, a, n);
+        } else {
+          rc = launch_message<-1, -1, 64>(b, a, n);
         }
       } else if (mode != 0 && M <= PGBP_COOP_MAX) {
         if (M <= 16) rc = (mode == 4) ? launch_coop<16, 4>(b, a, n) : launch_coop<16, 8>(b, a, n);
