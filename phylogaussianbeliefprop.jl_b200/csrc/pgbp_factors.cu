@@ -715,8 +715,11 @@ struct AssignFast {
 #pragma unroll
           for (int t = 0; t < P; t++) *kaddr(stb, (uint32_t)(hs + pa + t), ld8) = anyfixed ? 0.0 - ca * jz[t] : 0.0;
         } else if (anyfixed) {
+          double oldh[P];
 #pragma unroll
-          for (int t = 0; t < P; t++) *kaddr(stb, (uint32_t)(hs + pa + t), ld8) -= ca * jz[t];
+          for (int t = 0; t < P; t++) oldh[t] = *kaddr(stb, (uint32_t)(hs + pa + t), ld8);
+#pragma unroll
+          for (int t = 0; t < P; t++) *kaddr(stb, (uint32_t)(hs + pa + t), ld8) = oldh[t] - ca * jz[t];
         }
         for (int bq = a; lead && bq < nm; bq++) {
           const int pb = F.mem_pos[k0 + bq];
@@ -725,17 +728,28 @@ struct AssignFast {
           const double cab = ca * cb;
           const bool diag = bq == a;
           const bool first = (fJ >> (a * 8 + bq)) & 1;
+          if (first) {
 #pragma unroll
-          for (int tb = 0; tb < P; tb++) {
-            const uint32_t colslot = (uint32_t)js + (uint32_t)tri(pb + tb) + (uint32_t)pa;  // pk(pa + ta, pb + tb)
+            for (int tb = 0; tb < P; tb++) {
+              const uint32_t colslot = (uint32_t)js + (uint32_t)tri(pb + tb) + (uint32_t)pa;  // pk(pa + ta, pb + tb)
 #pragma unroll
-            for (int ta = 0; ta < P; ta++) {
-              if (!diag || ta <= tb) {
-                double* d = kaddr(stb, colslot + ta, ld8);
-                const double x = cab * PGBP_JU(ta, tb);
-                if (first) *d = x;
-                else *d += x;
-              }
+              for (int ta = 0; ta < P; ta++)
+                if (!diag || ta <= tb) *kaddr(stb, colslot + ta, ld8) = cab * PGBP_JU(ta, tb);
+            }
+          } else {
+            // read-modify-write of a block another family wrote first: the P loads of a column are issued
+            // together, then the adds and stores (a load cannot be hoisted above a store the compiler cannot
+            // disambiguate: entry-by-entry "+=" exposed one L2 round trip per entry, 60 % long_sb in ncu)
+#pragma unroll
+            for (int tb = 0; tb < P; tb++) {
+              const uint32_t colslot = (uint32_t)js + (uint32_t)tri(pb + tb) + (uint32_t)pa;
+              double old[P];
+#pragma unroll
+              for (int ta = 0; ta < P; ta++)
+                if (!diag || ta <= tb) old[ta] = *kaddr(stb, colslot + ta, ld8);
+#pragma unroll
+              for (int ta = 0; ta < P; ta++)
+                if (!diag || ta <= tb) *kaddr(stb, colslot + ta, ld8) = old[ta] + cab * PGBP_JU(ta, tb);
             }
           }
         }
