@@ -538,10 +538,6 @@ int integrate_launch(pgbp_batch* b, int belief, double* d_mu_soa, double* d_norm
 
 }  // namespace pgbp
 
-extern "C" {
-
-}  // extern "C"
-
 // Enqueue one calibrate! call (validated arguments) on b->stream, eagerly.  *nlaunch_est: launches of
 // ONE element chunk.
 static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int32_t niter, uint32_t flags, bool lazy);

@@ -134,60 +134,61 @@ static int launch_smem_tile(pgbp_batch* b, const MsgArgs& a, int nmsg, int I, in
 }
 
 int launch_medium(pgbp_batch* b, const MsgArgs& a, int n, int I, int S) {
-      const int M = I + S;
-      int rc = 0;
-      // shared-precision mode: only the register / generic / copy bodies know about group leaders
-      const int mode = b->group_size > 1 ? 0 : b->coop_mode;
-      const bool fits = I <= 32 && sizeof(double) * 32 * (size_t)(I * (I + 1) / 2 + I * S + I) + 4 * (size_t)(M * (M + 3) / 2 + S * (S + 3) / 2 + 2) <= PGBP_SMEM_LIMIT;
-      // large I (C5: p = 16): one or two single-warp tiles per SM are latency-bound; share the tile among warps
-      const bool fits_mw = I >= 12 && I <= 16 && mw_bytes(I, S, 8) <= PGBP_SMEM_MW_LIMIT;
-      // (measured on C4: the multi-warp form for I = 8 -- 4 warps x 4 tiles or 2 warps x 8 tiles per SM at 128
-      // registers -- is SLOWER than the single-warp kernel with its unrolled S <= 8 variant: 70.6 / 68.5 ms per
-      // step against 60.3 ms; it stays reserved for I >= 12.)
-      if ((mode == -1 || mode == 2) && fits_mw) {
-        switch (I) {
-        // two tiles per SM with 4 warps each when they fit (233,472 bytes per SM, 1 KB reserved per block), else
-        // one tile with 8 warps
+  const int M = I + S;
+  int rc = 0;
+  // shared-precision mode: only the register / generic / copy bodies know about group leaders
+  const int mode = b->group_size > 1 ? 0 : b->coop_mode;
+  const bool fits = I <= 32 && sizeof(double) * 32 * (size_t)(I * (I + 1) / 2 + I * S + I) + 4 * (size_t)(M * (M + 3) / 2 + S * (S + 3) / 2 + 2) <= PGBP_SMEM_LIMIT;
+  // large I (C5: p = 16): one or two single-warp tiles per SM are latency-bound; share the tile among warps
+  const bool fits_mw = I >= 12 && I <= 16 && mw_bytes(I, S, 8) <= PGBP_SMEM_MW_LIMIT;
+  // (measured on C4: the multi-warp form for I = 8 -- 4 warps x 4 tiles or 2 warps x 8 tiles per SM at 128
+  // registers -- is SLOWER than the single-warp kernel with its unrolled S <= 8 variant: 70.6 / 68.5 ms per
+  // step against 60.3 ms; it stays reserved for I >= 12.)
+  if ((mode == -1 || mode == 2) && fits_mw) {
+    switch (I) {
+    // two tiles per SM with 4 warps each when they fit (233,472 bytes per SM, 1 KB reserved per block), else
+    // one tile with 8 warps
 #define PGBP_MW_CASE(I_) case I_: rc = (mode == 2 || 2 * (mw_bytes(I, S, 4) + 1024) <= 233472) ? launch_smem_mw<I_, 4>(b, a, n, S) : launch_smem_mw<I_, 8>(b, a, n, S); break;
-          PGBP_MW_CASE(12) PGBP_MW_CASE(13) PGBP_MW_CASE(14) PGBP_MW_CASE(15) PGBP_MW_CASE(16)
+      PGBP_MW_CASE(12) PGBP_MW_CASE(13) PGBP_MW_CASE(14) PGBP_MW_CASE(15) PGBP_MW_CASE(16)
 #undef PGBP_MW_CASE
-        }
-      } else if ((mode == -1 || mode == 1 || mode == 2) && fits) {
-        switch (I) {
+    }
+  } else if ((mode == -1 || mode == 1 || mode == 2) && fits) {
+    switch (I) {
 #define PGBP_SMEM_CASE(I_) case I_: rc = launch_smem<I_, true>(b, a, n, I, S); break;
-          PGBP_SMEM_CASE(1) PGBP_SMEM_CASE(2) PGBP_SMEM_CASE(3) PGBP_SMEM_CASE(4) PGBP_SMEM_CASE(5) PGBP_SMEM_CASE(6)
-          PGBP_SMEM_CASE(7) PGBP_SMEM_CASE(8) PGBP_SMEM_CASE(9) PGBP_SMEM_CASE(10) PGBP_SMEM_CASE(11)
-          PGBP_SMEM_CASE(12) PGBP_SMEM_CASE(13) PGBP_SMEM_CASE(14) PGBP_SMEM_CASE(15) PGBP_SMEM_CASE(16)
+      PGBP_SMEM_CASE(1) PGBP_SMEM_CASE(2) PGBP_SMEM_CASE(3) PGBP_SMEM_CASE(4) PGBP_SMEM_CASE(5) PGBP_SMEM_CASE(6)
+      PGBP_SMEM_CASE(7) PGBP_SMEM_CASE(8) PGBP_SMEM_CASE(9) PGBP_SMEM_CASE(10) PGBP_SMEM_CASE(11)
+      PGBP_SMEM_CASE(12) PGBP_SMEM_CASE(13) PGBP_SMEM_CASE(14) PGBP_SMEM_CASE(15) PGBP_SMEM_CASE(16)
 #undef PGBP_SMEM_CASE
-          default: rc = (I <= 24) ? launch_smem<24, false>(b, a, n, I, S) : launch_smem<32, false>(b, a, n, I, S);
-        }
-      } else if ((mode == -1 || mode == 1 || mode == 2) && I <= 32 &&
-                 sizeof(double) * 16 * (size_t)(I * (I + 1) / 2 + I * S + I) <= PGBP_SMEM_MW_LIMIT) {
-        // the 32-element factor does not fit (C5's (32,16)): tiles of 24 or 16 elements.  Measured on C5: the
-        // 16-lane cooperative kernel needs ~0.5 ms per launch of these messages (serial pivots with broadcasts)
-        if (mode == 1) {  // single-warp narrow tiles: measured 880 ms per C5 step (one warp per SM), kept for comparison
-          if (sizeof(double) * 24 * (size_t)(I * (I + 1) / 2 + I * S + I) <= PGBP_SMEM_MW_LIMIT) rc = launch_smem_tile<24>(b, a, n, I, S);
-          else rc = launch_smem_tile<16>(b, a, n, I, S);
-        } else if (I == 32 && mwp_bytes(I, S, 8, 24) <= PGBP_SMEM_MW_LIMIT) {
-          rc = launch_smem_mwp<32, 8, 24>(b, a, n, S);
-        } else if (M <= PGBP_COOP_MAX) {
-          rc = launch_coop<48, 16>(b, a, n);
-        } else {
-          rc = launch_message<-1, -1, 64>(b, a, n);
-        }
-      } else if (mode != 0 && M <= PGBP_COOP_MAX) {
-        if (M <= 16) rc = (mode == 4) ? launch_coop<16, 4>(b, a, n) : launch_coop<16, 8>(b, a, n);
-        else if (M <= 24) rc = launch_coop<24, 8>(b, a, n);
-        else if (M <= 32) rc = launch_coop<32, 8>(b, a, n);
-        else rc = launch_coop<48, 16>(b, a, n);  // 16 lanes per element: 2 elements per warp (half sectors)
-      } else if (b->group_size > 1) {
-        rc = (M <= 32) ? launch_message<-1, -1, 32, true>(b, a, n) : launch_message<-1, -1, 64, true>(b, a, n);
-      } else if (M <= 32) {
-        rc = launch_message<-1, -1, 32>(b, a, n);
-      } else {
-        rc = launch_message<-1, -1, 64>(b, a, n);
-      }
-      return rc;
+      default: rc = (I <= 24) ? launch_smem<24, false>(b, a, n, I, S) : launch_smem<32, false>(b, a, n, I, S);
+    }
+  } else if ((mode == -1 || mode == 1 || mode == 2) && I <= 32 &&
+             sizeof(double) * 16 * (size_t)(I * (I + 1) / 2 + I * S + I) <= PGBP_SMEM_MW_LIMIT) {
+    // the 32-element factor does not fit the SM (C5's (32,16) messages: 274 KB): I = 32 goes to the multi-warp
+    // kernel on 24-element tiles (on par with the 16-lane cooperative kernel on C5: 345 vs 355 ms per step),
+    // anything else to the cooperative / generic kernels as before
+    if (mode == 1) {  // single-warp narrow tiles: measured 880 ms per C5 step (one warp per SM), kept for comparison
+      if (sizeof(double) * 24 * (size_t)(I * (I + 1) / 2 + I * S + I) <= PGBP_SMEM_MW_LIMIT) rc = launch_smem_tile<24>(b, a, n, I, S);
+      else rc = launch_smem_tile<16>(b, a, n, I, S);
+    } else if (I == 32 && mwp_bytes(I, S, 8, 24) <= PGBP_SMEM_MW_LIMIT) {
+      rc = launch_smem_mwp<32, 8, 24>(b, a, n, S);
+    } else if (M <= PGBP_COOP_MAX) {
+      rc = launch_coop<48, 16>(b, a, n);
+    } else {
+      rc = launch_message<-1, -1, 64>(b, a, n);
+    }
+  } else if (mode != 0 && M <= PGBP_COOP_MAX) {
+    if (M <= 16) rc = (mode == 4) ? launch_coop<16, 4>(b, a, n) : launch_coop<16, 8>(b, a, n);
+    else if (M <= 24) rc = launch_coop<24, 8>(b, a, n);
+    else if (M <= 32) rc = launch_coop<32, 8>(b, a, n);
+    else rc = launch_coop<48, 16>(b, a, n);  // 16 lanes per element: 2 elements per warp (half sectors)
+  } else if (b->group_size > 1) {
+    rc = (M <= 32) ? launch_message<-1, -1, 32, true>(b, a, n) : launch_message<-1, -1, 64, true>(b, a, n);
+  } else if (M <= 32) {
+    rc = launch_message<-1, -1, 32>(b, a, n);
+  } else {
+    rc = launch_message<-1, -1, 64>(b, a, n);
+  }
+  return rc;
 }
 
 }  // namespace pgbp
