@@ -196,6 +196,34 @@ def test_c3_muller_loopy_bethe_vs_cport():
     assert np.max(np.abs(fes[0][:128, 1] / ref["fe"][:, 1] - 1)) <= 1e-4
 
 
+def test_c3_muller_loopy_ltrip_vs_cport():
+    # BASELINE configs[2], LTRIP(net) cluster graph (801 clusters / 1158 sepsets, sepsets of up to two nodes): the
+    # automatic strategy is the tile-walk kernel; per-step launches must give the same bits, the C twin the same
+    # calibration flags and factored energies to the loopy tolerance of the Bethe test above
+    lib = get_lib("cuda")
+    w = bench.C3L()
+    B = 512
+    params, tips = w.inputs(B, 0)
+    plan = plan_of(w, lib)
+    ref = COracle.from_plan_dict(w.d).run_batch(params, tips[:64], root_belief=w.d["root_cluster"], want_fe=True, **w.cpu_kw)
+    assert (ref["status"] == 0).all()
+    out = {}
+    for mode in (-1, 0):
+        bt = pgbp_b200.BatchedClusterGraphBelief(plan, B)
+        bt.set_tilewalk_mode(mode)
+        bt.assignfactors(params, tips)
+        bt.regularizebeliefs_bycluster()
+        bt.launch_count(reset=True)
+        succ, iscal = bt.calibrate(None, w.niter)
+        assert succ.all()
+        out[mode] = (iscal, bt.factored_energy(), bt.launch_count())
+    assert np.array_equal(out[-1][0], out[0][0]) and np.array_equal(out[-1][1], out[0][1])
+    assert out[-1][2] * 10 < out[0][2]
+    assert np.array_equal(out[-1][0][:64], ref["iscal"])
+    for k, tol in ((2, 2e-4), (0, 1e-4), (1, 1e-4)):
+        assert np.max(np.abs(out[-1][1][:64, k] / ref["fe"][:, k] - 1)) <= tol
+
+
 def test_c5_shapes_reduced_network_vs_cport():
     # BASELINE configs[4] at reduced size (2,000 tips instead of 100,000; the full network is a bench
     # workload: python bench.py --workload c5): MvFullBM p = 16, sender dimensions 16 / 32 / 48 -- the

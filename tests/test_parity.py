@@ -822,6 +822,37 @@ def test_tilewalk_kernel_matches_level_parallel(backend):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
+def test_muller_ltrip_tilewalk_vs_per_step_and_c_twin(backend):
+    # muller_2022, LTRIP(net) cluster graph (801 clusters / 1158 sepsets; sepsets of one or two nodes, so the
+    # tile-walk kernel sees the (1,2), (2,1), (1,1) and copy shapes), 10 iterations over both spanning trees:
+    # tile-walk (automatic) == per-step launches bit for bit, and both agree with the C twin of the oracle
+    import bench
+    from oracle.cport import COracle
+    lib = get_lib(backend)
+    w = bench.C3L()
+    d = w.d
+    plan = pgbp_b200.ClusterGraphPlan(d["nclusters"], d["belief_dim"], d["sepset_clusters"], d["upind"], d["trees"],
+                                      d["ntraits"], d["families"], lib)
+    B = 5
+    params, tips = w.inputs(B, 0)
+    ref = COracle.from_plan_dict(d).run_batch(params, tips, root_belief=d["root_cluster"], want_fe=True, **w.cpu_kw)
+    out = {}
+    for mode in (-1, 0):
+        bt = pgbp_b200.BatchedClusterGraphBelief(plan, B)
+        bt.set_tilewalk_mode(mode)
+        bt.assignfactors(params, tips)
+        bt.regularizebeliefs_bycluster()
+        bt.launch_count(reset=True)
+        succ, iscal = bt.calibrate(None, w.niter)
+        assert succ.all()
+        out[mode] = (iscal, bt.factored_energy(), bt.launch_count())
+    assert out[-1][2] * 10 < out[0][2]
+    assert np.array_equal(out[-1][0], out[0][0]) and np.array_equal(out[-1][1], out[0][1])
+    assert np.array_equal(out[-1][0], ref["iscal"])
+    assert np.max(np.abs(out[-1][1] / ref["fe"] - 1)) <= 1e-10
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
 def test_integratebelief_with_covariance(backend):
     # conditional moments of every belief after calibration: mean, inv(J), norm (the inputs of
     # calibrate_exact_cliquetree!, src/calibration.jl:462-463; test/test_exactBM.jl:26-52 checks them

@@ -63,3 +63,5 @@ if __name__ == "__main__":
     # (1557 clusters / 1914 sepsets), univariate, spanningtrees_clusterlist schedule (2 trees)
     MULLER = json.load(open(os.path.join(ROOT, "tests", "golden", "muller_2022.json")))
     dump("muller_bethe_p1", MULLER["newick"], "bethe", 1, None)
+    # same network, LTRIP(net) cluster graph (801 clusters / 1158 sepsets, docs/src/man/clustergraphs.md:131-132)
+    dump("muller_ltrip_p1", MULLER["newick"], "ltrip", 1, None)
