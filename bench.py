@@ -702,7 +702,7 @@ def main():
                     "c4 = configs[3] (10k-tip synthetic network, p=8)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-batches", type=int, default=3, help="batches (= host threads) alternating in the end-to-end arm")
+    ap.add_argument("--e2e-batches", type=int, default=4, help="batches (= host threads) alternating in the end-to-end arm")
     ap.add_argument("--pipeline", type=int, default=None, help="element chunks of a calibration (-1 auto, 1 off)")
     ap.add_argument("--tilewalk", type=int, default=None, help="tile-walk kernel (-1 auto, 0 off, 1 on)")
     ap.add_argument("--tw-lanes", type=int, default=0, help="tile-walk message lanes per block (4, 8, 16)")

@@ -47,6 +47,21 @@ static int need_slot_table(pgbp_batch* b, size_t n) {
   return 0;
 }
 
+void* batch_pinned(pgbp_batch* b, size_t bytes) {
+#ifdef PGBP_HOST_EMUL
+  (void)b; (void)bytes;
+  return nullptr;
+#else
+  if (bytes <= b->h_pinned_bytes) return b->h_pinned;
+  if (b->h_pinned) { cudaStreamSynchronize(b->stream); cudaFreeHost(b->h_pinned); b->h_pinned = nullptr; b->h_pinned_bytes = 0; }
+  void* v = nullptr;
+  if (cudaHostAlloc(&v, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  b->h_pinned = v;
+  b->h_pinned_bytes = bytes;
+  return v;
+#endif
+}
+
 int batch_zero_sepsets(pgbp_batch* b, bool lazy) {
   const pgbp_plan* p = b->plan;
   if (lazy) { b->sepsets_lazy_zero = true; return 0; }
@@ -326,6 +341,7 @@ int32_t pgbp_batch_destroy(pgbp_batch* b) {
   for (auto s : b->pipe_streams) cudaStreamDestroy(s);
   for (auto ev : b->pipe_events) cudaEventDestroy((cudaEvent_t)ev);
   if (b->own_stream) cudaStreamDestroy(b->stream);
+  if (b->h_pinned) cudaFreeHost(b->h_pinned);
 #endif
   delete b;
   return 0;
@@ -391,8 +407,11 @@ int32_t pgbp_get_residual(pgbp_batch* b, int32_t j, int32_t to_cluster, double* 
 int32_t pgbp_get_status(pgbp_batch* b, int32_t* status) {
   if (!b || !status) PGBP_FAIL(PGBP_EINVAL, "null argument");
   PGBP_TRY(set_device(b->device));
-  PGBP_TRY(d2h(status, b->status, sizeof(int32_t) * (size_t)b->B, b->stream));
-  return stream_sync(b->stream);
+  int32_t* pin = (int32_t*)batch_pinned(b, sizeof(int32_t) * (size_t)b->B);
+  PGBP_TRY(d2h(pin ? pin : status, b->status, sizeof(int32_t) * (size_t)b->B, b->stream));
+  PGBP_TRY(stream_sync(b->stream));
+  if (pin) memcpy(status, pin, sizeof(int32_t) * (size_t)b->B);
+  return 0;
 }
 int32_t pgbp_clear_status(pgbp_batch* b) {
   if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");

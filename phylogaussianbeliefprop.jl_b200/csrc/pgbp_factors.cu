@@ -1397,8 +1397,11 @@ int32_t pgbp_factored_energy(pgbp_batch* b, double* out) {
   PGBP_TRY(factored_energy_launch(b, d_soa, b->ld));
   double* d_aos = d_soa + 3 * b->ld;
   PGBP_TRY(soa_to_aos(b, d_soa, b->ld, d_aos, 3, nullptr));
-  PGBP_TRY(d2h(out, d_aos, sizeof(double) * 3 * (size_t)b->B, b->stream));
-  return stream_sync(b->stream);
+  double* pin = (double*)batch_pinned(b, sizeof(double) * 3 * (size_t)b->B);  // results through pinned memory
+  PGBP_TRY(d2h(pin ? pin : out, d_aos, sizeof(double) * 3 * (size_t)b->B, b->stream));
+  PGBP_TRY(stream_sync(b->stream));
+  if (pin) memcpy(out, pin, sizeof(double) * 3 * (size_t)b->B);
+  return 0;
 }
 
 int32_t pgbp_regularize_bycluster(pgbp_batch* b) {

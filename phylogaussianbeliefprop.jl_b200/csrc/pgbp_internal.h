@@ -181,6 +181,10 @@ struct pgbp_batch {
   // re-runs K1 straight into the beliefs (one write of every cluster) instead of copying (one read + one write).
   struct LazyFactors { bool pending = false; bool valid = false; int32_t ncolors = 1; int64_t nparamsets = 0, ndatasets = 0; int32_t pairing = 0; } lazy_factors;
   int32_t coop_mode = -1;  // medium shapes: -1 auto (cooperative), 0 thread-local generic, 4 / 8 lanes for m <= 16
+  // pinned host bounce buffer for the small per-call results (status / iscal / log-likelihoods): a device-to-host
+  // copy into pageable memory is staged by the driver synchronously; through pinned memory it is a plain DMA
+  void* h_pinned = nullptr;
+  size_t h_pinned_bytes = 0;
   int32_t* d_slot = nullptr;  // device scratch for transpose slot tables
   size_t d_slot_len = 0;
 };

@@ -23,5 +23,7 @@ int batch_materialize_factors(pgbp_batch* b);
 // beliefs <- factors by re-running K1 into the state array; returns 1 if done, 0 if the factors are not K1's
 // output any more (caller copies), < 0 on error
 int batch_reset_by_assign(pgbp_batch* b);
+// pinned host staging of at least `bytes` (nullptr when unavailable: host emulation, allocation failure)
+void* batch_pinned(pgbp_batch* b, size_t bytes);
 MsgArgs make_args(pgbp_batch* b, uint32_t opts, int32_t ref_base, bool use_done);
 }  // namespace pgbp

@@ -729,13 +729,18 @@ int32_t pgbp_calibrate(pgbp_batch* b, const int32_t* tree_ids, int32_t ntrees, i
   b->want_info = false;
   PGBP_TRY(rc);
   const int64_t B = b->B;
-  std::vector<int32_t> st;
+  // results go through the batch's pinned bounce buffer when it is available: [status | iscal]
+  int32_t* pin = (succ || iscal) ? (int32_t*)batch_pinned(b, sizeof(int32_t) * 2 * (size_t)B) : nullptr;
+  std::vector<int32_t> st_v;
+  int32_t* st = nullptr;
+  const bool want_ic = iscal && b->iscal && (flags & PGBP_CAL_RESIDNORM);
   if (succ || iscal) {
-    st.resize(B);
-    PGBP_TRY(d2h(st.data(), b->status, sizeof(int32_t) * B, b->stream));
+    if (pin) st = pin;
+    else { st_v.resize(B); st = st_v.data(); }
+    PGBP_TRY(d2h(st, b->status, sizeof(int32_t) * B, b->stream));
   }
   if (iscal) {
-    if (b->iscal && (flags & PGBP_CAL_RESIDNORM)) PGBP_TRY(d2h(iscal, b->iscal, sizeof(int32_t) * B, b->stream));
+    if (want_ic) PGBP_TRY(d2h(pin ? pin + B : iscal, b->iscal, sizeof(int32_t) * B, b->stream));
     else memset(iscal, 0, sizeof(int32_t) * B);
   }
   std::vector<int32_t> itr;
@@ -746,6 +751,7 @@ int32_t pgbp_calibrate(pgbp_batch* b, const int32_t* tree_ids, int32_t ntrees, i
     }
   }
   PGBP_TRY(stream_sync(b->stream));
+  if (want_ic && pin) memcpy(iscal, pin + B, sizeof(int32_t) * B);
   if (succ) for (int64_t e = 0; e < B; e++) succ[e] = st[e] == 0;
   if (iscal) for (int64_t e = 0; e < B; e++) if (st[e] != 0) iscal[e] = 0;  // (false,false) on failure
   if (iter_tree) for (int64_t e = 0; e < B; e++) {
@@ -831,13 +837,16 @@ int32_t pgbp_integrate(pgbp_batch* b, int32_t belief, double* mu, double* norm) 
   double* d_norm = b->scratch;
   double* d_mu = mu ? b->scratch + ld : nullptr;
   PGBP_TRY(integrate_launch(b, belief, d_mu, d_norm, ld, nullptr));
-  PGBP_TRY(d2h(norm, d_norm, sizeof(double) * b->B, b->stream));
+  double* pin = (double*)batch_pinned(b, sizeof(double) * (size_t)b->B);  // log-likelihoods through pinned memory
+  PGBP_TRY(d2h(pin ? pin : norm, d_norm, sizeof(double) * b->B, b->stream));
   if (mu && M > 0) {
     double* d_aos = b->scratch + ld * (int64_t)(M + 1);
     PGBP_TRY(soa_to_aos(b, d_mu, ld, d_aos, M, nullptr));
     PGBP_TRY(d2h(mu, d_aos, sizeof(double) * b->B * M, b->stream));
   }
-  return stream_sync(b->stream);
+  PGBP_TRY(stream_sync(b->stream));
+  if (pin) memcpy(norm, pin, sizeof(double) * b->B);
+  return 0;
 }
 
 int32_t pgbp_integrate_cov(pgbp_batch* b, int32_t belief, double* mu, double* cov, double* norm) {
