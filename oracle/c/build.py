@@ -8,6 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "pgbp_oracle.c")
 LIB = os.path.join(HERE, "libpgbp_oracle.so")
+LIBQ = os.path.join(HERE, "libpgbp_oracle_quad.so")  # same source in IEEE binary128 (-DPGBPO_QUAD, libquadmath)
 TAG = LIB + ".host"
 
 
@@ -20,16 +21,20 @@ def _host():
         return "unknown"
 
 
-def build(force=False):
+def build(force=False, quad=False):
     host = _host()
-    stale = (force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC)
-             or not os.path.exists(TAG) or open(TAG).read().strip() != host)
+    lib = LIBQ if quad else LIB
+    tag = lib + ".host"
+    stale = (force or not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(SRC)
+             or not os.path.exists(tag) or open(tag).read().strip() != host)
     if stale:
-        subprocess.run(["gcc", "-O2", "-march=native", "-fopenmp", "-fPIC", "-shared", "-std=c11", "-o", LIB, SRC, "-lm"],
-                       check=True)
-        open(TAG, "w").write(host)
-    return LIB
+        extra = ["-DPGBPO_QUAD"] if quad else []
+        subprocess.run(["gcc", "-O2", "-march=native", "-fopenmp", "-fPIC", "-shared", "-std=gnu11", "-ffp-contract=off"]
+                       + extra + ["-o", lib, SRC, "-lm"] + (["-lquadmath"] if quad else []), check=True)
+        open(tag, "w").write(host)
+    return lib
 
 
 if __name__ == "__main__":
     print(build(force=True))
+    print(build(force=True, quad=True))

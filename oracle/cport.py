@@ -29,18 +29,18 @@ class _Fam(C.Structure):
                 ("node_datarow", P(i32))]
 
 
-_dll = None
+_dll = {}
 
 
-def dll():
-    global _dll
-    if _dll is None:
+def dll(quad=False):
+    """quad=True: the same C source compiled in IEEE binary128 (oracle/c/build.py) -- the >= 100-bit adjudicator."""
+    if quad not in _dll:
         spec = importlib.util.spec_from_file_location("pgbp_oracle_build", os.path.join(HERE, "c", "build.py"))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
-        _dll = C.CDLL(mod.build())
-        _dll.pgbpo_num_threads.restype = i32
-    return _dll
+        _dll[quad] = C.CDLL(mod.build(quad=quad))
+        _dll[quad].pgbpo_num_threads.restype = i32
+    return _dll[quad]
 
 
 def _i(x):
@@ -110,7 +110,8 @@ class COracle:
         self.state_size = int(self.off[-1])
 
     def run_batch(self, params, tipdata, ncolors=1, pairing="zip", niter=1, post=True, pre=True, residnorm=True,
-                  auto=False, root_belief=0, want_fe=False, want_state=False, nthreads=0, B=None, reg_bycluster=False):
+                  auto=False, root_belief=0, want_fe=False, want_state=False, nthreads=0, B=None, reg_bycluster=False,
+                  quad=False):
         params = np.ascontiguousarray(np.atleast_2d(np.asarray(params, dtype=float)))
         tip = np.ascontiguousarray(np.asarray(tipdata, dtype=float))
         if tip.ndim == 2:
@@ -121,7 +122,7 @@ class COracle:
         ll = np.empty(B); st = np.zeros(B, dtype=np.int32); isc = np.zeros(B, dtype=np.int32)
         fe = np.empty((B, 3)) if want_fe else None
         so = np.empty((B, self.state_size)) if want_state else None
-        rc = dll().pgbpo_run_batch(C.byref(self.G), C.byref(self.F), i32(ncolors), _p(params, f64), i64(npar),
+        rc = dll(quad).pgbpo_run_batch(C.byref(self.G), C.byref(self.F), i32(ncolors), _p(params, f64), i64(npar),
                                    _p(tip, f64), i64(nd), i32(1 if pairing == "product" else 0), i32(self.ntrees),
                                    _p(self.tree_off, i32), _p(self.tsep, i32), _p(self.tpar, i32), _p(self.tchi, i32),
                                    i32(niter), i32(post), i32(pre), i32(residnorm), i32(auto), i32(root_belief), i64(B),

@@ -88,6 +88,7 @@ class ClusterGraphPlan:
         self.nsepsets = len(self.belief_dim) - self.nclusters
         self.sepset_clusters = [(int(a), int(b)) for a, b in sepset_clusters]
         self.trees = [(list(map(int, p)), list(map(int, c))) for p, c in trees]
+        self.upind = [([int(x) for x in ua], [int(x) for x in ub]) for ua, ub in upind]
         self.ntraits = int(ntraits)
         self.families = families
         keep = []  # keep numpy buffers alive during the call

@@ -250,7 +250,9 @@ int32_t pgbp_batch_create_shared(const pgbp_plan* plan, int64_t B, int64_t group
     PGBP_FAIL(PGBP_EINVAL, "cluster graph too large for int32 slot tables");
   if ((B + 31) / 32 * 32 * 8 >= (int64_t)1 << 32) PGBP_FAIL(PGBP_EINVAL, "batch too large: row pitch must stay below 4 GiB");
   PGBP_TRY(set_device(device));
-  std::unique_ptr<pgbp_batch> b(new pgbp_batch);
+  // any failure below releases the stream and every device buffer allocated so far
+  struct Destroy { void operator()(pgbp_batch* x) const { pgbp_batch_destroy(x); } };
+  std::unique_ptr<pgbp_batch, Destroy> b(new pgbp_batch);
   b->plan = plan;
   b->B = B;
   b->ld = (B + 31) / 32 * 32;
@@ -319,8 +321,8 @@ int32_t pgbp_batch_create_shared(const pgbp_plan* plan, int64_t B, int64_t group
     PGBP_TRY(h2d(b->d_walk[t], w.data(), w.size() * sizeof(MsgDesc), b->stream));
   }
   PGBP_TRY(stream_sync(b->stream));
-  *out = b.release();
-  if (flags & PGBP_BATCH_RESIDUALS) PGBP_TRY(pgbp_reset_calibration_flags(*out, 1));
+  if (flags & PGBP_BATCH_RESIDUALS) PGBP_TRY(pgbp_reset_calibration_flags(b.get(), 1));
+  *out = b.release();  // only after the last fallible step
   return 0;
 }
 

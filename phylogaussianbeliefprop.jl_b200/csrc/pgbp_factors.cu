@@ -1424,7 +1424,7 @@ int32_t pgbp_regularize_onschedule(pgbp_batch* b) {
   if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
   PGBP_TRY(set_device(b->device));
   PGBP_TRY(batch_materialize_sepsets(b));
-  pgbp_plan* p = const_cast<pgbp_plan*>(b->plan);
+  const pgbp_plan* p = b->plan;
   DevTables* dt;
   PGBP_TRY(get_tables(b, &dt));
   // the op list of src/clustergraphbeliefs.jl:376-403
@@ -1459,7 +1459,6 @@ int32_t pgbp_regularize_onschedule(pgbp_batch* b) {
       msgs.push_back(md);
     }
   }
-  PGBP_TRY(batch_upload_tables(b));
   void* v = nullptr;
   PGBP_TRY(dev_malloc(&v, std::max<size_t>(1, msgs.size()) * sizeof(MsgDesc)));
   MsgDesc* d_msgs = (MsgDesc*)v;

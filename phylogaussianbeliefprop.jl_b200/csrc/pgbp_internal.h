@@ -74,6 +74,8 @@ struct Tree {
   Traversal trav[2];  // 0 postorder, 1 preorder
   std::vector<MsgDesc> walk;  // postorder then preorder messages in reference order
   bool walkable = false;      // every message is inside the walk family of ntraits
+  bool covers_sepsets = false;  // the edges are nsepsets DISTINCT sepsets: one traversal writes every sepset exactly once
+                                // (condition of the lazy sepset zero)
 };
 
 struct FamilyTable {
@@ -115,9 +117,10 @@ struct pgbp_plan {
   pgbp::FamilyTable fam;
   int32_t max_dim = 0;
 
-  int32_t intern_table(const std::vector<int32_t>& t);
-  // build the descriptor of message from -> to through sepset j
-  int make_msg(int32_t from, int32_t j, int32_t to, pgbp::MsgDesc* out);
+  int32_t intern_table(const std::vector<int32_t>& t);        // plan creation only
+  int32_t find_table(const std::vector<int32_t>& t) const;  // -1 if absent
+  // build the descriptor of message from -> to through sepset j (read-only: every table is interned at creation)
+  int make_msg(int32_t from, int32_t j, int32_t to, pgbp::MsgDesc* out) const;
 };
 
 struct pgbp_batch {

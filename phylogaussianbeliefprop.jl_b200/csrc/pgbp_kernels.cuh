@@ -75,12 +75,13 @@ PGBP_HD constexpr int colof(int q) {
 // calibration flag of one residual (src/beliefs.jl:994-1003):
 // max|dh|/sqrt(s) <= 1e-5 && max|dJ|/sqrt(s^2) <= 1e-5.  max_i(|x_i|/c) == (max_i|x_i|)/c
 // exactly (division by c > 0 is monotone, so is rounding).
-PGBP_HD void store_flag(const MsgArgs& a, int dmsg, int64_t e, int S, double maxJ, double maxh) {
+// hlive = false: a failed group leader of a shared-precision batch that only carries the group's J forward
+PGBP_HD void store_flag(const MsgArgs& a, int dmsg, int64_t e, int S, double maxJ, double maxh, bool hlive = true) {
   if ((a.opts & PGBP_CAL_RESIDNORM) && a.calflag) {
     const bool okh = S > 0 ? (maxh / sqrt((double)S) <= 1e-5) : true;
     const bool okJ = S > 0 ? (maxJ / (double)S <= 1e-5) : true;
     if (a.gs > 1) {  // J part kept apart: it is the group's, not the element's
-      a.calflag[(int64_t)dmsg * a.ld + e] = okh ? 1 : 0;
+      if (hlive) a.calflag[(int64_t)dmsg * a.ld + e] = okh ? 1 : 0;
       if (e % a.gs == 0) a.calflagJ[(int64_t)dmsg * a.ld + e] = okJ ? 1 : 0;
     } else {
       a.calflag[(int64_t)dmsg * a.ld + e] = (okh && okJ) ? 1 : 0;
@@ -119,13 +120,17 @@ template <int CI, int CS, bool SH = false>
 PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
   constexpr int I = CI, S = CS, M = I + S, SI = I * (I + 1) / 2, SS = S * (S + 1) / 2;
   const MsgDesc md = a.msgs[msg_index];  // by value: lives in registers, never re-read after a store
-  if (a.status[e] != 0) return;
+  const int64_t ej = SH ? jcol(a, e) : e;
+  const bool lead = SH ? ej == e : true;  // this thread owns (writes) the J rows
+  // A failed element stops updating -- except a group leader of a shared-precision batch: J depends on the shared
+  // parameters only, so the leader keeps carrying the group's J rows forward (hlive = false: no h / g / status
+  // writes) even when its own data failed (e.g. a NaN tip value, status set by K1).
+  bool hlive = SH ? a.status[e] == 0 : true;
+  if (SH ? (!hlive && !lead) : a.status[e] != 0) return;
   if (a.done && a.done[e]) return;
   const uint32_t ld8 = (uint32_t)(a.ld * 8);  // (batches with 8*ld >= 2^32 are refused at creation)
   char* st = (char*)(a.state + e);
   char* rs = a.resid ? (char*)(a.resid + e) : nullptr;
-  const int64_t ej = SH ? jcol(a, e) : e;
-  const bool lead = SH ? ej == e : true;  // this thread owns (writes) the J rows
   char* stj = SH ? (char*)(a.state + ej) : st;  // J rows are read from the leader's column
   const int32_t* __restrict__ gat = a.tab + md.gat;
   const int32_t* __restrict__ sca = a.tab + md.sca;
@@ -177,9 +182,24 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
 #pragma unroll
   for (int q = 0; q < I * S; q++)
     if (!(fabs(Bm[q]) <= PGBP_EPS)) allzero = false;
+  if constexpr (SH) {
+    // group leader: the J part of the message must not depend on this element's h.  Zero precision with a
+    // non-zero (or NaN) h_I fails this element (potrf info = 1) while the group's J moves on as in the shortcut.
+    bool hzero = true;
 #pragma unroll
-  for (int k = 0; k < I; k++)
-    if (!(fabs(hI[k]) <= PGBP_EPS)) allzero = false;
+    for (int k = 0; k < I; k++)
+      if (!(fabs(hI[k]) <= PGBP_EPS)) hzero = false;
+    if (lead && allzero && !hzero) {
+      if (hlive) status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, 1));
+      hlive = false;
+    } else if (!hzero) {
+      allzero = false;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < I; k++)
+      if (!(fabs(hI[k]) <= PGBP_EPS)) allzero = false;
+  }
 
   if (!allzero) {
     double logdet = 0.0, ww = 0.0;
@@ -187,7 +207,7 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
     for (int k = 0; k < I; k++) {
       const double d = AI[pk(k, k)];
       if (!(d > 0.0)) {  // LAPACK potrf: info = k+1 (also catches NaN)
-        status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, k + 1));
+        if (hlive) status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, k + 1));
         return;
       }
       logdet += log(d);
@@ -263,22 +283,26 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
 #pragma unroll
       for (int i = 0; i < I; i++) nv = nfma(Bm[i * S + k], hI[i], nv);
       const double d = nv - so[k];
-      *slot_ptr(st, sh + k, ld8) = nv;
-      *ta[k] = to[k] + d;
-      if (rs) *slot_ptr(rs, rh + k, ld8) = d;
+      if (hlive) {
+        *slot_ptr(st, sh + k, ld8) = nv;
+        *ta[k] = to[k] + d;
+        if (rs) *slot_ptr(rs, rh + k, ld8) = d;
+      }
       absmax(maxh, d);
     }
   }
-  *slot_ptr(st, (uint32_t)md.sg, ld8) = g;
-  *slot_ptr(st, (uint32_t)md.tg, ld8) = tg_old + (g - sg_old);
-  store_flag(a, md.dmsg, e, S, maxJ, maxh);
+  if (hlive) {
+    *slot_ptr(st, (uint32_t)md.sg, ld8) = g;
+    *slot_ptr(st, (uint32_t)md.tg, ld8) = tg_old + (g - sg_old);
+  }
+  store_flag(a, md.dmsg, e, S, maxJ, maxh, hlive);
 }
 
 // Runtime-shape variants share this tail: divide / multiply / residual / flag with
 // chunked prefetch.  newJ(r,c,q), newh(k) give the outgoing message.
 template <bool SH = false, class FJ, class FH>
 PGBP_HD void divide_mult_store(const MsgArgs& a, const MsgDesc& md, int64_t e, int S, FJ newJ, FH newh,
-                               double newg) {
+                               double newg, bool hlive = true) {
   const int64_t ld = a.ld;
   double* st = a.state + e;
   double* rs = a.resid ? a.resid + e : nullptr;
@@ -330,15 +354,19 @@ PGBP_HD void divide_mult_store(const MsgArgs& a, const MsgDesc& md, int64_t e, i
     for (int k = 0; k < PGBP_CHUNK; k++)
       if (k0 + k < S) {
         const double d = nv[k] - so[k];
-        st[(md.sh + k0 + k) * ld] = nv[k];
-        st[ta[k]] = to[k] + d;
-        if (rs) rs[(md.rh + k0 + k) * ld] = d;
+        if (hlive) {
+          st[(md.sh + k0 + k) * ld] = nv[k];
+          st[ta[k]] = to[k] + d;
+          if (rs) rs[(md.rh + k0 + k) * ld] = d;
+        }
         absmax(maxh, d);
       }
   }
-  st[md.sg * ld] = newg;
-  st[md.tg * ld] = tg_old + (newg - sg_old);
-  store_flag(a, md.dmsg, e, S, maxJ, maxh);
+  if (hlive) {
+    st[md.sg * ld] = newg;
+    st[md.tg * ld] = tg_old + (newg - sg_old);
+  }
+  store_flag(a, md.dmsg, e, S, maxJ, maxh, hlive);
 }
 
 struct TrailJ {
@@ -371,7 +399,8 @@ template <int MAXM, bool SH = false>
 PGBP_HD void message_thread_rt(const MsgArgs& a, int msg_index, int64_t e) {
   constexpr int NA = MAXM * (MAXM + 1) / 2;
   const MsgDesc md = a.msgs[msg_index];
-  if (a.status[e] != 0) return;
+  bool hlive = a.status[e] == 0;  // a failed group leader of a shared-precision batch keeps carrying the group's J
+  if (!hlive && !(SH && jcol(a, e) == e)) return;
   if (a.done && a.done[e]) return;
   const int I = md.mF - md.s, S = md.s, M = md.mF;
   const int64_t ld = a.ld;
@@ -392,14 +421,21 @@ PGBP_HD void message_thread_rt(const MsgArgs& a, int msg_index, int64_t e) {
     for (int r = 0; r < rmax; r++)
       if (!(fabs(A[pk(r, c)]) <= PGBP_EPS)) allzero = false;
   }
+  bool hzero = true;
   for (int k = 0; k < I; k++)
-    if (!(fabs(hv[k]) <= PGBP_EPS)) allzero = false;
+    if (!(fabs(hv[k]) <= PGBP_EPS)) hzero = false;
+  if (SH && jcol(a, e) == e && allzero && !hzero) {  // see message_thread_t0: the group's J must not depend on this h
+    if (hlive) status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, 1));
+    hlive = false;
+  } else if (!hzero) {
+    allzero = false;
+  }
   if (!allzero) {
     double logdet = 0.0, ww = 0.0;
     for (int k = 0; k < I; k++) {
       const double d = A[pk(k, k)];
       if (!(d > 0.0)) {
-        status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, k + 1));
+        if (hlive) status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, k + 1));
         return;
       }
       logdet += log(d);
@@ -415,7 +451,7 @@ PGBP_HD void message_thread_rt(const MsgArgs& a, int msg_index, int64_t e) {
     }
     g += 0.5 * ((double)I * PGBP_LOG2PI - logdet + ww);
   }
-  divide_mult_store<SH>(a, md, e, S, TrailJ{A, I}, TrailH{hv, I}, g);
+  divide_mult_store<SH>(a, md, e, S, TrailJ{A, I}, TrailH{hv, I}, g, hlive);
 }
 
 // Message with nothing to integrate out (src/beliefupdates.jl:56): the outgoing
@@ -423,7 +459,8 @@ PGBP_HD void message_thread_rt(const MsgArgs& a, int msg_index, int64_t e) {
 template <bool SH = false>
 PGBP_HD void message_copy_thread(const MsgArgs& a, int msg_index, int64_t e) {
   const MsgDesc md = a.msgs[msg_index];
-  if (a.status[e] != 0) return;
+  const bool hlive = a.status[e] == 0;
+  if (!hlive && !(SH && jcol(a, e) == e)) return;
   if (a.done && a.done[e]) return;
   const int S = md.s;
   const int64_t ld = a.ld;
@@ -431,7 +468,7 @@ PGBP_HD void message_copy_thread(const MsgArgs& a, int msg_index, int64_t e) {
   const int32_t* __restrict__ gat = a.tab + md.gat;
   const int SS = tri(S);
   const double g = st[md.fg * ld];
-  divide_mult_store<SH>(a, md, e, S, GatherJ{SH ? a.state + jcol(a, e) : st, gat, md.fJ, ld}, GatherH{st, gat + SS, md.fh, ld}, g);
+  divide_mult_store<SH>(a, md, e, S, GatherJ{SH ? a.state + jcol(a, e) : st, gat, md.fJ, ld}, GatherH{st, gat + SS, md.fh, ld}, g, hlive);
 }
 
 // residual_kldiv! (src/beliefs.jl:1060-1075): KL divergence between the message just sent (the new

@@ -556,6 +556,7 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
   if ((flags & PGBP_CAL_RESIDKLDIV) && !b->kldiv)
     PGBP_FAIL(PGBP_ESTATE, "update_residualkldiv requested but the batch was created without PGBP_BATCH_RESIDUALS");
   std::vector<int32_t> ids;
+  if (tree_ids && ntrees < 0) PGBP_FAIL(PGBP_EINVAL, "ntrees < 0");
   if (tree_ids) ids.assign(tree_ids, tree_ids + ntrees);
   else for (int t = 0; t < (int)p->trees.size(); t++) ids.push_back(t);
   if (ids.empty()) PGBP_FAIL(PGBP_EINVAL, "empty schedule");
@@ -565,7 +566,7 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
   // sepset (a spanning tree of a clique tree), through the per-step launches
   if (b->sepsets_lazy_zero) {
     const pgbp::Tree& t0 = p->trees[ids[0]];
-    const bool ok = (flags & PGBP_CAL_POSTORDER) && (int)t0.parent.size() == p->nsepsets && !use_walk(b, ids[0]) &&
+    const bool ok = (flags & PGBP_CAL_POSTORDER) && t0.covers_sepsets && !use_walk(b, ids[0]) &&
                     !(flags & PGBP_CAL_RESIDKLDIV);
     if (!ok) PGBP_TRY(batch_materialize_sepsets(b));
   }
@@ -800,16 +801,14 @@ int32_t pgbp_batch_set_coop_mode(pgbp_batch* b, int32_t mode) {
 
 int32_t pgbp_propagate(pgbp_batch* b, int32_t from_cluster, int32_t sepset, int32_t to_cluster, uint32_t flags) {
   if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
-  pgbp_plan* p = const_cast<pgbp_plan*>(b->plan);
+  const pgbp_plan* p = b->plan;
   if (from_cluster < 0 || from_cluster >= p->nclusters || to_cluster < 0 || to_cluster >= p->nclusters)
     PGBP_FAIL(PGBP_EINVAL, "cluster index out of range");
   const int j = sepset >= p->nclusters ? sepset - p->nclusters : sepset;  // accept belief index or sepset index
   MsgDesc md;
-  const size_t tab_before = p->tab.size();
-  PGBP_TRY(p->make_msg(from_cluster, j, to_cluster, &md));
+  PGBP_TRY(p->make_msg(from_cluster, j, to_cluster, &md));  // the plan is immutable: no table ever grows here
   PGBP_TRY(set_device(b->device));
   PGBP_TRY(batch_materialize_sepsets(b));
-  if (p->tab.size() != tab_before) PGBP_TRY(batch_upload_tables(b));
   PGBP_TRY(h2d(b->d_one, &md, sizeof md, b->stream));
   PGBP_TRY(stream_sync(b->stream));  // md is a stack object
   LaunchGroup g;

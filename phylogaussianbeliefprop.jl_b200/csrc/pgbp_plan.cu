@@ -27,7 +27,40 @@ int32_t pgbp_plan::intern_table(const std::vector<int32_t>& t) {
   return off;
 }
 
-int pgbp_plan::make_msg(int32_t from, int32_t j, int32_t to, MsgDesc* out) {
+int32_t pgbp_plan::find_table(const std::vector<int32_t>& t) const {
+  auto it = tab_index.find(t);
+  return it == tab_index.end() ? -1 : it->second;
+}
+
+// gather table of the sender in [I;K] order and scatter table of the receiver for message from -> to through j
+static void msg_tables(const pgbp_plan* p, int mF, int s, const std::vector<int32_t>& upF, const std::vector<int32_t>& upT,
+                       std::vector<int32_t>* g, std::vector<int32_t>* sc) {
+  (void)p;
+  std::vector<char> keep(mF, 0);
+  for (int k : upF) keep[k] = 1;
+  std::vector<int32_t> perm;
+  perm.reserve(mF);
+  for (int k = 0; k < mF; k++) if (!keep[k]) perm.push_back(k);
+  for (int k : upF) perm.push_back(k);
+  g->clear();
+  g->reserve(tri(mF) + mF);
+  for (int c = 0; c < mF; c++)
+    for (int r = 0; r <= c; r++) {
+      int a = perm[r], b = perm[c];
+      g->push_back(pk(std::min(a, b), std::max(a, b)));
+    }
+  for (int k = 0; k < mF; k++) g->push_back(perm[k]);
+  sc->clear();
+  sc->reserve(tri(s) + s);
+  for (int c = 0; c < s; c++)
+    for (int r = 0; r <= c; r++) sc->push_back(pk(upT[r], upT[c]));
+  for (int k = 0; k < s; k++) sc->push_back(upT[k]);
+}
+
+// The plan is immutable once created (it is shared by every batch, possibly from several host threads): the
+// tables of BOTH directed messages of EVERY sepset are interned by pgbp_plan_create, so a descriptor can be
+// built for any edge (pgbp_propagate on an edge that is in no tree) without growing `tab`.
+int pgbp_plan::make_msg(int32_t from, int32_t j, int32_t to, MsgDesc* out) const {
   if (j < 0 || j >= nsepsets) PGBP_FAIL(PGBP_EINVAL, "sepset %d out of range", j);
   const std::vector<int32_t>*upF, *upT;
   int side;
@@ -47,28 +80,11 @@ int pgbp_plan::make_msg(int32_t from, int32_t j, int32_t to, MsgDesc* out) {
   m.rJ = rjslot[m.dmsg]; m.rh = rhslot[m.dmsg];
   m.mF = mF; m.s = s; m.ref = 0;
   m.wid = walk_shape_id(ntraits, mF - s, s);
-  // sender gather table in [I;K] order
-  std::vector<char> keep(mF, 0);
-  for (int k : *upF) keep[k] = 1;
-  std::vector<int32_t> perm;
-  perm.reserve(mF);
-  for (int k = 0; k < mF; k++) if (!keep[k]) perm.push_back(k);
-  for (int k : *upF) perm.push_back(k);
-  std::vector<int32_t> g;
-  g.reserve(tri(mF) + mF);
-  for (int c = 0; c < mF; c++)
-    for (int r = 0; r <= c; r++) {
-      int a = perm[r], b = perm[c];
-      g.push_back(pk(std::min(a, b), std::max(a, b)));
-    }
-  for (int k = 0; k < mF; k++) g.push_back(perm[k]);
-  m.gat = intern_table(g);
-  std::vector<int32_t> sc;
-  sc.reserve(tri(s) + s);
-  for (int c = 0; c < s; c++)
-    for (int r = 0; r <= c; r++) sc.push_back(pk((*upT)[r], (*upT)[c]));
-  for (int k = 0; k < s; k++) sc.push_back((*upT)[k]);
-  m.sca = intern_table(sc);
+  std::vector<int32_t> g, sc;
+  msg_tables(this, mF, s, *upF, *upT, &g, &sc);
+  m.gat = find_table(g);
+  m.sca = find_table(sc);
+  if (m.gat < 0 || m.sca < 0) PGBP_FAIL(PGBP_ESTATE, "internal: index tables of sepset %d missing from the plan", j);
   *out = m;
   return 0;
 }
@@ -240,6 +256,14 @@ int32_t pgbp_plan_create(const pgbp_plan_desc* d, pgbp_plan** out) {
   }
   p->nslots_resid = rslot;
   for (auto& v : p->nbrs) std::sort(v.begin(), v.end());
+  for (int j = 0; j < p->nsepsets; j++) {  // both directed messages of every sepset (see make_msg)
+    std::vector<int32_t> g, sc;
+    const int s = p->dim[p->nclusters + j];
+    msg_tables(p.get(), p->dim[p->sep_a[j]], s, p->up_a[j], p->up_b[j], &g, &sc);
+    p->intern_table(g); p->intern_table(sc);
+    msg_tables(p.get(), p->dim[p->sep_b[j]], s, p->up_b[j], p->up_a[j], &g, &sc);
+    p->intern_table(g); p->intern_table(sc);
+  }
   // trees
   if (d->ntrees < 0) PGBP_FAIL(PGBP_EINVAL, "ntrees < 0");
   p->trees.resize(d->ntrees);
@@ -255,6 +279,10 @@ int32_t pgbp_plan_create(const pgbp_plan_desc* d, pgbp_plan** out) {
       auto it = p->sep_of.find(std::make_pair(std::min(a, b), std::max(a, b)));
       if (it == p->sep_of.end()) PGBP_FAIL(PGBP_EINVAL, "tree %d edge %d: clusters (%d,%d) are not adjacent", t, i, a, b);
       tr.sepset[i] = it->second;
+    }
+    {
+      std::set<int32_t> distinct(tr.sepset.begin(), tr.sepset.end());
+      tr.covers_sepsets = n == p->nsepsets && (int)distinct.size() == n;
     }
     // postorder: i = n-1..0, child -> parent (src/calibration.jl:121-125)
     std::vector<int32_t> f(n), s(n), to(n);

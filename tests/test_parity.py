@@ -1043,3 +1043,83 @@ def test_assignfactors_ou_device_vs_oracle_and_golden(backend):
             assert abs(ll[e] / OBP.integratebelief_cgb(cgbs[e], spt[2][0])[1] - 1) <= TOL
         if k == 0:
             assert abs(ll[0] / -42.31401134496844 - 1) <= 1e-9
+
+
+# ------------------------------------------------------------------ regressions (round-1 advisor findings)
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_two_batches_one_plan_propagate_over_edge_outside_every_tree(backend):
+    # The plan is immutable and shared: propagate_belief! over an edge that is in no spanning tree must not grow
+    # the plan's index tables (a second batch created earlier would index past its device copy).  Plan without
+    # any tree: every message descriptor comes from pgbp_propagate.
+    lib = get_lib(backend)
+    p = 2
+    R = np.array([[1.0, 0.3], [0.3, 2.0]])
+    taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
+    rng = np.random.default_rng(19)
+    data = rng.normal(size=(2, 7, p))
+    model = M.MvFullBrownianMotion(R, np.zeros(p))
+    case = Case(GOLD["lazaridis"], "cliquetree", data[0], taxa, model, lib, order_hint=GOLD["lazaridis_cluster_labels"])
+    fam = None
+    plan = pgbp_b200.ClusterGraphPlan(case.plan.nclusters, case.plan.belief_dim, case.plan.sepset_clusters,
+                                      case.plan.upind, [], p, fam, lib)
+    A = pgbp_b200.BatchedClusterGraphBelief(plan, 2)
+    Bb = pgbp_b200.BatchedClusterGraphBelief(plan, 2)
+    cgbs = [case.oracle_cgb(tbl=data[e]) for e in range(2)]
+    case.upload(A, cgbs)
+    case.upload(Bb, cgbs)
+    spt = case.sched[0]
+    par, chi = spt[2][-1], spt[3][-1]  # a real edge of the clique tree (1-based cluster indices)
+    sep = None
+    for j, (a, b_) in enumerate(plan.sepset_clusters):
+        if {a + 1, b_ + 1} == {par, chi}:
+            sep = plan.nclusters + 1 + j
+    assert sep is not None
+    A.propagate_belief(par, sep, chi)
+    Bb.propagate_belief(par, sep, chi)   # crashed (out-of-bounds table read) before the plan became immutable
+    A.propagate_belief(chi, sep, par)
+    Bb.propagate_belief(chi, sep, par)
+    for j in (par, chi, sep):
+        for u, v in zip(A.get_belief(j), Bb.get_belief(j)):
+            assert np.array_equal(u, v)
+    for e in range(2):
+        bl = cgbs[e].belief
+        assert OBP.propagate_belief(bl[par - 1], bl[sep - 1], bl[chi - 1]) is None
+        assert OBP.propagate_belief(bl[chi - 1], bl[sep - 1], bl[par - 1]) is None
+    J, h, g = A.get_belief(par)
+    for e in range(2):
+        ob = cgbs[e].belief[par - 1]
+        assert relerr(J[e], ob.J) <= TOL and relerr(h[e], ob.h) <= TOL and abs(g[e] - ob.g) <= TOL * max(1, abs(ob.g))
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_shared_precision_failed_leader_does_not_stall_its_group(backend):
+    # A per-element failure on a group LEADER (here: NaN tip data, status set by factor assignment) must not stop
+    # the J updates of its group: J depends on the shared parameters only.  The other elements of the group must
+    # get exactly the results of an ordinary batch.
+    lib = get_lib(backend)
+    p = 3
+    rng = np.random.default_rng(77)
+    A_ = rng.normal(size=(p, p))
+    R = A_ @ A_.T / p + 0.1 * np.eye(p)
+    taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
+    B, gs = 8, 4
+    data = rng.normal(size=(B, 7, p))
+    data[4, 2, 1] = np.nan  # element 4 leads the second group
+    model = M.MvFullBrownianMotion(R, np.zeros(p))
+    case = Case(GOLD["lazaridis"], "cliquetree", data[0], taxa, model, lib, order_hint=GOLD["lazaridis_cluster_labels"])
+    params = pgbp_b200.bm_params([R], np.zeros(p))
+    out = {}
+    for name, group in (("own", 0), ("shared", gs)):
+        bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B, shared_precision_group=group)
+        bt.assignfactors(params, data)
+        succ, iscal = bt.calibrate(case.sched, 1)
+        out[name] = (succ, bt.status(), bt.integratebelief(case.sched[0][2][0])[1], bt.factored_energy(),
+                     [bt.get_belief(j) for j in (1, 5, case.nclusters + 2)])
+    keep = np.arange(B) != 4
+    so, ss = out["own"], out["shared"]
+    assert not so[0][4] and not ss[0][4] and so[0][keep].all() and ss[0][keep].all()
+    assert (ss[1][keep] == 0).all() and ss[1][4] != 0
+    assert np.array_equal(so[2][keep], ss[2][keep]) and np.array_equal(so[3][keep], ss[3][keep])
+    for x, y in zip(so[4], ss[4]):
+        # J of the failed leader's group is still the group's J (read through the leader's column)
+        assert np.array_equal(x[0][5:], y[0][5:]) and np.array_equal(x[1][keep], y[1][keep])
