@@ -273,9 +273,42 @@ class C5(C4):
 WORKLOADS = {"c2": C2, "c2s": C2S, "c3": C3, "c3l": C3L, "c4": C4, "c5": C5}
 
 
+# ----------------------------------------------------------------------------- config shared by both arms
+def messages_per_unit(w):
+    d = w.d
+    if w.key in ("c2", "c2s", "c5"):
+        return 2 * len(d["trees"][0][0])
+    if w.key == "c4":
+        return len(d["trees"][0][0])
+    return 2 * sum(len(t[0]) for t in d["trees"])  # loopy: one iteration over all spanning trees
+
+
+def state_bytes_per_element(w):
+    """HBM bytes of one batch element (beliefs + factor snapshot + residuals), from the belief dimensions."""
+    d = w.d
+    dims, nc = d["belief_dim"], d["nclusters"]
+    slots = sum(m * (m + 1) // 2 + m + 1 for m in dims)
+    if w.residuals:
+        slots += sum(m * (m + 1) // 2 + m + 1 for m in dims[:nc])           # ClusterFactor snapshot
+        slots += 2 * sum(m * (m + 1) // 2 + m for m in dims[nc:])          # MessageResidual per directed message
+    return 8 * slots
+
+
+def make_config(w, B, n_gpus):
+    """The `config` object of the JSON line: identical in the GPU arm and in the reference arm."""
+    st = state_bytes_per_element(w) * B / 1e9
+    gather = ("; the per-replicate results of all ranks are gathered every step (GPU arm: written by the integrate kernel "
+              "into every rank's window over NVLink peer stores; checked against one NCCL all_gather)" if n_gpus > 1 else "")
+    return {"workload": w.workload, "batch_per_gpu": int(B), "ntraits": int(w.d["ntraits"]),
+            "messages_per_unit": int(messages_per_unit(w)), "step": w.step_text + gather,
+            "l2": "inputs larger than L2: %.2f GB of beliefs%s per GPU rewritten every step (L2 = 126 MB)"
+                  % (st, " + factors + residuals" if w.residuals else ""),
+            "parallelism": f"batch sharded over {n_gpus} GPU(s), plan replicated, no data-path collective"}
+
+
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
-def cpu_port_rate(w, params, tips, seconds, nthreads=0, steps=1, warmup=0):
-    """units/s of the C/OpenMP oracle port on a bounded sample of the workload."""
+def cpu_port_rate(w, params, tips, seconds, nthreads=0, steps=2, warmup=1):
+    """units/s of the C/OpenMP oracle port on a bounded sample of the workload (warmed up, mean of `steps`)."""
     from oracle.cport import COracle, dll
     co = COracle.from_plan_dict(w.d)
     kw = dict(root_belief=w.d["root_cluster"], nthreads=nthreads, ncolors=w.ncolors, want_fe=(w.key in ("c3", "c3l")), **w.cpu_kw)
@@ -301,6 +334,10 @@ def cpu_port_rate(w, params, tips, seconds, nthreads=0, steps=1, warmup=0):
     return n / dt, cores, n, dt, (out["fe"][:, 2] if w.key in ("c3", "c3l") else out["loglik"])
 
 
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -309,16 +346,16 @@ def run_reference(args):
     B = args.batch or w.default_batch
     params, tips = w.inputs(B, 0)
     # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it explicitly)
-    nthr = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    value, cores, n, dt, _ = cpu_port_rate(w, params, tips, 3.0, nthreads=nthr, steps=args.steps, warmup=args.warmup)
+    value, cores, n, dt, _ = cpu_port_rate(w, params, tips, 3.0, nthreads=host_threads(), steps=args.steps, warmup=args.warmup)
     value *= getattr(w, "niter", 1)
     sample = f"{n} of {B} batch elements per step ({w.cpu_text})"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": w.unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w.workload, "note": "reference is Julia (absent from the image): C/OpenMP restatement of "
-                   "its algorithm (oracle/c), all host threads, bounded sample per step"},
+        "config": make_config(w, B, args.gpus),
+        "reference_note": "the reference is Julia (absent from the image): C/OpenMP restatement of its algorithm (oracle/c), "
+                          "all host threads, bounded sample per step",
         "cpu_baseline": {"value": value, "unit": w.unit, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": w.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -402,75 +439,135 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def run_gpu(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Process-wide state of the GPU arm (one process per GPU)."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        if args.gpus != self.world and self.rank == 0:
+            print(f"warning: --gpus {args.gpus} but WORLD_SIZE={self.world}; reporting n_gpus={self.world}", file=sys.stderr)
+        self.stream = torch.cuda.current_stream()
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            self.peak, self.peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            self.peak, self.peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+
+def measure(w, args, ctx, steps, headline, cpu_seconds, e2e_steps_cap, min_region_s):
+    """One workload on this rank's GPU: device-resident arm (value, roofline), end-to-end arm (host buffers), CPU
+    check on a bounded sample (rank 0 of a single-GPU run).  Returns the dict of the JSON line (rank 0) or None."""
     import pgbp_b200
     from pgbp_b200 import _lib as L
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    if args.gpus != world and rank == 0:
-        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; reporting n_gpus={world}", file=sys.stderr)
-    w = WORKLOADS[args.workload]()
+    from pgbp_b200 import sharding
+    torch, dist = ctx.torch, ctx.dist
+    rank, world, local, dev, stream = ctx.rank, ctx.world, ctx.local, ctx.dev, ctx.stream
     d = w.d
-    B = args.batch or w.default_batch
+    B = (args.batch if headline else 0) or w.default_batch
     p = d["ntraits"]
     params, tips = w.inputs(B, rank)
     lib = pgbp_b200.default_library()
     plan = pgbp_b200.ClusterGraphPlan(d["nclusters"], d["belief_dim"], d["sepset_clusters"], d["upind"], d["trees"], p,
                                       d["families"], lib)
-    stream = torch.cuda.current_stream()
     group = B if getattr(w, "shared", False) else 0
     bt = pgbp_b200.BatchedClusterGraphBelief(plan, B, device=local, stream=stream.cuda_stream,
                                              factors=w.residuals, residuals=w.residuals, shared_precision_group=group)
-    if args.walk is not None:
-        bt.set_walk_mode(args.walk)
-    if args.pipeline is not None:
-        bt.set_pipeline(args.pipeline)
-    if args.graph is not None:
-        bt.set_graph_mode(args.graph)
-    if args.tilewalk is not None:
-        bt.set_tilewalk_mode(args.tilewalk)
-    if args.coop is not None:
-        bt.set_coop_mode(args.coop)
-    if args.tw_lanes or args.tw_wide:
-        bt.set_tilewalk_params(args.tw_lanes, args.tw_wide)
+    if headline:
+        if args.walk is not None:
+            bt.set_walk_mode(args.walk)
+        if args.pipeline is not None:
+            bt.set_pipeline(args.pipeline)
+        if args.graph is not None:
+            bt.set_graph_mode(args.graph)
+        if args.tilewalk is not None:
+            bt.set_tilewalk_mode(args.tilewalk)
+        if args.coop is not None:
+            bt.set_coop_mode(args.coop)
+        if args.tw_lanes or args.tw_wide:
+            bt.set_tilewalk_params(args.tw_lanes, args.tw_wide)
     root = d["root_cluster"] + 1
     bytes_unit, flops_unit = w.cost(plan)
-    nmsg = ({"c2": 2 * len(d["trees"][0][0]), "c2s": 2 * len(d["trees"][0][0]), "c4": len(d["trees"][0][0]),
-             "c5": 2 * len(d["trees"][0][0])}.get(w.key)
-            or 2 * sum(len(t[0]) for t in d["trees"]) * w.niter)
+    nmsg = messages_per_unit(w) * getattr(w, "niter", 1)
     upe = getattr(w, "niter", 1)  # metric units per element per step
+    loopy = w.key in ("c3", "c3l")
 
-    # ---- device-resident arm: inputs in HBM before the timed region -----------------------
+    # ---- gather of the per-element results (N > 1) ------------------------------------------------
+    # Default: fused into the producing kernel -- pgbp_integrate_gather / pgbp_comm_put store every result into
+    # row `rank` of every rank's window over NVLink peer stores (no collective launch on the step's critical
+    # path).  --gather nccl (or a failed IPC mapping on some rank): asynchronous double-buffered NCCL all-gather.
     _, ld, _ = bt.device_view()
-    # two result buffers: the NCCL gather of step k (on NCCL's stream) overlaps the kernels of step k+1
+    comm, gather_kind = None, "none"
+    if world > 1:
+        ok = 1.0
+        if args.gather == "peer":
+            try:
+                comm = sharding.PeerGather(lib, local, rank, world, ld, nbuffers=2)
+            except Exception as ex:  # noqa: BLE001
+                print(f"rank {rank}: peer windows unavailable ({ex}); falling back to the NCCL all-gather", file=sys.stderr)
+                ok = 0.0
+        else:
+            ok = 0.0
+        ok = -ctx.max_over_ranks([-ok])[0]  # min over ranks: every rank must use the same transport
+        if ok < 0.5:  # some rank could not map its peers: every rank drops its window (unmap, barrier, free)
+            if comm is not None:
+                lib.pgbp_comm_disconnect(comm.handle)
+            ctx.sync()
+            if comm is not None:
+                comm.close()
+                comm = None
+        gather_kind = "peer" if comm is not None else "nccl"
     d_norms = [torch.empty(ld, dtype=torch.float64, device=dev) for _ in range(2)]
-    gathered = [torch.empty(world * ld, dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+    gathered = [torch.empty(world * ld, dtype=torch.float64, device=dev) for _ in range(2)] if gather_kind == "nccl" else None
     pending = [None, None]
     counter = [0]
+    d_fe = torch.empty(3 * ld, dtype=torch.float64, device=dev) if loopy else None
 
-    def finish(ev=None):
-        """integratebelief! at the root + (N > 1) asynchronous all-gather of the log-likelihoods."""
+    def finish():
+        """per-element result of the step (integratebelief! at the root, or the factored energy for loopy BP)
+        + (N > 1) its gather."""
         k = counter[0] % 2
         counter[0] += 1
         if pending[k] is not None:
             pending[k].wait()  # stream-level wait: buffer k is free again
             pending[k] = None
-        bt.integrate_device(root, d_norms[k].data_ptr())
-        if world > 1:
+        if loopy:
+            bt.factored_energy_device(d_fe.data_ptr())
+            if comm is not None:
+                comm.put(bt, k, d_fe[2 * ld:3 * ld].data_ptr())
+            else:
+                d_norms[k].copy_(d_fe[2 * ld:3 * ld])
+        elif comm is not None:
+            comm.integrate_gather(bt, root, k)
+        else:
+            bt.integrate_device(root, d_norms[k].data_ptr())
+        if gather_kind == "nccl":
             pending[k] = dist.all_gather_into_tensor(gathered[k], d_norms[k], async_op=True)
-        return d_norms[k]
+
     if w.key in ("c2", "c2s"):
-        bt.assignfactors(params, tips)  # factors resident in HBM
+        bt.assignfactors(params, tips)  # factors resident in HBM (K1 is outside the device-resident timed region)
 
         def step(ev=None):
             bt.init_beliefs_reset_fromfactors()
@@ -480,20 +577,8 @@ def run_gpu(args):
             if ev:
                 ev[1].record(stream)
             finish()
-    elif w.key in ("c3", "c3l"):
+    elif loopy:
         bt.assignfactors(params, tips)
-        d_fe = torch.empty(3 * ld, dtype=torch.float64, device=dev)
-
-        def finish(ev=None):  # noqa: F811  (loopy objective: factored energy instead of integratebelief!)
-            k = counter[0] % 2
-            counter[0] += 1
-            if pending[k] is not None:
-                pending[k].wait()
-                pending[k] = None
-            bt.factored_energy_device(d_fe.data_ptr())
-            d_norms[k].copy_(d_fe[2 * ld:3 * ld])
-            if world > 1:
-                pending[k] = dist.all_gather_into_tensor(gathered[k], d_norms[k], async_op=True)
 
         def step(ev=None):
             bt.init_beliefs_reset_fromfactors()
@@ -524,21 +609,32 @@ def run_gpu(args):
             if pending[k] is not None:
                 pending[k].wait()
                 pending[k] = None
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+        ctx.sync()
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    # Inner repeats: the timed region is `steps` x `inner` passes, long enough (>= min_region_s) that one launch
+    # hiccup or a clock ramp cannot decide the number; everything below is reported per pass.
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record(stream)
+    for _ in range(3):
+        step()
+    pe1.record(stream)
+    barrier()
+    t_probe = pe0.elapsed_time(pe1) / 3 * 1e-3
+    inner = int(min(256, max(1, np.ceil(min_region_s / max(steps * t_probe, 1e-9)))))
+    inner = int(ctx.max_over_ranks([inner])[0])
+    nsteps = steps * inner
+    sampler = ClockSampler(local) if (rank == 0 and headline) else None
     bt.launch_count(reset=True)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     t0 = time.perf_counter()
     e0.record(stream)
-    for k in range(args.steps):
+    for k in range(nsteps):
         step(evs[k])
     e1.record(stream)
     barrier()
@@ -547,33 +643,47 @@ def run_gpu(args):
     ms_total = e0.elapsed_time(e1)
     ms_msgs = sum(a.elapsed_time(b) for a, b in evs)
     clocks = sampler.stop(t0, t1) if sampler else None
-    tt = torch.tensor([ms_total, ms_msgs], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total, ms_msgs = float(tt[0]), float(tt[1])
-    value = world * B * upe * args.steps / (ms_total * 1e-3)
+    ms_total, ms_msgs = ctx.max_over_ranks([ms_total, ms_msgs])
+    value = world * B * upe * nsteps / (ms_total * 1e-3)
     st = bt.status()
     assert (st == 0).all(), "numerical failure inside the timed region"
-    loglik_dev = d_norms[(counter[0] - 1) % 2][:B].cpu().numpy()
-    if world > 1:  # the gathered vector holds every rank's log-likelihoods; this rank's slice must match
-        mine = gathered[(counter[0] - 1) % 2].view(world, ld)[rank, :B].cpu().numpy()
-        assert np.array_equal(mine, loglik_dev)
+    # the gathered vector of the LAST step: every rank's results in rank order; it must equal an NCCL all-gather of
+    # the same values (peer transport) and this rank's own slice (both transports)
+    klast = (counter[0] - 1) % 2
+    gather_checked = None
+    if comm is not None:
+        comm.wait(bt, klast)
+        comm.check(bt)
+        ctx.sync()
+        win = comm.read(bt, klast)
+        wld = comm.ld
+        loglik_dev = win[rank, :B].copy()
+        mine = torch.from_numpy(win[rank].copy()).to(dev)
+        ref_all = torch.empty(world * wld, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(ref_all, mine)  # NCCL cross-check of the peer-written window
+        assert np.array_equal(ref_all.cpu().numpy().reshape(world, wld)[:, :B], win[:, :B]), "peer-gathered window != NCCL all_gather"
+        gather_checked = "window of every rank == NCCL all_gather of the same values (bitwise)"
+    else:
+        loglik_dev = d_norms[klast][:B].cpu().numpy()
+        if world > 1:
+            mine = gathered[klast].view(world, ld)[rank, :B].cpu().numpy()
+            assert np.array_equal(mine, loglik_dev)
+            gather_checked = "own slice of the NCCL-gathered vector == local result (bitwise)"
 
     # ---- end-to-end arm: public host-buffer API, pinned host inputs, D2H of the result -------
     # Every step = one synchronous sequence of public calls on one batch: H2D of that step's inputs
-    # (pinned) + K1, message passing, integratebelief! with the D2H of the result.  When two batches
-    # fit in HBM the steps alternate between two batches driven by two host threads (the ABI allows
-    # distinct batches on distinct threads): the H2D / D2H of one step overlaps the kernels of the other.
+    # (pinned) + K1, message passing, integratebelief! with the D2H of the result.  When several batches
+    # fit in HBM the steps alternate between batches driven by their own host threads (the ABI allows
+    # distinct batches on distinct threads): the H2D / D2H of one step overlaps the kernels of the others.
     big = params if w.key == "c4" else tips
-    e2e_steps = args.steps if w.key in ("c2", "c2s") else min(args.steps, 5)
+    e2e_steps = min(nsteps, e2e_steps_cap)
     free_b, total_b = torch.cuda.mem_get_info()
     nb_e2e = max(1, min(args.e2e_batches, 1 + int(free_b / (bt.device_bytes() * 1.1))))
-    two = nb_e2e > 1
     bts = [bt]
     for _ in range(nb_e2e - 1):
         bts.append(pgbp_b200.BatchedClusterGraphBelief(plan, B, device=local, factors=w.residuals, residuals=w.residuals,
                                                        shared_precision_group=group))
-        if args.pipeline is not None:
+        if headline and args.pipeline is not None:
             bts[-1].set_pipeline(args.pipeline)
     pin_np = [torch.from_numpy(big.copy()).pin_memory().numpy() for _ in bts]
     results = [None] * len(bts)
@@ -583,7 +693,7 @@ def run_gpu(args):
         if w.key in ("c2", "c2s"):
             b_.assignfactors(params, pin_np[i])                 # H2D of this step's inputs + K1
             succ, iscal = b_.calibrate(None, 1)                 # D2H of succ / iscal
-        elif w.key in ("c3", "c3l"):
+        elif loopy:
             b_.assignfactors(params, pin_np[i])
             b_.regularizebeliefs_bycluster()
             succ, iscal = b_.calibrate(None, w.niter)
@@ -602,12 +712,12 @@ def run_gpu(args):
         for _ in range(n):
             e2e_step(i)
 
-    def run_e2e(nsteps):
+    def run_e2e(n):
         if len(bts) == 1:
-            worker(0, nsteps)
+            worker(0, n)
             return
         nb = len(bts)
-        ths = [threading.Thread(target=worker, args=(i, nsteps // nb + (i < nsteps % nb))) for i in range(nb)]
+        ths = [threading.Thread(target=worker, args=(i, n // nb + (i < n % nb))) for i in range(nb)]
         for t in ths:
             t.start()
         for t in ths:
@@ -618,83 +728,128 @@ def run_gpu(args):
     run_e2e(e2e_steps)
     barrier()
     dte = time.perf_counter() - t0e
-    te = torch.tensor([dte], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * upe * e2e_steps / float(te[0])
+    dte = ctx.max_over_ranks([dte])[0]
+    e2e_value = world * B * upe * e2e_steps / dte
     h2d = tips.nbytes + params.nbytes
-    ll_host = results[0]
-    d2h = ll_host.nbytes + (1 if w.key == "c4" else 2) * 4 * B
+    d2h = results[0].nbytes + (1 if w.key == "c4" else 2) * 4 * B
     for r_ in results:
         assert np.allclose(r_, loglik_dev, rtol=1e-12, atol=0)  # same kernels, same inputs: identical
     del bts[1:]
-
+    if comm is not None:
+        comm.close(ctx.sync)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
-    # ---- roofline of the dominant kernel family (k_message*) ----------------------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = bytes_unit * B * args.steps / (ms_msgs * 1e-3) / 1e9
+    # ---- roofline of the dominant kernel family (k_message*): ALGORITHMIC bytes / device time -----------
+    achieved = bytes_unit * B * nsteps / (ms_msgs * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(w.key, {}).get("dram_bytes_per_unit_per_element")
         if traffic is not None:
             traffic = traffic * B
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": w.kernel_text,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
+                "traffic": traffic, "peak_source": ctx.peak_src, "kernel": w.kernel_text,
+                "basis": "algorithmic-bytes roofline: SURVEY 8(d) bytes of every message / CUDA-event time of the message "
+                         "kernels; the lazy sepset zero, L2 hits on lines written by the previous level and (c2s) shared J "
+                         "rows make the DRAM traffic smaller than the algorithmic count, see dram_gbs_from_traffic",
+                "dram_gbs_from_traffic": (traffic * nsteps / (ms_msgs * 1e-3) / 1e9) if traffic else None,
                 "algorithmic_bytes_per_unit_per_element": bytes_unit,
                 "algorithmic_flops_per_unit_per_element": flops_unit,
-                "fp64_gflops_achieved": flops_unit * B * args.steps / (ms_msgs * 1e-3) / 1e9,
+                "fp64_gflops_achieved": flops_unit * B * nsteps / (ms_msgs * 1e-3) / 1e9,
                 "share_of_step": ms_msgs / ms_total}
 
-    # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------
+    # ---- CPU baseline + parity of the results (rank 0, N = 1 only) -------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        nthr = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        rate, cores, n, dt, ll_cpu = cpu_port_rate(w, params, tips, args.cpu_seconds, nthreads=nthr)
+        rate, cores, n, dt, ll_cpu = cpu_port_rate(w, params, tips, cpu_seconds, nthreads=host_threads())
         rate *= upe
         err = float(np.max(np.abs(ll_cpu / loglik_dev[:n] - 1)))
         cpu = {"value": rate, "unit": w.unit, "cores": cores, "kind": "port",
-               "sample": f"{n} of {B} batch elements in {dt:.1f} s ({w.cpu_text}, C/OpenMP restatement of the Julia "
-                         f"reference)",
+               "sample": f"{n} of {B} batch elements in {dt:.2f} s per pass, warmed up, mean of 2 passes ({w.cpu_text}, "
+                         f"C/OpenMP restatement of the Julia reference)",
                "max_rel_err_gpu_vs_cpu_loglik": err}
-        # (c3: loopy BP with eps = 2.2e-16 regularisation of factor-less clusters is ill-conditioned: restatements
-        # of the reference's own formulation differ by 6e-7 already; see tests/test_fullsize.py)
-        assert err < (2e-4 if w.key in ("c3", "c3l") else 1e-10), err
+        # c3 (Bethe): the reference's own algorithm evaluated in binary64 is ~3e-5 away from its exact (binary128)
+        # result after 10 loopy iterations (oracle/tools/adjudicate_c3.py): stated tolerance 1e-4
+        assert err < (1e-4 if w.key == "c3" else 1e-10), err
 
     line = {
-        "metric": METRIC, "value": value, "unit": w.unit, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "metric": METRIC, "value": value, "unit": w.unit, "n_gpus": world, "steps": steps,
+        "warmup": warm, "ms_per_step": ms_total / nsteps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w.workload, "batch_per_gpu": B, "ntraits": p, "messages_per_unit": nmsg,
-                   "step": w.step_text + (" + nccl all_gather(loglik), double-buffered and asynchronous: it overlaps "
-                                          "the next step's kernels" if world > 1 else ""),
-                   "l2": "inputs larger than L2 (state %.2f GB per GPU)" % (bt.device_bytes() / 1e9),
-                   "parallelism": f"batch sharded over {world} GPU(s), plan replicated"},
+        "config": make_config(w, B, world),
+        "timing": {"inner_repeats": inner, "passes_timed": nsteps, "timed_region_ms": ms_total,
+                   "note": "steps x inner_repeats passes inside one CUDA-event pair (max over ranks); ms_per_step is per pass"
+                           + ("; device-resident passes start from the factors resident in HBM (factor assignment, K1, is "
+                              "outside this arm and inside e2e)" if w.key in ("c2", "c2s", "c3", "c3l") else "")},
+        "gather": {"kind": gather_kind, "checked": gather_checked} if world > 1 else None,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": w.unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "path": w.e2e_text + ((" (%d batches x %d host threads: copies of one step overlap the "
-                                                          "kernels of the others)" % (nb_e2e, nb_e2e)) if two else "")},
+                                                          "kernels of the others)" % (nb_e2e, nb_e2e)) if nb_e2e > 1 else "")},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
+def compact(line):
+    """What the headline line keeps of another workload's measurement."""
+    r = line["roofline"]
+    out = {"workload": line["config"]["workload"], "batch_per_gpu": line["config"]["batch_per_gpu"], "unit": line["unit"],
+           "value": line["value"], "ms_per_step": line["ms_per_step"], "passes_timed": line["timing"]["passes_timed"],
+           "n_gpus": line["n_gpus"],
+           "roofline": {"bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"], "unit": r["unit"], "frac": r["frac"],
+                        "traffic": r["traffic"], "kernel": r["kernel"], "share_of_step": r["share_of_step"]},
+           "e2e": line["e2e"], "gpu_launches": line["gpu_launches"], "gather": line["gather"]}
+    if line["cpu_baseline"]:
+        out["cpu_baseline"] = {k: line["cpu_baseline"][k] for k in ("value", "cores", "kind", "sample")}
+        out["max_rel_err"] = line["cpu_baseline"]["max_rel_err_gpu_vs_cpu_loglik"]
+    return out
+
+
+def run_gpu(args):
+    import gc
+    ctx = Ctx(args)
+    t_start = time.perf_counter()
+    w = WORKLOADS[args.workload]()
+    line = measure(w, args, ctx, args.steps, True, args.cpu_seconds, 10 ** 9 if args.workload in ("c2", "c2s") else 5, 0.5)
+    # The other BASELINE configurations, each measured the same way at reduced step counts, so that the driver's
+    # own run holds them too (configs[3] = the north-star target: 10k-tip network, p = 8, 4,096 parameter vectors).
+    others = {}
+    if args.workload == "c2" and not args.no_others:
+        plan = [("c4", 3, 3.0), ("c3", 2, 3.0), ("c3l", 2, 3.0), ("c5", 2, 4.0)]
+        for key, k_steps, cpu_s in plan:
+            if key == "c5" and (args.no_c5 or time.perf_counter() - t_start > args.others_budget_s):
+                if ctx.rank == 0:
+                    others[key] = {"skipped": "time budget of the default run" if not args.no_c5 else "--no-c5"}
+                continue
+            gc.collect()
+            ctx.torch.cuda.empty_cache()
+            try:
+                ww = WORKLOADS[key]()
+                ln = measure(ww, args, ctx, k_steps, False, cpu_s, 4, 0.0)
+                if ctx.rank == 0:
+                    others[key] = compact(ln)
+                del ww
+            except AssertionError:
+                raise
+            except Exception as ex:  # noqa: BLE001  (e.g. out of memory for c5 on a smaller GPU)
+                if ctx.rank == 0:
+                    others[key] = {"failed": repr(ex)[:300]}
+    if ctx.rank == 0:
+        if others:
+            line["other_workloads"] = others
+        print(json.dumps(line))
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="batch elements per GPU (default: the workload's)")
@@ -702,6 +857,11 @@ def main():
                     "c4 = configs[3] (10k-tip synthetic network, p=8)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="headline workload only (skip the other_workloads block)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the 100k-tip workload in the other_workloads block")
+    ap.add_argument("--others-budget-s", type=float, default=150.0, help="c5 is skipped when the run is already older than this")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: results gathered through NVLink peer "
+                    "windows fused into the integrate kernel (default) or an asynchronous NCCL all-gather per step")
     ap.add_argument("--e2e-batches", type=int, default=4, help="batches (= host threads) alternating in the end-to-end arm")
     ap.add_argument("--pipeline", type=int, default=None, help="element chunks of a calibration (-1 auto, 1 off)")
     ap.add_argument("--tilewalk", type=int, default=None, help="tile-walk kernel (-1 auto, 0 off, 1 on)")

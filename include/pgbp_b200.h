@@ -259,6 +259,11 @@ int32_t pgbp_assign_factors_ou(pgbp_batch* batch, const double* params, int64_t 
 #define PGBP_CAL_RESIDNORM 4u       /* update_residualnorm  (default true in the reference)  */
 #define PGBP_CAL_RESIDKLDIV 8u      /* update_residualkldiv (default false)                  */
 #define PGBP_CAL_AUTO 16u           /* auto: an element stops at its first calibrated tree   */
+#define PGBP_CAL_REFORDER 32u       /* validation mode: every message in the reference's own operation order (LAPACK-order
+                                       upper Cholesky of J_I with division by the pivot, X_invA_Xt accumulated un-fused,
+                                       src/beliefupdates.jl:68-81) instead of the fused right-looking form; J and h then
+                                       agree bit for bit with a LAPACK-style evaluation of the reference even on
+                                       ill-conditioned loopy configurations.  Slow (thread-local kernel); never automatic. */
 
 /* calibrate!(beliefs, schedule, niter; auto, update_residualnorm, update_residualkldiv)
  * (src/calibration.jl:35-60) per element.  tree_ids selects/permutes plan trees
@@ -314,6 +319,36 @@ int32_t pgbp_regularize_bynodesubtree(pgbp_batch* batch, int32_t nnodes, const i
 int32_t pgbp_device_view(pgbp_batch* batch, double** base, int64_t* ld, int64_t* nslots);
 int32_t pgbp_belief_slot(const pgbp_plan* plan, int32_t belief, int64_t* jslot, int64_t* hslot,
                          int64_t* gslot);
+
+/* ---------------------------------------------------------------- multi-GPU gather over NVLink peer memory
+ * The path shards by batch element (one process per GPU, the plan replicated); its only exchange is the gather
+ * of the per-replicate results (log-likelihoods), the role of the closing `Threads.@threads` join + result
+ * vector of the reference's replicate loop.  Instead of a collective launch per step the exchange is fused into
+ * the producing kernel: every rank owns a window of `nbuffers` x `nranks` rows of `ld` doubles, exported with CUDA
+ * IPC; after pgbp_comm_connect each rank's integratebelief! kernel stores its results into row `rank` of EVERY
+ * rank's window through the peer mappings and publishes a sequence number; pgbp_comm_wait enqueues a wait (on the
+ * batch's stream) until all ranks' rows of a buffer have landed.  Handles are 64 opaque bytes the host exchanges
+ * itself (torch.distributed / MPI.Allgather).  Ranks call put / gather the same number of times per buffer. */
+typedef struct pgbp_comm pgbp_comm;
+int32_t pgbp_comm_create(int32_t device, int32_t rank, int32_t nranks, int64_t ld, int32_t nbuffers,
+                         pgbp_comm** out);
+int32_t pgbp_comm_handle(pgbp_comm* comm, uint8_t* handle64);
+int32_t pgbp_comm_connect(pgbp_comm* comm, const uint8_t* handles /* [nranks][64], rank order */);
+/* teardown across processes: every rank disconnects (unmaps its peers), the ranks synchronise, every rank destroys */
+int32_t pgbp_comm_disconnect(pgbp_comm* comm);
+int32_t pgbp_comm_destroy(pgbp_comm* comm);
+/* this rank's window of `buffer`: [nranks][ld] doubles (device pointer) */
+int32_t pgbp_comm_window(pgbp_comm* comm, int32_t buffer, double** d_ptr, int64_t* ld);
+/* integratebelief!(beliefs, j) for every element, norm[e] written into row `rank` of `buffer` on every rank
+ * (enqueue only; src/clustergraphbeliefs.jl:194, src/beliefupdates.jl:168-200) */
+int32_t pgbp_integrate_gather(pgbp_batch* batch, int32_t belief, pgbp_comm* comm, int32_t buffer);
+/* same exchange for any per-element device vector d_src[B] (e.g. the factored energy of loopy BP) */
+int32_t pgbp_comm_put(pgbp_comm* comm, pgbp_batch* batch, int32_t buffer, const double* d_src);
+int32_t pgbp_comm_wait(pgbp_comm* comm, pgbp_batch* batch, int32_t buffer, int32_t timeout_ms);
+/* host copy of this rank's window of `buffer` ([nranks][ld] doubles); synchronous on the batch's stream */
+int32_t pgbp_comm_read(pgbp_comm* comm, pgbp_batch* batch, int32_t buffer, double* host);
+/* synchronise the batch's stream and report a wait that timed out (names the missing rank) */
+int32_t pgbp_comm_check(pgbp_comm* comm, pgbp_batch* batch);
 
 #ifdef __cplusplus
 }

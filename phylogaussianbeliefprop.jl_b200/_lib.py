@@ -85,11 +85,22 @@ SIGNATURES = {
     "pgbp_regularize_bynodesubtree": (i32, [vp, i32] + [P(i32)] * 8),
     "pgbp_device_view": (i32, [vp, P(vp), P(i64), P(i64)]),
     "pgbp_belief_slot": (i32, [vp, i32, P(i64), P(i64), P(i64)]),
+    "pgbp_comm_create": (i32, [i32, i32, i32, i64, i32, P(vp)]),
+    "pgbp_comm_handle": (i32, [vp, P(u8)]),
+    "pgbp_comm_connect": (i32, [vp, P(u8)]),
+    "pgbp_comm_disconnect": (i32, [vp]),
+    "pgbp_comm_destroy": (i32, [vp]),
+    "pgbp_comm_window": (i32, [vp, i32, P(vp), P(i64)]),
+    "pgbp_integrate_gather": (i32, [vp, i32, vp, i32]),
+    "pgbp_comm_put": (i32, [vp, vp, i32, vp]),
+    "pgbp_comm_wait": (i32, [vp, vp, i32, i32]),
+    "pgbp_comm_read": (i32, [vp, vp, i32, P(f64)]),
+    "pgbp_comm_check": (i32, [vp, vp]),
 }
 
 # flags (mirror the header)
 BATCH_FACTORS, BATCH_RESIDUALS = 1, 2
-CAL_POSTORDER, CAL_PREORDER, CAL_BOTH, CAL_RESIDNORM, CAL_RESIDKLDIV, CAL_AUTO = 1, 2, 3, 4, 8, 16
+CAL_POSTORDER, CAL_PREORDER, CAL_BOTH, CAL_RESIDNORM, CAL_RESIDKLDIV, CAL_AUTO, CAL_REFORDER = 1, 2, 3, 4, 8, 16, 32
 PAIR_ZIP, PAIR_PRODUCT = 0, 1
 
 

@@ -427,8 +427,8 @@ class BatchedClusterGraphBelief:
         self.lib.check(self.lib.pgbp_reset_calibration_flags(self.handle, int(reset_kl)))
 
     # -- message passing -------------------------------------------------------
-    def _flags(self, update_residualnorm, update_residualkldiv, auto):
-        f = 0
+    def _flags(self, update_residualnorm, update_residualkldiv, auto, reference_order=False):
+        f = L.CAL_REFORDER if reference_order else 0
         if update_residualnorm:
             f |= L.CAL_RESIDNORM
         if update_residualkldiv:
@@ -438,16 +438,17 @@ class BatchedClusterGraphBelief:
         return f
 
     def calibrate(self, schedule=None, niter=1, auto=False, info=False, verbose=True,
-                  update_residualnorm=True, update_residualkldiv=False, direction=L.CAL_BOTH):
+                  update_residualnorm=True, update_residualkldiv=False, direction=L.CAL_BOTH, reference_order=False):
         """calibrate!(beliefs, schedule, niter; ...) -> (succ[B], iscal[B])
-        [, iter_tree[B,2] if info]."""
+        [, iter_tree[B,2] if info].  reference_order=True: validation mode PGBP_CAL_REFORDER (every message in the
+        reference's LAPACK-style operation order; slow)."""
         ids = None if schedule is None else [self.plan.tree_id(s) for s in schedule]
         ida, idp = (None, None) if ids is None else _ia(ids)
         succ = np.zeros(self.B, dtype=np.int32); iscal = np.zeros(self.B, dtype=np.int32)
         it = np.zeros((self.B, 2), dtype=np.int32) if info else None
         self.lib.check(self.lib.pgbp_calibrate(
             self.handle, idp, 0 if ids is None else len(ids), int(niter),
-            direction | self._flags(update_residualnorm, update_residualkldiv, auto),
+            direction | self._flags(update_residualnorm, update_residualkldiv, auto, reference_order),
             succ.ctypes.data_as(_i32p), iscal.ctypes.data_as(_i32p), None if it is None else it.ctypes.data_as(_i32p)))
         if info:
             return succ.astype(bool), iscal.astype(bool), it

@@ -454,6 +454,92 @@ PGBP_HD void message_thread_rt(const MsgArgs& a, int msg_index, int64_t e) {
   divide_mult_store<SH>(a, md, e, S, TrailJ{A, I}, TrailH{hv, I}, g, hlive);
 }
 
+// Reference-order message body (PGBP_CAL_REFORDER): the same message computed in the REFERENCE's operation
+// order instead of the fused right-looking form above -- marginalize as PDMats does it (src/beliefupdates.jl:68-81):
+// left-looking upper Cholesky of J_I in LAPACK dpotf2 order with a division by the pivot, Z = J_KI / U by forward
+// substitution, X_invA_Xt = Z Z' accumulated from 0 with un-fused products and subtracted once, mu_I = U \ (U' \ h_I),
+// h_K - J_KI mu_I, logdet = 2 sum log U_kk, h_I' mu_I.  A validation mode: it removes every difference in rounding
+// ORDER between this library and a LAPACK-style evaluation of the reference, so that on ill-conditioned loopy
+// configurations (BASELINE configs[2] on the Bethe graph) J and h can be compared bit for
+// bit.  One thread per (message, element), thread-local storage: slow, never selected automatically.
+template <int MAXM>
+PGBP_HD void message_thread_ref(const MsgArgs& a, int msg_index, int64_t e) {
+  constexpr int NA = MAXM * (MAXM + 1) / 2, NZ = (MAXM / 2) * (MAXM - MAXM / 2) > 0 ? (MAXM / 2) * (MAXM - MAXM / 2) : 1;
+  const MsgDesc md = a.msgs[msg_index];
+  if (a.status[e] != 0) return;
+  if (a.done && a.done[e]) return;
+  const int I = md.mF - md.s, S = md.s, M = md.mF;
+  const int64_t ld = a.ld;
+  const double* st = a.state + e;
+  const int32_t* __restrict__ gat = a.tab + md.gat;
+  double A[NA], hv[MAXM], Z[NZ], mu[MAXM];
+  const int SM = tri(M);
+  for (int q = 0; q < SM; q++) A[q] = st[(md.fJ + gat[q]) * ld];
+  for (int k = 0; k < M; k++) hv[k] = st[(md.fh + gat[SM + k]) * ld];
+  double g = st[md.fg * ld];
+  bool allzero = true;
+  for (int c = 0; c < M; c++) {
+    const int rmax = c < I ? c + 1 : I;
+    for (int r = 0; r < rmax; r++)
+      if (!(fabs(A[pk(r, c)]) <= PGBP_EPS)) allzero = false;
+  }
+  for (int k = 0; k < I; k++)
+    if (!(fabs(hv[k]) <= PGBP_EPS)) allzero = false;
+  if (I > 0 && !allzero) {
+    for (int j = 0; j < I; j++) {  // dpotf2('U')
+      double ajj = A[pk(j, j)];
+      for (int k = 0; k < j; k++) ajj -= A[pk(k, j)] * A[pk(k, j)];
+      if (!(ajj > 0.0)) {
+        status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, j + 1));
+        return;
+      }
+      ajj = sqrt(ajj);
+      A[pk(j, j)] = ajj;
+      for (int c = j + 1; c < I; c++) {
+        double s = A[pk(j, c)];
+        for (int k = 0; k < j; k++) s -= A[pk(k, j)] * A[pk(k, c)];
+        A[pk(j, c)] = s / ajj;
+      }
+    }
+    for (int r = 0; r < S; r++) {  // row r of Z solves U' z = J_KI[r, :]'
+      for (int c = 0; c < I; c++) {
+        double s = A[pk(c, I + r)];
+        for (int k = 0; k < c; k++) s -= A[pk(k, c)] * Z[r * I + k];
+        Z[r * I + c] = s / A[pk(c, c)];
+      }
+    }
+    for (int c = 0; c < S; c++)
+      for (int r = 0; r <= c; r++) {
+        double d = 0.0;
+        for (int k = 0; k < I; k++) d += Z[r * I + k] * Z[c * I + k];
+        A[pk(I + r, I + c)] -= d;
+      }
+    for (int r = 0; r < I; r++) {  // U' y = h_I
+      double s = hv[r];
+      for (int k = 0; k < r; k++) s -= A[pk(k, r)] * mu[k];
+      mu[r] = s / A[pk(r, r)];
+    }
+    for (int r = I - 1; r >= 0; r--) {  // U mu = y
+      double s = mu[r];
+      for (int k = r + 1; k < I; k++) s -= A[pk(r, k)] * mu[k];
+      mu[r] = s / A[pk(r, r)];
+    }
+    double logdet = 0.0, quad = 0.0;
+    for (int k = 0; k < I; k++) {
+      logdet += log(A[pk(k, k)]);
+      quad += hv[k] * mu[k];
+    }
+    logdet *= 2.0;
+    for (int r = 0; r < S; r++) {
+      double d = 0.0;
+      for (int c = 0; c < I; c++) d += A[pk(c, I + r)] * mu[c];
+      hv[I + r] -= d;
+    }
+    g = g + ((double)I * PGBP_LOG2PI - logdet + quad) / 2;
+  }
+  divide_mult_store<false>(a, md, e, S, TrailJ{A, I}, TrailH{hv, I}, g);
+}
+
 // Message with nothing to integrate out (src/beliefupdates.jl:56): the outgoing
 // message is the sender's belief re-ordered; streamed, no local storage.
 template <bool SH = false>

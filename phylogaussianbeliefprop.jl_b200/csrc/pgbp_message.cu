@@ -258,6 +258,13 @@ __global__ void __launch_bounds__(32 * LANES, MINB) k_tilewalk(MsgArgs a, const 
 }
 
 template <int MAXM>
+__global__ void __launch_bounds__(128) k_message_ref(MsgArgs a) {
+  const int64_t e = a.e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.B) return;
+  message_thread_ref<MAXM>(a, blockIdx.y, e);
+}
+
+template <int MAXM>
 __global__ void __launch_bounds__(128) k_kldiv(MsgArgs a, double* kldiv) {
   const int64_t e = a.e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.B) return;
@@ -291,6 +298,27 @@ static int launch_copy(pgbp_batch* b, const MsgArgs& a, int nmsg) {
   return check_launch("k_message_copy");
 }
 
+// reference-order validation mode (PGBP_CAL_REFORDER): every message with something to integrate out goes
+// through message_thread_ref
+template <int MAXM>
+static int launch_ref_t(pgbp_batch* b, const MsgArgs& a, int n) {
+#ifdef PGBP_HOST_EMUL
+  for (int m = 0; m < n; m++)
+    for (int64_t e = a.e0; e < a.B; e++) message_thread_ref<MAXM>(a, m, e);
+#else
+  dim3 grid((unsigned)((a.B - a.e0 + 127) / 128), (unsigned)n);
+  k_message_ref<MAXM><<<grid, 128, 0, b->stream>>>(a);
+#endif
+  b->launches++;
+  return check_launch("k_message_ref");
+}
+static int launch_ref(pgbp_batch* b, const MsgArgs& a, int n, int mF) {
+  if (mF <= 8) return launch_ref_t<8>(b, a, n);
+  if (mF <= 16) return launch_ref_t<16>(b, a, n);
+  if (mF <= 32) return launch_ref_t<32>(b, a, n);
+  return launch_ref_t<PGBP_MAX_DIM>(b, a, n);
+}
+
 // One launch group (same step, same shape class).  blockIdx.y is limited to
 // 65535: split larger groups.
 int launch_group(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGroup& g) {
@@ -301,6 +329,8 @@ int launch_group(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGr
     int rc = 0;
     if (g.ci == 0) {
       rc = launch_copy(b, a, n);
+    } else if (a.opts & PGBP_CAL_REFORDER) {
+      rc = launch_ref(b, a, n, g.ci > 0 ? g.ci + g.cs : g.maxm + g.cs);
     } else if (g.ci > 0) {
       if (b->group_size > 1) {
         rc = launch_t0s_part0(b, a, n, g.ci, g.cs);
@@ -407,7 +437,7 @@ bool use_walk(const pgbp_batch* b, int tree) {
 // b->tw_wide messages are split off into ordinary launches (LANES lanes would serialise them); runs of
 // narrower steps in between go to one tile-walk launch each.
 static bool use_tilewalk(const pgbp_batch* b, const Traversal& tv, uint32_t opts) {
-  if (b->tilewalk_mode == 0 || (opts & PGBP_CAL_RESIDKLDIV) || tv.tw.empty() || b->group_size > 1) return false;
+  if (b->tilewalk_mode == 0 || (opts & (PGBP_CAL_RESIDKLDIV | PGBP_CAL_REFORDER)) || tv.tw.empty() || b->group_size > 1) return false;
   if (b->tilewalk_mode == 1) return true;
   return tv.nsteps >= 24 && (int64_t)tv.msgs.size() < 32 * (int64_t)tv.nsteps;
 }
@@ -553,6 +583,8 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
     PGBP_FAIL(PGBP_ESTATE, "residual tracking requested but the batch was created without PGBP_BATCH_RESIDUALS");
   if (b->group_size > 1 && (flags & PGBP_CAL_AUTO))
     PGBP_FAIL(PGBP_EINVAL, "auto-stop is per element: not available in shared-precision mode (the group's J keeps moving)");
+  if ((flags & PGBP_CAL_REFORDER) && b->group_size > 1)
+    PGBP_FAIL(PGBP_EINVAL, "the reference-order validation mode is not available for shared-precision batches");
   if ((flags & PGBP_CAL_RESIDKLDIV) && !b->kldiv)
     PGBP_FAIL(PGBP_ESTATE, "update_residualkldiv requested but the batch was created without PGBP_BATCH_RESIDUALS");
   std::vector<int32_t> ids;
@@ -566,7 +598,7 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
   // sepset (a spanning tree of a clique tree), through the per-step launches
   if (b->sepsets_lazy_zero) {
     const pgbp::Tree& t0 = p->trees[ids[0]];
-    const bool ok = (flags & PGBP_CAL_POSTORDER) && t0.covers_sepsets && !use_walk(b, ids[0]) &&
+    const bool ok = (flags & PGBP_CAL_POSTORDER) && t0.covers_sepsets && !(use_walk(b, ids[0]) && !(flags & PGBP_CAL_REFORDER)) &&
                     !(flags & PGBP_CAL_RESIDKLDIV);
     if (!ok) PGBP_TRY(batch_materialize_sepsets(b));
   }
@@ -635,7 +667,7 @@ static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int
   if (b->done) PGBP_TRY(dev_memset(b->done, 0, (size_t)b->ld, b->stream));
   if (b->itertree) PGBP_TRY(dev_memset(b->itertree, 0, sizeof(int32_t) * 2 * (size_t)b->ld, b->stream));
   if (b->iscal) PGBP_TRY(dev_memset(b->iscal, 0, sizeof(int32_t) * (size_t)b->ld, b->stream));
-  const uint32_t opts = flags & (PGBP_CAL_RESIDNORM | PGBP_CAL_RESIDKLDIV);
+  const uint32_t opts = flags & (PGBP_CAL_RESIDNORM | PGBP_CAL_RESIDKLDIV | PGBP_CAL_REFORDER);
   // the whole schedule for the element range [b->chunk_begin, b->chunk_end) on b->stream
   auto enqueue = [&]() -> int {
     int32_t ref = 0;
@@ -644,7 +676,7 @@ static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int
         const uint32_t sepzero = (lazy && it == 1 && j == 0) ? PGBP_OPT_SEPZERO : 0u;
         const int t = ids[j];
         const int n = (int)p->trees[t].parent.size();
-        if (use_walk(b, t) && !(opts & PGBP_CAL_RESIDKLDIV)) {
+        if (use_walk(b, t) && !(opts & (PGBP_CAL_RESIDKLDIV | PGBP_CAL_REFORDER))) {
           const bool po = flags & PGBP_CAL_POSTORDER, pr = flags & PGBP_CAL_PREORDER;
           const int first = po ? 0 : n, count = (po ? n : 0) + (pr ? n : 0);
           PGBP_TRY(run_walk(b, t, first, count, opts, ref, autostop));
@@ -814,8 +846,8 @@ int32_t pgbp_propagate(pgbp_batch* b, int32_t from_cluster, int32_t sepset, int3
   LaunchGroup g;
   g.step = 0; g.first = 0; g.count = 1;
   shape_class(md.mF - md.s, md.s, &g.ci, &g.cs, &g.maxm);
-  MsgArgs a = make_args(b, flags & PGBP_CAL_RESIDNORM, 0x3ffff0, false);
-  if (!b->calflag) a.opts = 0;
+  MsgArgs a = make_args(b, flags & (PGBP_CAL_RESIDNORM | PGBP_CAL_REFORDER), 0x3ffff0, false);
+  if (!b->calflag) a.opts &= ~PGBP_CAL_RESIDNORM;
   return launch_group(b, a, b->d_one, g);
 }
 

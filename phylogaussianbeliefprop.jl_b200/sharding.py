@@ -52,3 +52,84 @@ def shard_inputs(arrays, B: int, rank: int, world: int):
         a = np.asarray(a)
         out.append(a[sl] if a.shape[0] == B else a)
     return out
+
+
+class PeerGather:
+    """Gather of per-element results fused into the producing kernel (pgbp_comm_*, include/pgbp_b200.h).
+
+    Every rank owns a window [nbuffers][world][ld] in HBM, exported with CUDA IPC and mapped by all peers;
+    `integrate_gather(batch, j, k)` runs integratebelief! and stores each log-likelihood into row `rank` of buffer k
+    on EVERY rank through NVLink peer stores -- no collective launch, nothing on the step's critical path.
+    The 64-byte IPC handles are exchanged once, at construction, through `torch.distributed`
+    (`handles=` takes them directly instead: tests, other launchers)."""
+
+    def __init__(self, lib, device, rank, world, ld, nbuffers=2, group=None, handles=None, connect=True):
+        import ctypes as C
+        self.lib, self.rank, self.world, self.ld, self.nbuffers = lib, int(rank), int(world), int(ld), int(nbuffers)
+        h = C.c_void_p()
+        lib.check(lib.pgbp_comm_create(int(device), self.rank, self.world, self.ld, self.nbuffers, C.byref(h)))
+        self.handle = h
+        mine = (C.c_uint8 * 64)()
+        lib.check(lib.pgbp_comm_handle(h, mine))
+        self.ipc_handle = bytes(mine)
+        if handles is None and connect:
+            import torch
+            import torch.distributed as dist
+            if self.world == 1:
+                handles = [self.ipc_handle]
+            else:
+                dev = torch.device("cuda", int(device)) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+                t = torch.tensor(list(self.ipc_handle), dtype=torch.uint8, device=dev)
+                out = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(out, t, group=group)
+                flat = bytes(out.cpu().tolist())
+                handles = [flat[64 * r:64 * (r + 1)] for r in range(self.world)]
+        if handles is not None:
+            self.connect(handles)
+
+    def connect(self, handles):
+        import ctypes as C
+        buf = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(handles))
+        self.lib.check(self.lib.pgbp_comm_connect(self.handle, buf))
+
+    def window_ptr(self, buffer):
+        import ctypes as C
+        p, ld = C.c_void_p(), C.c_int64()
+        self.lib.check(self.lib.pgbp_comm_window(self.handle, buffer, C.byref(p), C.byref(ld)))
+        return p.value, ld.value
+
+    def integrate_gather(self, batch, j, buffer):
+        """integratebelief!(beliefs, j) (1-based belief index) + store into every rank's window; enqueue only."""
+        self.lib.check(self.lib.pgbp_integrate_gather(batch.handle, j - 1, self.handle, buffer))
+
+    def put(self, batch, buffer, d_src_ptr):
+        import ctypes as C
+        self.lib.check(self.lib.pgbp_comm_put(self.handle, batch.handle, buffer, C.c_void_p(int(d_src_ptr))))
+
+    def wait(self, batch, buffer, timeout_ms=2000):
+        self.lib.check(self.lib.pgbp_comm_wait(self.handle, batch.handle, buffer, timeout_ms))
+
+    def check(self, batch):
+        self.lib.check(self.lib.pgbp_comm_check(self.handle, batch.handle))
+
+    def read(self, batch, buffer):
+        """Host copy [world, ld] of this rank's window (synchronous on the batch's stream)."""
+        import ctypes as C
+        out = np.empty((self.world, self.ld))
+        self.lib.check(self.lib.pgbp_comm_read(self.handle, batch.handle, buffer, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def close(self, barrier=None):
+        """Teardown: unmap the peers, `barrier()` (all ranks have unmapped), free the local window."""
+        if getattr(self, "handle", None):
+            self.lib.pgbp_comm_disconnect(self.handle)
+            if barrier is not None:
+                barrier()
+            self.lib.pgbp_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -37,6 +37,12 @@ G = {
   "lazaridis_sched_child": [12,14,13,8,7,9,17,5,6,11,4,15,2,1,3,10],
   "lazaridis_norm": -11.273958980921247,
   "lazaridis_fe": -11.273958980921261,
+  # test/example_networks/lipson_2020b.phy ; docs/src/man/regularization.md:150-201 (trait x in tiplabels order, the two
+  # ill-defined messages of an unregularised iteration on the Bethe graph, none after either regularisation)
+  "lipson": "((((#H1:0.01::0.04,Altai:0.71)I2:0.16,((South_Africa_HG:0.16,((#H2:0.01::0.28,#H4:0.01::0.25)I3:0.01,((((French:0.12,((Agaw:0.01)#H3:0.01::0.9)#H2:0.01::0.72)I1:0.21)#H1:0.01::0.96,((#H3:0.01::0.1,Mota:1.3)I4:0.15)#H5:0.01::0.58)I5:0.16,((Cameroon_SMA:0.08)#H7:0.01::0.68,((((Biaka:0.03)#H8:0.01::0.62,#H9:0.01::0.3)I6:1.0,Lemande:0.01)I7:0.01,(Yoruba:0.01,(Mende:0.01)#H10:0.01::0.97)I8:0.01)I9:0.03)#H6:0.01::0.84)I10:0.04)I11:0.28)I12:0.04,(((#H8:0.01::0.38,#H7:0.01::0.32)I13:0.07,((Mbuti:0.1)#H4:0.01::0.75)#H9:0.01::0.7)I14:0.13,(#H5:0.01::0.42,((#H6:0.01::0.16,#H10:0.01::0.03)I15:0.01)#H11:0.01::0.7)I16:0.53)I17:0.01)I18:0.5)I19:0.09,#H11:0.01::0.3)I20:0.5,Chimp:0.5)I21;",
+  "lipson_taxa": ["Altai","South_Africa_HG","French","Agaw","Mota","Cameroon_SMA","Biaka","Lemande","Yoruba","Mende","Mbuti","Chimp"],
+  "lipson_x": [0.431,1.606,0.72,0.944,0.647,1.263,0.46,1.079,0.877,0.748,1.529,-0.469],
+  "lipson_bethe_failing_beliefs": [["H5I5I16", [2, 3]], ["H10I8I15", [2, 3]]],
   # test/test_evomodels.jl:85,96,107,120,180,190,200,212,223,234,247,262
   "evomodels": [
     {"id":"uniBM_fixed_y","model":"UnivariateBrownianMotion","args":"(2,3,0)","traits":"y","loglik":-10.732857817537196},

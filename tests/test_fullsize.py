@@ -184,22 +184,34 @@ def test_c3_muller_loopy_bethe_vs_cport():
         assert np.array_equal(bt.factored_energy(), fes[0]), (mode, lanes, wide)
         if mode == 0:
             assert bt.launch_count(reset=True) > 10 * n_auto / 3
-    # Tolerance: this configuration is ILL-CONDITIONED by construction.  regularizebeliefs_bycluster!
-    # gives the 800 factor-less variable clusters of the Bethe graph eps = max(eps(Float64), max|J|) =
-    # 2.2e-16 (src/clustergraphbeliefs.jl:244), so their messages are differences of O(1) quantities
-    # carried at 1e-16 scale.  Two restatements of the reference's OWN formulation (NumPy/LAPACK vs the
-    # hand-rolled Cholesky of oracle/c) already differ by 6e-7 on the factored energy after one iteration
-    # (DESIGN.md section 2); the GPU path differs from either by up to ~2e-5 over 10 iterations.
-    # The 1e-10 bound of the clique-tree configurations applies to well-posed (exact) calibrations only.
-    assert np.max(np.abs(fes[0][:128, 2] / ref["fe"][:, 2] - 1)) <= 2e-4
+    # Tolerance (adjudicated, tests/test_adjudication.py): regularizebeliefs_bycluster! gives the
+    # 800 factor-less variable clusters eps = 2.2e-16 (src/clustergraphbeliefs.jl:244) and the reference's recursion
+    # evaluated in binary64 is unstable on them -- its OWN formulation (the C twin) ends 3e-5 away from the exact
+    # (binary128) factored energy after 10 iterations, this library's fused formulation 4.5e-5, while the exact
+    # answer itself moves by 1e-16 under 1-ulp input perturbations.  Stated tolerance of configs[2]-Bethe: 1e-4
+    # against exact; against the binary64 twin the same bound.  In reference-order mode (PGBP_CAL_REFORDER) the
+    # beliefs equal the twin bit for bit (next test).
+    exact = COracle.from_plan_dict(w.d).run_batch(params, tips[:32], root_belief=w.d["root_cluster"], want_fe=True, quad=True,
+                                                  **w.cpu_kw)["fe"]
+    assert np.max(np.abs(fes[0][:32, 2] / exact[:, 2] - 1)) <= 1e-4
+    assert np.max(np.abs(ref["fe"][:32, 2] / exact[:, 2] - 1)) <= 1e-4
+    assert np.max(np.abs(fes[0][:128, 2] / ref["fe"][:, 2] - 1)) <= 1e-4
     assert np.max(np.abs(fes[0][:128, 0] / ref["fe"][:, 0] - 1)) <= 1e-4
-    assert np.max(np.abs(fes[0][:128, 1] / ref["fe"][:, 1] - 1)) <= 1e-4
+    assert np.max(np.abs(fes[0][:128, 1] / ref["fe"][:, 1] - 1)) <= 1e-6
+    # reference-order validation mode on the GPU: factored energy equal to the twin's to the clique-tree tolerance
+    bt.set_tilewalk_mode(-1)
+    bt.init_beliefs_reset_fromfactors()
+    bt.init_messagecalibrationflags_reset()
+    bt.regularizebeliefs_bycluster()
+    succ, iscal = bt.calibrate(None, w.niter, reference_order=True)
+    assert succ.all() and np.array_equal(iscal[:128], ref["iscal"])
+    assert np.max(np.abs(bt.factored_energy()[:128] / ref["fe"] - 1)) <= TOL
 
 
 def test_c3_muller_loopy_ltrip_vs_cport():
     # BASELINE configs[2], LTRIP(net) cluster graph (801 clusters / 1158 sepsets, sepsets of up to two nodes): the
     # automatic strategy is the tile-walk kernel; per-step launches must give the same bits, the C twin the same
-    # calibration flags and factored energies to the loopy tolerance of the Bethe test above
+    # calibration flags and factored energies to 1e-10
     lib = get_lib("cuda")
     w = bench.C3L()
     B = 512
@@ -220,8 +232,8 @@ def test_c3_muller_loopy_ltrip_vs_cport():
     assert np.array_equal(out[-1][0], out[0][0]) and np.array_equal(out[-1][1], out[0][1])
     assert out[-1][2] * 10 < out[0][2]
     assert np.array_equal(out[-1][0][:64], ref["iscal"])
-    for k, tol in ((2, 2e-4), (0, 1e-4), (1, 1e-4)):
-        assert np.max(np.abs(out[-1][1][:64, k] / ref["fe"][:, k] - 1)) <= tol
+    for k in range(3):  # the LTRIP graph has no factor-less clusters: the clique-tree tolerance holds
+        assert np.max(np.abs(out[-1][1][:64, k] / ref["fe"][:, k] - 1)) <= TOL
 
 
 def test_c5_shapes_reduced_network_vs_cport():
@@ -247,3 +259,31 @@ def test_c5_shapes_reduced_network_vs_cport():
     for j in rng.choice(plan.nclusters, size=10, replace=False) + 1:
         if bt.dimension(int(j)) > 0:
             assert np.max(np.abs(bt.integratebelief(int(j), want_mu=False)[1] / ll - 1)) <= 1e-8, j
+
+
+def test_c5_full_network_vs_cport():
+    # BASELINE configs[4] at FULL size: the 100,000-tip network with 10,000 reticulations (219,999 nodes, clique tree of
+    # 209,998 clusters, sender dimensions 16 / 32 / 48), MvFullBM p = 16, 8 replicates (7.4 GB of state): full
+    # calibration (419,994 messages per replicate), log-likelihood at the root against the C twin, agreement of
+    # distant clusters on the log-likelihood (calibrated clique tree), determinism of a repeated run
+    lib = get_lib("cuda")
+    w = bench.C5()
+    B = 8
+    params, tips = w.inputs(B, 0)
+    plan = plan_of(w, lib)
+    root = w.d["root_cluster"] + 1
+    ref = COracle.from_plan_dict(w.d).run_batch(params, tips, root_belief=w.d["root_cluster"], B=B, **w.cpu_kw)
+    assert (ref["status"] == 0).all()
+    bt = pgbp_b200.BatchedClusterGraphBelief(plan, B, factors=False, residuals=False)
+    bt.assignfactors(params, tips)
+    succ, _ = bt.calibrate(None, 1, update_residualnorm=False)
+    assert succ.all() and (bt.status() == 0).all()
+    ll = bt.integratebelief(root, want_mu=False)[1]
+    assert np.max(np.abs(ll / ref["loglik"] - 1)) <= TOL
+    rng = np.random.default_rng(7)
+    for j in rng.choice(plan.nclusters + plan.nsepsets, size=16, replace=False) + 1:
+        if bt.dimension(int(j)) > 0:
+            assert np.max(np.abs(bt.integratebelief(int(j), want_mu=False)[1] / ll - 1)) <= 1e-9, j
+    bt.assignfactors(params, tips)
+    bt.calibrate(None, 1, update_residualnorm=False)
+    assert np.array_equal(bt.integratebelief(root, want_mu=False)[1], ll)

@@ -93,3 +93,55 @@ def test_shard_slices_cover_batch():
                 seen.extend(range(sl.start, sl.stop))
                 assert sl.stop - sl.start <= sharding.shard_size(B, world)
             assert seen == list(range(B))
+
+
+def test_peer_gather_two_ranks_in_process():
+    # The fused integratebelief! + gather (pgbp_comm_*): two "ranks" with their own batch and window in one
+    # process on the host-emulation build (handles are plain pointers there); every window must end up holding
+    # both ranks' log-likelihoods in rank order, equal to the ordinary integratebelief! results; a wait before the
+    # peer has put is an error.
+    import pgbp_b200
+    from harness import get_lib
+    from pgbp_b200 import sharding
+    B, world = 11, 2
+    case, R, data = _problem(B)
+    lib = get_lib("emul")
+    p = R.shape[0]
+    shards = [sharding.shard_inputs([data], B, r, world)[0] for r in range(world)]
+    ld = 32
+    comms = [sharding.PeerGather(lib, 0, r, world, ld, nbuffers=2, connect=False) for r in range(world)]
+    handles = [c.ipc_handle for c in comms]
+    for c in comms:
+        c.connect(handles)
+    bts, ref = [], []
+    for r in range(world):
+        bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, shards[r].shape[0])
+        bt.assignfactors(pgbp_b200.bm_params([R], np.zeros(p)), shards[r])
+        bt.calibrate(case.sched)
+        ref.append(bt.integratebelief(case.sched[0][2][0])[1])
+        bts.append(bt)
+    comms[0].integrate_gather(bts[0], case.sched[0][2][0], 1)
+    with pytest.raises(pgbp_b200.PgbpError):
+        comms[0].wait(bts[0], 1)  # rank 1 has not put buffer 1 yet
+    comms[1].integrate_gather(bts[1], case.sched[0][2][0], 1)
+    for r in range(world):
+        comms[r].wait(bts[r], 1)
+        comms[r].check(bts[r])
+        win = comms[r].read(bts[r], 1)
+        for q in range(world):
+            assert np.array_equal(win[q, :shards[q].shape[0]], ref[q])
+        assert np.array_equal(comms[r].read(bts[r], 0), np.zeros((world, ld)))
+    # generic put of a device vector (here: the same log-likelihoods) into buffer 0
+    import ctypes as C
+    for r in range(world):
+        src = np.ascontiguousarray(ref[r] * 2.0)
+        comms[r].put(bts[r], 0, src.ctypes.data_as(C.c_void_p).value)
+    for r in range(world):
+        comms[r].wait(bts[r], 0)
+        win = comms[r].read(bts[r], 0)
+        for q in range(world):
+            assert np.array_equal(win[q, :shards[q].shape[0]], 2.0 * ref[q])
+    with pytest.raises(pgbp_b200.PgbpError):
+        sharding.PeerGather(lib, 0, 0, 1, 4, connect=False).integrate_gather(bts[0], 1, 0)  # window shorter than the batch
+    for c in comms:
+        c.close()
