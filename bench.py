@@ -307,7 +307,7 @@ def make_config(w, B, n_gpus):
 
 
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
-def cpu_port_rate(w, params, tips, seconds, nthreads=0, steps=2, warmup=1):
+def cpu_port_rate(w, params, tips, seconds, nthreads=0, steps=2, warmup=1, min_sample=64):
     """units/s of the C/OpenMP oracle port on a bounded sample of the workload (warmed up, mean of `steps`)."""
     from oracle.cport import COracle, dll
     co = COracle.from_plan_dict(w.d)
@@ -317,7 +317,7 @@ def cpu_port_rate(w, params, tips, seconds, nthreads=0, steps=2, warmup=1):
     def run(n):
         return co.run_batch(params[:n] if params.shape[0] > 1 else params, tips[:n] if tips.shape[0] > 1 else tips,
                             B=n, **kw)
-    n0 = min(max(64, B // 32), B)
+    n0 = min(max(min_sample, B // 32), B)
     run(n0)  # warm-up (thread pool, page faults)
     t = time.perf_counter()
     run(n0)
@@ -762,7 +762,8 @@ def measure(w, args, ctx, steps, headline, cpu_seconds, e2e_steps_cap, min_regio
     # ---- CPU baseline + parity of the results (rank 0, N = 1 only) -------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        rate, cores, n, dt, ll_cpu = cpu_port_rate(w, params, tips, cpu_seconds, nthreads=host_threads())
+        rate, cores, n, dt, ll_cpu = cpu_port_rate(w, params, tips, cpu_seconds, nthreads=host_threads(),
+                                                   min_sample=64 if headline else 8)
         rate *= upe
         err = float(np.max(np.abs(ll_cpu / loglik_dev[:n] - 1)))
         cpu = {"value": rate, "unit": w.unit, "cores": cores, "kind": "port",
