@@ -98,16 +98,7 @@ class C2S(C2):
     kernel_text = "k_message<i,s> family, shared-precision mode (32 messages of a calibration)"
 
     def cost(self, plan):
-        d = self.d
-        dims = d["belief_dim"]
-        by = 0.0
-        for dr in (0, 1):
-            lv = plan.levels(0, dr)
-            for f, sp in zip(lv["frm"], lv["sepset"]):
-                mF, s_ = dims[f], dims[sp]
-                by += 8.0 * (mF + 1 + 4 * (s_ + 1) + s_)
-        fl = plan.traversal_cost(0, 0, True)[1] + plan.traversal_cost(0, 1, True)[1]
-        return by, fl
+        return shared_cost(self, plan, (0, 1))
 
 
 class C4(C2):
@@ -270,13 +261,58 @@ class C5(C4):
     cpu_kw = dict(post=True, pre=True, residnorm=False)
 
 
-WORKLOADS = {"c2": C2, "c2s": C2S, "c3": C3, "c3l": C3L, "c4": C4, "c5": C5}
+def shared_cost(w, plan, directions):
+    """Algorithmic bytes / flops per element of a shared-precision batch: per message and element only h and g move
+    (8 (m_F + 1 + 4 (s + 1) [+ s with residuals]) bytes) and w = U^-T h_I, h_K - Z'w are applied
+    (i^2 + 2 i s + 2 i flops); the J part is per group and not counted."""
+    dims = w.d["belief_dim"]
+    by = fl = 0.0
+    for dr in directions:
+        lv = plan.levels(0, dr)
+        for f, sp in zip(lv["frm"], lv["sepset"]):
+            mF, s_ = dims[f], dims[sp]
+            i_ = mF - s_
+            by += 8.0 * (mF + 1 + 4 * (s_ + 1) + (s_ if w.residuals else 0))
+            fl += i_ * i_ + 2 * i_ * s_ + 2 * i_ + 4 * s_
+    return by, fl
+
+
+class C5S(C5):
+    """BASELINE configs[4] as the reference states it -- ONE parameter vector, the replicate batch sharded across
+    GPUs -- on the shared-precision path: J once per GPU, h and g per replicate (72 MB instead of
+    926 MB of HBM each), so 1,536 replicates fit one GPU instead of 128."""
+    key = "c5s"
+    shared = True
+    default_batch = 1536
+    nsim = 32
+    workload = ("synthetic level-1 network, 100,000 tips + 10,000 reticulations (219,999 nodes; clique tree of 209,998 "
+                "clusters, sender dimensions 16 / 32 / 48), MvFullBrownianMotion p=16, ONE parameter vector, 1,536 trait "
+                "replicates per GPU on the SHARED-PRECISION path (J stored and factorised once per GPU, h and g per replicate: "
+                "72 MB of HBM each = 111 GB; 32 replicates simulated down the network, the others are rescaled copies "
+                "x (1 + 0.001 k)), assignfactors! + calibrate! (post+pre order) + integratebelief!(root) "
+                "[BASELINE configs[4], shared-J path of SURVEY 8f-1: own byte count 8*(m_F + 1 + 4*(s+1)) per message]")
+    step_text = "assign_factors (K1: J once, h / g per replicate) + calibrate (419,994 messages: group pass + element pass) + integrate(root)"
+    kernel_text = "k_hmsg<I> family (element pass of the 419,994 messages; the group pass k_jmsg runs once per GPU)"
+
+    def inputs(self, B, rank):
+        params, base = C5.inputs(self, min(B, self.nsim), rank)
+        if B <= base.shape[0]:
+            return params, base
+        reps = -(-B // base.shape[0])
+        tips = np.concatenate([base * (1.0 + 0.001 * k) for k in range(reps)])[:B]
+        return params, np.ascontiguousarray(tips)
+
+    def cost(self, plan):
+        return shared_cost(self, plan, (0, 1))
+
+
+WORKLOADS = {"c2": C2, "c2s": C2S, "c3": C3, "c3l": C3L, "c4": C4, "c5": C5, "c5s": C5S}
 
 
 # ----------------------------------------------------------------------------- config shared by both arms
 def messages_per_unit(w):
     d = w.d
-    if w.key in ("c2", "c2s", "c5"):
+    if w.key in ("c2", "c2s", "c5", "c5s"):
         return 2 * len(d["trees"][0][0])
     if w.key == "c4":
         return len(d["trees"][0][0])
@@ -488,7 +524,17 @@ def measure(w, args, ctx, steps, headline, cpu_seconds, e2e_steps_cap, min_regio
     d = w.d
     B = (args.batch if headline else 0) or w.default_batch
     p = d["ntraits"]
+    # host memory guard for the big workloads (c5 / c5s hold GBs of tip data per rank): refuse rather than swap
+    need = 8.0 * B * len(d["tip_nodes"]) * p
+    if need > 1e9:
+        import psutil
+        avail = psutil.virtual_memory().available
+        if 3.0 * need * world > avail:
+            raise RuntimeError("host memory: %.0f GB of tip data per rank x %d ranks, %.0f GB available" % (need / 1e9, world, avail / 1e9))
     params, tips = w.inputs(B, rank)
+    if tips.nbytes > 2e9:  # keep ONE host copy of big inputs, in pinned memory (it is also the e2e arm's source buffer)
+        pinned_tips = torch.from_numpy(tips).pin_memory()
+        tips = pinned_tips.numpy()
     lib = pgbp_b200.default_library()
     plan = pgbp_b200.ClusterGraphPlan(d["nclusters"], d["belief_dim"], d["sepset_clusters"], d["upind"], d["trees"], p,
                                       d["families"], lib)
@@ -593,7 +639,7 @@ def measure(w, args, ctx, steps, headline, cpu_seconds, e2e_steps_cap, min_regio
     else:
         d_params = torch.from_numpy(params).to(dev)
         d_tips = torch.from_numpy(tips).to(dev)
-        direction = L.CAL_BOTH if w.key == "c5" else L.CAL_POSTORDER
+        direction = L.CAL_BOTH if w.key in ("c5", "c5s") else L.CAL_POSTORDER
 
         def step(ev=None):
             bt.assignfactors_device(d_params.data_ptr(), params.shape[0], d_tips.data_ptr(), tips.shape[0], ncolors=w.ncolors)
@@ -685,7 +731,7 @@ def measure(w, args, ctx, steps, headline, cpu_seconds, e2e_steps_cap, min_regio
                                                        shared_precision_group=group))
         if headline and args.pipeline is not None:
             bts[-1].set_pipeline(args.pipeline)
-    pin_np = [torch.from_numpy(big.copy()).pin_memory().numpy() for _ in bts]
+    pin_np = [big if (big.nbytes > 2e9 and big is tips) else torch.from_numpy(big.copy()).pin_memory().numpy() for _ in bts]
     results = [None] * len(bts)
 
     def e2e_step(i):
@@ -699,7 +745,7 @@ def measure(w, args, ctx, steps, headline, cpu_seconds, e2e_steps_cap, min_regio
             succ, iscal = b_.calibrate(None, w.niter)
             results[i] = b_.factored_energy()[:, 2]
             return
-        elif w.key == "c5":
+        elif w.key in ("c5", "c5s"):
             b_.assignfactors(params, pin_np[i])
             succ, _ = b_.calibrate(None, 1, update_residualnorm=False)
         else:
@@ -820,9 +866,9 @@ def run_gpu(args):
     # own run holds them too (configs[3] = the north-star target: 10k-tip network, p = 8, 4,096 parameter vectors).
     others = {}
     if args.workload == "c2" and not args.no_others:
-        plan = [("c4", 3, 3.0), ("c3", 2, 3.0), ("c3l", 2, 3.0), ("c5", 2, 4.0)]
+        plan = [("c4", 3, 3.0), ("c3", 2, 3.0), ("c3l", 2, 3.0), ("c2s", 20, 2.0), ("c5", 2, 4.0), ("c5s", 2, 4.0)]
         for key, k_steps, cpu_s in plan:
-            if key == "c5" and (args.no_c5 or time.perf_counter() - t_start > args.others_budget_s):
+            if key in ("c5", "c5s") and (args.no_c5 or time.perf_counter() - t_start > args.others_budget_s):
                 if ctx.rank == 0:
                     others[key] = {"skipped": "time budget of the default run" if not args.no_c5 else "--no-c5"}
                 continue
@@ -860,7 +906,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="headline workload only (skip the other_workloads block)")
     ap.add_argument("--no-c5", action="store_true", help="skip the 100k-tip workload in the other_workloads block")
-    ap.add_argument("--others-budget-s", type=float, default=150.0, help="c5 is skipped when the run is already older than this")
+    ap.add_argument("--others-budget-s", type=float, default=240.0, help="c5 / c5s are skipped when the run is already older than this")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: results gathered through NVLink peer "
                     "windows fused into the integrate kernel (default) or an asynchronous NCCL all-gather per step")
     ap.add_argument("--e2e-batches", type=int, default=4, help="batches (= host threads) alternating in the end-to-end arm")

@@ -140,11 +140,14 @@ int32_t pgbp_plan_traversal_cost(const pgbp_plan* plan, int32_t tree, int32_t di
 int32_t pgbp_batch_create(const pgbp_plan* plan, int64_t B, int32_t device, uint32_t flags,
                           pgbp_batch** out);
 /* Shared-precision batch: the `group_size` consecutive elements of a group use ONE parameter vector
- * (trait replicates under one theta), so every J of the group is the same matrix: it is stored and
- * updated once (in the group's first element), read by all -- per message and element only h and g
- * move through HBM.  Same calls, same results as an ordinary batch given the same inputs;
- * restrictions: pgbp_assign_factors needs one parameter set per group, calibrate has no auto-stop
- * (it is per element), pgbp_set_belief takes J from each group's first element.
+ * (trait replicates under one theta), so every J of the group is the same matrix (only h and g depend on
+ * the data, src/beliefupdates.jl:77-81).  J is stored ONCE per group (HBM per element: 8 (m+1) bytes per belief
+ * instead of 8 (m(m+1)/2 + m + 1)); a message factorises J_I once per group (one warp per (message, group)),
+ * caches U, Z = U^-T J_IK and logdet, and every element only applies them to its h and g.  Same calls, same
+ * results (bit for bit) as an ordinary batch given the same inputs; restrictions: pgbp_assign_factors needs one
+ * parameter set per group, calibrate has no auto-stop (it is per element) and no reference-order mode,
+ * pgbp_set_belief takes J from each group's first element, an element whose h_I is non-zero where the group's
+ * J_I, J_IK are zero fails (status) instead of taking the reference's data-dependent branch.
  * group_size 0 or 1 = ordinary batch (every element its own J). */
 int32_t pgbp_batch_create_shared(const pgbp_plan* plan, int64_t B, int64_t group_size, int32_t device,
                                  uint32_t flags, pgbp_batch** out);
@@ -319,6 +322,10 @@ int32_t pgbp_regularize_bynodesubtree(pgbp_batch* batch, int32_t nnodes, const i
 int32_t pgbp_device_view(pgbp_batch* batch, double** base, int64_t* ld, int64_t* nslots);
 int32_t pgbp_belief_slot(const pgbp_plan* plan, int32_t belief, int64_t* jslot, int64_t* hslot,
                          int64_t* gslot);
+/* Rows of belief i's h (m rows from *hrow) and g (*grow) in the array pgbp_device_view returns.  Ordinary batches:
+ * the plan's slots.  Shared-precision batches: that array holds h and g only, in compact rows (the J rows live
+ * once per group in an internal group batch). */
+int32_t pgbp_batch_belief_rows(const pgbp_batch* batch, int32_t belief, int64_t* hrow, int64_t* grow);
 
 /* ---------------------------------------------------------------- multi-GPU gather over NVLink peer memory
  * The path shards by batch element (one process per GPU, the plan replicated); its only exchange is the gather

@@ -85,6 +85,7 @@ SIGNATURES = {
     "pgbp_regularize_bynodesubtree": (i32, [vp, i32] + [P(i32)] * 8),
     "pgbp_device_view": (i32, [vp, P(vp), P(i64), P(i64)]),
     "pgbp_belief_slot": (i32, [vp, i32, P(i64), P(i64), P(i64)]),
+    "pgbp_batch_belief_rows": (i32, [vp, i32, P(i64), P(i64)]),
     "pgbp_comm_create": (i32, [i32, i32, i32, i64, i32, P(vp)]),
     "pgbp_comm_handle": (i32, [vp, P(u8)]),
     "pgbp_comm_connect": (i32, [vp, P(u8)]),

@@ -306,6 +306,13 @@ class BatchedClusterGraphBelief:
     def device_bytes(self):
         return self.lib.pgbp_batch_device_bytes(self.handle)
 
+    def belief_rows(self, j):
+        """Rows (h first row, g row) of belief j (1-based) in the array device_view() returns: the plan's slots, or
+        the compact numbering of a shared-precision batch."""
+        h, g = C.c_int64(), C.c_int64()
+        self.lib.check(self.lib.pgbp_batch_belief_rows(self.handle, j - 1, C.byref(h), C.byref(g)))
+        return h.value, g.value
+
     def launch_count(self, reset=False):
         return self.lib.pgbp_batch_launch_count(self.handle, int(reset))
 

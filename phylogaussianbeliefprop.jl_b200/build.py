@@ -20,9 +20,7 @@ SOURCES = [("pgbp_plan.cu", [], "pgbp_plan"), ("pgbp_batch.cu", [], "pgbp_batch"
            ("pgbp_message_t0.cu", ["PGBP_T0_PART=0"], "pgbp_message_t0_0"),
            ("pgbp_message_t0.cu", ["PGBP_T0_PART=1"], "pgbp_message_t0_1"),
            ("pgbp_message_t0.cu", ["PGBP_T0_PART=2"], "pgbp_message_t0_2"),
-           ("pgbp_message_t0.cu", ["PGBP_T0_PART=0", "PGBP_T0_SHARED=1"], "pgbp_message_t0s_0"),
-           ("pgbp_message_t0.cu", ["PGBP_T0_PART=1", "PGBP_T0_SHARED=1"], "pgbp_message_t0s_1"),
-           ("pgbp_message_t0.cu", ["PGBP_T0_PART=2", "PGBP_T0_SHARED=1"], "pgbp_message_t0s_2")]
+           ("pgbp_shared.cu", [], "pgbp_shared")]
 HEADERS = ["pgbp_backend.h", "pgbp_internal.h", "pgbp_kernels.cuh", "pgbp_launch.h", "pgbp_shapes.h", "pgbp_msg_t0.cuh",
            "pgbp_coop.cuh", "pgbp_factors.cuh", os.path.join("..", "..", "include", "pgbp_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

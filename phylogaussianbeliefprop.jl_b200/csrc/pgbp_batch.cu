@@ -64,6 +64,12 @@ void* batch_pinned(pgbp_batch* b, size_t bytes) {
 
 int batch_zero_sepsets(pgbp_batch* b, bool lazy) {
   const pgbp_plan* p = b->plan;
+  if (b->jb) {  // shared-precision batch: J rows of the sepsets in the group batch, h / g rows here; always eager
+    b->jb->stream = b->stream;
+    PGBP_TRY(batch_zero_sepsets(b->jb, false));
+    return dev_memset(b->state + (size_t)b->nrows_efactor * (size_t)b->ld, 0,
+                      sizeof(double) * (size_t)(b->nrows_e - b->nrows_efactor) * (size_t)b->ld, b->stream);
+  }
   if (lazy) { b->sepsets_lazy_zero = true; return 0; }
   b->sepsets_lazy_zero = false;
   return dev_memset(b->state + (size_t)p->nslots_factor * (size_t)b->ld, 0,
@@ -218,7 +224,7 @@ static int access_hJg(pgbp_batch* b, bool put, double* d_arr, int m, int64_t js,
   std::vector<int32_t> sl;
   if (J && m > 0) {
     square_slots(m, js, put, &sl);
-    PGBP_TRY(put ? put_columns(b, J, m * m, sl, d_arr, b->group_size) : get_columns(b, J, m * m, sl, d_arr, b->group_size));
+    PGBP_TRY(put ? put_columns(b, J, m * m, sl, d_arr) : get_columns(b, J, m * m, sl, d_arr));
   }
   if (h && m > 0) {
     sl.resize(m);
@@ -241,8 +247,10 @@ int32_t pgbp_batch_create(const pgbp_plan* plan, int64_t B, int32_t device, uint
   return pgbp_batch_create_shared(plan, B, 0, device, flags, out);
 }
 
-int32_t pgbp_batch_create_shared(const pgbp_plan* plan, int64_t B, int64_t group_size, int32_t device, uint32_t flags,
-                                 pgbp_batch** out) {
+// ld_align: row pitch granularity in elements (32 = 256-byte rows; the group batch of a shared-precision batch
+// uses 4: it is addressed per (message, group), not per warp of elements)
+static int batch_create_impl(const pgbp_plan* plan, int64_t B, int64_t group_size, int32_t device, uint32_t flags,
+                             int64_t ld_align, pgbp_batch** out) {
   if (!plan || !out || B <= 0) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
   if (group_size < 0 || (group_size > 1 && B % group_size != 0))
     PGBP_FAIL(PGBP_EINVAL, "group size must divide the batch size");
@@ -255,7 +263,7 @@ int32_t pgbp_batch_create_shared(const pgbp_plan* plan, int64_t B, int64_t group
   std::unique_ptr<pgbp_batch, Destroy> b(new pgbp_batch);
   b->plan = plan;
   b->B = B;
-  b->ld = (B + 31) / 32 * 32;
+  b->ld = (B + ld_align - 1) / ld_align * ld_align;
   b->device = device;
   b->flags = flags;
   b->group_size = group_size > 1 ? group_size : 0;
@@ -263,6 +271,18 @@ int32_t pgbp_batch_create_shared(const pgbp_plan* plan, int64_t B, int64_t group
   PGBP_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   b->own_stream = true;
 #endif
+  if (b->group_size > 1) {
+    // shared-precision batch: h, g per element here (compact rows), every J row once per group in `jb`
+    PGBP_TRY(shared_create(b.get()));
+    pgbp_batch* jb = nullptr;
+    PGBP_TRY(batch_create_impl(plan, B / group_size, 0, device, flags, 4, &jb));
+    b->jb = jb;
+    PGBP_TRY(pgbp_batch_set_stream(jb, (void*)b->stream));  // one stream, program order
+    b->device_bytes += jb->device_bytes;
+    if (flags & PGBP_BATCH_RESIDUALS) PGBP_TRY(pgbp_reset_calibration_flags(b.get(), 1));
+    *out = b.release();
+    return 0;
+  }
   const size_t ld = (size_t)b->ld;
   PGBP_TRY(alloc(b.get(), &b->state, (size_t)plan->nslots_state * ld));
   PGBP_TRY(dev_memset(b->state, 0, sizeof(double) * (size_t)plan->nslots_state * ld, b->stream));
@@ -276,7 +296,6 @@ int32_t pgbp_batch_create_shared(const pgbp_plan* plan, int64_t B, int64_t group
     PGBP_TRY(dev_memset(b->resid, 0, sizeof(double) * std::max<size_t>(1, (size_t)plan->nslots_resid) * ld, b->stream));
     PGBP_TRY(alloc(b.get(), &b->kldiv, std::max<size_t>(1, nd) * ld));
     PGBP_TRY(alloc(b.get(), &b->calflag, std::max<size_t>(1, nd) * ld));
-    if (b->group_size > 1) PGBP_TRY(alloc(b.get(), &b->calflagJ, std::max<size_t>(1, nd) * ld));
     PGBP_TRY(alloc(b.get(), &b->done, ld));
     PGBP_TRY(alloc(b.get(), &b->iscal, ld));
     PGBP_TRY(alloc(b.get(), &b->itertree, 2 * ld));
@@ -326,6 +345,11 @@ int32_t pgbp_batch_create_shared(const pgbp_plan* plan, int64_t B, int64_t group
   return 0;
 }
 
+int32_t pgbp_batch_create_shared(const pgbp_plan* plan, int64_t B, int64_t group_size, int32_t device, uint32_t flags,
+                                 pgbp_batch** out) {
+  return batch_create_impl(plan, B, group_size, device, flags, 32, out);
+}
+
 int32_t pgbp_batch_destroy(pgbp_batch* b) {
   if (!b) return 0;
   set_device(b->device);
@@ -333,6 +357,7 @@ int32_t pgbp_batch_destroy(pgbp_batch* b) {
   dev_free(b->state); dev_free(b->factor); dev_free(b->resid); dev_free(b->kldiv);
   dev_free(b->calflag); dev_free(b->calflagJ); dev_free(b->done); dev_free(b->status); dev_free(b->iscal); dev_free(b->itertree);
   dev_free(b->d_tab); dev_free(b->d_one); dev_free(b->scratch); dev_free(b->d_slot); free_tables(b);
+  shared_destroy(b);
   for (auto* p : b->d_msgs) dev_free(p);
   for (auto* p : b->d_walk) dev_free(p);
   for (auto* p : b->d_step_off) dev_free(p);
@@ -357,6 +382,7 @@ int32_t pgbp_batch_set_stream(pgbp_batch* b, void* s) {
   b->stream = (cudaStream_t)s;
 #endif
   b->own_stream = false;
+  if (b->jb) b->jb->stream = b->stream;
   return 0;
 }
 
@@ -373,14 +399,42 @@ int64_t pgbp_batch_launch_count(pgbp_batch* b, int32_t reset) {
   return n;
 }
 
+// shared-precision batches: J of a belief / factor / residual lives once per group in the group batch.  Host side:
+// set takes each group's FIRST element, get broadcasts the group's matrix to its elements.
+static int shared_put_J(pgbp_batch* b, int m, const double* J, int (*put)(pgbp_batch*, int32_t, const double*), int32_t idx) {
+  const size_t mm = (size_t)m * m;
+  std::vector<double> Jg((size_t)b->ngroups * mm);
+  for (int64_t g = 0; g < b->ngroups; g++) memcpy(Jg.data() + g * mm, J + (size_t)(g * b->group_size) * mm, sizeof(double) * mm);
+  return put(b->jb, idx, Jg.data());
+}
+static void shared_broadcast_J(const pgbp_batch* b, int m, const std::vector<double>& Jg, double* J) {
+  const size_t mm = (size_t)m * m;
+  for (int64_t e = 0; e < b->B; e++) memcpy(J + (size_t)e * mm, Jg.data() + (size_t)(e / b->group_size) * mm, sizeof(double) * mm);
+}
+
 int32_t pgbp_set_belief(pgbp_batch* b, int32_t i, const double* J, const double* h, const double* g) {
   if (!b || i < 0 || i >= b->plan->nbeliefs) PGBP_FAIL(PGBP_EINVAL, "bad batch / belief index");
   const pgbp_plan* p = b->plan;
+  if (b->jb) {
+    b->jb->stream = b->stream;
+    if (J && p->dim[i] > 0)
+      PGBP_TRY(shared_put_J(b, p->dim[i], J, [](pgbp_batch* jb, int32_t k, const double* Jg) { return (int)pgbp_set_belief(jb, k, Jg, nullptr, nullptr); }, i));
+    return access_hJg(b, true, b->state, p->dim[i], 0, batch_hrow(b, i), batch_grow(b, i), nullptr, (double*)h, (double*)g);
+  }
   return access_hJg(b, true, b->state, p->dim[i], p->jslot[i], p->hslot[i], p->gslot[i], (double*)J, (double*)h, (double*)g);
 }
 int32_t pgbp_get_belief(pgbp_batch* b, int32_t i, double* J, double* h, double* g) {
   if (!b || i < 0 || i >= b->plan->nbeliefs) PGBP_FAIL(PGBP_EINVAL, "bad batch / belief index");
   const pgbp_plan* p = b->plan;
+  if (b->jb) {
+    b->jb->stream = b->stream;
+    if (J && p->dim[i] > 0) {
+      std::vector<double> Jg((size_t)b->ngroups * p->dim[i] * p->dim[i]);
+      PGBP_TRY(pgbp_get_belief(b->jb, i, Jg.data(), nullptr, nullptr));
+      shared_broadcast_J(b, p->dim[i], Jg, J);
+    }
+    return access_hJg(b, false, b->state, p->dim[i], 0, batch_hrow(b, i), batch_grow(b, i), nullptr, h, g);
+  }
   return access_hJg(b, false, b->state, p->dim[i], p->jslot[i], p->hslot[i], p->gslot[i], J, h, g);
 }
 int32_t pgbp_get_factor(pgbp_batch* b, int32_t i, double* J, double* h, double* g) {
@@ -388,6 +442,15 @@ int32_t pgbp_get_factor(pgbp_batch* b, int32_t i, double* J, double* h, double* 
   if (!b->factor) PGBP_FAIL(PGBP_ESTATE, "batch was created without PGBP_BATCH_FACTORS");
   const pgbp_plan* p = b->plan;
   PGBP_TRY(set_device(b->device));
+  if (b->jb) {
+    b->jb->stream = b->stream;
+    if (J && p->dim[i] > 0) {
+      std::vector<double> Jg((size_t)b->ngroups * p->dim[i] * p->dim[i]);
+      PGBP_TRY(pgbp_get_factor(b->jb, i, Jg.data(), nullptr, nullptr));
+      shared_broadcast_J(b, p->dim[i], Jg, J);
+    }
+    return access_hJg(b, false, b->factor, p->dim[i], 0, batch_hrow(b, i), batch_grow(b, i), nullptr, h, g);
+  }
   PGBP_TRY(batch_materialize_factors(b));
   return access_hJg(b, false, b->factor, p->dim[i], p->jslot[i], p->hslot[i], p->gslot[i], J, h, g);
 }
@@ -401,7 +464,26 @@ int32_t pgbp_get_residual(pgbp_batch* b, int32_t j, int32_t to_cluster, double* 
   else if (to_cluster == p->sep_b[j]) side = 1;
   else PGBP_FAIL(PGBP_EINVAL, "cluster %d is not an end of sepset %d", to_cluster, j);
   const int d = 2 * j + side;
-  PGBP_TRY(access_hJg(b, false, b->resid, p->dim[p->nclusters + j], p->rjslot[d], p->rhslot[d], -1, dJ, dh, nullptr));
+  const int s = p->dim[p->nclusters + j];
+  if (b->jb) {
+    b->jb->stream = b->stream;
+    std::vector<uint8_t> fJ((size_t)b->ngroups);
+    if (dJ && s > 0) {
+      std::vector<double> Jg((size_t)b->ngroups * s * s);
+      PGBP_TRY(pgbp_get_residual(b->jb, j, to_cluster, Jg.data(), nullptr, nullptr, nullptr));
+      shared_broadcast_J(b, s, Jg, dJ);
+    }
+    PGBP_TRY(access_hJg(b, false, b->resid, s, 0, b->erh[d], -1, nullptr, dh, nullptr));
+    if (iscal_resid) {  // flag of the message = h part (element) AND J part (group)
+      PGBP_TRY(d2h(iscal_resid, b->calflag + (int64_t)d * b->ld, (size_t)b->B, b->stream));
+      PGBP_TRY(d2h(fJ.data(), b->jb->calflag + (int64_t)d * b->jb->ld, (size_t)b->ngroups, b->stream));
+    }
+    if (kldiv) PGBP_TRY(d2h(kldiv, b->kldiv + (int64_t)d * b->ld, sizeof(double) * (size_t)b->B, b->stream));
+    PGBP_TRY(stream_sync(b->stream));
+    if (iscal_resid) for (int64_t e = 0; e < b->B; e++) iscal_resid[e] = iscal_resid[e] && fJ[e / b->group_size];
+    return 0;
+  }
+  PGBP_TRY(access_hJg(b, false, b->resid, s, p->rjslot[d], p->rhslot[d], -1, dJ, dh, nullptr));
   if (iscal_resid) PGBP_TRY(d2h(iscal_resid, b->calflag + (int64_t)d * b->ld, (size_t)b->B, b->stream));
   if (kldiv) PGBP_TRY(d2h(kldiv, b->kldiv + (int64_t)d * b->ld, sizeof(double) * (size_t)b->B, b->stream));
   return stream_sync(b->stream);
@@ -425,6 +507,11 @@ int32_t pgbp_reset_beliefs(pgbp_batch* b) {
   if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
   PGBP_TRY(set_device(b->device));
   b->sepsets_lazy_zero = false;
+  if (b->jb) {
+    b->jb->stream = b->stream;
+    PGBP_TRY(pgbp_reset_beliefs(b->jb));
+    return dev_memset(b->state, 0, sizeof(double) * (size_t)b->nrows_e * (size_t)b->ld, b->stream);
+  }
   return dev_memset(b->state, 0, sizeof(double) * (size_t)b->plan->nslots_state * (size_t)b->ld, b->stream);
 }
 int32_t pgbp_factors_from_beliefs(pgbp_batch* b) {
@@ -433,6 +520,11 @@ int32_t pgbp_factors_from_beliefs(pgbp_batch* b) {
   PGBP_TRY(set_device(b->device));
   b->lazy_factors.pending = false;
   b->lazy_factors.valid = false;
+  if (b->jb) {
+    b->jb->stream = b->stream;
+    PGBP_TRY(pgbp_factors_from_beliefs(b->jb));
+    return d2d(b->factor, b->state, sizeof(double) * (size_t)b->nrows_efactor * (size_t)b->ld, b->stream);
+  }
   return d2d(b->factor, b->state, sizeof(double) * (size_t)b->plan->nslots_factor * (size_t)b->ld, b->stream);
 }
 int32_t pgbp_reset_from_factors(pgbp_batch* b) {
@@ -441,6 +533,12 @@ int32_t pgbp_reset_from_factors(pgbp_batch* b) {
   PGBP_TRY(set_device(b->device));
   const pgbp_plan* p = b->plan;
   const size_t ld = (size_t)b->ld;
+  if (b->jb) {
+    b->jb->stream = b->stream;
+    PGBP_TRY(pgbp_reset_from_factors(b->jb));
+    PGBP_TRY(d2d(b->state, b->factor, sizeof(double) * (size_t)b->nrows_efactor * ld, b->stream));
+    return batch_zero_sepsets(b, false);
+  }
   {  // factors that are still K1's output: re-run K1 into the beliefs (write only) instead of copying
     const int r = batch_reset_by_assign(b);
     if (r < 0) return r;
@@ -456,6 +554,10 @@ int32_t pgbp_reset_calibration_flags(pgbp_batch* b, int32_t reset_kl) {
   PGBP_TRY(set_device(b->device));
   // empty messages are born calibrated and are never reset (src/beliefs.jl:919-922, 973-974)
   const pgbp_plan* p = b->plan;
+  if (b->jb) {
+    b->jb->stream = b->stream;
+    PGBP_TRY(pgbp_reset_calibration_flags(b->jb, 0));
+  }
   PGBP_TRY(dev_memset(b->calflag, 0, 2 * (size_t)p->nsepsets * (size_t)b->ld, b->stream));
   if (b->calflagJ) PGBP_TRY(dev_memset(b->calflagJ, 0, 2 * (size_t)p->nsepsets * (size_t)b->ld, b->stream));
   for (int j = 0; j < p->nsepsets; j++)
@@ -471,13 +573,21 @@ int32_t pgbp_reset_calibration_flags(pgbp_batch* b, int32_t reset_kl) {
   return 0;
 }
 
+int32_t pgbp_batch_belief_rows(const pgbp_batch* b, int32_t belief, int64_t* hrow, int64_t* grow) {
+  if (!b || belief < 0 || belief >= b->plan->nbeliefs) PGBP_FAIL(PGBP_EINVAL, "bad batch / belief index");
+  if (hrow) *hrow = batch_hrow(b, belief);
+  if (grow) *grow = batch_grow(b, belief);
+  return 0;
+}
+
 int32_t pgbp_device_view(pgbp_batch* b, double** base, int64_t* ld, int64_t* nslots) {
   if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
   PGBP_TRY(set_device(b->device));
   PGBP_TRY(batch_materialize_sepsets(b));  // the caller may read any row
   if (base) *base = b->state;
   if (ld) *ld = b->ld;
-  if (nslots) *nslots = b->plan->nslots_state;
+  // (shared-precision batches: the element array holds h and g only, in compact rows -- pgbp_batch_belief_rows)
+  if (nslots) *nslots = b->jb ? b->nrows_e : b->plan->nslots_state;
   return 0;
 }
 

@@ -55,12 +55,12 @@ static PeerWin peer_win(const pgbp_comm* c, int buffer) {
 // integratebelief! of one belief for every element, log-likelihood stored into slot `rank` of every rank's window
 template <int MAXM>
 __global__ void __launch_bounds__(128) k_integrate_gather(const double* state, int32_t* status, int64_t B, int64_t ld,
-                                                          int64_t jslot, int64_t hslot, int64_t gslot, int M, int64_t gsz,
+                                                          int64_t jslot, int64_t hslot, int64_t gslot, int M, JSide js,
                                                           PeerWin w, int rank, int nranks) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= B) return;
   double* mine = w.data[rank];
-  integrate_thread<MAXM>(state, status, ld, e, jslot, hslot, gslot, M, nullptr, mine, ld, nullptr, gsz);
+  integrate_thread<MAXM>(state, status, ld, e, jslot, hslot, gslot, M, nullptr, mine, ld, nullptr, jcolumn(js, e), js.ld);
   const double v = mine[e];
   for (int r = 0; r < nranks; r++)
     if (r != rank) w.data[r][e] = v;  // posted NVLink store
@@ -218,16 +218,17 @@ int32_t pgbp_integrate_gather(pgbp_batch* b, int32_t belief, pgbp_comm* c, int32
   PGBP_TRY(set_device(b->device));
   if (belief >= p->nclusters) PGBP_TRY(batch_materialize_sepsets(b));
   const int M = p->dim[belief];
-  const int64_t js = p->jslot[belief], hs = p->hslot[belief], gs = p->gslot[belief];
+  const int64_t js = p->jslot[belief], hs = batch_hrow(b, belief), gs = batch_grow(b, belief);
+  const JSide jside = batch_jside(b);
   const PeerWin w = peer_win(c, buffer);
 #ifdef PGBP_HOST_EMUL
   for (int64_t e = 0; e < b->B; e++) {
-    integrate_thread<PGBP_MAX_DIM>(b->state, b->status, b->ld, e, js, hs, gs, M, nullptr, w.data[c->rank], b->ld, nullptr, b->group_size);
+    integrate_thread<PGBP_MAX_DIM>(b->state, b->status, b->ld, e, js, hs, gs, M, nullptr, w.data[c->rank], b->ld, nullptr, jcolumn(jside, e), jside.ld);
     for (int r = 0; r < c->nranks; r++) w.data[r][e] = w.data[c->rank][e];
   }
 #else
   const unsigned grid = (unsigned)((b->B + 127) / 128);
-#define PGBP_IG(MAXM) k_integrate_gather<MAXM><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, b->group_size, w, c->rank, c->nranks)
+#define PGBP_IG(MAXM) k_integrate_gather<MAXM><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, jside, w, c->rank, c->nranks)
   if (M <= 4) PGBP_IG(4);
   else if (M <= 12) PGBP_IG(12);
   else if (M <= 32) PGBP_IG(32);

@@ -130,7 +130,8 @@ struct AssignBody {
   int64_t np, nd;
   int pairing;
   ThetaRows tr;
-  int64_t gs = 0;  // shared-precision mode: J rows live in (and are written by) the group leader's column
+  int64_t gs = 0;  // != 0: element side of a shared-precision batch -- h and g only (compact rows in cl_hslot / cl_gslot);
+                   // the J rows are the group batch's and are assigned there
   int y0 = 0;
   PGBP_HD void operator()(int64_t e, int y) const { run(e, y + y0); }
   PGBP_HD void run(int64_t e, int c) const {
@@ -141,8 +142,7 @@ struct AssignBody {
     const double* th = theta + ip;
     const double* td = tip + id;
     double* st = state + e;
-    const int64_t ej = this->gs > 1 ? e - e % this->gs : e;
-    const bool lead = ej == e;
+    const bool lead = this->gs == 0;
     const int64_t js = F.cl_jslot[c], hs = F.cl_hslot[c], gs = F.cl_gslot[c];
     const int m = F.cl_dim[c];
     if (lead) for (int q = 0; q < tri(m); q++) st[(js + q) * ld] = 0.0;
@@ -363,8 +363,7 @@ struct AssignScoped {
     const double* th = gen.theta + ip;
     const double* td = gen.tip + idd;
     double* st = gen.state + e;
-    const int64_t ej = gen.gs > 1 ? e - e % gen.gs : e;
-    const bool lead = ej == e;
+    const bool lead = gen.gs == 0;
     const int64_t js = F.cl_jslot[c], hs = F.cl_hslot[c], gsl = F.cl_gslot[c];
     const int m = F.cl_dim[c];
     if (lead) for (int q = 0; q < tri(m); q++) st[(js + q) * ld] = 0.0;
@@ -514,7 +513,7 @@ struct AssignOU {
     const double sigma2 = th[0], alpha = th[1], theta = th[2], mu = th[3], v = th[4];
     const double* td = tip + id;
     double* st = state + e;
-    const bool lead = gs > 1 ? (e % gs == 0) : true;
+    const bool lead = gs == 0;
     const int64_t js = F.cl_jslot[c], hs = F.cl_hslot[c], gsl = F.cl_gslot[c];
     const int m = F.cl_dim[c];
     if (lead) for (int q = 0; q < tri(m); q++) st[(js + q) * ld] = 0.0;
@@ -593,7 +592,7 @@ struct AssignFast {
     const double* th = gen.theta + ip;
     const double* td = gen.tip + id;
     double* st = gen.state + e;
-    const bool lead = SH ? (e % gen.gs == 0) : true;  // shared-precision mode: J rows are the leader's
+    const bool lead = !SH;  // SH: element side of a shared-precision batch (h and g only)
     const int64_t js = F.cl_jslot[c], hs = F.cl_hslot[c], gs = F.cl_gslot[c];
     const double kind = th[(int64_t)tr.kind() * ldp];
     if (kind < 0.0) { gen.run(e, c); return; }  // invalid parameters: generic path records the status
@@ -776,16 +775,16 @@ struct EnergyClusterBody {
   double* part;         // [2*nclusters + nsepsets][ld]: energy_c, entropy_c, entropy_s
   int nclusters;
   int64_t ld;
-  int64_t gs = 0;       // shared-precision mode: J rows (belief and factor) from the group leader's column
+  JSide sj{nullptr, 0, 0}, fj{nullptr, 0, 0};  // shared-precision batches: J rows of beliefs / factors in the group batch
   int y0 = 0;
   PGBP_HD void operator()(int64_t e, int y) const {
     const int c = list[y + y0];
     const int M = cl_dim[c];
-    const int64_t ej = gs > 1 ? e - e % gs : e;
     const double* st = state + e;
     const double* fa = factor + e;
-    const double* stj = state + ej;
-    const double* faj = factor + ej;
+    const double* stj = sj.base ? jcolumn(sj, e) : st;
+    const double* faj = fj.base ? jcolumn(fj, e) : fa;
+    const int64_t ldj = sj.base ? sj.ld : ld;
     const int64_t js = cl_jslot[c], hs = cl_hslot[c], gs = cl_gslot[c];
     const double gf = fa[gs * ld];
     if (M == 0) {  // src/score.jl:170-171
@@ -796,7 +795,7 @@ struct EnergyClusterBody {
     constexpr int NA = MAXM * (MAXM + 1) / 2;
     double A[NA], mu[MAXM], x[MAXM];
     const int SM = tri(M);
-    for (int q = 0; q < SM; q++) A[q] = stj[(js + q) * ld];
+    for (int q = 0; q < SM; q++) A[q] = stj[(js + q) * ldj];
     for (int k = 0; k < M; k++) mu[k] = st[(hs + k) * ld];
     double logdet = 0.0;
     for (int k = 0; k < M; k++) {  // U'U = J_b; forward solve w = U^-T h
@@ -829,7 +828,7 @@ struct EnergyClusterBody {
     for (int k = 0; k < M; k++) {
       double fk_mu = 0.0;
       for (int r = 0; r < M; r++) {
-        const double f = faj[(js + (r <= k ? pk(r, k) : pk(k, r))) * ld];
+        const double f = faj[(js + (r <= k ? pk(r, k) : pk(k, r))) * ldj];
         x[r] = f;
         fk_mu = fma(f, mu[r], fk_mu);
       }
@@ -861,7 +860,7 @@ struct EntropySepsetBody {
   double* part;
   int nclusters;
   int64_t ld;
-  int64_t gs = 0;
+  JSide sj{nullptr, 0, 0};
   int y0 = 0;
   PGBP_HD void operator()(int64_t e, int y) const {
     const int j = list[y + y0];
@@ -870,9 +869,10 @@ struct EntropySepsetBody {
     if (M == 0) { *out = 0.0; return; }
     constexpr int NA = MAXM * (MAXM + 1) / 2;
     double A[NA];
-    const double* st = state + (gs > 1 ? e - e % gs : e);
+    const double* st = sj.base ? jcolumn(sj, e) : state + e;
+    const int64_t ldj = sj.base ? sj.ld : ld;
     const int64_t js = jslot[nclusters + j];
-    for (int q = 0; q < tri(M); q++) A[q] = st[(js + q) * ld];
+    for (int q = 0; q < tri(M); q++) A[q] = st[(js + q) * ldj];
     double logdet = 0.0;
     for (int k = 0; k < M; k++) {
       const double d = A[pk(k, k)];
@@ -1084,8 +1084,15 @@ static int get_tables(pgbp_batch* b, DevTables** out) {
   const pgbp_plan* p = b->plan;
   std::unique_ptr<DevTables> dt(new DevTables);
   PGBP_TRY(upload(b, dt.get(), &dt->jslot, p->jslot));
-  PGBP_TRY(upload(b, dt.get(), &dt->hslot, p->hslot));
-  PGBP_TRY(upload(b, dt.get(), &dt->gslot, p->gslot));
+  if (b->jb) {  // shared-precision batch: the element array holds h and g only, in compact rows
+    std::vector<int64_t> hr(p->nbeliefs), gr(p->nbeliefs);
+    for (int i = 0; i < p->nbeliefs; i++) { hr[i] = batch_hrow(b, i); gr[i] = batch_grow(b, i); }
+    PGBP_TRY(upload(b, dt.get(), &dt->hslot, hr));
+    PGBP_TRY(upload(b, dt.get(), &dt->gslot, gr));
+  } else {
+    PGBP_TRY(upload(b, dt.get(), &dt->hslot, p->hslot));
+    PGBP_TRY(upload(b, dt.get(), &dt->gslot, p->gslot));
+  }
   PGBP_TRY(upload(b, dt.get(), &dt->dim, p->dim));
   PGBP_TRY(upload(b, dt.get(), &dt->sep_a, p->sep_a));
   PGBP_TRY(upload(b, dt.get(), &dt->sep_b, p->sep_b));
@@ -1155,13 +1162,18 @@ static int launch_energy_bucket(pgbp_batch* b, DevTables* dt, const std::vector<
   if (!cl.empty()) {
     PGBP_TRY(h2d(d_list, cl.data(), cl.size() * sizeof(int32_t), b->stream));
     EnergyClusterBody<MAXM> body{b->state, b->factor, b->status, dt->jslot, dt->hslot, dt->gslot, dt->dim, d_list,
-                                 part, p->nclusters, b->ld, b->group_size};
+                                 part, p->nclusters, b->ld};
+    if (b->jb) {
+      body.sj = batch_jside(b);
+      body.fj = JSide{b->jb->factor, b->jb->ld, b->group_size};
+    }
     PGBP_TRY(launch_generic(b, "k_energy_cluster", b->B, (int)cl.size(), body));
   }
   if (!sp.empty()) {
     int32_t* d_list2 = d_list + p->nclusters;
     PGBP_TRY(h2d(d_list2, sp.data(), sp.size() * sizeof(int32_t), b->stream));
-    EntropySepsetBody<MAXM> body{b->state, dt->jslot, dt->dim, d_list2, part, p->nclusters, b->ld, b->group_size};
+    EntropySepsetBody<MAXM> body{b->state, dt->jslot, dt->dim, d_list2, part, p->nclusters, b->ld};
+    if (b->jb) body.sj = batch_jside(b);
     PGBP_TRY(launch_generic(b, "k_entropy_sepset", b->B, (int)sp.size(), body));
   }
   return 0;
@@ -1172,6 +1184,11 @@ static int factored_energy_launch(pgbp_batch* b, double* d_out_soa, int64_t ldo)
   PGBP_TRY(batch_materialize_sepsets(b));
   if (!b->factor) PGBP_FAIL(PGBP_ESTATE, "batch was created without PGBP_BATCH_FACTORS");
   PGBP_TRY(batch_materialize_factors(b));
+  if (b->jb) {  // the J rows of beliefs and factors are read from the group batch
+    b->jb->stream = b->stream;
+    PGBP_TRY(batch_materialize_sepsets(b->jb));
+    PGBP_TRY(batch_materialize_factors(b->jb));
+  }
   DevTables* dt;
   PGBP_TRY(get_tables(b, &dt));
   const size_t nrows = 2 * (size_t)p->nclusters + p->nsepsets;
@@ -1256,6 +1273,28 @@ static int assign_enqueue(pgbp_batch* b, pgbp::DevTables* dt, int32_t ncolors, c
     PGBP_TRY(rc);
   }
   PGBP_TRY(assign_launch(b, dt, b->state, ncolors, nparamsets, ndatasets, pairing));
+  if (b->jb) {
+    // shared-precision batch: the launch above wrote h and g per element; the J rows are assigned once per group in
+    // the group batch, from the same prepared tables (group g = elements [g gs, (g+1) gs): its parameter set, any
+    // of its data sets -- J does not depend on the data)
+    pgbp_batch* jb = b->jb;
+    jb->stream = b->stream;
+    DevTables* jdt;
+    PGBP_TRY(get_tables(jb, &jdt));
+    const int64_t jnd = pairing == PGBP_PAIR_PRODUCT ? ndatasets / b->group_size : 1;
+    std::swap(jdt->theta, dt->theta); std::swap(jdt->ldp, dt->ldp); std::swap(jdt->tip, dt->tip); std::swap(jdt->ldd, dt->ldd);
+    const int rc = assign_launch(jb, jdt, jb->state, ncolors, nparamsets, jnd, pairing);
+    std::swap(jdt->theta, dt->theta); std::swap(jdt->ldp, dt->ldp); std::swap(jdt->tip, dt->tip); std::swap(jdt->ldd, dt->ldd);
+    PGBP_TRY(rc);
+    jb->lazy_factors.pending = false;
+    jb->lazy_factors.valid = false;
+    PGBP_TRY(batch_zero_sepsets(b, false));
+    if (b->factor) {
+      PGBP_TRY(d2d(jb->factor, jb->state, sizeof(double) * (size_t)p->nslots_factor * (size_t)jb->ld, b->stream));
+      PGBP_TRY(d2d(b->factor, b->state, sizeof(double) * (size_t)b->nrows_efactor * (size_t)b->ld, b->stream));
+    }
+    return 0;
+  }
   // sepsets <- 0 (src/beliefs.jl:796), lazily; factor snapshot (src/clustergraphbeliefs.jl:106), lazily
   PGBP_TRY(batch_zero_sepsets(b, true));
   if (b->factor) b->lazy_factors = pgbp_batch::LazyFactors{true, true, ncolors, nparamsets, ndatasets, pairing};
@@ -1343,9 +1382,28 @@ int32_t pgbp_assign_factors_ou(pgbp_batch* b, const double* params, int64_t npar
   AssignOU body{fd, b->scratch, dt->tip, dt->ldd, b->state, b->status, b->ld, nparamsets, ndatasets, pairing};
   body.gs = b->group_size;
   PGBP_TRY(launch_generic(b, "k_assign_ou", b->B, p->nclusters, body));
-  PGBP_TRY(batch_zero_sepsets(b, true));
   b->lazy_factors.pending = false;  // (the OU parameters live in scratch memory: eager snapshot)
   b->lazy_factors.valid = false;
+  if (b->jb) {  // shared-precision batch: J rows once per group in the group batch (see assign_enqueue)
+    pgbp_batch* jb = b->jb;
+    jb->stream = b->stream;
+    DevTables* jdt;
+    PGBP_TRY(get_tables(jb, &jdt));
+    FamDev jfd{jdt->node_cluster, jdt->mem_off, jdt->mem_pos, jdt->mem_length, jdt->mem_gamma, jdt->mem_color,
+               jdt->node_datarow, jdt->clu_off, jdt->clu_node, jdt->jslot, jdt->hslot, jdt->gslot, jdt->dim, 1, 1, F.root_fixed};
+    const int64_t jnd = pairing == PGBP_PAIR_PRODUCT ? ndatasets / b->group_size : 1;
+    AssignOU jbody{jfd, b->scratch, dt->tip, dt->ldd, jb->state, jb->status, jb->ld, nparamsets, jnd, pairing};
+    PGBP_TRY(launch_generic(jb, "k_assign_ou", jb->B, p->nclusters, jbody));
+    jb->lazy_factors.pending = false;
+    jb->lazy_factors.valid = false;
+    PGBP_TRY(batch_zero_sepsets(b, false));
+    if (b->factor) {
+      PGBP_TRY(d2d(jb->factor, jb->state, sizeof(double) * (size_t)p->nslots_factor * (size_t)jb->ld, b->stream));
+      PGBP_TRY(d2d(b->factor, b->state, sizeof(double) * (size_t)b->nrows_efactor * (size_t)b->ld, b->stream));
+    }
+    return stream_sync(b->stream);
+  }
+  PGBP_TRY(batch_zero_sepsets(b, true));
   if (b->factor) PGBP_TRY(d2d(b->factor, b->state, sizeof(double) * (size_t)p->nslots_factor * (size_t)b->ld, b->stream));
   return stream_sync(b->stream);
 }
@@ -1407,16 +1465,18 @@ int32_t pgbp_factored_energy(pgbp_batch* b, double* out) {
 int32_t pgbp_regularize_bycluster(pgbp_batch* b) {
   if (!b) PGBP_FAIL(PGBP_EINVAL, "null batch");
   PGBP_TRY(set_device(b->device));
+  if (b->jb) {  // the regularisers only touch J: the group batch's
+    b->jb->stream = b->stream;
+    return pgbp_regularize_bycluster(b->jb);
+  }
   PGBP_TRY(batch_materialize_sepsets(b));
   const pgbp_plan* p = b->plan;
   DevTables* dt;
   PGBP_TRY(get_tables(b, &dt));
   PGBP_TRY(batch_need_scratch(b, sizeof(double) * (size_t)p->nclusters * (size_t)b->ld));
   RegClusterBody a{b->state, b->scratch, dt->jslot, dt->dim, dt->reg_off, dt->reg_pos, b->ld, PGBP_EPS};
-  a.gs = b->group_size;
   PGBP_TRY(launch_generic(b, "k_reg_cluster", b->B, p->nclusters, a));
   RegSepsetBody s{b->state, b->scratch, dt->jslot, dt->dim, dt->sep_a, dt->sep_b, p->nclusters, b->ld};
-  s.gs = b->group_size;
   return launch_generic(b, "k_reg_sepset", b->B, p->nsepsets, s);
 }
 
@@ -1466,20 +1526,23 @@ int32_t pgbp_regularize_onschedule(pgbp_batch* b) {
   int32_t* d_up = (int32_t*)v;
   int rc = h2d(d_msgs, msgs.data(), msgs.size() * sizeof(MsgDesc), b->stream);
   if (!rc) rc = h2d(d_up, uptab.data(), uptab.size() * sizeof(int32_t), b->stream);
-  if (!rc) rc = batch_need_scratch(b, sizeof(double) * (size_t)b->ld);
+  // eps and the diagonal bumps only touch J: on a shared-precision batch they run on the group batch
+  pgbp_batch* jt = b->jb ? b->jb : b;
+  if (b->jb) { jt->stream = b->stream; if (!rc) rc = batch_materialize_sepsets(jt); }
+  if (!rc) rc = batch_need_scratch(jt, sizeof(double) * (size_t)jt->ld);
   const double eps0 = sqrt(PGBP_EPS);
   for (size_t k = 0; k < ops.size() && !rc; k++) {
     const Op& o = ops[k];
     if (o.kind == 0) {
-      EpsOneBody body{b->state, b->scratch, p->jslot[o.c], b->ld, p->dim[o.c], eps0};
-      body.gs = b->group_size;
-      rc = launch_generic(b, "k_eps_one", b->B, 1, body);
+      EpsOneBody body{jt->state, jt->scratch, p->jslot[o.c], jt->ld, p->dim[o.c], eps0};
+      rc = launch_generic(jt, "k_eps_one", jt->B, 1, body);
     } else if (o.kind == 1) {
       const int S = p->dim[p->nclusters + o.j];
       if (S == 0) continue;  // isempty(upind) && return
-      RegOneBody body{b->state, b->scratch, d_up + upoff[o.nb], p->jslot[o.c], p->jslot[p->nclusters + o.j], b->ld, S};
-      body.gs = b->group_size;
-      rc = launch_generic(b, "k_reg_one", b->B, 1, body);
+      RegOneBody body{jt->state, jt->scratch, d_up + upoff[o.nb], p->jslot[o.c], p->jslot[p->nclusters + o.j], jt->ld, S};
+      rc = launch_generic(jt, "k_reg_one", jt->B, 1, body);
+    } else if (b->jb) {
+      rc = shared_propagate(b, msgs[o.nb], 0, 0x3ffff0);  // residual stored, flags untouched (:400)
     } else {
       const MsgDesc& md = msgs[o.nb];
       LaunchGroup g;
@@ -1500,6 +1563,11 @@ int32_t pgbp_regularize_bynodesubtree(pgbp_batch* b, int32_t nnodes, const int32
                                       const int32_t* idx_off, const int32_t* idx_cluster, const int32_t* idx_sepset) {
   if (!b || nnodes < 0 || !eps_off || !step_off) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
   PGBP_TRY(set_device(b->device));
+  if (b->jb) {  // J only: the group batch's
+    b->jb->stream = b->stream;
+    return pgbp_regularize_bynodesubtree(b->jb, nnodes, eps_off, eps_cluster, step_off, step_cluster, step_sepset, idx_off,
+                                         idx_cluster, idx_sepset);
+  }
   PGBP_TRY(batch_materialize_sepsets(b));
   const pgbp_plan* p = b->plan;
   DevTables* dt;
@@ -1530,7 +1598,6 @@ int32_t pgbp_regularize_bynodesubtree(pgbp_batch* b, int32_t nnodes, const int32
     if (step_off[n + 1] == step_off[n]) continue;
     RegNodeBody body{b->state, dt->jslot, dt->dim, d, nullptr, d + o_sc, d + o_ss, d + o_io, d + o_ic, d + o_is,
                      eps_off[n], eps_off[n + 1], step_off[n], step_off[n + 1], p->nclusters, b->ld};
-    body.gs = b->group_size;
     rc = launch_generic(b, "k_reg_node", b->B, 1, body);
   }
   if (!rc) rc = stream_sync(b->stream);

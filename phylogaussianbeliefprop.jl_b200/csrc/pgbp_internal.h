@@ -15,6 +15,14 @@ PGBP_HD int tri(int m) { return m * (m + 1) / 2; }
 // packed upper, column-major: (r <= c) -> c(c+1)/2 + r
 PGBP_HD int pk(int r, int c) { return c * (c + 1) / 2 + r; }
 
+// Where the J rows of an element live.  Ordinary batches: base == nullptr (the element's own column of the state
+// array).  Shared-precision batches: the array of the group batch (pgbp_batch::jb), pitch ld, column e / gs.
+struct JSide {
+  const double* base;
+  int64_t ld, gs;
+};
+PGBP_HD const double* jcolumn(const JSide& j, int64_t e) { return j.base ? j.base + e / j.gs : nullptr; }
+
 // One message F -> T through sepset S (src/beliefupdates.jl:650-665), as index
 // data only.  Slots index rows of the batch's SoA arrays.
 struct MsgDesc {
@@ -135,8 +143,26 @@ struct pgbp_batch {
   double* resid = nullptr;
   double* kldiv = nullptr;
   uint8_t* calflag = nullptr;  // [2*nsepsets][ld]
-  uint8_t* calflagJ = nullptr; // [2*nsepsets][ld], shared-precision mode: J part of the flags (leader columns)
+  uint8_t* calflagJ = nullptr; // (unused since the factored shared-precision layout: the J part of the flags lives in jb->calflag)
   int64_t group_size = 0;      // > 1: shared-precision mode, elements [k*gs, (k+1)*gs) share every J
+  // ---- shared-precision batches (group_size > 1): factored layout -------------------------------------------
+  // The precisions J of a group depend on its parameter vector only (src/beliefupdates.jl:77-81: only h and g see
+  // the data), so they are kept ONCE per group, in `jb`: an ordinary batch with one element per group (row pitch
+  // jb->ld ~ ngroups) that owns every J row, the J part of the residuals and of the calibration flags.  This batch
+  // then holds per ELEMENT only h and g, in a compact row numbering: belief i owns rows eh[i] .. eh[i]+m-1 (h) and
+  // eh[i]+m (g) of `state` (clusters first: the first nrows_efactor rows are also the layout of `factor`);
+  // directed message d owns rows erh[d] .. erh[d]+s-1 of `resid` (dh).  A message is passed in two kernels:
+  // k_jmsg (one warp per (message, group)) factorises J_I, updates the J part and leaves U, 1/diag(U),
+  // Z = U^-T J_IK and logdet in `cache`; k_hmsg (one thread per (message, element)) applies them to h and g.
+  pgbp_batch* jb = nullptr;
+  int64_t ngroups = 0;
+  std::vector<int64_t> eh, erh;       // compact rows per belief / per directed message
+  int64_t nrows_e = 0, nrows_efactor = 0, nrows_eresid = 0;
+  std::vector<double*> jcache;        // index 2*tree+dir: [ngroups][jcache_len] factor records of one traversal
+  std::vector<int64_t*> d_jcache_off; // index 2*tree+dir: record offset (doubles) of every message, execution order
+  std::vector<int64_t> jcache_len;    // index 2*tree+dir: doubles per group
+  double* jcache_one = nullptr;       // scratch record for single messages (pgbp_propagate, regularize_onschedule)
+  int64_t* d_zero64 = nullptr;        // device constant 0 (record offset of a single message)
   uint8_t* done = nullptr;     // [ld] (auto-stop mask)
   int32_t* status = nullptr;   // [ld]
   int32_t* iscal = nullptr;    // [ld]

@@ -25,16 +25,7 @@ struct MsgArgs {
   uint32_t opts;     // PGBP_CAL_RESIDNORM | PGBP_CAL_RESIDKLDIV | PGBP_OPT_SEPZERO
   int32_t ref_base;
   int64_t e0;
-  // Shared-precision mode (gs > 1): the gs consecutive elements of a group share every J (same parameter
-  // vector, different data).  J rows are valid in the group LEADER's column only; all threads read them
-  // from there (a warp-wide broadcast instead of 256 bytes), only the leader's thread writes J, the J
-  // part of the residual and the J part of the calibration flag (calflagJ).  h and g stay per element.
-  int64_t gs;
-  uint8_t* calflagJ;
 };
-
-// column holding the J rows of element e, and whether e owns them
-PGBP_HD int64_t jcol(const MsgArgs& a, int64_t e) { return a.gs > 1 ? e - e % a.gs : e; }
 
 // NaN-propagating running maximum of |x| (Julia's maximum(abs, x))
 PGBP_HD void absmax(double& m, double x) {
@@ -75,17 +66,11 @@ PGBP_HD constexpr int colof(int q) {
 // calibration flag of one residual (src/beliefs.jl:994-1003):
 // max|dh|/sqrt(s) <= 1e-5 && max|dJ|/sqrt(s^2) <= 1e-5.  max_i(|x_i|/c) == (max_i|x_i|)/c
 // exactly (division by c > 0 is monotone, so is rounding).
-// hlive = false: a failed group leader of a shared-precision batch that only carries the group's J forward
-PGBP_HD void store_flag(const MsgArgs& a, int dmsg, int64_t e, int S, double maxJ, double maxh, bool hlive = true) {
+PGBP_HD void store_flag(const MsgArgs& a, int dmsg, int64_t e, int S, double maxJ, double maxh) {
   if ((a.opts & PGBP_CAL_RESIDNORM) && a.calflag) {
     const bool okh = S > 0 ? (maxh / sqrt((double)S) <= 1e-5) : true;
     const bool okJ = S > 0 ? (maxJ / (double)S <= 1e-5) : true;
-    if (a.gs > 1) {  // J part kept apart: it is the group's, not the element's
-      if (hlive) a.calflag[(int64_t)dmsg * a.ld + e] = okh ? 1 : 0;
-      if (e % a.gs == 0) a.calflagJ[(int64_t)dmsg * a.ld + e] = okJ ? 1 : 0;
-    } else {
-      a.calflag[(int64_t)dmsg * a.ld + e] = (okh && okJ) ? 1 : 0;
-    }
+    a.calflag[(int64_t)dmsg * a.ld + e] = (okh && okJ) ? 1 : 0;
   }
 }
 
@@ -114,24 +99,16 @@ PGBP_HD double* slot_ptr(char* base, uint32_t slot, uint32_t ld8) {
   return (double*)(base + (uint64_t)slot * (uint64_t)ld8);
 }
 
-// SH: shared-precision mode compiled in (J rows read from / written by the group leader's column);
-// the ordinary instantiation (SH = false) carries none of that logic.
-template <int CI, int CS, bool SH = false>
+template <int CI, int CS>
 PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
   constexpr int I = CI, S = CS, M = I + S, SI = I * (I + 1) / 2, SS = S * (S + 1) / 2;
   const MsgDesc md = a.msgs[msg_index];  // by value: lives in registers, never re-read after a store
-  const int64_t ej = SH ? jcol(a, e) : e;
-  const bool lead = SH ? ej == e : true;  // this thread owns (writes) the J rows
-  // A failed element stops updating -- except a group leader of a shared-precision batch: J depends on the shared
-  // parameters only, so the leader keeps carrying the group's J rows forward (hlive = false: no h / g / status
-  // writes) even when its own data failed (e.g. a NaN tip value, status set by K1).
-  bool hlive = SH ? a.status[e] == 0 : true;
-  if (SH ? (!hlive && !lead) : a.status[e] != 0) return;
+  if (a.status[e] != 0) return;
   if (a.done && a.done[e]) return;
   const uint32_t ld8 = (uint32_t)(a.ld * 8);  // (batches with 8*ld >= 2^32 are refused at creation)
   char* st = (char*)(a.state + e);
   char* rs = a.resid ? (char*)(a.resid + e) : nullptr;
-  char* stj = SH ? (char*)(a.state + ej) : st;  // J rows are read from the leader's column
+  char* stj = st;
   const int32_t* __restrict__ gat = a.tab + md.gat;
   const int32_t* __restrict__ sca = a.tab + md.sca;
   const uint32_t fJ = (uint32_t)md.fJ, fh = (uint32_t)md.fh, sJ = (uint32_t)md.sJ, sh = (uint32_t)md.sh,
@@ -182,24 +159,9 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
 #pragma unroll
   for (int q = 0; q < I * S; q++)
     if (!(fabs(Bm[q]) <= PGBP_EPS)) allzero = false;
-  if constexpr (SH) {
-    // group leader: the J part of the message must not depend on this element's h.  Zero precision with a
-    // non-zero (or NaN) h_I fails this element (potrf info = 1) while the group's J moves on as in the shortcut.
-    bool hzero = true;
 #pragma unroll
-    for (int k = 0; k < I; k++)
-      if (!(fabs(hI[k]) <= PGBP_EPS)) hzero = false;
-    if (lead && allzero && !hzero) {
-      if (hlive) status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, 1));
-      hlive = false;
-    } else if (!hzero) {
-      allzero = false;
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < I; k++)
-      if (!(fabs(hI[k]) <= PGBP_EPS)) allzero = false;
-  }
+  for (int k = 0; k < I; k++)
+    if (!(fabs(hI[k]) <= PGBP_EPS)) allzero = false;
 
   if (!allzero) {
     double logdet = 0.0, ww = 0.0;
@@ -207,7 +169,7 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
     for (int k = 0; k < I; k++) {
       const double d = AI[pk(k, k)];
       if (!(d > 0.0)) {  // LAPACK potrf: info = k+1 (also catches NaN)
-        if (hlive) status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, k + 1));
+        status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, k + 1));
         return;
       }
       logdet += log(d);
@@ -243,7 +205,7 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
 
   double maxJ = 0.0, maxh = 0.0;
   constexpr int NCH = (SS + PGBP_CHUNK - 1) / PGBP_CHUNK;
-  if (lead) static_for<NCH>([&](auto chc) {
+  static_for<NCH>([&](auto chc) {
     constexpr int q0 = decltype(chc)::value * PGBP_CHUNK;
     constexpr int n = (SS - q0) < PGBP_CHUNK ? (SS - q0) : PGBP_CHUNK;
     double jo[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
@@ -283,26 +245,22 @@ PGBP_HD void message_thread_t0(const MsgArgs& a, int msg_index, int64_t e) {
 #pragma unroll
       for (int i = 0; i < I; i++) nv = nfma(Bm[i * S + k], hI[i], nv);
       const double d = nv - so[k];
-      if (hlive) {
-        *slot_ptr(st, sh + k, ld8) = nv;
-        *ta[k] = to[k] + d;
-        if (rs) *slot_ptr(rs, rh + k, ld8) = d;
-      }
+      *slot_ptr(st, sh + k, ld8) = nv;
+      *ta[k] = to[k] + d;
+      if (rs) *slot_ptr(rs, rh + k, ld8) = d;
       absmax(maxh, d);
     }
   }
-  if (hlive) {
-    *slot_ptr(st, (uint32_t)md.sg, ld8) = g;
-    *slot_ptr(st, (uint32_t)md.tg, ld8) = tg_old + (g - sg_old);
-  }
-  store_flag(a, md.dmsg, e, S, maxJ, maxh, hlive);
+  *slot_ptr(st, (uint32_t)md.sg, ld8) = g;
+  *slot_ptr(st, (uint32_t)md.tg, ld8) = tg_old + (g - sg_old);
+  store_flag(a, md.dmsg, e, S, maxJ, maxh);
 }
 
 // Runtime-shape variants share this tail: divide / multiply / residual / flag with
 // chunked prefetch.  newJ(r,c,q), newh(k) give the outgoing message.
-template <bool SH = false, class FJ, class FH>
+template <class FJ, class FH>
 PGBP_HD void divide_mult_store(const MsgArgs& a, const MsgDesc& md, int64_t e, int S, FJ newJ, FH newh,
-                               double newg, bool hlive = true) {
+                               double newg) {
   const int64_t ld = a.ld;
   double* st = a.state + e;
   double* rs = a.resid ? a.resid + e : nullptr;
@@ -312,8 +270,7 @@ PGBP_HD void divide_mult_store(const MsgArgs& a, const MsgDesc& md, int64_t e, i
   const double sg_old = sz ? 0.0 : st[md.sg * ld], tg_old = st[md.tg * ld];
   double maxJ = 0.0, maxh = 0.0;
   int r = 0, c = 0;  // (r,c) of packed index q, advanced incrementally
-  const bool lead = SH ? jcol(a, e) == e : true;  // shared-precision mode: only the group leader updates J rows
-  for (int q0 = 0; lead && q0 < SS; q0 += PGBP_CHUNK) {
+  for (int q0 = 0; q0 < SS; q0 += PGBP_CHUNK) {
     double nv[PGBP_CHUNK], so[PGBP_CHUNK], to[PGBP_CHUNK];
     int64_t ta[PGBP_CHUNK];
 #pragma unroll
@@ -354,19 +311,15 @@ PGBP_HD void divide_mult_store(const MsgArgs& a, const MsgDesc& md, int64_t e, i
     for (int k = 0; k < PGBP_CHUNK; k++)
       if (k0 + k < S) {
         const double d = nv[k] - so[k];
-        if (hlive) {
-          st[(md.sh + k0 + k) * ld] = nv[k];
-          st[ta[k]] = to[k] + d;
-          if (rs) rs[(md.rh + k0 + k) * ld] = d;
-        }
+        st[(md.sh + k0 + k) * ld] = nv[k];
+        st[ta[k]] = to[k] + d;
+        if (rs) rs[(md.rh + k0 + k) * ld] = d;
         absmax(maxh, d);
       }
   }
-  if (hlive) {
-    st[md.sg * ld] = newg;
-    st[md.tg * ld] = tg_old + (newg - sg_old);
-  }
-  store_flag(a, md.dmsg, e, S, maxJ, maxh, hlive);
+  st[md.sg * ld] = newg;
+  st[md.tg * ld] = tg_old + (newg - sg_old);
+  store_flag(a, md.dmsg, e, S, maxJ, maxh);
 }
 
 struct TrailJ {
@@ -395,17 +348,16 @@ struct GatherH {
 // Generic message kernel body: runtime shape, the whole sender belief gathered in
 // [I;K] order into thread-local memory sized for MAXM, right-looking partial
 // Cholesky over the first i pivots; the trailing block is the outgoing message.
-template <int MAXM, bool SH = false>
+template <int MAXM>
 PGBP_HD void message_thread_rt(const MsgArgs& a, int msg_index, int64_t e) {
   constexpr int NA = MAXM * (MAXM + 1) / 2;
   const MsgDesc md = a.msgs[msg_index];
-  bool hlive = a.status[e] == 0;  // a failed group leader of a shared-precision batch keeps carrying the group's J
-  if (!hlive && !(SH && jcol(a, e) == e)) return;
+  if (a.status[e] != 0) return;
   if (a.done && a.done[e]) return;
   const int I = md.mF - md.s, S = md.s, M = md.mF;
   const int64_t ld = a.ld;
   const double* st = a.state + e;
-  const double* stj = SH ? a.state + jcol(a, e) : st;
+  const double* stj = st;
   const int32_t* __restrict__ gat = a.tab + md.gat;
   double A[NA];
   double hv[MAXM];
@@ -421,21 +373,14 @@ PGBP_HD void message_thread_rt(const MsgArgs& a, int msg_index, int64_t e) {
     for (int r = 0; r < rmax; r++)
       if (!(fabs(A[pk(r, c)]) <= PGBP_EPS)) allzero = false;
   }
-  bool hzero = true;
   for (int k = 0; k < I; k++)
-    if (!(fabs(hv[k]) <= PGBP_EPS)) hzero = false;
-  if (SH && jcol(a, e) == e && allzero && !hzero) {  // see message_thread_t0: the group's J must not depend on this h
-    if (hlive) status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, 1));
-    hlive = false;
-  } else if (!hzero) {
-    allzero = false;
-  }
+    if (!(fabs(hv[k]) <= PGBP_EPS)) allzero = false;
   if (!allzero) {
     double logdet = 0.0, ww = 0.0;
     for (int k = 0; k < I; k++) {
       const double d = A[pk(k, k)];
       if (!(d > 0.0)) {
-        if (hlive) status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, k + 1));
+        status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, k + 1));
         return;
       }
       logdet += log(d);
@@ -451,7 +396,7 @@ PGBP_HD void message_thread_rt(const MsgArgs& a, int msg_index, int64_t e) {
     }
     g += 0.5 * ((double)I * PGBP_LOG2PI - logdet + ww);
   }
-  divide_mult_store<SH>(a, md, e, S, TrailJ{A, I}, TrailH{hv, I}, g, hlive);
+  divide_mult_store(a, md, e, S, TrailJ{A, I}, TrailH{hv, I}, g);
 }
 
 // Reference-order message body (PGBP_CAL_REFORDER): the same message computed in the REFERENCE's operation
@@ -537,16 +482,14 @@ PGBP_HD void message_thread_ref(const MsgArgs& a, int msg_index, int64_t e) {
     }
     g = g + ((double)I * PGBP_LOG2PI - logdet + quad) / 2;
   }
-  divide_mult_store<false>(a, md, e, S, TrailJ{A, I}, TrailH{hv, I}, g);
+  divide_mult_store(a, md, e, S, TrailJ{A, I}, TrailH{hv, I}, g);
 }
 
 // Message with nothing to integrate out (src/beliefupdates.jl:56): the outgoing
 // message is the sender's belief re-ordered; streamed, no local storage.
-template <bool SH = false>
 PGBP_HD void message_copy_thread(const MsgArgs& a, int msg_index, int64_t e) {
   const MsgDesc md = a.msgs[msg_index];
-  const bool hlive = a.status[e] == 0;
-  if (!hlive && !(SH && jcol(a, e) == e)) return;
+  if (a.status[e] != 0) return;
   if (a.done && a.done[e]) return;
   const int S = md.s;
   const int64_t ld = a.ld;
@@ -554,15 +497,18 @@ PGBP_HD void message_copy_thread(const MsgArgs& a, int msg_index, int64_t e) {
   const int32_t* __restrict__ gat = a.tab + md.gat;
   const int SS = tri(S);
   const double g = st[md.fg * ld];
-  divide_mult_store<SH>(a, md, e, S, GatherJ{SH ? a.state + jcol(a, e) : st, gat, md.fJ, ld}, GatherH{st, gat + SS, md.fh, ld}, g, hlive);
+  divide_mult_store(a, md, e, S, GatherJ{st, gat, md.fJ, ld}, GatherH{st, gat + SS, md.fh, ld}, g);
 }
 
 // residual_kldiv! (src/beliefs.jl:1060-1075): KL divergence between the message just sent (the new
 // sepset belief, J0 = J_s) and the sepset belief before the update (J1 = J_s - dJ, h1 = h_s - dh):
 //   ( -tr(J0^-1 dJ) + (mu1-mu0)' J1 (mu1-mu0) + logdet J0 - logdet J1 ) / 2.
 // If either matrix is not positive definite nothing is updated (the reference returns false silently).
+// stj / rsj / ldj: where the J rows of the sepset and of the residual live (shared-precision batches keep them per
+// group, in their own arrays with their own pitch); null = the element's own column of a.state / a.resid.
 template <int MAXM>
-PGBP_HD void kldiv_thread(const MsgArgs& a, double* kldiv, int msg_index, int64_t e) {
+PGBP_HD void kldiv_thread(const MsgArgs& a, double* kldiv, int msg_index, int64_t e, const double* stj = nullptr,
+                          const double* rsj = nullptr, int64_t ldj = 0) {
   constexpr int NA = MAXM * (MAXM + 1) / 2;
   const MsgDesc md = a.msgs[msg_index];
   if (a.status[e] != 0) return;
@@ -572,12 +518,11 @@ PGBP_HD void kldiv_thread(const MsgArgs& a, double* kldiv, int msg_index, int64_
   const int64_t ld = a.ld;
   const double* st = a.state + e;
   const double* rs = a.resid + e;
-  const double* stj = a.state + jcol(a, e);
-  const double* rsj = a.resid + jcol(a, e);
+  if (!stj) { stj = a.state + e; rsj = a.resid + e; ldj = ld; }
   double U0[NA], U1[NA], D[NA], m0[MAXM], m1[MAXM];
   const int SS = tri(S);
   for (int q = 0; q < SS; q++) {
-    const double j0 = stj[(md.sJ + q) * ld], dj = rsj[(md.rJ + q) * ld];
+    const double j0 = stj[(md.sJ + q) * ldj], dj = rsj[(md.rJ + q) * ldj];
     U0[q] = j0; D[q] = dj; U1[q] = j0 - dj;
   }
   for (int k = 0; k < S; k++) {
@@ -632,7 +577,7 @@ PGBP_HD void kldiv_thread(const MsgArgs& a, double* kldiv, int msg_index, int64_
     double s = 0.0;
     for (int c = 0; c < S; c++) {
       const int q = r <= c ? pk(r, c) : pk(c, r);
-      const double j1 = stj[(md.sJ + q) * ld] - D[q];
+      const double j1 = stj[(md.sJ + q) * ldj] - D[q];
       s = fma(j1, m1[c] - m0[c], s);
     }
     quad = fma(m1[r] - m0[r], s, quad);
@@ -645,16 +590,16 @@ PGBP_HD void kldiv_thread(const MsgArgs& a, double* kldiv, int msg_index, int64_
 template <int MAXM>
 PGBP_HD void integrate_thread(const double* state, int32_t* status, int64_t ld, int64_t e, int64_t jslot,
                               int64_t hslot, int64_t gslot, int M, double* mu_soa, double* norm, int64_t ld_out,
-                              double* cov_soa = nullptr, int64_t gs = 0) {
+                              double* cov_soa = nullptr, const double* stj = nullptr, int64_t ldj = 0) {
   constexpr int NA = MAXM * (MAXM + 1) / 2;
   double A[NA > 0 ? NA : 1];
   double hv[MAXM > 0 ? MAXM : 1];
   const double* st = state + e;
-  const double* stj = state + (gs > 1 ? e - e % gs : e);  // shared-precision mode: J from the group leader
+  if (!stj) { stj = st; ldj = ld; }  // (shared-precision batches: J rows of the element's group, own array and pitch)
   const int SM = tri(M);
   bool zero = true;
   for (int q = 0; q < SM; q++) {
-    A[q] = stj[(jslot + q) * ld];
+    A[q] = stj[(jslot + q) * ldj];
     if (A[q] != 0.0) zero = false;
   }
   for (int k = 0; k < M; k++) {

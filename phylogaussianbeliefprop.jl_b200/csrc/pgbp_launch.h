@@ -26,4 +26,19 @@ int batch_reset_by_assign(pgbp_batch* b);
 // pinned host staging of at least `bytes` (nullptr when unavailable: host emulation, allocation failure)
 void* batch_pinned(pgbp_batch* b, size_t bytes);
 MsgArgs make_args(pgbp_batch* b, uint32_t opts, int32_t ref_base, bool use_done);
+struct LaunchGroup;
+int launch_kldiv(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGroup& g);
+int launch_iscal(pgbp_batch* b, int it, int tr, int autostop);
+// rows of belief i's h / g in the batch's element array: the plan's slots, or the compact numbering of a
+// shared-precision batch (pgbp_batch::eh)
+inline int64_t batch_hrow(const pgbp_batch* b, int i) { return b->jb ? b->eh[i] : b->plan->hslot[i]; }
+inline int64_t batch_grow(const pgbp_batch* b, int i) { return b->jb ? b->eh[i] + b->plan->dim[i] : b->plan->gslot[i]; }
+inline JSide batch_jside(const pgbp_batch* b) { return JSide{b->jb ? b->jb->state : nullptr, b->jb ? b->jb->ld : 0, b->group_size}; }
+// shared-precision batches (pgbp_shared.cu)
+int shared_create(pgbp_batch* b);    // group batch, compact layout, caches (called by pgbp_batch_create_shared)
+void shared_destroy(pgbp_batch* b);
+int shared_run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_t ref_base);
+int shared_propagate(pgbp_batch* b, const MsgDesc& md_plan, uint32_t opts, int32_t ref_base);
+// remap the h / g rows of a plan descriptor to the compact element numbering of shared-precision batch b
+MsgDesc shared_remap(const pgbp_batch* b, const MsgDesc& m);
 }  // namespace pgbp

@@ -13,11 +13,10 @@ namespace pgbp {
 #endif
 
 #ifndef PGBP_HOST_EMUL
-template <bool SH>
 __global__ void __launch_bounds__(256) k_message_copy(MsgArgs a) {
   const int64_t e = a.e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.B) return;
-  message_copy_thread<SH>(a, blockIdx.y, e);
+  message_copy_thread(a, blockIdx.y, e);
 }
 #endif
 
@@ -30,7 +29,7 @@ __global__ void __launch_bounds__(256) k_message_copy(MsgArgs a) {
 // every message still runs the register-resident specialised body.
 template <int P, int A_, int B_>
 PGBP_HD void walk_case(const MsgArgs& a, int m, int64_t e) {
-  if constexpr (A_ == 0) message_copy_thread<false>(a, m, e);
+  if constexpr (A_ == 0) message_copy_thread(a, m, e);
   else if constexpr ((A_ + B_) * P <= PGBP_T0_MAX) message_thread_t0<A_ * P, B_ * P>(a, m, e);
 }
 template <int P>
@@ -265,34 +264,30 @@ __global__ void __launch_bounds__(128) k_message_ref(MsgArgs a) {
 }
 
 template <int MAXM>
-__global__ void __launch_bounds__(128) k_kldiv(MsgArgs a, double* kldiv) {
+__global__ void __launch_bounds__(128) k_kldiv(MsgArgs a, double* kldiv, JSide js, JSide jr) {
   const int64_t e = a.e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.B) return;
-  kldiv_thread<MAXM>(a, kldiv, blockIdx.y, e);
+  kldiv_thread<MAXM>(a, kldiv, blockIdx.y, e, jcolumn(js, e), jcolumn(jr, e), js.ld);
 }
 
 template <int MAXM>
 __global__ void __launch_bounds__(128) k_integrate(const double* state, int32_t* status, int64_t B, int64_t ld,
                                                    int64_t jslot, int64_t hslot, int64_t gslot, int M,
                                                    double* mu_soa, double* norm, int64_t ld_out, double* cov_soa,
-                                                   int64_t gsz) {
+                                                   JSide js) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= B) return;
-  integrate_thread<MAXM>(state, status, ld, e, jslot, hslot, gslot, M, mu_soa, norm, ld_out, cov_soa, gsz);
+  integrate_thread<MAXM>(state, status, ld, e, jslot, hslot, gslot, M, mu_soa, norm, ld_out, cov_soa, jcolumn(js, e), js.ld);
 }
 #endif
 
 static int launch_copy(pgbp_batch* b, const MsgArgs& a, int nmsg) {
 #ifdef PGBP_HOST_EMUL
   for (int m = 0; m < nmsg; m++)
-    for (int64_t e = a.e0; e < a.B; e++) {
-      if (a.gs > 1) message_copy_thread<true>(a, m, e);
-      else message_copy_thread<false>(a, m, e);
-    }
+    for (int64_t e = a.e0; e < a.B; e++) message_copy_thread(a, m, e);
 #else
   dim3 grid((unsigned)((a.B - a.e0 + 255) / 256), (unsigned)nmsg);
-  if (a.gs > 1) k_message_copy<true><<<grid, 256, 0, b->stream>>>(a);
-  else k_message_copy<false><<<grid, 256, 0, b->stream>>>(a);
+  k_message_copy<<<grid, 256, 0, b->stream>>>(a);
 #endif
   b->launches++;
   return check_launch("k_message_copy");
@@ -332,15 +327,9 @@ int launch_group(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGr
     } else if (a.opts & PGBP_CAL_REFORDER) {
       rc = launch_ref(b, a, n, g.ci > 0 ? g.ci + g.cs : g.maxm + g.cs);
     } else if (g.ci > 0) {
-      if (b->group_size > 1) {
-        rc = launch_t0s_part0(b, a, n, g.ci, g.cs);
-        if (rc == PGBP_NOT_MINE) rc = launch_t0s_part1(b, a, n, g.ci, g.cs);
-        if (rc == PGBP_NOT_MINE) rc = launch_t0s_part2(b, a, n, g.ci, g.cs);
-      } else {
-        rc = launch_t0_part0(b, a, n, g.ci, g.cs);
-        if (rc == PGBP_NOT_MINE) rc = launch_t0_part1(b, a, n, g.ci, g.cs);
-        if (rc == PGBP_NOT_MINE) rc = launch_t0_part2(b, a, n, g.ci, g.cs);
-      }
+      rc = launch_t0_part0(b, a, n, g.ci, g.cs);
+      if (rc == PGBP_NOT_MINE) rc = launch_t0_part1(b, a, n, g.ci, g.cs);
+      if (rc == PGBP_NOT_MINE) rc = launch_t0_part2(b, a, n, g.ci, g.cs);
       if (rc == PGBP_NOT_MINE) PGBP_FAIL(PGBP_ESTATE, "no specialised kernel for shape (%d,%d)", g.ci, g.cs);
     } else {  // medium / large class: the group is uniform in (I, S) = (g.maxm, g.cs)
       rc = launch_medium(b, a, n, g.maxm, g.cs);
@@ -355,16 +344,18 @@ int launch_group(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGr
 template <int MAXM>
 static int launch_kldiv_t(pgbp_batch* b, const MsgArgs& a, int n) {
 #ifdef PGBP_HOST_EMUL
+  const JSide js = batch_jside(b), jr{b->jb ? b->jb->resid : nullptr, js.ld, js.gs};
   for (int m = 0; m < n; m++)
-    for (int64_t e = a.e0; e < a.B; e++) kldiv_thread<MAXM>(a, b->kldiv, m, e);
+    for (int64_t e = a.e0; e < a.B; e++) kldiv_thread<MAXM>(a, b->kldiv, m, e, jcolumn(js, e), jcolumn(jr, e), js.ld);
 #else
+  const JSide js = batch_jside(b), jr{b->jb ? b->jb->resid : nullptr, js.ld, js.gs};
   dim3 grid((unsigned)((a.B - a.e0 + 127) / 128), (unsigned)n);
-  k_kldiv<MAXM><<<grid, 128, 0, b->stream>>>(a, b->kldiv);
+  k_kldiv<MAXM><<<grid, 128, 0, b->stream>>>(a, b->kldiv, js, jr);
 #endif
   b->launches++;
   return check_launch("k_kldiv");
 }
-static int launch_kldiv(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGroup& g) {
+int launch_kldiv(pgbp_batch* b, MsgArgs a, const MsgDesc* d_msgs, const LaunchGroup& g) {
   int maxs = g.ci == 0 ? PGBP_MAX_DIM : g.cs;  // copy groups mix sepset dimensions
   if (g.ci > 0) maxs = g.cs;
   int done = 0;
@@ -391,8 +382,6 @@ MsgArgs make_args(pgbp_batch* b, uint32_t opts, int32_t ref_base, bool use_done)
   a.done = use_done ? b->done : nullptr;
   a.B = b->chunk_end > 0 ? b->chunk_end : b->B;
   a.e0 = b->chunk_begin;
-  a.gs = b->group_size;
-  a.calflagJ = b->calflagJ;
   a.ld = b->ld;
   a.opts = opts;
   a.ref_base = ref_base;
@@ -426,7 +415,7 @@ int run_walk(pgbp_batch* b, int tree, int first, int count, uint32_t opts, int32
 
 bool use_walk(const pgbp_batch* b, int tree) {
   const Tree& tr = b->plan->trees[tree];
-  if (!tr.walkable || b->plan->ntraits > PGBP_WALK_MAXP || b->group_size > 1) return false;
+  if (!tr.walkable || b->plan->ntraits > PGBP_WALK_MAXP || b->jb) return false;
   // measured on B200 (lazaridis p=3, B=65536): level-parallel 70.3M calibrations/s, walk 46.5M
   // (8 warps/SM at 255 registers cannot hide HBM latency) => the walk kernel is opt-in only
   return b->walk_mode == 1;
@@ -437,7 +426,7 @@ bool use_walk(const pgbp_batch* b, int tree) {
 // b->tw_wide messages are split off into ordinary launches (LANES lanes would serialise them); runs of
 // narrower steps in between go to one tile-walk launch each.
 static bool use_tilewalk(const pgbp_batch* b, const Traversal& tv, uint32_t opts) {
-  if (b->tilewalk_mode == 0 || (opts & (PGBP_CAL_RESIDKLDIV | PGBP_CAL_REFORDER)) || tv.tw.empty() || b->group_size > 1) return false;
+  if (b->tilewalk_mode == 0 || (opts & (PGBP_CAL_RESIDKLDIV | PGBP_CAL_REFORDER)) || tv.tw.empty() || b->jb) return false;
   if (b->tilewalk_mode == 1) return true;
   return tv.nsteps >= 24 && (int64_t)tv.msgs.size() < 32 * (int64_t)tv.nsteps;
 }
@@ -500,13 +489,13 @@ int run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_t ref_b
 // (src/clustergraphbeliefs.jl:168-169); with auto, freeze calibrated elements.
 PGBP_HD void iscal_thread(const uint8_t* calflag, int nd, int64_t ld, const int32_t* status, uint8_t* done,
                           int32_t* iscal, int32_t* itertree, int32_t it, int32_t tr, int autostop, int64_t e,
-                          const uint8_t* calflagJ, int64_t gs) {
+                          const uint8_t* calflagJ, int64_t ldJ, int64_t gs) {
   if (done && done[e]) return;  // frozen: keeps its (true) result
   int ok = status[e] == 0;
   for (int d = 0; d < nd && ok; d++) ok = calflag[(int64_t)d * ld + e] != 0;
-  if (gs > 1) {  // shared-precision mode: the J part of every flag lives in the group leader's column
-    const int64_t ej = e - e % gs;
-    for (int d = 0; d < nd && ok; d++) ok = calflagJ[(int64_t)d * ld + ej] != 0;
+  if (calflagJ) {  // shared-precision batches: the J part of every flag is the group's (jb->calflag)
+    const int64_t g = e / gs;
+    for (int d = 0; d < nd && ok; d++) ok = calflagJ[(int64_t)d * ldJ + g] != 0;
   }
   iscal[e] = ok;
   if (ok) {
@@ -521,22 +510,24 @@ PGBP_HD void iscal_thread(const uint8_t* calflag, int nd, int64_t ld, const int3
 #ifndef PGBP_HOST_EMUL
 __global__ void k_iscal(const uint8_t* calflag, int nd, int64_t e0, int64_t B, int64_t ld, const int32_t* status,
                         uint8_t* done, int32_t* iscal, int32_t* itertree, int32_t it, int32_t tr, int autostop,
-                        const uint8_t* calflagJ, int64_t gs) {
+                        const uint8_t* calflagJ, int64_t ldJ, int64_t gs) {
   const int64_t e = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= B) return;
-  iscal_thread(calflag, nd, ld, status, done, iscal, itertree, it, tr, autostop, e, calflagJ, gs);
+  iscal_thread(calflag, nd, ld, status, done, iscal, itertree, it, tr, autostop, e, calflagJ, ldJ, gs);
 }
 #endif
 
-static int launch_iscal(pgbp_batch* b, int it, int tr, int autostop) {
+int launch_iscal(pgbp_batch* b, int it, int tr, int autostop) {
   const int nd = 2 * b->plan->nsepsets;
   const int64_t e0 = b->chunk_begin, e1 = b->chunk_end > 0 ? b->chunk_end : b->B;
+  const uint8_t* fJ = b->jb ? b->jb->calflag : nullptr;
+  const int64_t ldJ = b->jb ? b->jb->ld : 0;
 #ifdef PGBP_HOST_EMUL
   for (int64_t e = e0; e < e1; e++)
-    iscal_thread(b->calflag, nd, b->ld, b->status, b->done, b->iscal, b->itertree, it, tr, autostop, e, b->calflagJ, b->group_size);
+    iscal_thread(b->calflag, nd, b->ld, b->status, b->done, b->iscal, b->itertree, it, tr, autostop, e, fJ, ldJ, b->group_size);
 #else
   k_iscal<<<(unsigned)((e1 - e0 + 255) / 256), 256, 0, b->stream>>>(b->calflag, nd, e0, e1, b->ld, b->status, b->done,
-                                                                     b->iscal, b->itertree, it, tr, autostop, b->calflagJ,
+                                                                     b->iscal, b->itertree, it, tr, autostop, fJ, ldJ,
                                                                      b->group_size);
 #endif
   b->launches++;
@@ -547,20 +538,21 @@ int integrate_launch(pgbp_batch* b, int belief, double* d_mu_soa, double* d_norm
   const pgbp_plan* p = b->plan;
   if (belief >= p->nclusters) PGBP_TRY(batch_materialize_sepsets(b));
   const int M = p->dim[belief];
-  const int64_t js = p->jslot[belief], hs = p->hslot[belief], gs = p->gslot[belief];
+  const int64_t js = p->jslot[belief], hs = batch_hrow(b, belief), gs = batch_grow(b, belief);
+  const JSide jside = batch_jside(b);
 #ifdef PGBP_HOST_EMUL
   for (int64_t e = 0; e < b->B; e++)
-    integrate_thread<PGBP_MAX_DIM>(b->state, b->status, b->ld, e, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, b->group_size);
+    integrate_thread<PGBP_MAX_DIM>(b->state, b->status, b->ld, e, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, jcolumn(jside, e), jside.ld);
 #else
   const unsigned grid = (unsigned)((b->B + 127) / 128);
   if (M <= 4)
-    k_integrate<4><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, b->group_size);
+    k_integrate<4><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, jside);
   else if (M <= 12)
-    k_integrate<12><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, b->group_size);
+    k_integrate<12><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, jside);
   else if (M <= 32)
-    k_integrate<32><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, b->group_size);
+    k_integrate<32><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, jside);
   else
-    k_integrate<PGBP_MAX_DIM><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, b->group_size);
+    k_integrate<PGBP_MAX_DIM><<<grid, 128, 0, b->stream>>>(b->state, b->status, b->B, b->ld, js, hs, gs, M, d_mu_soa, d_norm, ld_out, d_cov_soa, jside);
 #endif
   b->launches++;
   return check_launch("k_integrate");
@@ -676,7 +668,10 @@ static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int
         const uint32_t sepzero = (lazy && it == 1 && j == 0) ? PGBP_OPT_SEPZERO : 0u;
         const int t = ids[j];
         const int n = (int)p->trees[t].parent.size();
-        if (use_walk(b, t) && !(opts & (PGBP_CAL_RESIDKLDIV | PGBP_CAL_REFORDER))) {
+        if (b->jb) {  // shared-precision batch: group pass (J, factor cache) + element pass (h, g) per traversal
+          if (flags & PGBP_CAL_POSTORDER) { PGBP_TRY(shared_run_traversal(b, t, 0, opts, ref)); ref += n; }
+          if (flags & PGBP_CAL_PREORDER) { PGBP_TRY(shared_run_traversal(b, t, 1, opts, ref)); ref += n; }
+        } else if (use_walk(b, t) && !(opts & (PGBP_CAL_RESIDKLDIV | PGBP_CAL_REFORDER))) {
           const bool po = flags & PGBP_CAL_POSTORDER, pr = flags & PGBP_CAL_PREORDER;
           const int first = po ? 0 : n, count = (po ? n : 0) + (pr ? n : 0);
           PGBP_TRY(run_walk(b, t, first, count, opts, ref, autostop));
@@ -696,7 +691,7 @@ static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int
   // (threads per launch ~ B x messages per step) and the chunks stay >= 8192 elements
   int nchunk = 1;
 #ifndef PGBP_HOST_EMUL
-  if (b->group_size > 1) nchunk = 1;  // chunks on different streams would race on the shared J rows
+  if (b->jb) nchunk = 1;  // shared-precision batches: the group pass is not chunked
   else if (b->pipeline > 1) nchunk = b->pipeline;
   else if (b->pipeline < 0) {
     int64_t nmsg = 0, nlaunch = 0;
@@ -841,6 +836,7 @@ int32_t pgbp_propagate(pgbp_batch* b, int32_t from_cluster, int32_t sepset, int3
   PGBP_TRY(p->make_msg(from_cluster, j, to_cluster, &md));  // the plan is immutable: no table ever grows here
   PGBP_TRY(set_device(b->device));
   PGBP_TRY(batch_materialize_sepsets(b));
+  if (b->jb) return shared_propagate(b, md, flags & PGBP_CAL_RESIDNORM, 0x3ffff0);
   PGBP_TRY(h2d(b->d_one, &md, sizeof md, b->stream));
   PGBP_TRY(stream_sync(b->stream));  // md is a stack object
   LaunchGroup g;

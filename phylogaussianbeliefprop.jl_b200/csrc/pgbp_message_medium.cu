@@ -136,8 +136,7 @@ static int launch_smem_tile(pgbp_batch* b, const MsgArgs& a, int nmsg, int I, in
 int launch_medium(pgbp_batch* b, const MsgArgs& a, int n, int I, int S) {
   const int M = I + S;
   int rc = 0;
-  // shared-precision mode: only the register / generic / copy bodies know about group leaders
-  const int mode = b->group_size > 1 ? 0 : b->coop_mode;
+  const int mode = b->coop_mode;
   const bool fits = I <= 32 && sizeof(double) * 32 * (size_t)(I * (I + 1) / 2 + I * S + I) + 4 * (size_t)(M * (M + 3) / 2 + S * (S + 3) / 2 + 2) <= PGBP_SMEM_LIMIT;
   // large I (C5: p = 16): one or two single-warp tiles per SM are latency-bound; share the tile among warps
   const bool fits_mw = I >= 12 && I <= 16 && mw_bytes(I, S, 8) <= PGBP_SMEM_MW_LIMIT;
@@ -181,8 +180,6 @@ int launch_medium(pgbp_batch* b, const MsgArgs& a, int n, int I, int S) {
     else if (M <= 24) rc = launch_coop<24, 8>(b, a, n);
     else if (M <= 32) rc = launch_coop<32, 8>(b, a, n);
     else rc = launch_coop<48, 16>(b, a, n);  // 16 lanes per element: 2 elements per warp (half sectors)
-  } else if (b->group_size > 1) {
-    rc = (M <= 32) ? launch_message<-1, -1, 32, true>(b, a, n) : launch_message<-1, -1, 64, true>(b, a, n);
   } else if (M <= 32) {
     rc = launch_message<-1, -1, 32>(b, a, n);
   } else {

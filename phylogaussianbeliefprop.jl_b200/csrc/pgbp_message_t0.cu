@@ -1,18 +1,11 @@
 // One third of the register-resident message kernels (see pgbp_msg_t0.cuh).  -DPGBP_T0_PART=0: i in 1..3,
-// 1: i in 4..6, 2: i in 7..12.  -DPGBP_T0_SHARED=1: the shared-precision instantiations of the same shapes.
+// 1: i in 4..6, 2: i in 7..12.
 #include "pgbp_msg_t0.cuh"
 
 #ifndef PGBP_T0_PART
 #error "compile with -DPGBP_T0_PART=0|1|2"
 #endif
-#ifndef PGBP_T0_SHARED
-#define PGBP_T0_SHARED 0
-#endif
-#if PGBP_T0_SHARED
-#define PGBP_FN(n) launch_t0s_part##n
-#else
 #define PGBP_FN(n) launch_t0_part##n
-#endif
 #if PGBP_T0_PART == 0
 #define PGBP_PART_LO 1
 #define PGBP_PART_HI 3
@@ -32,7 +25,7 @@ namespace pgbp {
 template <int I_, int S_>
 static int try_shape(pgbp_batch* b, const MsgArgs& a, int nmsg, int ci, int cs) {
   if constexpr (I_ >= PGBP_PART_LO && I_ <= PGBP_PART_HI) {
-    if (ci == I_ && cs == S_) return launch_message<I_, S_, 0, (PGBP_T0_SHARED != 0)>(b, a, nmsg);
+    if (ci == I_ && cs == S_) return launch_message<I_, S_, 0>(b, a, nmsg);
   }
   return PGBP_NOT_MINE;
 }

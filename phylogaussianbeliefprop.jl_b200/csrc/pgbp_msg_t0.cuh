@@ -13,26 +13,26 @@ namespace pgbp {
 #ifndef PGBP_MSG_MINBLOCKS
 #define PGBP_MSG_MINBLOCKS 1  // measured on C2 (B200): 1 -> 0.641 of HBM roofline, 2 -> 0.641, 3 -> 0.594, 4 -> 0.548
 #endif
-template <int CI, int CS, int MAXM, bool SH = false>
+template <int CI, int CS, int MAXM>
 __global__ void __launch_bounds__(PGBP_MSG_THREADS, (CI >= 0 ? PGBP_MSG_MINBLOCKS : 1)) k_message(MsgArgs a) {
   const int64_t e = a.e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.B) return;
-  if constexpr (CI >= 0) message_thread_t0<CI, CS, SH>(a, blockIdx.y, e);
-  else message_thread_rt<MAXM, SH>(a, blockIdx.y, e);
+  if constexpr (CI >= 0) message_thread_t0<CI, CS>(a, blockIdx.y, e);
+  else message_thread_rt<MAXM>(a, blockIdx.y, e);
 }
 #endif
 
-template <int CI, int CS, int MAXM, bool SH = false>
+template <int CI, int CS, int MAXM>
 static inline int launch_message(pgbp_batch* b, const MsgArgs& a, int nmsg) {
 #ifdef PGBP_HOST_EMUL
   for (int m = 0; m < nmsg; m++)
     for (int64_t e = a.e0; e < a.B; e++) {
-      if constexpr (CI >= 0) message_thread_t0<CI, CS, SH>(a, m, e);
-      else message_thread_rt<MAXM, SH>(a, m, e);
+      if constexpr (CI >= 0) message_thread_t0<CI, CS>(a, m, e);
+      else message_thread_rt<MAXM>(a, m, e);
     }
 #else
   dim3 grid((unsigned)((a.B - a.e0 + PGBP_MSG_THREADS - 1) / PGBP_MSG_THREADS), (unsigned)nmsg);
-  k_message<CI, CS, MAXM, SH><<<grid, PGBP_MSG_THREADS, 0, b->stream>>>(a);
+  k_message<CI, CS, MAXM><<<grid, PGBP_MSG_THREADS, 0, b->stream>>>(a);
 #endif
   b->launches++;
   return check_launch("k_message");
@@ -44,10 +44,6 @@ static inline int launch_message(pgbp_batch* b, const MsgArgs& a, int nmsg) {
 int launch_t0_part0(pgbp_batch* b, const MsgArgs& a, int nmsg, int ci, int cs);
 int launch_t0_part1(pgbp_batch* b, const MsgArgs& a, int nmsg, int ci, int cs);
 int launch_t0_part2(pgbp_batch* b, const MsgArgs& a, int nmsg, int ci, int cs);
-// the same shapes compiled for shared-precision batches (-DPGBP_T0_SHARED=1)
-int launch_t0s_part0(pgbp_batch* b, const MsgArgs& a, int nmsg, int ci, int cs);
-int launch_t0s_part1(pgbp_batch* b, const MsgArgs& a, int nmsg, int ci, int cs);
-int launch_t0s_part2(pgbp_batch* b, const MsgArgs& a, int nmsg, int ci, int cs);
 // medium / large shapes (pgbp_message_medium.cu): shared-memory, cooperative or generic kernel
 int launch_medium(pgbp_batch* b, const MsgArgs& a, int nmsg, int I, int S);
 

@@ -1,0 +1,530 @@
+// Shared-precision batches: message passing in two kernels.
+//
+// In the reference only h and g of a message depend on the data (src/beliefupdates.jl:77-81): trait replicates under
+// one parameter vector have the same J in every belief at every step.  A shared-precision batch therefore keeps the
+// J rows once per GROUP (pgbp_batch::jb: an ordinary batch with one element per group) and only h, g per element
+// (compact rows, pgbp_internal.h).  One message F -> T through sepset S is then
+//
+//   k_jmsg  one WARP per (message, group): gathers J_F in [I;K] order into shared memory, right-looking U'U of the
+//           integrated block, Schur complement, divide / multiply / residual / flag of the J part, and leaves the
+//           factor record   [info | logdet | 1/U_kk (I) | rows k < I of the scaled factor: U_k,k+1.. and Z_k,.]
+//           in the traversal's cache;
+//   k_hmsg  one THREAD per (message, element): w = U^-T h_I by forward substitution with the cached rows,
+//           h_K - Z'w, g + (I log 2pi - logdet + w'w)/2, divide / multiply / residual / flag of the h part.
+//
+// Per element and message only 8 (m_F + 1 + 4 (s + 1) + s) bytes move and I^2/2 + I S fused multiply-adds are spent
+// instead of the I^3/3 + .. of the factorisation.  Every entry sees the same operations in the same order as in the
+// register kernels (message_thread_t0): results are bit-identical to an ordinary batch given the same inputs
+// (tests/test_parity.py::test_shared_precision_batch_is_bit_identical).
+#include <algorithm>
+
+#include "pgbp_kernels.cuh"
+#include "pgbp_launch.h"
+#include "pgbp_shapes.h"
+
+namespace pgbp {
+
+struct JArgs {
+  const MsgDesc* msgs;       // plan numbering (the group batch's own descriptors)
+  const int32_t* tab;
+  double* state;             // group batch: J rows live here
+  double* resid;             // may be null
+  uint8_t* calflag;          // may be null: J part of the calibration flags
+  int32_t* status;           // per group
+  int64_t ld, G;
+  double* cache;             // [G][stride]
+  const int64_t* cache_off;  // per message of the launch's descriptor array
+  int64_t stride;
+  uint32_t opts;
+  int32_t ref_base;
+};
+
+struct HArgs {
+  const MsgDesc* msgs;       // h / g rows remapped to the compact element numbering
+  const int32_t* tab;
+  double* state;             // element array: h, g rows
+  double* resid;             // may be null (dh rows)
+  uint8_t* calflag;          // may be null: h part of the calibration flags
+  int32_t* status;           // per element
+  int64_t B, ld, gs;
+  const double* cache;
+  const int64_t* cache_off;
+  int64_t stride;
+  uint32_t opts;
+  int32_t ref_base;
+};
+
+PGBP_HD int64_t jrec_len(int I, int S) { return I == 0 ? 0 : 2 + I + (int64_t)I * (I + S) - (int64_t)I * (I + 1) / 2; }
+
+// the lanes that share one (message, group): a warp on the device, a single "lane" in the host emulation
+struct OneLane {
+  static constexpr int n = 1;
+  int lane = 0;
+  PGBP_HD void sync() const {}
+  PGBP_HD bool all(bool p) const { return p; }
+  PGBP_HD double maxnan(double x) const { return x; }
+};
+#ifndef PGBP_HOST_EMUL
+struct WarpLanes {
+  static constexpr int n = 32;
+  int lane;
+  __device__ void sync() const { __syncwarp(); }
+  __device__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
+  __device__ double maxnan(double x) const {  // NaN-propagating maximum over the warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double y = __shfl_xor_sync(0xffffffffu, x, o);
+      x = (x != x || y != y) ? NAN : (y > x ? y : x);
+    }
+    return x;
+  }
+};
+#endif
+
+// J part of one message for one group.  A: tri(mF) doubles shared by the lanes.
+template <class W>
+PGBP_HD void jmsg_body(const JArgs& a, int mi, int64_t g, const W& w, double* A) {
+  const MsgDesc md = a.msgs[mi];
+  if (a.status[g] != 0) return;  // the group failed earlier: its J stops moving (uniform over the lanes)
+  const int I = md.mF - md.s, S = md.s, M = md.mF;
+  const int SM = tri(M);
+  const int64_t ld = a.ld;
+  double* st = a.state + g;
+  const int32_t* __restrict__ gat = a.tab + md.gat;
+  const int32_t* __restrict__ sca = a.tab + md.sca;
+  double* rec = I > 0 ? a.cache + g * a.stride + a.cache_off[mi] : nullptr;
+  for (int q = w.lane; q < SM; q += W::n) A[q] = st[(md.fJ + gat[q]) * ld];
+  w.sync();
+  if (I > 0) {
+    bool z = true;  // "Ji = Jki = 0", src/beliefupdates.jl:62-66 (the h_I part of the test is the elements')
+    for (int c = 0; c < M; c++) {
+      const int rmax = c < I ? c + 1 : I;
+      for (int r = w.lane; r < rmax; r += W::n)
+        if (!(fabs(A[pk(r, c)]) <= PGBP_EPS)) z = false;
+    }
+    if (!w.all(z)) {
+      double logdet = 0.0;
+      for (int k = 0; k < I; k++) {
+        const double d = A[pk(k, k)];
+        if (!(d > 0.0)) {  // LAPACK potrf: info = k+1 (also catches NaN); every element of the group fails here
+          if (w.lane == 0) {
+            status_fail(a.status, g, PGBP_STATUS(a.ref_base + md.ref, k + 1));
+            rec[0] = (double)(k + 1);
+          }
+          return;
+        }
+        logdet += log(d);
+        const double rinv = 1.0 / sqrt(d);
+        for (int c = k + 1 + w.lane; c < M; c += W::n) A[pk(k, c)] *= rinv;
+        if (w.lane == 0) rec[2 + k] = rinv;
+        w.sync();
+        for (int c = k + 1; c < M; c++) {
+          const double akc = A[pk(k, c)];
+          for (int r = k + 1 + w.lane; r <= c; r += W::n) A[pk(r, c)] = nfma(A[pk(k, r)], akc, A[pk(r, c)]);
+        }
+        w.sync();
+      }
+      if (w.lane == 0) { rec[0] = 0.0; rec[1] = logdet; }
+      int64_t off = 2 + I;
+      for (int k = 0; k < I; k++) {
+        for (int c = k + 1 + w.lane; c < M; c += W::n) rec[off + (c - k - 1)] = A[pk(k, c)];
+        off += M - 1 - k;
+      }
+    } else if (w.lane == 0) {
+      rec[0] = -1.0;  // shortcut: the message is (J_KK, h_K, g) as they are
+    }
+  }
+  // divide! / mult! / residual of the J part (src/beliefupdates.jl:579-587, 483-488, 646-647)
+  double* rs = a.resid ? a.resid + g : nullptr;
+  double maxJ = 0.0;
+  for (int c = 0; c < S; c++)
+    for (int r = w.lane; r <= c; r += W::n) {
+      const int q = pk(r, c);
+      const double nv = A[pk(I + r, I + c)];
+      double* sp = st + (md.sJ + q) * ld;
+      double* tp = st + (md.tJ + sca[q]) * ld;
+      const double d = nv - *sp;
+      *sp = nv;
+      *tp = *tp + d;
+      if (rs) rs[(md.rJ + q) * ld] = d;
+      absmax(maxJ, d);
+    }
+  maxJ = w.maxnan(maxJ);
+  if (w.lane == 0 && (a.opts & PGBP_CAL_RESIDNORM) && a.calflag)
+    a.calflag[(int64_t)md.dmsg * ld + g] = (S > 0 ? (maxJ / (double)S <= 1e-5) : true) ? 1 : 0;
+}
+
+// h, g part of one message for one element.  CI >= 0: compile-time integrated dimension (w in registers);
+// CI < 0: runtime (thread-local array).
+#define PGBP_HMSG_CHUNK 4
+template <int CI>
+PGBP_HD void hmsg_thread(const HArgs& a, int mi, int64_t e) {
+  const MsgDesc md = a.msgs[mi];
+  if (a.status[e] != 0) return;
+  const int I = CI >= 0 ? CI : md.mF - md.s, S = md.s, M = I + S;
+  const int64_t ld = a.ld;
+  double* st = a.state + e;
+  double* rs = a.resid ? a.resid + e : nullptr;
+  const int32_t* __restrict__ gat = a.tab + md.gat + tri(M);  // sender positions of [I;K]
+  const int32_t* __restrict__ sca = a.tab + md.sca + tri(S);  // receiver positions of the sepset's variables
+  double g = st[md.fg * ld];
+  const double sg_old = st[md.sg * ld], tg_old = st[md.tg * ld];
+  double hI[CI > 0 ? CI : (CI == 0 ? 1 : PGBP_MAX_DIM)];
+  const double* __restrict__ rec = nullptr;
+  bool zeroZ = true;
+  if (I > 0) {
+    rec = a.cache + (e / a.gs) * a.stride + a.cache_off[mi];
+#pragma unroll
+    for (int k = 0; k < I; k++) hI[k] = st[(md.fh + gat[k]) * ld];
+    const double info = rec[0];
+    if (info > 0.0) {  // the factorisation of the group's J_I failed at this pivot
+      status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, (int)info));
+      return;
+    }
+    if (info < 0.0) {  // J_I = J_IK = 0: the message is the kept part unchanged -- if this element's h_I is 0 too
+      bool hz = true;
+#pragma unroll
+      for (int k = 0; k < I; k++)
+        if (!(fabs(hI[k]) <= PGBP_EPS)) hz = false;
+      if (!hz) {  // the reference would factorise a zero matrix here
+        status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, 1));
+        return;
+      }
+    } else {
+      zeroZ = false;
+      double ww = 0.0;
+      const double* row = rec + 2 + I;
+#pragma unroll
+      for (int k = 0; k < I; k++) {
+        const double wk = hI[k] * rec[2 + k];
+        hI[k] = wk;
+        ww = fma(wk, wk, ww);
+#pragma unroll
+        for (int c = k + 1; c < I; c++) hI[c] = nfma(row[c - k - 1], wk, hI[c]);
+        row += M - 1 - k;
+      }
+      g += 0.5 * ((double)I * PGBP_LOG2PI - rec[1] + ww);
+    }
+  }
+  double maxh = 0.0;
+  for (int k0 = 0; k0 < S; k0 += PGBP_HMSG_CHUNK) {
+    double nv[PGBP_HMSG_CHUNK], so[PGBP_HMSG_CHUNK], to[PGBP_HMSG_CHUNK];
+    double* tp[PGBP_HMSG_CHUNK];
+#pragma unroll
+    for (int j = 0; j < PGBP_HMSG_CHUNK; j++)
+      if (k0 + j < S) {
+        tp[j] = st + (md.th + sca[k0 + j]) * ld;
+        nv[j] = st[(md.fh + gat[I + k0 + j]) * ld];
+        so[j] = st[(md.sh + k0 + j) * ld];
+        to[j] = *tp[j];
+      }
+    if (!zeroZ) {
+      const double* row = rec + 2 + I;
+#pragma unroll
+      for (int i = 0; i < I; i++) {
+        const double wi = hI[i];
+#pragma unroll
+        for (int j = 0; j < PGBP_HMSG_CHUNK; j++)
+          if (k0 + j < S) nv[j] = nfma(row[(I - 1 - i) + k0 + j], wi, nv[j]);
+        row += M - 1 - i;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PGBP_HMSG_CHUNK; j++)
+      if (k0 + j < S) {
+        const double d = nv[j] - so[j];
+        st[(md.sh + k0 + j) * ld] = nv[j];
+        *tp[j] = to[j] + d;
+        if (rs) rs[(md.rh + k0 + j) * ld] = d;
+        absmax(maxh, d);
+      }
+  }
+  st[md.sg * ld] = g;
+  st[md.tg * ld] = tg_old + (g - sg_old);
+  if ((a.opts & PGBP_CAL_RESIDNORM) && a.calflag)
+    a.calflag[(int64_t)md.dmsg * ld + e] = (S > 0 ? (maxh / sqrt((double)S) <= 1e-5) : true) ? 1 : 0;
+}
+
+#ifndef PGBP_HOST_EMUL
+__global__ void __launch_bounds__(32) k_jmsg(JArgs a) {
+  extern __shared__ double jA[];
+  const WarpLanes w{(int)threadIdx.x};
+  for (int64_t g = blockIdx.y; g < a.G; g += gridDim.y) {
+    jmsg_body(a, blockIdx.x, g, w, jA);
+    __syncwarp();
+  }
+}
+template <int CI>
+__global__ void __launch_bounds__(128) k_hmsg(HArgs a) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.B) return;
+  hmsg_thread<CI>(a, blockIdx.y, e);
+}
+#endif
+
+static int launch_jmsg(pgbp_batch* b, JArgs a, int nmsg, int maxM) {
+  pgbp_batch* jb = b->jb;
+  int done = 0;
+  while (done < nmsg) {
+    const int n = std::min(nmsg - done, 1 << 30);
+    JArgs c = a;
+    c.msgs = a.msgs + done;
+    c.cache_off = a.cache_off + done;
+#ifdef PGBP_HOST_EMUL
+    std::vector<double> A((size_t)tri(maxM) + 1);
+    for (int m = 0; m < n; m++)
+      for (int64_t g = 0; g < c.G; g++) jmsg_body(c, m, g, OneLane{}, A.data());
+#else
+    dim3 grid((unsigned)n, (unsigned)std::min<int64_t>(c.G, 65535));
+    k_jmsg<<<grid, 32, sizeof(double) * (size_t)(tri(maxM) + 1), jb->stream>>>(c);
+#endif
+    b->launches++;
+    PGBP_TRY(check_launch("k_jmsg"));
+    done += n;
+  }
+  return 0;
+}
+
+template <int CI>
+static int launch_hmsg_t(pgbp_batch* b, const HArgs& a, int nmsg) {
+#ifdef PGBP_HOST_EMUL
+  for (int m = 0; m < nmsg; m++)
+    for (int64_t e = 0; e < a.B; e++) hmsg_thread<CI>(a, m, e);
+#else
+  dim3 grid((unsigned)((a.B + 127) / 128), (unsigned)nmsg);
+  k_hmsg<CI><<<grid, 128, 0, b->stream>>>(a);
+#endif
+  b->launches++;
+  return check_launch("k_hmsg");
+}
+
+static int launch_hmsg(pgbp_batch* b, HArgs a, int nmsg, int I) {
+  int done = 0;
+  while (done < nmsg) {
+    const int n = std::min(nmsg - done, 65535);
+    HArgs c = a;
+    c.msgs = a.msgs + done;
+    c.cache_off = a.cache_off + done;
+    int rc;
+    switch (I) {
+#define PGBP_H_CASE(I_) case I_: rc = launch_hmsg_t<I_>(b, c, n); break;
+      PGBP_H_CASE(0) PGBP_H_CASE(1) PGBP_H_CASE(2) PGBP_H_CASE(3) PGBP_H_CASE(4) PGBP_H_CASE(5) PGBP_H_CASE(6)
+      PGBP_H_CASE(7) PGBP_H_CASE(8) PGBP_H_CASE(9) PGBP_H_CASE(10) PGBP_H_CASE(11) PGBP_H_CASE(12) PGBP_H_CASE(16)
+      PGBP_H_CASE(24) PGBP_H_CASE(32)
+#undef PGBP_H_CASE
+      default: rc = launch_hmsg_t<-1>(b, c, n);
+    }
+    PGBP_TRY(rc);
+    done += n;
+  }
+  return 0;
+}
+
+static JArgs make_jargs(pgbp_batch* b, uint32_t opts, int32_t ref_base) {
+  pgbp_batch* jb = b->jb;
+  JArgs a;
+  a.msgs = nullptr;
+  a.tab = jb->d_tab;
+  a.state = jb->state;
+  a.resid = jb->resid;
+  a.calflag = jb->calflag;
+  a.status = jb->status;
+  a.ld = jb->ld;
+  a.G = b->ngroups;
+  a.cache = nullptr;
+  a.cache_off = nullptr;
+  a.stride = 0;
+  a.opts = opts;
+  a.ref_base = ref_base;
+  return a;
+}
+static HArgs make_hargs(pgbp_batch* b, uint32_t opts, int32_t ref_base) {
+  HArgs a;
+  a.msgs = nullptr;
+  a.tab = b->d_tab;
+  a.state = b->state;
+  a.resid = b->resid;
+  a.calflag = b->calflag;
+  a.status = b->status;
+  a.B = b->B;
+  a.ld = b->ld;
+  a.gs = b->group_size;
+  a.cache = nullptr;
+  a.cache_off = nullptr;
+  a.stride = 0;
+  a.opts = opts;
+  a.ref_base = ref_base;
+  return a;
+}
+
+// the group batch runs on the element batch's stream (one stream, program order: group pass, element pass)
+static void adopt_stream(pgbp_batch* b) { b->jb->stream = b->stream; }
+
+int shared_run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_t ref_base) {
+  const Traversal& tv = b->plan->trees[tree].trav[dir];
+  const int td = 2 * tree + dir;
+  if (tv.msgs.empty()) return 0;
+  adopt_stream(b);
+  JArgs ja = make_jargs(b, opts, ref_base);
+  ja.msgs = b->jb->d_msgs[td];
+  ja.cache = b->jcache[td];
+  ja.cache_off = b->d_jcache_off[td];
+  ja.stride = b->jcache_len[td];
+  // group pass: one launch per step (messages of a step touch disjoint beliefs)
+  for (int s = 0; s < tv.nsteps; s++) {
+    const int first = tv.step_off[s], count = tv.step_off[s + 1] - first;
+    if (count <= 0) continue;
+    int maxM = 0;
+    for (int k = first; k < first + count; k++) maxM = std::max(maxM, tv.msgs[k].mF);
+    JArgs c = ja;
+    c.msgs = ja.msgs + first;
+    c.cache_off = ja.cache_off + first;
+    PGBP_TRY(launch_jmsg(b, c, count, maxM));
+  }
+  // element pass: the plan's launch groups (same step, same shape class)
+  HArgs ha = make_hargs(b, opts, ref_base);
+  ha.cache = b->jcache[td];
+  ha.stride = b->jcache_len[td];
+  for (const LaunchGroup& g : tv.groups) {
+    HArgs c = ha;
+    c.msgs = b->d_msgs[td] + g.first;
+    c.cache_off = b->d_jcache_off[td] + g.first;
+    PGBP_TRY(launch_hmsg(b, c, g.count, g.ci >= 0 ? g.ci : g.maxm));
+    if (opts & PGBP_CAL_RESIDKLDIV) {
+      MsgArgs ma = make_args(b, opts, ref_base, false);
+      PGBP_TRY(launch_kldiv(b, ma, b->d_msgs[td], g));
+    }
+  }
+  return 0;
+}
+
+int shared_propagate(pgbp_batch* b, const MsgDesc& md_plan, uint32_t opts, int32_t ref_base) {
+  adopt_stream(b);
+  pgbp_batch* jb = b->jb;
+  const MsgDesc mh = shared_remap(b, md_plan);
+  PGBP_TRY(h2d(jb->d_one, &md_plan, sizeof(MsgDesc), b->stream));
+  PGBP_TRY(h2d(b->d_one, &mh, sizeof(MsgDesc), b->stream));
+  JArgs ja = make_jargs(b, b->jb->calflag ? opts : (opts & ~PGBP_CAL_RESIDNORM), ref_base);
+  ja.msgs = jb->d_one;
+  ja.cache = b->jcache_one;
+  ja.cache_off = b->d_zero64;
+  ja.stride = jrec_len(PGBP_MAX_DIM, 0) + (int64_t)PGBP_MAX_DIM * PGBP_MAX_DIM;
+  PGBP_TRY(launch_jmsg(b, ja, 1, md_plan.mF));
+  HArgs ha = make_hargs(b, b->calflag ? opts : (opts & ~PGBP_CAL_RESIDNORM), ref_base);
+  ha.msgs = b->d_one;
+  ha.cache = b->jcache_one;
+  ha.cache_off = b->d_zero64;
+  ha.stride = ja.stride;
+  PGBP_TRY(launch_hmsg(b, ha, 1, md_plan.mF - md_plan.s));
+  return stream_sync(b->stream);  // the descriptors are stack objects
+}
+
+MsgDesc shared_remap(const pgbp_batch* b, const MsgDesc& m) {
+  const pgbp_plan* p = b->plan;
+  auto belief_of = [&](int64_t hslot) {
+    return (int)(std::lower_bound(p->hslot.begin(), p->hslot.end(), hslot) - p->hslot.begin());
+  };
+  const int f = belief_of(m.fh), s = belief_of(m.sh), t = belief_of(m.th);
+  MsgDesc r = m;
+  r.fh = b->eh[f]; r.fg = b->eh[f] + p->dim[f];
+  r.sh = b->eh[s]; r.sg = b->eh[s] + p->dim[s];
+  r.th = b->eh[t]; r.tg = b->eh[t] + p->dim[t];
+  r.rh = b->erh[m.dmsg];
+  return r;
+}
+
+template <class T>
+static int salloc(pgbp_batch* b, T** p, size_t n) {
+  void* v = nullptr;
+  PGBP_TRY(dev_malloc(&v, std::max<size_t>(1, n) * sizeof(T)));
+  *p = (T*)v;
+  b->device_bytes += (int64_t)(n * sizeof(T));
+  return 0;
+}
+
+// Element side of a shared-precision batch (the caller has set plan, B, ld, group_size, device, flags, stream):
+// compact layout, descriptors, caches, and the group batch.
+int shared_create(pgbp_batch* b) {
+  const pgbp_plan* p = b->plan;
+  b->ngroups = b->B / b->group_size;
+  b->eh.resize(p->nbeliefs);
+  int64_t row = 0;
+  for (int i = 0; i < p->nbeliefs; i++) {
+    if (i == p->nclusters) b->nrows_efactor = row;
+    b->eh[i] = row;
+    row += p->dim[i] + 1;
+  }
+  if (p->nsepsets == 0) b->nrows_efactor = row;
+  b->nrows_e = row;
+  b->erh.resize(2 * (size_t)p->nsepsets);
+  row = 0;
+  for (int d = 0; d < 2 * p->nsepsets; d++) { b->erh[d] = row; row += p->dim[p->nclusters + d / 2]; }
+  b->nrows_eresid = row;
+  const size_t ld = (size_t)b->ld;
+  PGBP_TRY(salloc(b, &b->state, (size_t)b->nrows_e * ld));
+  PGBP_TRY(dev_memset(b->state, 0, sizeof(double) * (size_t)b->nrows_e * ld, b->stream));
+  if (b->flags & PGBP_BATCH_FACTORS) {
+    PGBP_TRY(salloc(b, &b->factor, (size_t)b->nrows_efactor * ld));
+    PGBP_TRY(dev_memset(b->factor, 0, sizeof(double) * (size_t)b->nrows_efactor * ld, b->stream));
+  }
+  if (b->flags & PGBP_BATCH_RESIDUALS) {
+    const size_t nd = 2 * (size_t)p->nsepsets;
+    PGBP_TRY(salloc(b, &b->resid, std::max<size_t>(1, (size_t)b->nrows_eresid) * ld));
+    PGBP_TRY(dev_memset(b->resid, 0, sizeof(double) * std::max<size_t>(1, (size_t)b->nrows_eresid) * ld, b->stream));
+    PGBP_TRY(salloc(b, &b->kldiv, std::max<size_t>(1, nd) * ld));
+    PGBP_TRY(salloc(b, &b->calflag, std::max<size_t>(1, nd) * ld));
+    PGBP_TRY(salloc(b, &b->iscal, ld));
+    PGBP_TRY(salloc(b, &b->itertree, 2 * ld));
+    PGBP_TRY(dev_memset(b->iscal, 0, sizeof(int32_t) * ld, b->stream));
+    PGBP_TRY(dev_memset(b->itertree, 0, sizeof(int32_t) * 2 * ld, b->stream));
+  }
+  PGBP_TRY(salloc(b, &b->status, ld));
+  PGBP_TRY(dev_memset(b->status, 0, sizeof(int32_t) * ld, b->stream));
+  PGBP_TRY(salloc(b, &b->d_one, 1));
+  PGBP_TRY(batch_upload_tables(b));
+  // descriptors with compact h / g rows, record offsets and caches per traversal
+  const size_t nt = p->trees.size();
+  b->d_msgs.assign(2 * nt, nullptr);
+  b->jcache.assign(2 * nt, nullptr);
+  b->d_jcache_off.assign(2 * nt, nullptr);
+  b->jcache_len.assign(2 * nt, 0);
+  for (size_t t = 0; t < nt; t++)
+    for (int dir = 0; dir < 2; dir++) {
+      const Traversal& tv = p->trees[t].trav[dir];
+      const size_t n = tv.msgs.size();
+      std::vector<MsgDesc> rm(n);
+      std::vector<int64_t> off(n + 1, 0);
+      for (size_t k = 0; k < n; k++) {
+        rm[k] = shared_remap(b, tv.msgs[k]);
+        off[k + 1] = off[k] + jrec_len(tv.msgs[k].mF - tv.msgs[k].s, tv.msgs[k].s);
+      }
+      const size_t td = 2 * t + dir;
+      PGBP_TRY(salloc(b, &b->d_msgs[td], n));
+      PGBP_TRY(h2d(b->d_msgs[td], rm.data(), n * sizeof(MsgDesc), b->stream));
+      PGBP_TRY(salloc(b, &b->d_jcache_off[td], n + 1));
+      PGBP_TRY(h2d(b->d_jcache_off[td], off.data(), (n + 1) * sizeof(int64_t), b->stream));
+      b->jcache_len[td] = off[n];
+      PGBP_TRY(salloc(b, &b->jcache[td], (size_t)off[n] * (size_t)b->ngroups));
+      PGBP_TRY(stream_sync(b->stream));  // rm / off are locals
+    }
+  const int64_t onelen = jrec_len(PGBP_MAX_DIM, 0) + (int64_t)PGBP_MAX_DIM * PGBP_MAX_DIM;
+  PGBP_TRY(salloc(b, &b->jcache_one, (size_t)onelen * (size_t)b->ngroups));
+  PGBP_TRY(salloc(b, &b->d_zero64, 1));
+  PGBP_TRY(dev_memset(b->d_zero64, 0, sizeof(int64_t), b->stream));
+  return stream_sync(b->stream);
+}
+
+void shared_destroy(pgbp_batch* b) {
+  for (auto* q : b->jcache) dev_free(q);
+  for (auto* q : b->d_jcache_off) dev_free(q);
+  dev_free(b->jcache_one);
+  dev_free(b->d_zero64);
+  if (b->jb) {
+    b->jb->stream = 0;  // borrowed from the element batch
+    b->jb->own_stream = false;
+    pgbp_batch_destroy(b->jb);
+    b->jb = nullptr;
+  }
+}
+
+}  // namespace pgbp

@@ -1294,3 +1294,116 @@ def test_lipson_bethe_regularisation_behaviour(backend):
         for c in cgbs:
             assert OBP.calibrate(c, case.sched, 1)[0]
         check_all_beliefs(case, bt, cgbs, tol=TOL)
+
+
+# ------------------------------------------------------------------ shared-precision batches: factored layout, wider coverage
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_shared_precision_layout_memory_and_rows(backend):
+    # J rows once per group: device memory of a shared batch ~ (h, g rows) x B + one group batch, far below an ordinary
+    # batch; pgbp_batch_belief_rows names the compact rows of the device view
+    lib = get_lib(backend)
+    p = 6
+    rng = np.random.default_rng(8)
+    taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
+    A = rng.normal(size=(p, p))
+    R = A @ A.T / p + 0.1 * np.eye(p)
+    B = 512
+    data = rng.normal(size=(B, 7, p))
+    model = M.MvFullBrownianMotion(R, np.zeros(p))
+    case = Case(GOLD["lazaridis"], "cliquetree", data[0], taxa, model, lib, order_hint=GOLD["lazaridis_cluster_labels"])
+    own = pgbp_b200.BatchedClusterGraphBelief(case.plan, B)
+    sh = pgbp_b200.BatchedClusterGraphBelief(case.plan, B, shared_precision_group=B)
+    assert sh.device_bytes() < own.device_bytes() / 4
+    dims = case.plan.belief_dim
+    row = 0
+    for j in range(1, len(dims) + 1):
+        hrow, grow = sh.belief_rows(j)
+        assert (hrow, grow) == (row, row + dims[j - 1])
+        row += dims[j - 1] + 1
+    base, ld, nrows = sh.device_view()
+    assert nrows == row and ld >= B
+    h_own, g_own = own.belief_rows(3)
+    assert (h_own, g_own) == case.plan.belief_slot(2)[1:]
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_shared_precision_large_shapes_and_single_messages(backend):
+    # p = 16 on a small synthetic level-1 network (sender dimensions 16 / 32 / 48: the compile-time I = 16 / 32 element
+    # kernels and the warp-cooperative group kernel on 48 x 48 matrices), and the single-message paths
+    # (propagate_belief!, regularizebeliefs_onschedule!) -- everything bit-identical to an ordinary batch
+    lib = get_lib(backend)
+    import bench
+    w = bench.C5(ntips=60, nretic=6)
+    d = w.d
+    B = 6
+    params, tips = w.inputs(B, 0)
+    plan = pgbp_b200.ClusterGraphPlan(d["nclusters"], d["belief_dim"], d["sepset_clusters"], d["upind"], d["trees"],
+                                      d["ntraits"], d["families"], lib)
+    out = {}
+    for name, group in (("own", 0), ("shared", B)):
+        bt = pgbp_b200.BatchedClusterGraphBelief(plan, B, shared_precision_group=group)
+        bt.assignfactors(params, tips)
+        succ, iscal = bt.calibrate(None, 1)
+        root = d["root_cluster"] + 1
+        rec = dict(succ=succ, iscal=iscal, ll=bt.integratebelief(root)[1], fe=bt.factored_energy(),
+                   b=[bt.get_belief(j) for j in (1, 2, root, plan.nclusters + 1, plan.nclusters + plan.nsepsets)])
+        # one more message by hand over the first tree edge, both directions, then a regularised restart
+        par, chi = d["trees"][0][0][0] + 1, d["trees"][0][1][0] + 1
+        sep = next(plan.nclusters + 1 + j for j, ab in enumerate(plan.sepset_clusters) if set(ab) == {par - 1, chi - 1})
+        bt.propagate_belief(par, sep, chi)
+        bt.propagate_belief(chi, sep, par)
+        rec["p"] = [bt.get_belief(j) for j in (par, chi, sep)]
+        bt.init_beliefs_reset_fromfactors()
+        bt.init_messagecalibrationflags_reset()
+        bt.regularizebeliefs_onschedule()
+        succ2, _ = bt.calibrate(None, 1)
+        rec["r"] = [bt.get_belief(j) for j in (1, root, plan.nclusters + 1)] + [(succ2,)]
+        rec["st"] = bt.status()
+        out[name] = rec
+    a, s_ = out["own"], out["shared"]
+    assert a["succ"].all() and np.array_equal(a["succ"], s_["succ"]) and np.array_equal(a["iscal"], s_["iscal"])
+    assert np.array_equal(a["ll"], s_["ll"]) and np.array_equal(a["fe"], s_["fe"]) and np.array_equal(a["st"], s_["st"])
+    for key in ("b", "p", "r"):
+        for x, y in zip(a[key], s_[key]):
+            for u, v in zip(x, y):
+                assert np.array_equal(u, v), key
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_shared_precision_missing_data_and_ou(backend):
+    # trait-level scopes (missing data: scoped K1 path, all-zero shortcut of marginalize) and the OU model on
+    # shared-precision batches: equal to ordinary batches bit for bit
+    lib = get_lib(backend)
+    m = M.MvDiagBrownianMotion([2, 1], [3, -3], [0.1, 10])
+    case = Case(GOLD["netstr_named"], "cliquetree", TBL, TAXA, m, lib, schedule="spanningtree")
+    B = 4
+    rng = np.random.default_rng(21)
+    data = np.repeat(TBL[None], B, axis=0)
+    data[1:] += 0.2 * rng.normal(size=(B - 1,) + TBL.shape)
+    par = pgbp_b200.bm_params([np.diag([2.0, 1.0])], [3, -3], np.diag([0.1, 10.0]))
+    res = {}
+    for name, group in (("own", 0), ("shared", 2)):
+        bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B, shared_precision_group=group)
+        bt.assignfactors(par, data)
+        succ, _ = bt.calibrate(case.sched)
+        res[name] = (succ, bt.status(), bt.integratebelief(case.sched[0][2][0])[1],
+                     [bt.get_belief(j) for j in range(1, len(case.b) + 1)])
+    assert res["own"][0].all() and np.array_equal(res["own"][1], res["shared"][1])
+    assert np.array_equal(res["own"][2], res["shared"][2])
+    assert abs(res["own"][2][0] / -21.347496753649892 - 1) <= TOL  # test/test_evomodels.jl:190
+    for x, y in zip(res["own"][3], res["shared"][3]):
+        for u, v in zip(x, y):
+            assert np.array_equal(u, v, equal_nan=True)
+    # OU, one trait
+    tbl = TBL[:, [1]]
+    model = M.UnivariateOrnsteinUhlenbeck(2.0, 3.0, -2.0, 0.0, 0.4)
+    case = Case(GOLD["netstr_named"], "cliquetree", tbl, TAXA, model, lib, schedule="spanningtree")
+    data = np.stack([tbl, tbl + 0.25, 2 * tbl, tbl - 1])
+    res = {}
+    for name, group in (("own", 0), ("shared", 4)):
+        bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, 4, shared_precision_group=group)
+        bt.assignfactors_ou([[2.0, 3.0, -2.0, 0.0, 0.4]], data)
+        assert bt.calibrate(case.sched)[0].all()
+        res[name] = (bt.integratebelief(case.sched[0][2][0])[1], bt.factored_energy())
+    assert np.array_equal(res["own"][0], res["shared"][0]) and np.array_equal(res["own"][1], res["shared"][1])
+    assert abs(res["own"][0][0] / -42.31401134496844 - 1) <= TOL
