@@ -95,7 +95,8 @@ def calibrate_exact_cliquetree(plan_improper: ClusterGraphPlan, plan_fixed: Clus
 
 def _bm_transforms(model, p, v):
     """params_optimize / params_original of the Brownian-motion models
-    (src/evomodels/homogeneousbrownianmotion.jl:48-49, 89-90): log-rates and root means."""
+    (src/evomodels/homogeneousbrownianmotion.jl:48-49, 89-90, 130-159): log-rates (log-Cholesky factor for the full
+    multivariate model) and root means."""
     V = np.zeros((p, p)) if v is None else np.atleast_2d(np.asarray(v, dtype=float))
     if model == "UnivariateBrownianMotion":
         if p != 1:
@@ -105,7 +106,23 @@ def _bm_transforms(model, p, v):
     if model == "MvDiagBrownianMotion":
         return (lambda R, mu: np.concatenate([np.log(np.asarray(R, float)), np.asarray(mu, float)]),
                 lambda th: bm_params([np.exp(th[:p])], th[p:], V))
-    raise ValueError("model must be UnivariateBrownianMotion or MvDiagBrownianMotion")
+    if model == "MvFullBrownianMotion":
+        # log-Cholesky parametrisation (src/evomodels/homogeneousbrownianmotion.jl:130-159): R = U'U, the log of
+        # U's diagonal first, then the entries above the diagonal column by column, then the root mean
+        iu = [(i, j) for j in range(1, p) for i in range(j)]
+
+        def to_opt(R, mu):
+            U = np.linalg.cholesky(np.asarray(R, float)).T
+            return np.concatenate([np.log(np.diag(U)), [U[i, j] for i, j in iu], np.asarray(mu, float)])
+
+        def to_orig(th):
+            U = np.zeros((p, p))
+            U[np.arange(p), np.arange(p)] = np.exp(th[:p])
+            for k, (i, j) in enumerate(iu):
+                U[i, j] = th[p + k]
+            return bm_params([U.T @ U], th[p + len(iu):], V)
+        return to_opt, to_orig
+    raise ValueError("model must be UnivariateBrownianMotion, MvDiagBrownianMotion or MvFullBrownianMotion")
 
 
 def calibrate_optimize_cliquetree(plan: ClusterGraphPlan, spt, tipdata, model="UnivariateBrownianMotion", start=(1.0, 0.0),

@@ -1407,3 +1407,42 @@ def test_shared_precision_missing_data_and_ou(backend):
         res[name] = (bt.integratebelief(case.sched[0][2][0])[1], bt.factored_energy())
     assert np.array_equal(res["own"][0], res["shared"][0]) and np.array_equal(res["own"][1], res["shared"][1])
     assert abs(res["own"][0][0] / -42.31401134496844 - 1) <= TOL
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_calibrate_optimize_cliquetree_mvfull_closed_form(backend):
+    # calibrate_optimize_cliquetree! for MvFullBrownianMotion through the log-Cholesky transform of
+    # params_optimize / params_original (src/evomodels/homogeneousbrownianmotion.jl:130-159, src/calibration.jl:182-234)
+    # on a network with complete bivariate data, against the closed-form ML fit of a matrix-normal model:
+    # mu = (1'V^-1 1)^-1 1'V^-1 Y, R = (Y - 1 mu)'V^-1 (Y - 1 mu) / n with V the network's tip covariance at unit rate
+    from oracle import densemvn
+    lib = get_lib(backend)
+    netstr = "(((A:4.0,((B1:1.0,B2:1.0)i6:0.6)#H5:1.1::0.9)i4:0.5,(#H5:2.0::0.1,C:0.1)i2:1.0)i1:3.0);"
+    taxa = ["A", "B1", "B2", "C"]
+    Y = np.array([[10.0, 1.0], [10.0, 0.9], [2.0, 1.0], [0.0, -1.0]])
+    n, p = Y.shape
+    c = Case(netstr, "cliquetree", Y, taxa, M.MvFullBrownianMotion(np.eye(p), np.zeros(p)), lib, schedule="spanningtree")
+    C1 = densemvn.network_covariance(c.net, lambda e: np.eye(1), 1)
+    idx = {v.name: i for i, v in enumerate(c.net.vec_node)}
+    sel = [idx[t] for t in taxa]
+    V = C1[np.ix_(sel, sel)]
+    Vi = np.linalg.inv(V)
+    one = np.ones(n)
+    mu_ml = (one @ Vi @ Y) / (one @ Vi @ one)
+    E = Y - mu_ml
+    R_ml = E.T @ Vi @ E / n
+    ll_ml = -0.5 * (n * p * np.log(2 * np.pi) + p * np.linalg.slogdet(V)[1] + n * np.linalg.slogdet(R_ml)[1] + n * p)
+    theta, ll, res = pgbp_b200.calibrate_optimize_cliquetree(c.plan, c.sched[0], Y, model="MvFullBrownianMotion",
+                                                              start=(np.array([[2.0, 0.3], [0.3, 1.0]]), np.array([3.0, 0.0])),
+                                                              maxiter=200)
+    R_hat = theta[:p * p].reshape(p, p)
+    mu_hat = theta[p * p:p * p + p]
+    assert abs(ll / ll_ml - 1) <= 1e-8
+    assert np.allclose(R_hat, R_ml, rtol=2e-3, atol=0) and np.allclose(mu_hat, mu_ml, rtol=2e-3, atol=1e-4)
+    # the transform round-trips
+    from pgbp_b200.drivers import _bm_transforms
+    to_opt, to_orig = _bm_transforms("MvFullBrownianMotion", p, None)
+    th = to_opt(R_ml, mu_ml)
+    assert th.size == p * (p + 1) // 2 + p
+    back = to_orig(th)
+    assert np.allclose(back[:p * p].reshape(p, p), R_ml, rtol=1e-13) and np.allclose(back[p * p:p * p + p], mu_ml, rtol=1e-13)
