@@ -580,6 +580,12 @@ struct AssignFast {
   const uint8_t* cflag;       // [nclusters] bit 0: zero-fill first
   const uint64_t* first_J;    // [nnodes] bit a*8+b: family v is the first writer of block (a, b), a <= b
   const uint8_t* first_h;     // [nnodes] bit a: first writer of member a's h segment
+  // Shared-precision batches: the family precision block j, its log-normaliser and the failure code depend on the
+  // group's parameters only.  The group pass (SH = false on the group batch, jucache != null) STORES them per
+  // (family, group): [v][P(P+1)/2 + 2][G]; the element pass (SH = true) READS them instead of recomputing a
+  // P x P block per element (at P = 16 that block lived in thread-local memory).
+  double* jucache = nullptr;
+  int64_t juG = 0;
   int y0 = 0;
   PGBP_HD void operator()(int64_t e, int y) const {
     const int c = y + y0;
@@ -629,9 +635,18 @@ struct AssignFast {
         continue;
       }
       // precision block j (symmetric: upper triangle kept, 36 registers at P = 8) and log-normaliser
-      double ju[P * (P + 1) / 2];
-#define PGBP_JU(r_, c_) ju[(r_) <= (c_) ? pk((r_), (c_)) : pk((c_), (r_))]
+      constexpr int NJ = P * (P + 1) / 2;
+      double ju[NJ];
+      double* juc = jucache ? jucache + (int64_t)v * (NJ + 2) * juG + (SH ? e / gen.gs : e) : nullptr;
+      const int64_t jus = juG;  // stride between the entries of one cached block
+#define PGBP_JU(r_, c_) ((SH && juc) ? juc[(int64_t)((r_) <= (c_) ? pk((r_), (c_)) : pk((c_), (r_))) * jus] \
+                                     : ju[(r_) <= (c_) ? pk((r_), (c_)) : pk((c_), (r_))])
       double gv;
+      if (SH && juc) {  // element pass of a shared-precision batch: the group pass left j, g0 and the failure code
+        const double info = juc[(int64_t)(NJ + 1) * jus];
+        if (info != 0.0) { status_fail(gen.status, e, PGBP_STATUS(0x7ffffc, (int)info)); st[gs * ld] = NAN; return; }
+        gv = juc[(int64_t)NJ * jus];
+      } else {
       bool samecolor = true;
       for (int k = k0 + 2; k < k0 + nm; k++) if (F.mem_color[k] != F.mem_color[k0 + 1]) samecolor = false;
       if (samecolor) {
@@ -663,13 +678,23 @@ struct AssignFast {
         }
         double ldv;
         const int info = spd_inverse_logdet(w, jl, P, &ldv);
-        if (info) { status_fail(gen.status, e, PGBP_STATUS(0x7ffffc, info)); st[gs * ld] = NAN; return; }
+        if (info) {
+          if (!SH && juc) juc[(int64_t)(NJ + 1) * jus] = (double)info;
+          status_fail(gen.status, e, PGBP_STATUS(0x7ffffc, info)); st[gs * ld] = NAN; return;
+        }
 #pragma unroll
         for (int cc = 0; cc < P; cc++) {
 #pragma unroll
           for (int r = 0; r <= cc; r++) ju[pk(r, cc)] = jl[cc * P + r];
         }
         gv = -0.5 * (P * PGBP_LOG2PI + ldv);
+      }
+      if (!SH && juc) {  // group pass: leave the block for the element pass
+#pragma unroll
+        for (int q = 0; q < NJ; q++) juc[(int64_t)q * jus] = ju[q];
+        juc[(int64_t)NJ * jus] = gv;
+        juc[(int64_t)(NJ + 1) * jus] = 0.0;
+      }
       }
       // evidence: z = sum over fixed members of c_a * value_a
       bool anyfixed = false;
@@ -1272,13 +1297,13 @@ static int assign_enqueue(pgbp_batch* b, pgbp::DevTables* dt, int32_t ncolors, c
     b->B = saveB;
     PGBP_TRY(rc);
   }
-  PGBP_TRY(assign_launch(b, dt, b->state, ncolors, nparamsets, ndatasets, pairing));
   if (b->jb) {
-    // shared-precision batch: the launch above wrote h and g per element; the J rows are assigned once per group in
-    // the group batch, from the same prepared tables (group g = elements [g gs, (g+1) gs): its parameter set, any
-    // of its data sets -- J does not depend on the data)
+    // shared-precision batch: the J rows are assigned once per group in the group batch, from the same prepared
+    // tables (group g = elements [g gs, (g+1) gs): its parameter set, any of its data sets -- J does not depend on
+    // the data); that pass also leaves the family precision blocks for the element pass, which writes h and g
     pgbp_batch* jb = b->jb;
     jb->stream = b->stream;
+    jb->jparent = b;
     DevTables* jdt;
     PGBP_TRY(get_tables(jb, &jdt));
     const int64_t jnd = pairing == PGBP_PAIR_PRODUCT ? ndatasets / b->group_size : 1;
@@ -1288,6 +1313,7 @@ static int assign_enqueue(pgbp_batch* b, pgbp::DevTables* dt, int32_t ncolors, c
     PGBP_TRY(rc);
     jb->lazy_factors.pending = false;
     jb->lazy_factors.valid = false;
+    PGBP_TRY(assign_launch(b, dt, b->state, ncolors, nparamsets, ndatasets, pairing));
     PGBP_TRY(batch_zero_sepsets(b, false));
     if (b->factor) {
       PGBP_TRY(d2d(jb->factor, jb->state, sizeof(double) * (size_t)p->nslots_factor * (size_t)jb->ld, b->stream));
@@ -1295,6 +1321,7 @@ static int assign_enqueue(pgbp_batch* b, pgbp::DevTables* dt, int32_t ncolors, c
     }
     return 0;
   }
+  PGBP_TRY(assign_launch(b, dt, b->state, ncolors, nparamsets, ndatasets, pairing));
   // sepsets <- 0 (src/beliefs.jl:796), lazily; factor snapshot (src/clustergraphbeliefs.jl:106), lazily
   PGBP_TRY(batch_zero_sepsets(b, true));
   if (b->factor) b->lazy_factors = pgbp_batch::LazyFactors{true, true, ncolors, nparamsets, ndatasets, pairing};
@@ -1316,11 +1343,33 @@ static int assign_launch(pgbp_batch* b, pgbp::DevTables* dt, double* out, int32_
   body.gs = b->group_size;
   if (F.scoped)  // trait-level scopes (missing data): the reference's absorb / marginalise sequence
     return launch_generic(b, "k_assign_scoped", b->B, p->nclusters, AssignScoped{body, dt->mem_tpos, dt->tip_missing});
+  // shared-precision batches: cache of the family precision blocks, written by the group pass (this function called
+  // on the group batch: b->jparent set) and read by the element pass (b->jb set)
+  double* juc = nullptr;
+  int64_t juG = 0;
+  {
+    pgbp_batch* owner = b->jb ? b : b->jparent;
+    if (owner && out == b->state) {
+      const size_t need = (size_t)F.nnodes * (size_t)(pt * (pt + 1) / 2 + 2) * (size_t)owner->ngroups;
+      if (owner->jucache_len < need) {
+        PGBP_TRY(stream_sync(b->stream));
+        dev_free(owner->jucache);
+        owner->jucache = nullptr; owner->jucache_len = 0;
+        void* v = nullptr;
+        PGBP_TRY(dev_malloc(&v, need * sizeof(double)));
+        owner->jucache = (double*)v;
+        owner->jucache_len = need;
+        owner->device_bytes += (int64_t)(need * sizeof(double));
+      }
+      juc = owner->jucache;
+      juG = owner->ngroups;
+    }
+  }
   switch (pt) {
 #define PGBP_FAST_CASE(P_) \
   case P_: \
-    if (b->group_size > 1) PGBP_TRY((launch_generic<AssignFast<P_, true>, 3>(b, "k_assign_factors", b->B, p->nclusters, AssignFast<P_, true>{body, dt->clu_flag, dt->first_J, dt->first_h}))); \
-    else PGBP_TRY((launch_generic<AssignFast<P_>, 3>(b, "k_assign_factors", b->B, p->nclusters, AssignFast<P_>{body, dt->clu_flag, dt->first_J, dt->first_h}))); \
+    if (b->group_size > 1) PGBP_TRY((launch_generic<AssignFast<P_, true>, 3>(b, "k_assign_factors", b->B, p->nclusters, AssignFast<P_, true>{body, dt->clu_flag, dt->first_J, dt->first_h, juc, juG}))); \
+    else PGBP_TRY((launch_generic<AssignFast<P_>, 3>(b, "k_assign_factors", b->B, p->nclusters, AssignFast<P_>{body, dt->clu_flag, dt->first_J, dt->first_h, juc, juG}))); \
     break;
     PGBP_FAST_CASE(1) PGBP_FAST_CASE(2) PGBP_FAST_CASE(3) PGBP_FAST_CASE(4) PGBP_FAST_CASE(5) PGBP_FAST_CASE(6)
     PGBP_FAST_CASE(7) PGBP_FAST_CASE(8)

@@ -155,12 +155,25 @@ struct pgbp_batch {
   // k_jmsg (one warp per (message, group)) factorises J_I, updates the J part and leaves U, 1/diag(U),
   // Z = U^-T J_IK and logdet in `cache`; k_hmsg (one thread per (message, element)) applies them to h and g.
   pgbp_batch* jb = nullptr;
+  pgbp_batch* jparent = nullptr;      // set on the group batch: the shared-precision batch it belongs to
   int64_t ngroups = 0;
+  double* jucache = nullptr;          // K1: family precision blocks per (node family, group), see AssignFast
+  size_t jucache_len = 0;
   std::vector<int64_t> eh, erh;       // compact rows per belief / per directed message
   int64_t nrows_e = 0, nrows_efactor = 0, nrows_eresid = 0;
   std::vector<double*> jcache;        // index 2*tree+dir: [ngroups][jcache_len] factor records of one traversal
   std::vector<int64_t*> d_jcache_off; // index 2*tree+dir: record offset (doubles) of every message, execution order
   std::vector<int64_t> jcache_len;    // index 2*tree+dir: doubles per group
+  // The group pass is latency-bound (one warp per (message, group), deep narrow schedules) and does not depend on
+  // the element pass: it runs on its own stream `jstream`, one event per step; the element pass of step s waits
+  // for event s only.  jcache_free[td]: recorded (main stream) after the element pass of traversal td, so that the
+  // next group pass does not overwrite records that are still being read.
+  pgbp_stream_t jstream = 0;
+  std::vector<void*> jstep_events;    // cudaEvent_t per step (grown on demand)
+  std::vector<void*> jcache_free;     // cudaEvent_t per traversal (null until first use)
+  std::vector<char> jcache_used;      // traversal already passed during the current calibrate! call
+  void* jfork_event = nullptr;
+  bool jfork_pending = true;          // set at the start of every calibrate! call
   double* jcache_one = nullptr;       // scratch record for single messages (pgbp_propagate, regularize_onschedule)
   int64_t* d_zero64 = nullptr;        // device constant 0 (record offset of a single message)
   uint8_t* done = nullptr;     // [ld] (auto-stop mask)

@@ -660,6 +660,7 @@ static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int
   if (b->itertree) PGBP_TRY(dev_memset(b->itertree, 0, sizeof(int32_t) * 2 * (size_t)b->ld, b->stream));
   if (b->iscal) PGBP_TRY(dev_memset(b->iscal, 0, sizeof(int32_t) * (size_t)b->ld, b->stream));
   const uint32_t opts = flags & (PGBP_CAL_RESIDNORM | PGBP_CAL_RESIDKLDIV | PGBP_CAL_REFORDER);
+  b->jfork_pending = true;  // (shared-precision batches: the group pass forks off the batch's stream here)
   // the whole schedule for the element range [b->chunk_begin, b->chunk_end) on b->stream
   auto enqueue = [&]() -> int {
     int32_t ref = 0;

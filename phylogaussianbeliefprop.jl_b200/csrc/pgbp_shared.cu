@@ -79,11 +79,51 @@ struct WarpLanes {
     return x;
   }
 };
+// a whole block of NT threads on one (message, group): large matrices (the factorisation of a 48 x 48 belief is a
+// chain of 32 dependent rank-1 updates: the more lanes per update, the shorter the chain)
+template <int NT>
+struct BlockLanes {
+  static constexpr int n = NT;
+  int lane;
+  double* red;  // NT / 32 doubles of shared memory
+  __device__ void sync() const { __syncthreads(); }
+  __device__ bool all(bool p) const { return __syncthreads_and(p) != 0; }
+  __device__ double maxnan(double x) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double y = __shfl_xor_sync(0xffffffffu, x, o);
+      x = (x != x || y != y) ? NAN : (y > x ? y : x);
+    }
+    if ((lane & 31) == 0) red[lane >> 5] = x;
+    __syncthreads();
+    double m = red[0];
+#pragma unroll
+    for (int k = 1; k < NT / 32; k++) {
+      const double y = red[k];
+      m = (m != m || y != y) ? NAN : (y > m ? y : m);
+    }
+    __syncthreads();
+    return m;
+  }
+};
 #endif
 
-// J part of one message for one group.  A: tri(mF) doubles shared by the lanes.
+// (row, column) of packed index q = c(c+1)/2 + r, q < nq, two bytes per entry
 template <class W>
-PGBP_HD void jmsg_body(const JArgs& a, int mi, int64_t g, const W& w, double* A) {
+PGBP_HD void fill_rc(uint8_t* rc, int nq, const W& w) {
+  for (int q = w.lane; q < nq; q += W::n) {
+    int c = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
+    while ((c + 1) * (c + 2) / 2 <= q) c++;
+    while (c * (c + 1) / 2 > q) c--;
+    rc[2 * q] = (uint8_t)(q - c * (c + 1) / 2);
+    rc[2 * q + 1] = (uint8_t)c;
+  }
+}
+
+// J part of one message for one group.  A: tri(mF) doubles shared by the lanes; rc: the (row, column) table of
+// fill_rc for at least tri(mF) entries.
+template <class W>
+PGBP_HD void jmsg_body(const JArgs& a, int mi, int64_t g, const W& w, double* A, const uint8_t* rc) {
   const MsgDesc md = a.msgs[mi];
   if (a.status[g] != 0) return;  // the group failed earlier: its J stops moving (uniform over the lanes)
   const int I = md.mF - md.s, S = md.s, M = md.mF;
@@ -118,9 +158,10 @@ PGBP_HD void jmsg_body(const JArgs& a, int mi, int64_t g, const W& w, double* A)
         for (int c = k + 1 + w.lane; c < M; c += W::n) A[pk(k, c)] *= rinv;
         if (w.lane == 0) rec[2 + k] = rinv;
         w.sync();
-        for (int c = k + 1; c < M; c++) {
-          const double akc = A[pk(k, c)];
-          for (int r = k + 1 + w.lane; r <= c; r += W::n) A[pk(r, c)] = nfma(A[pk(k, r)], akc, A[pk(r, c)]);
+        // trailing update, one entry per lane and pass: A[r,c] -= A[k,r] A[k,c] for k < r <= c
+        for (int q = pk(k + 1, k + 1) + w.lane; q < SM; q += W::n) {
+          const int r = rc[2 * q], c = rc[2 * q + 1];
+          if (r > k) A[q] = nfma(A[pk(k, r)], A[pk(k, c)], A[q]);
         }
         w.sync();
       }
@@ -156,26 +197,30 @@ PGBP_HD void jmsg_body(const JArgs& a, int mi, int64_t g, const W& w, double* A)
 
 // h, g part of one message for one element.  CI >= 0: compile-time integrated dimension (w in registers);
 // CI < 0: runtime (thread-local array).
-#define PGBP_HMSG_CHUNK 4
-template <int CI>
+// CH: kept entries per streaming chunk (3 CH loads in flight per thread; 8 measured against 4 on B200)
+template <int CI, int CH>
 PGBP_HD void hmsg_thread(const HArgs& a, int mi, int64_t e) {
-  const MsgDesc md = a.msgs[mi];
+  constexpr int PGBP_HMSG_CHUNK = CH;
+  const MsgDesc& md = a.msgs[mi];  // only the fields used below are loaded; rows fit 32 bits (checked at creation)
   if (a.status[e] != 0) return;
-  const int I = CI >= 0 ? CI : md.mF - md.s, S = md.s, M = I + S;
-  const int64_t ld = a.ld;
-  double* st = a.state + e;
-  double* rs = a.resid ? a.resid + e : nullptr;
+  const int S = md.s;
+  const int I = CI >= 0 ? CI : md.mF - S, M = I + S;
+  const uint32_t ld8 = (uint32_t)(a.ld * 8);
+  char* st = (char*)(a.state + e);
+  char* rs = a.resid ? (char*)(a.resid + e) : nullptr;
+  const uint32_t fh = (uint32_t)md.fh, sh = (uint32_t)md.sh, th = (uint32_t)md.th, rh = (uint32_t)md.rh;
+  const uint32_t sg = (uint32_t)md.sg, tg = (uint32_t)md.tg;
   const int32_t* __restrict__ gat = a.tab + md.gat + tri(M);  // sender positions of [I;K]
   const int32_t* __restrict__ sca = a.tab + md.sca + tri(S);  // receiver positions of the sepset's variables
-  double g = st[md.fg * ld];
-  const double sg_old = st[md.sg * ld], tg_old = st[md.tg * ld];
+  double g = *slot_ptr(st, (uint32_t)md.fg, ld8);
+  const double sg_old = *slot_ptr(st, sg, ld8), tg_old = *slot_ptr(st, tg, ld8);
   double hI[CI > 0 ? CI : (CI == 0 ? 1 : PGBP_MAX_DIM)];
   const double* __restrict__ rec = nullptr;
   bool zeroZ = true;
   if (I > 0) {
     rec = a.cache + (e / a.gs) * a.stride + a.cache_off[mi];
 #pragma unroll
-    for (int k = 0; k < I; k++) hI[k] = st[(md.fh + gat[k]) * ld];
+    for (int k = 0; k < I; k++) hI[k] = *slot_ptr(st, fh + gat[k], ld8);
     const double info = rec[0];
     if (info > 0.0) {  // the factorisation of the group's J_I failed at this pivot
       status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, (int)info));
@@ -213,9 +258,9 @@ PGBP_HD void hmsg_thread(const HArgs& a, int mi, int64_t e) {
 #pragma unroll
     for (int j = 0; j < PGBP_HMSG_CHUNK; j++)
       if (k0 + j < S) {
-        tp[j] = st + (md.th + sca[k0 + j]) * ld;
-        nv[j] = st[(md.fh + gat[I + k0 + j]) * ld];
-        so[j] = st[(md.sh + k0 + j) * ld];
+        tp[j] = slot_ptr(st, th + sca[k0 + j], ld8);
+        nv[j] = *slot_ptr(st, fh + gat[I + k0 + j], ld8);
+        so[j] = *slot_ptr(st, sh + k0 + j, ld8);
         to[j] = *tp[j];
       }
     if (!zeroZ) {
@@ -233,37 +278,53 @@ PGBP_HD void hmsg_thread(const HArgs& a, int mi, int64_t e) {
     for (int j = 0; j < PGBP_HMSG_CHUNK; j++)
       if (k0 + j < S) {
         const double d = nv[j] - so[j];
-        st[(md.sh + k0 + j) * ld] = nv[j];
+        *slot_ptr(st, sh + k0 + j, ld8) = nv[j];
         *tp[j] = to[j] + d;
-        if (rs) rs[(md.rh + k0 + j) * ld] = d;
+        if (rs) *slot_ptr(rs, rh + k0 + j, ld8) = d;
         absmax(maxh, d);
       }
   }
-  st[md.sg * ld] = g;
-  st[md.tg * ld] = tg_old + (g - sg_old);
+  *slot_ptr(st, sg, ld8) = g;
+  *slot_ptr(st, tg, ld8) = tg_old + (g - sg_old);
   if ((a.opts & PGBP_CAL_RESIDNORM) && a.calflag)
-    a.calflag[(int64_t)md.dmsg * ld + e] = (S > 0 ? (maxh / sqrt((double)S) <= 1e-5) : true) ? 1 : 0;
+    a.calflag[(int64_t)md.dmsg * a.ld + e] = (S > 0 ? (maxh / sqrt((double)S) <= 1e-5) : true) ? 1 : 0;
 }
 
 #ifndef PGBP_HOST_EMUL
-__global__ void __launch_bounds__(32) k_jmsg(JArgs a) {
+// dynamic shared memory: tri(maxM)+1 doubles | NT/32 doubles (reduction) | 2 tri(maxM) bytes ((row, column) table)
+template <int NT>
+__global__ void __launch_bounds__(NT) k_jmsg(JArgs a, int maxM) {
   extern __shared__ double jA[];
-  const WarpLanes w{(int)threadIdx.x};
-  for (int64_t g = blockIdx.y; g < a.G; g += gridDim.y) {
-    jmsg_body(a, blockIdx.x, g, w, jA);
+  const int nq = tri(maxM);
+  double* red = jA + nq + 1;
+  uint8_t* rc = (uint8_t*)(red + NT / 32);
+  if constexpr (NT == 32) {
+    const WarpLanes w{(int)threadIdx.x};
+    fill_rc(rc, nq, w);
     __syncwarp();
+    for (int64_t g = blockIdx.y; g < a.G; g += gridDim.y) {
+      jmsg_body(a, blockIdx.x, g, w, jA, rc);
+      __syncwarp();
+    }
+  } else {
+    const BlockLanes<NT> w{(int)threadIdx.x, red};
+    fill_rc(rc, nq, w);
+    __syncthreads();
+    for (int64_t g = blockIdx.y; g < a.G; g += gridDim.y) {
+      jmsg_body(a, blockIdx.x, g, w, jA, rc);
+      __syncthreads();
+    }
   }
 }
-template <int CI>
-__global__ void __launch_bounds__(128) k_hmsg(HArgs a) {
+template <int CI, int CH>
+__global__ void __launch_bounds__(128, (CH <= 4 ? 3 : 2)) k_hmsg(HArgs a) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.B) return;
-  hmsg_thread<CI>(a, blockIdx.y, e);
+  hmsg_thread<CI, CH>(a, blockIdx.y, e);
 }
 #endif
 
-static int launch_jmsg(pgbp_batch* b, JArgs a, int nmsg, int maxM) {
-  pgbp_batch* jb = b->jb;
+static int launch_jmsg(pgbp_batch* b, JArgs a, int nmsg, int maxM, pgbp_stream_t stream) {
   int done = 0;
   while (done < nmsg) {
     const int n = std::min(nmsg - done, 1 << 30);
@@ -271,12 +332,17 @@ static int launch_jmsg(pgbp_batch* b, JArgs a, int nmsg, int maxM) {
     c.msgs = a.msgs + done;
     c.cache_off = a.cache_off + done;
 #ifdef PGBP_HOST_EMUL
+    (void)stream;
     std::vector<double> A((size_t)tri(maxM) + 1);
+    std::vector<uint8_t> rc(2 * (size_t)tri(maxM) + 2);
+    fill_rc(rc.data(), tri(maxM), OneLane{});
     for (int m = 0; m < n; m++)
-      for (int64_t g = 0; g < c.G; g++) jmsg_body(c, m, g, OneLane{}, A.data());
+      for (int64_t g = 0; g < c.G; g++) jmsg_body(c, m, g, OneLane{}, A.data(), rc.data());
 #else
     dim3 grid((unsigned)n, (unsigned)std::min<int64_t>(c.G, 65535));
-    k_jmsg<<<grid, 32, sizeof(double) * (size_t)(tri(maxM) + 1), jb->stream>>>(c);
+    const size_t smem = sizeof(double) * (size_t)(tri(maxM) + 1 + 4) + 2 * (size_t)tri(maxM) + 8;
+    if (tri(maxM) >= 256) k_jmsg<128><<<grid, 128, smem, stream>>>(c, maxM);  // sender dimension >= 23
+    else k_jmsg<32><<<grid, 32, smem, stream>>>(c, maxM);
 #endif
     b->launches++;
     PGBP_TRY(check_launch("k_jmsg"));
@@ -285,14 +351,19 @@ static int launch_jmsg(pgbp_batch* b, JArgs a, int nmsg, int maxM) {
   return 0;
 }
 
+static int hmsg_chunk() {  // PGBP_HMSG_CHUNK=4|8 selects the streaming chunk of the element pass (tuning knob)
+  static const int v = [] { const char* e = getenv("PGBP_HMSG_CHUNK"); return (e && atoi(e) == 4) ? 4 : 8; }();
+  return v;
+}
 template <int CI>
 static int launch_hmsg_t(pgbp_batch* b, const HArgs& a, int nmsg) {
 #ifdef PGBP_HOST_EMUL
   for (int m = 0; m < nmsg; m++)
-    for (int64_t e = 0; e < a.B; e++) hmsg_thread<CI>(a, m, e);
+    for (int64_t e = 0; e < a.B; e++) hmsg_thread<CI, 8>(a, m, e);
 #else
   dim3 grid((unsigned)((a.B + 127) / 128), (unsigned)nmsg);
-  k_hmsg<CI><<<grid, 128, 0, b->stream>>>(a);
+  if (hmsg_chunk() == 4) k_hmsg<CI, 4><<<grid, 128, 0, b->stream>>>(a);
+  else k_hmsg<CI, 8><<<grid, 128, 0, b->stream>>>(a);
 #endif
   b->launches++;
   return check_launch("k_hmsg");
@@ -370,22 +441,60 @@ int shared_run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_
   ja.cache = b->jcache[td];
   ja.cache_off = b->d_jcache_off[td];
   ja.stride = b->jcache_len[td];
-  // group pass: one launch per step (messages of a step touch disjoint beliefs)
-  for (int s = 0; s < tv.nsteps; s++) {
-    const int first = tv.step_off[s], count = tv.step_off[s + 1] - first;
-    if (count <= 0) continue;
-    int maxM = 0;
-    for (int k = first; k < first + count; k++) maxM = std::max(maxM, tv.msgs[k].mF);
-    JArgs c = ja;
-    c.msgs = ja.msgs + first;
-    c.cache_off = ja.cache_off + first;
-    PGBP_TRY(launch_jmsg(b, c, count, maxM));
-  }
-  // element pass: the plan's launch groups (same step, same shape class)
   HArgs ha = make_hargs(b, opts, ref_base);
   ha.cache = b->jcache[td];
   ha.stride = b->jcache_len[td];
+  pgbp_stream_t js = b->stream;
+#ifndef PGBP_HOST_EMUL
+  // Group pass on its own stream: fork after everything already enqueued on the batch's stream (assignment,
+  // regularisation, the previous traversal's group pass is ordered by the stream itself) and after the last
+  // element pass that read this traversal's records.
+  if (!b->jstream) PGBP_CUDA(cudaStreamCreateWithFlags(&b->jstream, cudaStreamNonBlocking));
+  if (!b->jfork_event) { cudaEvent_t ev; PGBP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); b->jfork_event = (void*)ev; }
+  while ((int)b->jstep_events.size() < tv.nsteps) {
+    cudaEvent_t ev;
+    PGBP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    b->jstep_events.push_back((void*)ev);
+  }
+  if (b->jcache_free.size() < b->jcache.size()) b->jcache_free.resize(b->jcache.size(), nullptr);
+  if (b->jcache_used.size() < b->jcache.size()) b->jcache_used.resize(b->jcache.size(), 0);
+  js = b->jstream;
+  if (b->jfork_pending) {  // first traversal of a calibrate! call: after the work already enqueued on the batch's stream
+    PGBP_CUDA(cudaEventRecord((cudaEvent_t)b->jfork_event, b->stream));
+    PGBP_CUDA(cudaStreamWaitEvent(js, (cudaEvent_t)b->jfork_event, 0));
+    b->jfork_pending = false;
+    b->jcache_used.assign(b->jcache.size(), 0);  // the fork orders this call after every earlier element pass
+  }
+  // later traversals of the same call start as soon as the previous group pass is done (stream order): the group
+  // pass runs ahead of the element pass -- except that it must not overwrite records still being read
+  if (b->jcache_used[td]) PGBP_CUDA(cudaStreamWaitEvent(js, (cudaEvent_t)b->jcache_free[td], 0));  // (same call: same capture)
+#endif
+  // group pass: one launch per step (messages of a step touch disjoint beliefs)
+  for (int s = 0; s < tv.nsteps; s++) {
+    const int first = tv.step_off[s], count = tv.step_off[s + 1] - first;
+    if (count > 0) {
+      int maxM = 0;
+      for (int k = first; k < first + count; k++) maxM = std::max(maxM, tv.msgs[k].mF);
+      JArgs c = ja;
+      c.msgs = ja.msgs + first;
+      c.cache_off = ja.cache_off + first;
+      PGBP_TRY(launch_jmsg(b, c, count, maxM, js));
+    }
+#ifndef PGBP_HOST_EMUL
+    PGBP_CUDA(cudaEventRecord((cudaEvent_t)b->jstep_events[s], js));
+#endif
+  }
+  // element pass: the plan's launch groups (same step, same shape class), each step after its records exist
+  int waited = -1;
   for (const LaunchGroup& g : tv.groups) {
+#ifndef PGBP_HOST_EMUL
+    if (g.step != waited) {
+      PGBP_CUDA(cudaStreamWaitEvent(b->stream, (cudaEvent_t)b->jstep_events[g.step], 0));
+      waited = g.step;
+    }
+#else
+    (void)waited;
+#endif
     HArgs c = ha;
     c.msgs = b->d_msgs[td] + g.first;
     c.cache_off = b->d_jcache_off[td] + g.first;
@@ -395,6 +504,14 @@ int shared_run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_
       PGBP_TRY(launch_kldiv(b, ma, b->d_msgs[td], g));
     }
   }
+#ifndef PGBP_HOST_EMUL
+  // join: whatever follows on the batch's stream (integrate, energies, the next assignment) sees the final J; the
+  // last step's event was waited on above unless the traversal ended with copy-only steps
+  if (waited != tv.nsteps - 1) PGBP_CUDA(cudaStreamWaitEvent(b->stream, (cudaEvent_t)b->jstep_events[tv.nsteps - 1], 0));
+  if (!b->jcache_free[td]) { cudaEvent_t ev; PGBP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); b->jcache_free[td] = (void*)ev; }
+  PGBP_CUDA(cudaEventRecord((cudaEvent_t)b->jcache_free[td], b->stream));  // this traversal's records may be overwritten after this
+  b->jcache_used[td] = 1;
+#endif
   return 0;
 }
 
@@ -409,7 +526,7 @@ int shared_propagate(pgbp_batch* b, const MsgDesc& md_plan, uint32_t opts, int32
   ja.cache = b->jcache_one;
   ja.cache_off = b->d_zero64;
   ja.stride = jrec_len(PGBP_MAX_DIM, 0) + (int64_t)PGBP_MAX_DIM * PGBP_MAX_DIM;
-  PGBP_TRY(launch_jmsg(b, ja, 1, md_plan.mF));
+  PGBP_TRY(launch_jmsg(b, ja, 1, md_plan.mF, b->stream));
   HArgs ha = make_hargs(b, b->calflag ? opts : (opts & ~PGBP_CAL_RESIDNORM), ref_base);
   ha.msgs = b->d_one;
   ha.cache = b->jcache_one;
@@ -515,10 +632,19 @@ int shared_create(pgbp_batch* b) {
 }
 
 void shared_destroy(pgbp_batch* b) {
+#ifndef PGBP_HOST_EMUL
+  if (b->jstream) { cudaStreamSynchronize(b->jstream); cudaStreamDestroy(b->jstream); b->jstream = 0; }
+  for (void* ev : b->jstep_events) cudaEventDestroy((cudaEvent_t)ev);
+  for (void* ev : b->jcache_free) if (ev) cudaEventDestroy((cudaEvent_t)ev);
+  if (b->jfork_event) cudaEventDestroy((cudaEvent_t)b->jfork_event);
+  b->jstep_events.clear(); b->jcache_free.clear(); b->jfork_event = nullptr;
+#endif
   for (auto* q : b->jcache) dev_free(q);
   for (auto* q : b->d_jcache_off) dev_free(q);
   dev_free(b->jcache_one);
   dev_free(b->d_zero64);
+  dev_free(b->jucache);
+  b->jucache = nullptr;
   if (b->jb) {
     b->jb->stream = 0;  // borrowed from the element batch
     b->jb->own_stream = false;
