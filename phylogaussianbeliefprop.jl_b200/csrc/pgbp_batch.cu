@@ -64,13 +64,14 @@ void* batch_pinned(pgbp_batch* b, size_t bytes) {
 
 int batch_zero_sepsets(pgbp_batch* b, bool lazy) {
   const pgbp_plan* p = b->plan;
-  if (b->jb) {  // shared-precision batch: J rows of the sepsets in the group batch, h / g rows here; always eager
+  if (lazy) { b->sepsets_lazy_zero = true; return 0; }
+  if (b->jb) {  // shared-precision batch: J rows of the sepsets in the group batch, h / g rows here
+    b->sepsets_lazy_zero = false;
     b->jb->stream = b->stream;
     PGBP_TRY(batch_zero_sepsets(b->jb, false));
     return dev_memset(b->state + (size_t)b->nrows_efactor * (size_t)b->ld, 0,
                       sizeof(double) * (size_t)(b->nrows_e - b->nrows_efactor) * (size_t)b->ld, b->stream);
   }
-  if (lazy) { b->sepsets_lazy_zero = true; return 0; }
   b->sepsets_lazy_zero = false;
   return dev_memset(b->state + (size_t)p->nslots_factor * (size_t)b->ld, 0,
                     sizeof(double) * (size_t)(p->nslots_state - p->nslots_factor) * (size_t)b->ld, b->stream);
@@ -417,6 +418,8 @@ int32_t pgbp_set_belief(pgbp_batch* b, int32_t i, const double* J, const double*
   const pgbp_plan* p = b->plan;
   if (b->jb) {
     b->jb->stream = b->stream;
+    PGBP_TRY(set_device(b->device));
+    PGBP_TRY(batch_materialize_sepsets(b));
     if (J && p->dim[i] > 0)
       PGBP_TRY(shared_put_J(b, p->dim[i], J, [](pgbp_batch* jb, int32_t k, const double* Jg) { return (int)pgbp_set_belief(jb, k, Jg, nullptr, nullptr); }, i));
     return access_hJg(b, true, b->state, p->dim[i], 0, batch_hrow(b, i), batch_grow(b, i), nullptr, (double*)h, (double*)g);
@@ -428,6 +431,8 @@ int32_t pgbp_get_belief(pgbp_batch* b, int32_t i, double* J, double* h, double* 
   const pgbp_plan* p = b->plan;
   if (b->jb) {
     b->jb->stream = b->stream;
+    PGBP_TRY(set_device(b->device));
+    PGBP_TRY(batch_materialize_sepsets(b));
     if (J && p->dim[i] > 0) {
       std::vector<double> Jg((size_t)b->ngroups * p->dim[i] * p->dim[i]);
       PGBP_TRY(pgbp_get_belief(b->jb, i, Jg.data(), nullptr, nullptr));
@@ -536,8 +541,9 @@ int32_t pgbp_reset_from_factors(pgbp_batch* b) {
   if (b->jb) {
     b->jb->stream = b->stream;
     PGBP_TRY(pgbp_reset_from_factors(b->jb));
+    PGBP_TRY(batch_materialize_sepsets(b->jb));  // (the group batch's own laziness is not used: one flag, this batch's)
     PGBP_TRY(d2d(b->state, b->factor, sizeof(double) * (size_t)b->nrows_efactor * ld, b->stream));
-    return batch_zero_sepsets(b, false);
+    return batch_zero_sepsets(b, true);
   }
   {  // factors that are still K1's output: re-run K1 into the beliefs (write only) instead of copying
     const int r = batch_reset_by_assign(b);

@@ -247,6 +247,37 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// ---- bulk asynchronous copies (TMA engine, 1-D): one instruction moves a whole slot row of a tile ------------------
+// With the batch-innermost layout the TILE elements of a tile are contiguous in every slot row (8 TILE bytes, 16-byte
+// aligned), so one cp.async.bulk per row, issued by ONE thread, replaces TILE per-lane 8-byte cp.async (address
+// arithmetic, predicate and LDGSTS per lane).  Completion is counted in bytes on an mbarrier.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");  // visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // doubles of shared memory per element
 inline __host__ __device__ int smem_doubles(int I, int S) { return I * (I + 1) / 2 + I * S + I; }
 // bytes of shared memory per block (one warp) of k_message_smem<I>: element data + index tables
@@ -766,8 +797,10 @@ inline __host__ __device__ size_t smem_mw_block_bytes(int I, int S, int NW) {
 
 template <int I, int NW, int MINB = (NW <= 4 ? 2 : 1)>
 __global__ void __launch_bounds__(32 * NW, MINB) k_message_smem_mw(MsgArgs a) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(128) double sm[];  // bulk-copy destinations need 16-byte alignment
+  __shared__ __align__(8) unsigned long long mbar;
   const int tid = threadIdx.x, wid = threadIdx.y;
+  if (wid == 0 && tid == 0) mbar_init(&mbar, 1);  // (made visible to the other threads by the barrier after the tables)
   const int64_t e = a.e0 + (int64_t)blockIdx.x * 32 + tid;
   const MsgDesc md = a.msgs[blockIdx.y];
   const int S = md.s, M = md.mF;
@@ -814,15 +847,20 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_message_smem_mw(MsgArgs a) {
                  tJ = (uint32_t)md.tJ, th = (uint32_t)md.th, rJ = (uint32_t)md.rJ, rh = (uint32_t)md.rh;
   const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;
 
-  // ---- A: staging, entries dealt to the warps round-robin --------------------------------------
-  for (int n = wid; n < NE; n += NW) {
-    uint32_t slot;
-    if (n < TI) slot = fJ + gat[n];
-    else {
-      const int idx = n - TI, cc = idx / I, k = idx - cc * I;
-      slot = cc < S ? fJ + gat[tri(I + cc) + k] : fh + gat[SMM + k];
+  // ---- A: staging with bulk asynchronous copies: one 256-byte row (32 elements of one slot) per instruction,
+  //      rows dealt to the threads of the tile, completion counted in bytes on the tile's mbarrier ----------
+  {
+    const char* tileb = (const char*)(a.state + a.e0 + (int64_t)blockIdx.x * 32);
+    if (wid == 0 && tid == 0) mbar_expect_tx(&mbar, (unsigned)NE * 256u);
+    for (int n = wid * 32 + tid; n < NE; n += 32 * NW) {
+      uint32_t slot;
+      if (n < TI) slot = fJ + gat[n];
+      else {
+        const int idx = n - TI, cc = idx / I, k = idx - cc * I;
+        slot = cc < S ? fJ + gat[tri(I + cc) + k] : fh + gat[SMM + k];
+      }
+      bulk_g2s(sm + n * 32, tileb + (uint64_t)slot * (uint64_t)ld8, 256u, &mbar);
     }
-    cp_async8(smt + n * 32, gaddr(stb, slot, ld8));
   }
   double g = 0.0, sg_old = 0.0, tg_old = 0.0;
   if (wid == 0) {
@@ -843,7 +881,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_message_smem_mw(MsgArgs a) {
     if (!sz) prefetch_l2(gaddr(stb, sh + cc, ld8));
     prefetch_l2(gaddr(stb, th + sca[SS + cc], ld8));
   }
-  cp_async_wait_all();
+  mbar_wait(&mbar, 0);  // every staged row has landed (async-proxy writes are visible after the wait)
   __syncthreads();
 
   // ---- B1: U'U = J_II on warp 0 (left-looking, fully unrolled; as k_message_smem) ----------------
@@ -1033,8 +1071,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_message_smem_mw(MsgArgs a) {
 // -------------------------------------------------------------------------------------
 template <int I, int NW, int TILE>
 __global__ void __launch_bounds__(32 * NW, 1) k_message_smem_mwp(MsgArgs a) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(128) double sm[];  // bulk-copy destinations need 16-byte alignment
+  __shared__ __align__(8) unsigned long long mbar;
   const int tid = threadIdx.x, wid = threadIdx.y;
+  if (wid == 0 && tid == 0) mbar_init(&mbar, 1);  // (made visible to the other threads by the barrier after the tables)
   const bool lane_ok = tid < TILE;
   const int lane = lane_ok ? tid : 0;      // idle lanes never touch shared memory (all accesses are guarded)
   const int64_t e = a.e0 + (int64_t)blockIdx.x * TILE + lane;
@@ -1079,18 +1119,26 @@ __global__ void __launch_bounds__(32 * NW, 1) k_message_smem_mwp(MsgArgs a) {
                  tJ = (uint32_t)md.tJ, th = (uint32_t)md.th, rJ = (uint32_t)md.rJ, rh = (uint32_t)md.rh;
   const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;
 
-  // ---- A: staging, entries dealt to the warps round-robin --------------------------------------
+  // ---- A: staging with bulk asynchronous copies: one row of TILE elements (8 TILE bytes, 16-byte aligned) per
+  //      instruction, rows dealt to the threads of the tile, completion counted in bytes on the tile's mbarrier -----
   double g = 0.0, sg_old = 0.0, tg_old = 0.0;
-  if (lane_ok) {
-    for (int n = wid; n < NE; n += NW) {
+  {
+    const int64_t tile0 = a.e0 + (int64_t)blockIdx.x * TILE;
+    const char* tileb = (const char*)(a.state + tile0);
+    const int64_t room = a.ld - tile0;  // the last tile of a row may be cut by the row pitch
+    const unsigned rowbytes = (unsigned)((room < TILE ? room : TILE) * 8);
+    if (wid == 0 && tid == 0) mbar_expect_tx(&mbar, (unsigned)NE * rowbytes);
+    for (int n = wid * 32 + tid; n < NE; n += 32 * NW) {
       uint32_t slot;
       if (n < TI) slot = fJ + gat[n];
       else {
         const int idx = n - TI, cc = idx / I, k = idx - cc * I;
         slot = cc < S ? fJ + gat[tri(I + cc) + k] : fh + gat[SMM + k];
       }
-      cp_async8(smt + n * TILE, gaddr(stb, slot, ld8));
+      bulk_g2s(sm + n * TILE, tileb + (uint64_t)slot * (uint64_t)ld8, rowbytes, &mbar);
     }
+  }
+  if (lane_ok) {
     if (wid == 0) {
       g = *gaddr(stb, (uint32_t)md.fg, ld8);
       sg_old = sz ? 0.0 : *gaddr(stb, (uint32_t)md.sg, ld8);
@@ -1109,7 +1157,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k_message_smem_mwp(MsgArgs a) {
       prefetch_l2(gaddr(stb, th + sca[SS + cc], ld8));
     }
   }
-  cp_async_wait_all();
+  mbar_wait(&mbar, 0);  // every staged row has landed
   __syncthreads();
 
   // ---- B1: U'U = J_II, right-looking, columns dealt to the warps, one barrier per pivot ----------

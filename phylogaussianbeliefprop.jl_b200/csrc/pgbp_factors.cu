@@ -1314,7 +1314,7 @@ static int assign_enqueue(pgbp_batch* b, pgbp::DevTables* dt, int32_t ncolors, c
     jb->lazy_factors.pending = false;
     jb->lazy_factors.valid = false;
     PGBP_TRY(assign_launch(b, dt, b->state, ncolors, nparamsets, ndatasets, pairing));
-    PGBP_TRY(batch_zero_sepsets(b, false));
+    PGBP_TRY(batch_zero_sepsets(b, true));  // lazily: the first postorder traversal treats the sepsets as 0
     if (b->factor) {
       PGBP_TRY(d2d(jb->factor, jb->state, sizeof(double) * (size_t)p->nslots_factor * (size_t)jb->ld, b->stream));
       PGBP_TRY(d2d(b->factor, b->state, sizeof(double) * (size_t)b->nrows_efactor * (size_t)b->ld, b->stream));
@@ -1516,6 +1516,7 @@ int32_t pgbp_regularize_bycluster(pgbp_batch* b) {
   PGBP_TRY(set_device(b->device));
   if (b->jb) {  // the regularisers only touch J: the group batch's
     b->jb->stream = b->stream;
+    PGBP_TRY(batch_materialize_sepsets(b));
     return pgbp_regularize_bycluster(b->jb);
   }
   PGBP_TRY(batch_materialize_sepsets(b));
@@ -1614,6 +1615,7 @@ int32_t pgbp_regularize_bynodesubtree(pgbp_batch* b, int32_t nnodes, const int32
   PGBP_TRY(set_device(b->device));
   if (b->jb) {  // J only: the group batch's
     b->jb->stream = b->stream;
+    PGBP_TRY(batch_materialize_sepsets(b));
     return pgbp_regularize_bynodesubtree(b->jb, nnodes, eps_off, eps_cluster, step_off, step_cluster, step_sepset, idx_off,
                                          idx_cluster, idx_sepset);
   }

@@ -670,7 +670,7 @@ static int calibrate_enqueue(pgbp_batch* b, const std::vector<int32_t>& ids, int
         const int t = ids[j];
         const int n = (int)p->trees[t].parent.size();
         if (b->jb) {  // shared-precision batch: group pass (J, factor cache) + element pass (h, g) per traversal
-          if (flags & PGBP_CAL_POSTORDER) { PGBP_TRY(shared_run_traversal(b, t, 0, opts, ref)); ref += n; }
+          if (flags & PGBP_CAL_POSTORDER) { PGBP_TRY(shared_run_traversal(b, t, 0, opts | sepzero, ref)); ref += n; }
           if (flags & PGBP_CAL_PREORDER) { PGBP_TRY(shared_run_traversal(b, t, 1, opts, ref)); ref += n; }
         } else if (use_walk(b, t) && !(opts & (PGBP_CAL_RESIDKLDIV | PGBP_CAL_REFORDER))) {
           const bool po = flags & PGBP_CAL_POSTORDER, pr = flags & PGBP_CAL_PREORDER;

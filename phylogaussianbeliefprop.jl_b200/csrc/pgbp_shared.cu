@@ -176,6 +176,7 @@ PGBP_HD void jmsg_body(const JArgs& a, int mi, int64_t g, const W& w, double* A,
     }
   }
   // divide! / mult! / residual of the J part (src/beliefupdates.jl:579-587, 483-488, 646-647)
+  const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;  // lazy sepset zero: the old sepset value is 0, not loaded
   double* rs = a.resid ? a.resid + g : nullptr;
   double maxJ = 0.0;
   for (int c = 0; c < S; c++)
@@ -184,7 +185,7 @@ PGBP_HD void jmsg_body(const JArgs& a, int mi, int64_t g, const W& w, double* A,
       const double nv = A[pk(I + r, I + c)];
       double* sp = st + (md.sJ + q) * ld;
       double* tp = st + (md.tJ + sca[q]) * ld;
-      const double d = nv - *sp;
+      const double d = nv - (sz ? 0.0 : *sp);
       *sp = nv;
       *tp = *tp + d;
       if (rs) rs[(md.rJ + q) * ld] = d;
@@ -197,9 +198,10 @@ PGBP_HD void jmsg_body(const JArgs& a, int mi, int64_t g, const W& w, double* A,
 
 // h, g part of one message for one element.  CI >= 0: compile-time integrated dimension (w in registers);
 // CI < 0: runtime (thread-local array).
-// CH: kept entries per streaming chunk (3 CH loads in flight per thread; 8 measured against 4 on B200)
+// CH: kept entries per streaming chunk (3 CH loads in flight per thread).  Measured on B200: CH = 4 (168 registers,
+// 3 blocks per SM) beats CH = 8 (254 registers): c5s 4,801 vs 4,227 calibrations/s, c2s 137.7 vs 130.9 M/s
 template <int CI, int CH>
-PGBP_HD void hmsg_thread(const HArgs& a, int mi, int64_t e) {
+PGBP_HD void hmsg_thread(const HArgs& a, int mi, int64_t e, const double* srec = nullptr) {
   constexpr int PGBP_HMSG_CHUNK = CH;
   const MsgDesc& md = a.msgs[mi];  // only the fields used below are loaded; rows fit 32 bits (checked at creation)
   if (a.status[e] != 0) return;
@@ -212,13 +214,14 @@ PGBP_HD void hmsg_thread(const HArgs& a, int mi, int64_t e) {
   const uint32_t sg = (uint32_t)md.sg, tg = (uint32_t)md.tg;
   const int32_t* __restrict__ gat = a.tab + md.gat + tri(M);  // sender positions of [I;K]
   const int32_t* __restrict__ sca = a.tab + md.sca + tri(S);  // receiver positions of the sepset's variables
+  const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;  // lazy sepset zero: old sepset h, g are 0, not loaded
   double g = *slot_ptr(st, (uint32_t)md.fg, ld8);
-  const double sg_old = *slot_ptr(st, sg, ld8), tg_old = *slot_ptr(st, tg, ld8);
+  const double sg_old = sz ? 0.0 : *slot_ptr(st, sg, ld8), tg_old = *slot_ptr(st, tg, ld8);
   double hI[CI > 0 ? CI : (CI == 0 ? 1 : PGBP_MAX_DIM)];
   const double* __restrict__ rec = nullptr;
   bool zeroZ = true;
   if (I > 0) {
-    rec = a.cache + (e / a.gs) * a.stride + a.cache_off[mi];
+    rec = srec ? srec : a.cache + (e / a.gs) * a.stride + a.cache_off[mi];
 #pragma unroll
     for (int k = 0; k < I; k++) hI[k] = *slot_ptr(st, fh + gat[k], ld8);
     const double info = rec[0];
@@ -260,7 +263,7 @@ PGBP_HD void hmsg_thread(const HArgs& a, int mi, int64_t e) {
       if (k0 + j < S) {
         tp[j] = slot_ptr(st, th + sca[k0 + j], ld8);
         nv[j] = *slot_ptr(st, fh + gat[I + k0 + j], ld8);
-        so[j] = *slot_ptr(st, sh + k0 + j, ld8);
+        so[j] = sz ? 0.0 : *slot_ptr(st, sh + k0 + j, ld8);
         to[j] = *tp[j];
       }
     if (!zeroZ) {
@@ -316,11 +319,26 @@ __global__ void __launch_bounds__(NT) k_jmsg(JArgs a, int maxM) {
     }
   }
 }
+// reclen > 0: every message of the launch has a factor record of `reclen` doubles; when the block's 128 elements
+// belong to ONE group the record is staged in shared memory once (coalesced) and read from there (broadcast LDS)
+// instead of ~I (I + 2S) / 2 dependent global loads per thread.
 template <int CI, int CH>
-__global__ void __launch_bounds__(128, (CH <= 4 ? 3 : 2)) k_hmsg(HArgs a) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128, (CH <= 4 ? 3 : 2)) k_hmsg(HArgs a, int reclen) {
+  extern __shared__ double srec[];
+  const int64_t e0 = (int64_t)blockIdx.x * blockDim.x;
+  const int64_t e = e0 + threadIdx.x;
+  const double* rec = nullptr;
+  if (CI != 0 && reclen > 0) {
+    const int64_t elast = (e0 + blockDim.x - 1 < a.B ? e0 + blockDim.x - 1 : a.B - 1);
+    if (e0 / a.gs == elast / a.gs) {  // uniform over the block
+      const double* src = a.cache + (e0 / a.gs) * a.stride + a.cache_off[blockIdx.y];
+      for (int q = threadIdx.x; q < reclen; q += blockDim.x) srec[q] = src[q];
+      __syncthreads();
+      rec = srec;
+    }
+  }
   if (e >= a.B) return;
-  hmsg_thread<CI, CH>(a, blockIdx.y, e);
+  hmsg_thread<CI, CH>(a, blockIdx.y, e, rec);
 }
 #endif
 
@@ -351,25 +369,29 @@ static int launch_jmsg(pgbp_batch* b, JArgs a, int nmsg, int maxM, pgbp_stream_t
   return 0;
 }
 
-static int hmsg_chunk() {  // PGBP_HMSG_CHUNK=4|8 selects the streaming chunk of the element pass (tuning knob)
-  static const int v = [] { const char* e = getenv("PGBP_HMSG_CHUNK"); return (e && atoi(e) == 4) ? 4 : 8; }();
+static int hmsg_chunk() {  // PGBP_HMSG_CHUNK=8 selects the wider streaming chunk of the element pass (tuning knob; default 4)
+  static const int v = [] { const char* e = getenv("PGBP_HMSG_CHUNK"); return (e && atoi(e) == 8) ? 8 : 4; }();
   return v;
 }
 template <int CI>
-static int launch_hmsg_t(pgbp_batch* b, const HArgs& a, int nmsg) {
+static int launch_hmsg_t(pgbp_batch* b, const HArgs& a, int nmsg, int reclen) {
 #ifdef PGBP_HOST_EMUL
+  (void)reclen;
   for (int m = 0; m < nmsg; m++)
-    for (int64_t e = 0; e < a.B; e++) hmsg_thread<CI, 8>(a, m, e);
+    for (int64_t e = 0; e < a.B; e++) hmsg_thread<CI, 4>(a, m, e);
 #else
   dim3 grid((unsigned)((a.B + 127) / 128), (unsigned)nmsg);
-  if (hmsg_chunk() == 4) k_hmsg<CI, 4><<<grid, 128, 0, b->stream>>>(a);
-  else k_hmsg<CI, 8><<<grid, 128, 0, b->stream>>>(a);
+  if (reclen * 8 > 40 * 1024) reclen = 0;  // (records beyond the default dynamic shared memory: global loads)
+  const size_t smem = sizeof(double) * (size_t)reclen;
+  if (hmsg_chunk() == 4) k_hmsg<CI, 4><<<grid, 128, smem, b->stream>>>(a, reclen);
+  else k_hmsg<CI, 8><<<grid, 128, smem, b->stream>>>(a, reclen);
 #endif
   b->launches++;
   return check_launch("k_hmsg");
 }
 
-static int launch_hmsg(pgbp_batch* b, HArgs a, int nmsg, int I) {
+// reclen: record length shared by every message of the launch (0: mixed shapes, no staging)
+static int launch_hmsg(pgbp_batch* b, HArgs a, int nmsg, int I, int reclen) {
   int done = 0;
   while (done < nmsg) {
     const int n = std::min(nmsg - done, 65535);
@@ -378,12 +400,12 @@ static int launch_hmsg(pgbp_batch* b, HArgs a, int nmsg, int I) {
     c.cache_off = a.cache_off + done;
     int rc;
     switch (I) {
-#define PGBP_H_CASE(I_) case I_: rc = launch_hmsg_t<I_>(b, c, n); break;
+#define PGBP_H_CASE(I_) case I_: rc = launch_hmsg_t<I_>(b, c, n, reclen); break;
       PGBP_H_CASE(0) PGBP_H_CASE(1) PGBP_H_CASE(2) PGBP_H_CASE(3) PGBP_H_CASE(4) PGBP_H_CASE(5) PGBP_H_CASE(6)
       PGBP_H_CASE(7) PGBP_H_CASE(8) PGBP_H_CASE(9) PGBP_H_CASE(10) PGBP_H_CASE(11) PGBP_H_CASE(12) PGBP_H_CASE(16)
       PGBP_H_CASE(24) PGBP_H_CASE(32)
 #undef PGBP_H_CASE
-      default: rc = launch_hmsg_t<-1>(b, c, n);
+      default: rc = launch_hmsg_t<-1>(b, c, n, reclen);
     }
     PGBP_TRY(rc);
     done += n;
@@ -459,6 +481,9 @@ int shared_run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_
   if (b->jcache_free.size() < b->jcache.size()) b->jcache_free.resize(b->jcache.size(), nullptr);
   if (b->jcache_used.size() < b->jcache.size()) b->jcache_used.resize(b->jcache.size(), 0);
   js = b->jstream;
+  // update_residualkldiv reads the sepset's J and the residual's dJ from the group batch AFTER the element pass of
+  // the message: the next traversal's group pass must not have overwritten them -- no running ahead across traversals
+  if (opts & PGBP_CAL_RESIDKLDIV) b->jfork_pending = true;
   if (b->jfork_pending) {  // first traversal of a calibrate! call: after the work already enqueued on the batch's stream
     PGBP_CUDA(cudaEventRecord((cudaEvent_t)b->jfork_event, b->stream));
     PGBP_CUDA(cudaStreamWaitEvent(js, (cudaEvent_t)b->jfork_event, 0));
@@ -498,7 +523,8 @@ int shared_run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_
     HArgs c = ha;
     c.msgs = b->d_msgs[td] + g.first;
     c.cache_off = b->d_jcache_off[td] + g.first;
-    PGBP_TRY(launch_hmsg(b, c, g.count, g.ci >= 0 ? g.ci : g.maxm));
+    const int gI = g.ci >= 0 ? g.ci : g.maxm;
+    PGBP_TRY(launch_hmsg(b, c, g.count, gI, gI > 0 ? (int)jrec_len(gI, g.cs) : 0));
     if (opts & PGBP_CAL_RESIDKLDIV) {
       MsgArgs ma = make_args(b, opts, ref_base, false);
       PGBP_TRY(launch_kldiv(b, ma, b->d_msgs[td], g));
@@ -532,7 +558,7 @@ int shared_propagate(pgbp_batch* b, const MsgDesc& md_plan, uint32_t opts, int32
   ha.cache = b->jcache_one;
   ha.cache_off = b->d_zero64;
   ha.stride = ja.stride;
-  PGBP_TRY(launch_hmsg(b, ha, 1, md_plan.mF - md_plan.s));
+  PGBP_TRY(launch_hmsg(b, ha, 1, md_plan.mF - md_plan.s, (int)jrec_len(md_plan.mF - md_plan.s, md_plan.s)));
   return stream_sync(b->stream);  // the descriptors are stack objects
 }
 
