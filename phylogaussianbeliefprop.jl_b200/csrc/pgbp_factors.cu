@@ -27,6 +27,15 @@ __global__ void __launch_bounds__(128, MINB) k_generic_occ(F f, int64_t B) {
   if (e >= B) return;
   f(e, (int)blockIdx.y);
 }
+
+// Few elements, many rows (the group batch of a shared-precision batch: one element per parameter vector, 10^5
+// clusters): one thread per ROW y instead of one block per row with a single live thread.
+template <class F>
+__global__ void __launch_bounds__(128) k_generic_rows(F f, int64_t n, int ny) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= ny) return;
+  for (int64_t e = 0; e < n; e++) f(e, y);
+}
 #endif
 
 template <class F, int MINB = 0>
@@ -37,6 +46,13 @@ static int launch_generic(pgbp_batch* b, const char* name, int64_t n, int ny, F 
     for (int64_t e = 0; e < n; e++) f(e, y);
   b->launches++;
 #else
+  if (n <= 4 && ny >= 1024) {
+    F g = f;
+    g.y0 = 0;
+    k_generic_rows<<<(unsigned)((ny + 127) / 128), 128, 0, b->stream>>>(g, n, ny);
+    b->launches++;
+    return check_launch(name);
+  }
   for (int y0 = 0; y0 < ny; y0 += 65535) {
     const int cnt = std::min(65535, ny - y0);
     F g = f;
