@@ -652,13 +652,13 @@ struct AssignFast {
       }
       // precision block j (symmetric: upper triangle kept, 36 registers at P = 8) and log-normaliser
       constexpr int NJ = P * (P + 1) / 2;
-      double ju[NJ];
+      double ju[SH ? 1 : NJ];  // (element pass of a shared-precision batch: the block is read from the cache, never built)
       double* juc = jucache ? jucache + (int64_t)v * (NJ + 2) * juG + (SH ? e / gen.gs : e) : nullptr;
       const int64_t jus = juG;  // stride between the entries of one cached block
-#define PGBP_JU(r_, c_) ((SH && juc) ? juc[(int64_t)((r_) <= (c_) ? pk((r_), (c_)) : pk((c_), (r_))) * jus] \
-                                     : ju[(r_) <= (c_) ? pk((r_), (c_)) : pk((c_), (r_))])
+#define PGBP_JU(r_, c_) (SH ? juc[(int64_t)((r_) <= (c_) ? pk((r_), (c_)) : pk((c_), (r_))) * jus] \
+                            : ju[SH ? 0 : ((r_) <= (c_) ? pk((r_), (c_)) : pk((c_), (r_)))])
       double gv;
-      if (SH && juc) {  // element pass of a shared-precision batch: the group pass left j, g0 and the failure code
+      if constexpr (SH) {  // element pass of a shared-precision batch: the group pass left j, g0 and the failure code
         const double info = juc[(int64_t)(NJ + 1) * jus];
         if (info != 0.0) { status_fail(gen.status, e, PGBP_STATUS(0x7ffffc, (int)info)); st[gs * ld] = NAN; return; }
         gv = juc[(int64_t)NJ * jus];
@@ -1384,7 +1384,7 @@ static int assign_launch(pgbp_batch* b, pgbp::DevTables* dt, double* out, int32_
   switch (pt) {
 #define PGBP_FAST_CASE(P_) \
   case P_: \
-    if (b->group_size > 1) PGBP_TRY((launch_generic<AssignFast<P_, true>, 3>(b, "k_assign_factors", b->B, p->nclusters, AssignFast<P_, true>{body, dt->clu_flag, dt->first_J, dt->first_h, juc, juG}))); \
+    if (b->group_size > 1) PGBP_TRY((launch_generic<AssignFast<P_, true>, 5>(b, "k_assign_factors", b->B, p->nclusters, AssignFast<P_, true>{body, dt->clu_flag, dt->first_J, dt->first_h, juc, juG}))); \
     else PGBP_TRY((launch_generic<AssignFast<P_>, 3>(b, "k_assign_factors", b->B, p->nclusters, AssignFast<P_>{body, dt->clu_flag, dt->first_J, dt->first_h, juc, juG}))); \
     break;
     PGBP_FAST_CASE(1) PGBP_FAST_CASE(2) PGBP_FAST_CASE(3) PGBP_FAST_CASE(4) PGBP_FAST_CASE(5) PGBP_FAST_CASE(6)

@@ -172,6 +172,8 @@ struct pgbp_batch {
   std::vector<void*> jstep_events;    // cudaEvent_t per step (grown on demand)
   std::vector<void*> jcache_free;     // cudaEvent_t per traversal (null until first use)
   std::vector<char> jcache_used;      // traversal already passed during the current calibrate! call
+  std::vector<unsigned*> d_walkflags;  // per traversal: [nsteps][ngroups] executions of the group walk per step
+  std::vector<unsigned*> d_walkcount;  // per traversal: {executions of the element walk, blocks done in the current one}
   void* jfork_event = nullptr;
   bool jfork_pending = true;          // set at the start of every calibrate! call
   double* jcache_one = nullptr;       // scratch record for single messages (pgbp_propagate, regularize_onschedule)

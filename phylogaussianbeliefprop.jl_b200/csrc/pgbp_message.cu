@@ -603,7 +603,10 @@ int32_t pgbp_calibrate_async(pgbp_batch* b, const int32_t* tree_ids, int32_t ntr
   int64_t nl = 0;
   for (int t : ids) nl += (int64_t)p->trees[t].trav[0].groups.size() + (int64_t)p->trees[t].trav[1].groups.size();
   nl *= niter;
-  const bool want_graph = b->graph_mode == 1 || (b->graph_mode < 0 && nl >= 24);
+  // (shared-precision batches small enough for the walk kernels are not captured: the element walk spins on counters
+  // the group walk publishes from another stream, and a graph does not promise to run independent branches concurrently)
+  const bool walkable_shared = b->jb && (b->B + 127) / 128 <= 64 && b->ngroups <= 16;
+  const bool want_graph = !walkable_shared && (b->graph_mode == 1 || (b->graph_mode < 0 && nl >= 24));
   if (want_graph) {
     std::string key;
     for (int t : ids) key += std::to_string(t) + ",";

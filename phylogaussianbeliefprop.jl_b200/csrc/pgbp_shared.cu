@@ -24,6 +24,15 @@
 
 namespace pgbp {
 
+template <class T>
+static int salloc(pgbp_batch* b, T** p, size_t n) {
+  void* v = nullptr;
+  PGBP_TRY(dev_malloc(&v, std::max<size_t>(1, n) * sizeof(T)));
+  *p = (T*)v;
+  b->device_bytes += (int64_t)(n * sizeof(T));
+  return 0;
+}
+
 struct JArgs {
   const MsgDesc* msgs;       // plan numbering (the group batch's own descriptors)
   const int32_t* tab;
@@ -327,18 +336,111 @@ __global__ void __launch_bounds__(128, (CH <= 4 ? 3 : 2)) k_hmsg(HArgs a, int re
   extern __shared__ double srec[];
   const int64_t e0 = (int64_t)blockIdx.x * blockDim.x;
   const int64_t e = e0 + threadIdx.x;
-  const double* rec = nullptr;
+  bool staged = false;
   if (CI != 0 && reclen > 0) {
     const int64_t elast = (e0 + blockDim.x - 1 < a.B ? e0 + blockDim.x - 1 : a.B - 1);
     if (e0 / a.gs == elast / a.gs) {  // uniform over the block
       const double* src = a.cache + (e0 / a.gs) * a.stride + a.cache_off[blockIdx.y];
       for (int q = threadIdx.x; q < reclen; q += blockDim.x) srec[q] = src[q];
       __syncthreads();
-      rec = srec;
+      staged = true;
     }
   }
   if (e >= a.B) return;
-  hmsg_thread<CI, CH>(a, blockIdx.y, e, rec);
+  // two call sites so that the staged one is compiled with shared-memory loads (LDS), not generic ones
+  if (staged) hmsg_thread<CI, CH>(a, blockIdx.y, e, srec);
+  else hmsg_thread<CI, CH>(a, blockIdx.y, e, nullptr);
+}
+#endif
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Walk kernels: a RUN of consecutive narrow steps in ONE launch per pass.
+// Deep schedules (C5's clique tree: ~450 levels per direction, most of them one to four messages wide) spend their
+// time in launch gaps and single-message latencies: ~900 launches per pass and calibration.  For a run of narrow
+// steps the group pass becomes one block per group (8 warps, one message per warp, block barrier between steps) and
+// the element pass one block per 128 elements that walks the run for ITS elements (elements are independent: no
+// synchronisation between blocks).  The element pass of step s only needs the group pass of step s: the group walk
+// publishes a per-(step, group) counter after each step (release), the element walk spins on it (acquire, bounded).
+// The counters count executions, so a captured CUDA graph can be replayed: the element walk of execution k waits for
+// counter >= k, k = its own per-traversal execution count kept on the device.
+// Records are padded to whole 128-byte lines: a line never holds parts of two records, so reading a record after
+// its flag cannot see a stale L1 line from an earlier read of its neighbour.
+#define PGBP_SW_WIDE 8     // widest step (messages) of a walk run
+#define PGBP_SW_MINRUN 8   // shortest run worth a walk launch
+#ifndef PGBP_HOST_EMUL
+__global__ void __launch_bounds__(32 * PGBP_SW_WIDE) k_jwalk(JArgs a, const int32_t* __restrict__ step_off, int s0, int s1,
+                                                            unsigned* flags, int maxM) {
+  extern __shared__ double jA[];
+  const int nq = tri(maxM);
+  const int warp = threadIdx.x >> 5;
+  const WarpLanes w{(int)(threadIdx.x & 31)};
+  uint8_t* rc = (uint8_t*)(jA + (size_t)PGBP_SW_WIDE * (nq + 1));
+  double* A = jA + (size_t)warp * (nq + 1);
+  if (warp == 0) fill_rc(rc, nq, w);
+  __syncthreads();
+  for (int64_t g = blockIdx.x; g < a.G; g += gridDim.x) {
+    for (int s = s0; s < s1; s++) {
+      const int first = step_off[s], end = step_off[s + 1];
+      for (int m = first + warp; m < end; m += PGBP_SW_WIDE) {
+        jmsg_body(a, m, g, w, A, rc);
+        __syncwarp();
+      }
+      __syncthreads();  // the step's records and J rows are written (block scope) ...
+      if (threadIdx.x == 0) {
+        __threadfence();  // ... and visible device-wide before the counter moves
+        atomicAdd(&flags[(int64_t)s * a.G + g], 1u);
+      }
+    }
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(128) k_hwalk(HArgs a, const int32_t* __restrict__ step_off, int s0, int s1,
+                                                  const unsigned* flags, unsigned* hcount, unsigned* done_blocks, int64_t G) {
+  __shared__ unsigned need;
+  __shared__ int timed_out;
+  const int64_t e0 = (int64_t)blockIdx.x * blockDim.x;
+  const int64_t e = e0 + threadIdx.x;
+  const int64_t elast = (e0 + blockDim.x - 1 < a.B ? e0 + blockDim.x - 1 : a.B - 1);
+  const int64_t g0 = e0 / a.gs, g1 = elast / a.gs;
+  if (threadIdx.x == 0) { need = *(volatile unsigned*)hcount + 1u; timed_out = 0; }
+  __syncthreads();
+  for (int s = s0; s < s1; s++) {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      for (int64_t g = g0; g <= g1; g++)
+        while (*(volatile const unsigned*)&flags[(int64_t)s * G + g] < need) {
+          if (clock64() - t0 > 6000000000LL) { timed_out = 1; break; }  // ~3 s: the group walk is lost
+          __nanosleep(100);
+        }
+      __threadfence();
+    }
+    __syncthreads();
+    if (timed_out) break;
+    if (e < a.B) {
+      const int first = step_off[s], end = step_off[s + 1];
+      for (int m = first; m < end; m++) {
+        const int I = a.msgs[m].mF - a.msgs[m].s;
+        switch (I) {
+          case 0: hmsg_thread<0, CH>(a, m, e); break;
+          case 16: hmsg_thread<16, CH>(a, m, e); break;
+          case 32: hmsg_thread<32, CH>(a, m, e); break;
+          default: hmsg_thread<-1, CH>(a, m, e); break;
+        }
+      }
+    }
+  }
+  if (timed_out && e < a.B) status_fail(a.status, e, PGBP_STATUS(0x7ffff8, 1));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(done_blocks, 1u) == gridDim.x - 1) {  // last block of this execution
+      *done_blocks = 0;
+      __threadfence();
+      atomicAdd(hcount, 1u);
+    }
+  }
 }
 #endif
 
@@ -494,8 +596,47 @@ int shared_run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_
   // pass runs ahead of the element pass -- except that it must not overwrite records still being read
   if (b->jcache_used[td]) PGBP_CUDA(cudaStreamWaitEvent(js, (cudaEvent_t)b->jcache_free[td], 0));  // (same call: same capture)
 #endif
-  // group pass: one launch per step (messages of a step touch disjoint beliefs)
+  // walk runs: maximal runs of >= PGBP_SW_MINRUN consecutive steps of <= PGBP_SW_WIDE messages (walk_end[s] = end of the
+  // run starting at s, 0 elsewhere); only when the element walk leaves SMs free for the group walk it waits for
+  std::vector<int> walk_end(tv.nsteps + 1, 0);
+#ifndef PGBP_HOST_EMUL
+  {
+    static const bool walk_on = [] { const char* e = getenv("PGBP_SHARED_WALK"); return !(e && atoi(e) == 0); }();
+    const bool ok = walk_on && !(opts & PGBP_CAL_RESIDKLDIV) && (b->B + 127) / 128 <= 64 && b->ngroups <= 16;
+    for (int s = 0; ok && s < tv.nsteps;) {
+      int t = s;
+      while (t < tv.nsteps && tv.step_off[t + 1] - tv.step_off[t] <= PGBP_SW_WIDE) t++;
+      if (t - s >= PGBP_SW_MINRUN) walk_end[s] = t;
+      s = t > s ? t : s + 1;
+    }
+    if (!b->d_walkflags.size()) { b->d_walkflags.assign(b->jcache.size(), nullptr); b->d_walkcount.assign(b->jcache.size(), nullptr); }
+    if (!b->d_walkflags[td]) {
+      PGBP_TRY(salloc(b, &b->d_walkflags[td], (size_t)tv.nsteps * (size_t)b->ngroups));
+      PGBP_TRY(salloc(b, &b->d_walkcount[td], 2));
+      PGBP_TRY(dev_memset(b->d_walkflags[td], 0, sizeof(unsigned) * (size_t)tv.nsteps * (size_t)b->ngroups, b->stream));
+      PGBP_TRY(dev_memset(b->d_walkcount[td], 0, sizeof(unsigned) * 2, b->stream));
+      PGBP_TRY(stream_sync(b->stream));
+    }
+  }
+#endif
+  // group pass: one launch per step (messages of a step touch disjoint beliefs), one launch per walk run
   for (int s = 0; s < tv.nsteps; s++) {
+#ifndef PGBP_HOST_EMUL
+    if (walk_end[s]) {
+      const int s1 = walk_end[s];
+      int maxM = 0;
+      for (int k = tv.step_off[s]; k < tv.step_off[s1]; k++) maxM = std::max(maxM, tv.msgs[k].mF);
+      const size_t smem = sizeof(double) * (size_t)PGBP_SW_WIDE * (size_t)(tri(maxM) + 1) + 2 * (size_t)tri(maxM) + 16;
+      static bool attr_done = false;
+      if (!attr_done) { PGBP_CUDA(cudaFuncSetAttribute((const void*)k_jwalk, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_done = true; }
+      k_jwalk<<<(unsigned)std::min<int64_t>(b->ngroups, 1024), 32 * PGBP_SW_WIDE, smem, js>>>(ja, b->jb->d_step_off[td], s, s1, b->d_walkflags[td], maxM);
+      b->launches++;
+      PGBP_TRY(check_launch("k_jwalk"));
+      PGBP_CUDA(cudaEventRecord((cudaEvent_t)b->jstep_events[s1 - 1], js));
+      s = s1 - 1;
+      continue;
+    }
+#endif
     const int first = tv.step_off[s], count = tv.step_off[s + 1] - first;
     if (count > 0) {
       int maxM = 0;
@@ -510,9 +651,23 @@ int shared_run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_
 #endif
   }
   // element pass: the plan's launch groups (same step, same shape class), each step after its records exist
-  int waited = -1;
+  int waited = -1, walked_until = 0;
   for (const LaunchGroup& g : tv.groups) {
 #ifndef PGBP_HOST_EMUL
+    if (g.step < walked_until) continue;  // inside a run the element walk has been launched for
+    if (walk_end[g.step]) {
+      const int s1 = walk_end[g.step];
+      HArgs c = ha;
+      c.msgs = b->d_msgs[td];
+      c.cache_off = b->d_jcache_off[td];
+      const unsigned grid = (unsigned)((b->B + 127) / 128);
+      if (hmsg_chunk() == 4) k_hwalk<4><<<grid, 128, 0, b->stream>>>(c, b->jb->d_step_off[td], g.step, s1, b->d_walkflags[td], b->d_walkcount[td], b->d_walkcount[td] + 1, b->ngroups);
+      else k_hwalk<8><<<grid, 128, 0, b->stream>>>(c, b->jb->d_step_off[td], g.step, s1, b->d_walkflags[td], b->d_walkcount[td], b->d_walkcount[td] + 1, b->ngroups);
+      b->launches++;
+      PGBP_TRY(check_launch("k_hwalk"));
+      walked_until = s1;
+      continue;
+    }
     if (g.step != waited) {
       PGBP_CUDA(cudaStreamWaitEvent(b->stream, (cudaEvent_t)b->jstep_events[g.step], 0));
       waited = g.step;
@@ -576,15 +731,6 @@ MsgDesc shared_remap(const pgbp_batch* b, const MsgDesc& m) {
   return r;
 }
 
-template <class T>
-static int salloc(pgbp_batch* b, T** p, size_t n) {
-  void* v = nullptr;
-  PGBP_TRY(dev_malloc(&v, std::max<size_t>(1, n) * sizeof(T)));
-  *p = (T*)v;
-  b->device_bytes += (int64_t)(n * sizeof(T));
-  return 0;
-}
-
 // Element side of a shared-precision batch (the caller has set plan, B, ld, group_size, device, flags, stream):
 // compact layout, descriptors, caches, and the group batch.
 int shared_create(pgbp_batch* b) {
@@ -639,7 +785,7 @@ int shared_create(pgbp_batch* b) {
       std::vector<int64_t> off(n + 1, 0);
       for (size_t k = 0; k < n; k++) {
         rm[k] = shared_remap(b, tv.msgs[k]);
-        off[k + 1] = off[k] + jrec_len(tv.msgs[k].mF - tv.msgs[k].s, tv.msgs[k].s);
+        off[k + 1] = off[k] + (jrec_len(tv.msgs[k].mF - tv.msgs[k].s, tv.msgs[k].s) + 15) / 16 * 16;  // whole 128-byte lines
       }
       const size_t td = 2 * t + dir;
       PGBP_TRY(salloc(b, &b->d_msgs[td], n));
@@ -667,6 +813,8 @@ void shared_destroy(pgbp_batch* b) {
 #endif
   for (auto* q : b->jcache) dev_free(q);
   for (auto* q : b->d_jcache_off) dev_free(q);
+  for (auto* q : b->d_walkflags) dev_free(q);
+  for (auto* q : b->d_walkcount) dev_free(q);
   dev_free(b->jcache_one);
   dev_free(b->d_zero64);
   dev_free(b->jucache);

@@ -1446,3 +1446,34 @@ def test_calibrate_optimize_cliquetree_mvfull_closed_form(backend):
     assert th.size == p * (p + 1) // 2 + p
     back = to_orig(th)
     assert np.allclose(back[:p * p].reshape(p, p), R_ml, rtol=1e-13) and np.allclose(back[p * p:p * p + p], mu_ml, rtol=1e-13)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_shared_precision_wide_network_two_groups(backend):
+    # a network with > 1024 clusters and only two groups: on the GPU the group batch's K1 goes through the row-parallel
+    # launcher (one thread per cluster) and the group pass sees levels of hundreds of messages; product pairing with
+    # two parameter vectors x four data sets; heterogeneous colours through the K1 block cache
+    lib = get_lib(backend)
+    import bench
+    w = bench.C4(ntips=700, nretic=70, p=3)
+    d = w.d
+    assert d["nclusters"] > 1024
+    nth, nd = 2, 4
+    B = nth * nd
+    params, _ = w.inputs(nth, 0)
+    tips = w.synth.simulate_tips(d, lambda v, k: np.eye(3), nd, 99)
+    plan = pgbp_b200.ClusterGraphPlan(d["nclusters"], d["belief_dim"], d["sepset_clusters"], d["upind"], d["trees"],
+                                      d["ntraits"], d["families"], lib)
+    root = d["root_cluster"] + 1
+    out = {}
+    for name, group in (("own", 0), ("shared", nd)):
+        bt = pgbp_b200.BatchedClusterGraphBelief(plan, B, shared_precision_group=group)
+        bt.assignfactors(params, tips, ncolors=w.ncolors, pairing="product")
+        succ, iscal = bt.calibrate(None, 1)
+        out[name] = (succ, iscal, bt.status(), bt.integratebelief(root)[1], bt.factored_energy(),
+                     [bt.get_belief(j) for j in (1, 17, root, plan.nclusters + 5)])
+    a, s_ = out["own"], out["shared"]
+    assert a[0].all() and all(np.array_equal(a[k], s_[k]) for k in range(5))
+    for x, y in zip(a[5], s_[5]):
+        for u, v in zip(x, y):
+            assert np.array_equal(u, v)
