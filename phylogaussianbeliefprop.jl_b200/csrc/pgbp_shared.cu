@@ -18,6 +18,7 @@
 // (tests/test_parity.py::test_shared_precision_batch_is_bit_identical).
 #include <algorithm>
 
+#include "pgbp_bulk.cuh"
 #include "pgbp_kernels.cuh"
 #include "pgbp_launch.h"
 #include "pgbp_shapes.h"
@@ -64,6 +65,9 @@ struct HArgs {
 };
 
 PGBP_HD int64_t jrec_len(int I, int S) { return I == 0 ? 0 : 2 + I + (int64_t)I * (I + S) - (int64_t)I * (I + 1) / 2; }
+
+// record slot of the single-message path (pgbp_propagate): any shape, whole 128-byte lines
+static int64_t jrec_one_len() { return (jrec_len(PGBP_MAX_DIM, 0) + (int64_t)PGBP_MAX_DIM * PGBP_MAX_DIM + 31) / 16 * 16; }
 
 // the lanes that share one (message, group): a warp on the device, a single "lane" in the host emulation
 struct OneLane {
@@ -209,8 +213,10 @@ PGBP_HD void jmsg_body(const JArgs& a, int mi, int64_t g, const W& w, double* A,
 // CI < 0: runtime (thread-local array).
 // CH: kept entries per streaming chunk (3 CH loads in flight per thread).  Measured on B200: CH = 4 (168 registers,
 // 3 blocks per SM) beats CH = 8 (254 registers): c5s 4,801 vs 4,227 calibrations/s, c2s 137.7 vs 130.9 M/s
-template <int CI, int CH>
-PGBP_HD void hmsg_thread(const HArgs& a, int mi, int64_t e, const double* srec = nullptr) {
+// STAGED (device only): the block staged the message's record and its two index tables in dynamic shared memory
+// (k_hmsg); they are read through the shared window (LDS with immediate offsets), not through generic pointers.
+template <int CI, int CH, bool STAGED = false>
+PGBP_HD void hmsg_thread(const HArgs& a, int mi, int64_t e, int reclen = 0) {
   constexpr int PGBP_HMSG_CHUNK = CH;
   const MsgDesc& md = a.msgs[mi];  // only the fields used below are loaded; rows fit 32 bits (checked at creation)
   if (a.status[e] != 0) return;
@@ -221,8 +227,16 @@ PGBP_HD void hmsg_thread(const HArgs& a, int mi, int64_t e, const double* srec =
   char* rs = a.resid ? (char*)(a.resid + e) : nullptr;
   const uint32_t fh = (uint32_t)md.fh, sh = (uint32_t)md.sh, th = (uint32_t)md.th, rh = (uint32_t)md.rh;
   const uint32_t sg = (uint32_t)md.sg, tg = (uint32_t)md.tg;
-  const int32_t* __restrict__ gat = a.tab + md.gat + tri(M);  // sender positions of [I;K]
-  const int32_t* __restrict__ sca = a.tab + md.sca + tri(S);  // receiver positions of the sepset's variables
+#if !defined(PGBP_HOST_EMUL)
+  extern __shared__ double srec[];
+  const int32_t* stab = (const int32_t*)(srec + reclen);
+  const int32_t* __restrict__ gat = STAGED ? stab : a.tab + md.gat + tri(M);  // sender positions of [I;K]
+  const int32_t* __restrict__ sca = STAGED ? stab + M : a.tab + md.sca + tri(S);  // receiver positions of the sepset's variables
+#else
+  (void)reclen;
+  const int32_t* __restrict__ gat = a.tab + md.gat + tri(M);
+  const int32_t* __restrict__ sca = a.tab + md.sca + tri(S);
+#endif
   const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;  // lazy sepset zero: old sepset h, g are 0, not loaded
   double g = *slot_ptr(st, (uint32_t)md.fg, ld8);
   const double sg_old = sz ? 0.0 : *slot_ptr(st, sg, ld8), tg_old = *slot_ptr(st, tg, ld8);
@@ -230,7 +244,11 @@ PGBP_HD void hmsg_thread(const HArgs& a, int mi, int64_t e, const double* srec =
   const double* __restrict__ rec = nullptr;
   bool zeroZ = true;
   if (I > 0) {
-    rec = srec ? srec : a.cache + (e / a.gs) * a.stride + a.cache_off[mi];
+#if !defined(PGBP_HOST_EMUL)
+    if constexpr (STAGED) rec = srec;
+    else
+#endif
+      rec = a.cache + (e / a.gs) * a.stride + a.cache_off[mi];
 #pragma unroll
     for (int k = 0; k < I; k++) hI[k] = *slot_ptr(st, fh + gat[k], ld8);
     const double info = rec[0];
@@ -331,8 +349,11 @@ __global__ void __launch_bounds__(NT) k_jmsg(JArgs a, int maxM) {
 // reclen > 0: every message of the launch has a factor record of `reclen` doubles; when the block's 128 elements
 // belong to ONE group the record is staged in shared memory once (coalesced) and read from there (broadcast LDS)
 // instead of ~I (I + 2S) / 2 dependent global loads per thread.
+#ifndef PGBP_HMSG_MINB
+#define PGBP_HMSG_MINB 4  // resident blocks per SM of the element pass for I <= 16 (register cap 128)
+#endif
 template <int CI, int CH>
-__global__ void __launch_bounds__(128, (CH <= 4 ? 3 : 2)) k_hmsg(HArgs a, int reclen) {
+__global__ void __launch_bounds__(128, (CH <= 4 ? (CI >= 0 && CI <= 16 ? PGBP_HMSG_MINB : 3) : 2)) k_hmsg(HArgs a, int reclen) {
   extern __shared__ double srec[];
   const int64_t e0 = (int64_t)blockIdx.x * blockDim.x;
   const int64_t e = e0 + threadIdx.x;
@@ -340,24 +361,158 @@ __global__ void __launch_bounds__(128, (CH <= 4 ? 3 : 2)) k_hmsg(HArgs a, int re
   if (CI != 0 && reclen > 0) {
     const int64_t elast = (e0 + blockDim.x - 1 < a.B ? e0 + blockDim.x - 1 : a.B - 1);
     if (e0 / a.gs == elast / a.gs) {  // uniform over the block
+      const MsgDesc& md = a.msgs[blockIdx.y];
+      const int S = md.s, M = md.mF;
       const double* src = a.cache + (e0 / a.gs) * a.stride + a.cache_off[blockIdx.y];
       for (int q = threadIdx.x; q < reclen; q += blockDim.x) srec[q] = src[q];
+      int32_t* stab = (int32_t*)(srec + reclen);
+      const int32_t* gat = a.tab + md.gat + tri(M);
+      const int32_t* sca = a.tab + md.sca + tri(S);
+      for (int q = threadIdx.x; q < M + S; q += blockDim.x) stab[q] = q < M ? gat[q] : sca[q - M];
       __syncthreads();
       staged = true;
     }
   }
   if (e >= a.B) return;
-  // two call sites so that the staged one is compiled with shared-memory loads (LDS), not generic ones
-  if (staged) hmsg_thread<CI, CH>(a, blockIdx.y, e, srec);
-  else hmsg_thread<CI, CH>(a, blockIdx.y, e, nullptr);
+  if (staged) hmsg_thread<CI, CH, true>(a, blockIdx.y, e, reclen);
+  else hmsg_thread<CI, CH, false>(a, blockIdx.y, e);
+}
+
+// Element pass with bulk-copy staging: the wide levels of big graphs (C5: 420k messages x 1,536 replicates) are a
+// pure streaming problem -- 8 (m_F + 1 + 4 (s+1)) bytes and I^2/2 + I S FMAs per (message, element) -- and the
+// thread-per-element kernel above keeps too few bytes in flight (12-16 warps per SM x ~14 loads each; ncu: long
+// scoreboard 48 %, 2.8 TB/s).  Here a block of 128 threads owns 128 consecutive elements of ONE message: every slot
+// row the message reads (h of the sender in [I;K] order, old sepset h, target h at the sepset's positions, the three
+// g) is a contiguous 1 KB segment of the batch-innermost layout, so thread n issues ONE cp.async.bulk for row n, the
+// factor record arrives by a bulk copy too, and all of them (67 rows = 69 KB for an (I,S) = (16,16) message) are in
+// flight at once on one mbarrier, without holding a register.  Three blocks per SM keep ~200 KB in flight.  The
+// arithmetic (element = thread, operands from shared memory, conflict-free) repeats hmsg_thread operation by
+// operation: bit-identical results.
+template <int CI>
+__global__ void __launch_bounds__(128, (CI <= 16 ? 3 : 2)) k_hmsg_bulk(HArgs a, int reclen) {
+  extern __shared__ __align__(128) double sm[];
+  __shared__ __align__(8) unsigned long long mbar;
+  constexpr int I = CI;
+  const int tid = threadIdx.x;
+  const MsgDesc& md = a.msgs[blockIdx.y];
+  const int S = md.s, M = I + S;
+  const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;
+  const int nrows = M + S + 2 + (sz ? 0 : S + 1);
+  // rows: [0, M) sender h in [I;K] order | [M, M+S) target h | M+S: sender g | M+S+1: target g | (unless sz) M+S+2:
+  // sepset g | M+S+3+k: sepset h
+  const int64_t e0 = (int64_t)blockIdx.x * 128, e = e0 + tid;
+  const int64_t left = a.ld - e0;
+  const uint32_t rowbytes = (uint32_t)(left < 128 ? left : 128) * 8u;
+  const uint32_t ld8 = (uint32_t)(a.ld * 8);
+  double* rows = sm + reclen;
+  uint32_t* sslot = (uint32_t*)(rows + (size_t)nrows * 128);  // slot of every staged row
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    mbar_expect_tx(&mbar, (unsigned)reclen * 8u + (unsigned)nrows * rowbytes);
+  }
+  __syncthreads();
+  const char* tileb = (const char*)(a.state + e0);
+  if (tid == 0) bulk_g2s(sm, a.cache + (e0 / a.gs) * a.stride + a.cache_off[blockIdx.y], (unsigned)reclen * 8u, &mbar);
+  {
+    const int32_t* __restrict__ gat = a.tab + md.gat + tri(M);
+    const int32_t* __restrict__ sca = a.tab + md.sca + tri(S);
+    for (int n = tid; n < nrows; n += 128) {
+      uint32_t slot;
+      if (n < M) slot = (uint32_t)md.fh + (uint32_t)gat[n];
+      else if (n < M + S) slot = (uint32_t)md.th + (uint32_t)sca[n - M];
+      else if (n == M + S) slot = (uint32_t)md.fg;
+      else if (n == M + S + 1) slot = (uint32_t)md.tg;
+      else if (n == M + S + 2) slot = (uint32_t)md.sg;
+      else slot = (uint32_t)md.sh + (uint32_t)(n - (M + S + 3));
+      sslot[n] = slot;
+      bulk_g2s(rows + (size_t)n * 128, tileb + (uint64_t)slot * (uint64_t)ld8, rowbytes, &mbar);
+    }
+  }
+  const int32_t stat = e < a.B ? a.status[e] : 1;
+  __syncthreads();       // sslot
+  mbar_wait(&mbar, 0);   // every row and the record have landed (no thread leaves the block before that)
+  if (stat != 0) return;
+  char* st = (char*)(a.state + e);
+  char* rs = a.resid ? (char*)(a.resid + e) : nullptr;
+  const double* rec = sm;
+  const double* r = rows + tid;
+  double g = r[(M + S) * 128];
+  const double tg_old = r[(M + S + 1) * 128], sg_old = sz ? 0.0 : r[(M + S + 2) * 128];
+  double hI[I];
+#pragma unroll
+  for (int k = 0; k < I; k++) hI[k] = r[k * 128];
+  bool zeroZ = true;
+  const double info = rec[0];
+  if (info > 0.0) {
+    status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, (int)info));
+    return;
+  }
+  if (info < 0.0) {
+    bool hz = true;
+#pragma unroll
+    for (int k = 0; k < I; k++)
+      if (!(fabs(hI[k]) <= PGBP_EPS)) hz = false;
+    if (!hz) {
+      status_fail(a.status, e, PGBP_STATUS(a.ref_base + md.ref, 1));
+      return;
+    }
+  } else {
+    zeroZ = false;
+    double ww = 0.0;
+    const double* row = rec + 2 + I;
+#pragma unroll
+    for (int k = 0; k < I; k++) {
+      const double wk = hI[k] * rec[2 + k];
+      hI[k] = wk;
+      ww = fma(wk, wk, ww);
+#pragma unroll
+      for (int c = k + 1; c < I; c++) hI[c] = nfma(row[c - k - 1], wk, hI[c]);
+      row += M - 1 - k;
+    }
+    g += 0.5 * ((double)I * PGBP_LOG2PI - rec[1] + ww);
+  }
+  double maxh = 0.0;
+  constexpr int CH = 8;
+  for (int k0 = 0; k0 < S; k0 += CH) {
+    double nv[CH];
+#pragma unroll
+    for (int j = 0; j < CH; j++)
+      if (k0 + j < S) nv[j] = r[(I + k0 + j) * 128];
+    if (!zeroZ) {
+      const double* row = rec + 2 + I;
+#pragma unroll
+      for (int i = 0; i < I; i++) {
+        const double wi = hI[i];
+#pragma unroll
+        for (int j = 0; j < CH; j++)
+          if (k0 + j < S) nv[j] = nfma(row[(I - 1 - i) + k0 + j], wi, nv[j]);
+        row += M - 1 - i;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CH; j++)
+      if (k0 + j < S) {
+        const int k = k0 + j;
+        const double so = sz ? 0.0 : r[(M + S + 3 + k) * 128];
+        const double d = nv[j] - so;
+        *slot_ptr(st, (uint32_t)md.sh + k, ld8) = nv[j];
+        *slot_ptr(st, sslot[M + k], ld8) = r[(M + k) * 128] + d;
+        if (rs) *slot_ptr(rs, (uint32_t)md.rh + k, ld8) = d;
+        absmax(maxh, d);
+      }
+  }
+  *slot_ptr(st, (uint32_t)md.sg, ld8) = g;
+  *slot_ptr(st, (uint32_t)md.tg, ld8) = tg_old + (g - sg_old);
+  if ((a.opts & PGBP_CAL_RESIDNORM) && a.calflag)
+    a.calflag[(int64_t)md.dmsg * a.ld + e] = (S > 0 ? (maxh / sqrt((double)S) <= 1e-5) : true) ? 1 : 0;
 }
 #endif
 
-
 // ---------------------------------------------------------------------------------------------------------------
 // Walk kernels: a RUN of consecutive narrow steps in ONE launch per pass.
-// Deep schedules (C5's clique tree: ~450 levels per direction, most of them one to four messages wide) spend their
-// time in launch gaps and single-message latencies: ~900 launches per pass and calibration.  For a run of narrow
+// Deep schedules of narrow steps (loopy graphs, the thin ends of a clique tree's level order) spend their time in
+// launch gaps and single-message latencies.  (C5's clique tree is not one of them: 62 + 45 steps, 21 of them <= 8
+// messages wide -- its ~900 launches per pass are launch groups by shape; no measurable effect there.)  For a run of narrow
 // steps the group pass becomes one block per group (8 warps, one message per warp, block barrier between steps) and
 // the element pass one block per 128 elements that walks the run for ITS elements (elements are independent: no
 // synchronisation between blocks).  The element pass of step s only needs the group pass of step s: the group walk
@@ -475,6 +630,10 @@ static int hmsg_chunk() {  // PGBP_HMSG_CHUNK=8 selects the wider streaming chun
   static const int v = [] { const char* e = getenv("PGBP_HMSG_CHUNK"); return (e && atoi(e) == 8) ? 8 : 4; }();
   return v;
 }
+static bool hmsg_bulk() {  // PGBP_HMSG_BULK=0: the thread-per-element kernel everywhere (A/B switch)
+  static const bool v = [] { const char* e = getenv("PGBP_HMSG_BULK"); return !(e && atoi(e) == 0); }();
+  return v;
+}
 template <int CI>
 static int launch_hmsg_t(pgbp_batch* b, const HArgs& a, int nmsg, int reclen) {
 #ifdef PGBP_HOST_EMUL
@@ -483,8 +642,26 @@ static int launch_hmsg_t(pgbp_batch* b, const HArgs& a, int nmsg, int reclen) {
     for (int64_t e = 0; e < a.B; e++) hmsg_thread<CI, 4>(a, m, e);
 #else
   dim3 grid((unsigned)((a.B + 127) / 128), (unsigned)nmsg);
+  if constexpr (CI == 8 || CI == 12 || CI == 16 || CI == 24 || CI == 32) {
+    // bulk-copy staging (k_hmsg_bulk): every block of 128 elements inside one group, 16-byte aligned rows, one
+    // message shape per launch (reclen > 0), and the rows of a message fit the shared memory of an SM
+    if (hmsg_bulk() && reclen > 0 && (a.gs % 128 == 0 || a.gs >= a.B) && a.ld % 2 == 0 && a.B >= 64) {
+      const int S = (int)((reclen - 2 - CI - (CI * (CI - 1)) / 2) / CI);  // jrec_len(I, S) solved for S
+      const int reclen16 = (reclen + 15) / 16 * 16;
+      const int nrows = CI + 3 * S + 3;
+      const size_t smem = sizeof(double) * ((size_t)reclen16 + (size_t)nrows * 128) + sizeof(uint32_t) * (size_t)nrows;
+      if (jrec_len(CI, S) == reclen && smem <= 100 * 1024) {
+        static const cudaError_t attr = cudaFuncSetAttribute(k_hmsg_bulk<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (attr == cudaSuccess) {
+          k_hmsg_bulk<CI><<<grid, 128, smem, b->stream>>>(a, reclen16);
+          b->launches++;
+          return check_launch("k_hmsg_bulk");
+        }
+      }
+    }
+  }
   if (reclen * 8 > 40 * 1024) reclen = 0;  // (records beyond the default dynamic shared memory: global loads)
-  const size_t smem = sizeof(double) * (size_t)reclen;
+  const size_t smem = reclen ? sizeof(double) * (size_t)reclen + sizeof(int32_t) * 2 * PGBP_MAX_DIM : 0;
   if (hmsg_chunk() == 4) k_hmsg<CI, 4><<<grid, 128, smem, b->stream>>>(a, reclen);
   else k_hmsg<CI, 8><<<grid, 128, smem, b->stream>>>(a, reclen);
 #endif
@@ -706,7 +883,7 @@ int shared_propagate(pgbp_batch* b, const MsgDesc& md_plan, uint32_t opts, int32
   ja.msgs = jb->d_one;
   ja.cache = b->jcache_one;
   ja.cache_off = b->d_zero64;
-  ja.stride = jrec_len(PGBP_MAX_DIM, 0) + (int64_t)PGBP_MAX_DIM * PGBP_MAX_DIM;
+  ja.stride = jrec_one_len();
   PGBP_TRY(launch_jmsg(b, ja, 1, md_plan.mF, b->stream));
   HArgs ha = make_hargs(b, b->calflag ? opts : (opts & ~PGBP_CAL_RESIDNORM), ref_base);
   ha.msgs = b->d_one;
@@ -796,8 +973,7 @@ int shared_create(pgbp_batch* b) {
       PGBP_TRY(salloc(b, &b->jcache[td], (size_t)off[n] * (size_t)b->ngroups));
       PGBP_TRY(stream_sync(b->stream));  // rm / off are locals
     }
-  const int64_t onelen = jrec_len(PGBP_MAX_DIM, 0) + (int64_t)PGBP_MAX_DIM * PGBP_MAX_DIM;
-  PGBP_TRY(salloc(b, &b->jcache_one, (size_t)onelen * (size_t)b->ngroups));
+  PGBP_TRY(salloc(b, &b->jcache_one, (size_t)jrec_one_len() * (size_t)b->ngroups));
   PGBP_TRY(salloc(b, &b->d_zero64, 1));
   PGBP_TRY(dev_memset(b->d_zero64, 0, sizeof(int64_t), b->stream));
   return stream_sync(b->stream);

@@ -1326,16 +1326,18 @@ def test_shared_precision_layout_memory_and_rows(backend):
     assert (h_own, g_own) == case.plan.belief_slot(2)[1:]
 
 
+@pytest.mark.parametrize("B", [6, 200])
 @pytest.mark.parametrize("backend", BACKENDS)
-def test_shared_precision_large_shapes_and_single_messages(backend):
+def test_shared_precision_large_shapes_and_single_messages(backend, B):
     # p = 16 on a small synthetic level-1 network (sender dimensions 16 / 32 / 48: the compile-time I = 16 / 32 element
     # kernels and the warp-cooperative group kernel on 48 x 48 matrices), and the single-message paths
-    # (propagate_belief!, regularizebeliefs_onschedule!) -- everything bit-identical to an ordinary batch
+    # (propagate_belief!, regularizebeliefs_onschedule!) -- everything bit-identical to an ordinary batch.
+    # B = 200: on the GPU the element pass of the I = 16 / 32 messages goes through the bulk-copy kernel (k_hmsg_bulk:
+    # blocks of 128 elements, the second one ragged)
     lib = get_lib(backend)
     import bench
     w = bench.C5(ntips=60, nretic=6)
     d = w.d
-    B = 6
     params, tips = w.inputs(B, 0)
     plan = pgbp_b200.ClusterGraphPlan(d["nclusters"], d["belief_dim"], d["sepset_clusters"], d["upind"], d["trees"],
                                       d["ntraits"], d["families"], lib)
@@ -1472,6 +1474,38 @@ def test_shared_precision_wide_network_two_groups(backend):
         succ, iscal = bt.calibrate(None, 1)
         out[name] = (succ, iscal, bt.status(), bt.integratebelief(root)[1], bt.factored_energy(),
                      [bt.get_belief(j) for j in (1, 17, root, plan.nclusters + 5)])
+    a, s_ = out["own"], out["shared"]
+    assert a[0].all() and all(np.array_equal(a[k], s_[k]) for k in range(5))
+    for x, y in zip(a[5], s_[5]):
+        for u, v in zip(x, y):
+            assert np.array_equal(u, v)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_shared_precision_groups_of_128_elements(backend):
+    # two parameter vectors x 128 data sets, p = 8 (integrated dimensions 8 / 16): every block of 128 elements lies
+    # inside one group, which is the condition for the bulk-copy element pass on the GPU (k_hmsg_bulk), here with
+    # residual tracking and two iterations (second traversal reads non-zero sepsets); bit-identical to own-J batches
+    lib = get_lib(backend)
+    import bench
+    w = bench.C4(ntips=40, nretic=4, p=8)
+    d = w.d
+    nth, nd = 2, 128
+    B = nth * nd
+    params, _ = w.inputs(nth, 0)
+    tips = w.synth.simulate_tips(d, lambda v, k: np.eye(8), nd, 7)
+    plan = pgbp_b200.ClusterGraphPlan(d["nclusters"], d["belief_dim"], d["sepset_clusters"], d["upind"], d["trees"],
+                                      d["ntraits"], d["families"], lib)
+    root = d["root_cluster"] + 1
+    out = {}
+    for name, group in (("own", 0), ("shared", nd)):
+        bt = pgbp_b200.BatchedClusterGraphBelief(plan, B, shared_precision_group=group)
+        bt.assignfactors(params, tips, ncolors=w.ncolors, pairing="product")
+        succ, iscal = bt.calibrate(None, 2, update_residualkldiv=True)
+        out[name] = (succ, iscal, bt.status(), bt.integratebelief(root)[1], bt.factored_energy(),
+                     [bt.get_belief(j) for j in (1, 5, root, plan.nclusters + 3)]
+                     + [bt.get_residual(plan.nclusters + 1 + j, plan.sepset_clusters[j][s] + 1)
+                        for j in (0, 2) for s in (0, 1)])
     a, s_ = out["own"], out["shared"]
     assert a[0].all() and all(np.array_equal(a[k], s_[k]) for k in range(5))
     for x, y in zip(a[5], s_[5]):
