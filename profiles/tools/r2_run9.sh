@@ -6,7 +6,7 @@ T=r2_run9
 L=phylogaussianbeliefprop.jl_b200/lib
 timeout 900 python -m pytest tests -m gpu -x -q -k "shared" > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest.log
 timeout 900 python bench.py --workload c5s --steps 3 --warmup 3 --no-others --no-cpu > gpurun_out/${T}_c5s_bulk.json 2> gpurun_out/${T}_c5s_bulk.err; echo "rc=$?" >> gpurun_out/${T}_c5s_bulk.err
-PGBP_HMSG_BULK=0 timeout 900 python bench.py --workload c5s --steps 3 --warmup 3 --no-others --no-cpu --e2e-batches 0 > gpurun_out/${T}_c5s_mb4.json 2> gpurun_out/${T}_c5s_mb4.err; echo "rc=$?" >> gpurun_out/${T}_c5s_mb4.err
+PGBP_HMSG_BULK=0 timeout 900 python bench.py --workload c5s --steps 3 --warmup 3 --no-others --no-cpu > gpurun_out/${T}_c5s_mb4.json 2> gpurun_out/${T}_c5s_mb4.err; echo "rc=$?" >> gpurun_out/${T}_c5s_mb4.err
 for mb in 3 5; do
 PGBP_B200_LIB=$PWD/$L/libpgbp_b200_mb$mb.so timeout 900 python bench.py --workload c5s --steps 3 --warmup 3 --no-others --no-cpu > gpurun_out/${T}_c5s_mb$mb.json 2> gpurun_out/${T}_c5s_mb$mb.err; echo "rc=$?" >> gpurun_out/${T}_c5s_mb$mb.err
 done
