@@ -616,7 +616,13 @@ static int launch_jmsg(pgbp_batch* b, JArgs a, int nmsg, int maxM, pgbp_stream_t
 #else
     dim3 grid((unsigned)n, (unsigned)std::min<int64_t>(c.G, 65535));
     const size_t smem = sizeof(double) * (size_t)(tri(maxM) + 1 + 4) + 2 * (size_t)tri(maxM) + 8;
-    if (tri(maxM) >= 256) k_jmsg<128><<<grid, 128, smem, stream>>>(c, maxM);  // sender dimension >= 23
+    // sender dimension >= 23: a 128-thread block per (message, group) shortens the chain of dependent rank-1 updates
+    // -- the right trade on narrow levels, where that chain IS the run time.  On wide levels it is the wrong one:
+    // the block version spends 29.5k warp instructions per 32 x 32 message (ncu: issue slots 81 % busy, all 2,048
+    // thread slots of an SM taken, so the element pass on the other stream cannot overlap) against ~4.5k for one warp.
+    const char* we = getenv("PGBP_JMSG_WIDE");  // (read per call: a test switches it)
+    const int64_t wide = we ? atoll(we) : 1024;
+    if (tri(maxM) >= 256 && (int64_t)n * c.G < wide) k_jmsg<128><<<grid, 128, smem, stream>>>(c, maxM);
     else k_jmsg<32><<<grid, 32, smem, stream>>>(c, maxM);
 #endif
     b->launches++;

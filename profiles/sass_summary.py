@@ -52,7 +52,31 @@ def main(rep):
                 st[h[i]] += int(r[i] or 0)
         tt = max(1, sum(st.values()))
         print("   stalls: " + ", ".join(f"{n[6:]} {100 * v / tt:.0f}%" for n, v in st.most_common(7)))
+        if TOP:
+            # the TOP hottest SASS lines (by samples) with every non-zero memory column: which loads cost the traffic
+            mem = [i for i, x in enumerate(h) if any(w in x for w in ("Sector", "Bytes", "Access", "Requests"))]
+            print("   memory columns: " + "; ".join(h[i] for i in mem))
+            for r in sorted(k["rows"], key=lambda r: -int(r[isamp]))[:TOP]:
+                extra = ", ".join(f"{h[i]}={r[i]}" for i in mem if r[i] not in ("", "0"))
+                print(f"   {r[0][-6:]} samples {r[isamp]:>6} exec {r[ie]:>9}  {r[isrc][:70]}  {extra}")
+            # totals of the memory columns over global loads / stores
+            for pref in ("LDG", "LD.", "STG", "ST."):
+                tot_m = collections.Counter()
+                for r in k["rows"]:
+                    f = r[isrc].split()
+                    op = f[1] if f[0].startswith("@") else f[0]
+                    if op.startswith(pref):
+                        for i in mem:
+                            try:
+                                tot_m[h[i]] += float(r[i] or 0)
+                            except ValueError:
+                                pass
+                if tot_m:
+                    print(f"   {pref}* totals: " + ", ".join(f"{n}={v:.3g}" for n, v in tot_m.items() if v))
 
 
+TOP = 0
 if __name__ == "__main__":
+    if len(sys.argv) > 2:
+        TOP = int(sys.argv[2])
     main(sys.argv[1])

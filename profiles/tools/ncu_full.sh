@@ -5,7 +5,7 @@
 TAG=$1; RX=$2; SKIP=$3; CNT=$4; shift 4
 REP=/tmp/${TAG}.ncu-rep
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$RX" -s $SKIP -c $CNT -f -o /tmp/${TAG} python bench.py "$@" > gpurun_out/${TAG}_ncu.log 2>&1
-python profiles/sass_summary.py $REP > gpurun_out/${TAG}_full.txt 2>&1
+python profiles/sass_summary.py $REP ${NCU_TOP:-0} > gpurun_out/${TAG}_full.txt 2>&1
 ncu -i $REP --page raw --csv 2>/dev/null | python -c "
 import csv, sys
 rows = list(csv.reader(sys.stdin))

@@ -1326,14 +1326,17 @@ def test_shared_precision_layout_memory_and_rows(backend):
     assert (h_own, g_own) == case.plan.belief_slot(2)[1:]
 
 
-@pytest.mark.parametrize("B", [6, 200])
+@pytest.mark.parametrize("B,jmsg_wide", [(6, None), (200, None), (6, "1")])
 @pytest.mark.parametrize("backend", BACKENDS)
-def test_shared_precision_large_shapes_and_single_messages(backend, B):
+def test_shared_precision_large_shapes_and_single_messages(backend, B, jmsg_wide, monkeypatch):
     # p = 16 on a small synthetic level-1 network (sender dimensions 16 / 32 / 48: the compile-time I = 16 / 32 element
     # kernels and the warp-cooperative group kernel on 48 x 48 matrices), and the single-message paths
     # (propagate_belief!, regularizebeliefs_onschedule!) -- everything bit-identical to an ordinary batch.
     # B = 200: on the GPU the element pass of the I = 16 / 32 messages goes through the bulk-copy kernel (k_hmsg_bulk:
-    # blocks of 128 elements, the second one ragged)
+    # blocks of 128 elements, the second one ragged).  PGBP_JMSG_WIDE=1: the group pass takes the one-warp kernel for
+    # every launch (what it does on its own from 1,024 (message, group) pairs per launch upwards)
+    if jmsg_wide:
+        monkeypatch.setenv("PGBP_JMSG_WIDE", jmsg_wide)
     lib = get_lib(backend)
     import bench
     w = bench.C5(ntips=60, nretic=6)
