@@ -249,7 +249,8 @@ int32_t pgbp_batch_create(const pgbp_plan* plan, int64_t B, int32_t device, uint
 }
 
 // ld_align: row pitch granularity in elements (32 = 256-byte rows; the group batch of a shared-precision batch
-// uses 4: it is addressed per (message, group), not per warp of elements)
+// uses 4, or 1 below four groups: it is addressed per (message, group), not per warp of elements, and with ONE group
+// a pitch of 4 would leave 8 useful bytes in every 32-byte sector -- the group pass of C5 was DRAM-bound on that)
 static int batch_create_impl(const pgbp_plan* plan, int64_t B, int64_t group_size, int32_t device, uint32_t flags,
                              int64_t ld_align, pgbp_batch** out) {
   if (!plan || !out || B <= 0) PGBP_FAIL(PGBP_EINVAL, "bad arguments");
@@ -276,7 +277,7 @@ static int batch_create_impl(const pgbp_plan* plan, int64_t B, int64_t group_siz
     // shared-precision batch: h, g per element here (compact rows), every J row once per group in `jb`
     PGBP_TRY(shared_create(b.get()));
     pgbp_batch* jb = nullptr;
-    PGBP_TRY(batch_create_impl(plan, B / group_size, 0, device, flags, 4, &jb));
+    PGBP_TRY(batch_create_impl(plan, B / group_size, 0, device, flags, B / group_size >= 4 ? 4 : 1, &jb));
     b->jb = jb;
     PGBP_TRY(pgbp_batch_set_stream(jb, (void*)b->stream));  // one stream, program order
     b->device_bytes += jb->device_bytes;

@@ -712,6 +712,41 @@ struct AssignFast {
         juc[(int64_t)(NJ + 1) * jus] = 0.0;
       }
       }
+      if constexpr (SH) {
+        // Tip family (the node itself observed, its one parent free) on the element side of a shared-precision batch:
+        // the same operations as the general code below, row by row -- j z is consumed as it is produced instead of
+        // living in an array next to z and sixteen loads in flight (ncu on C5: the 96-register kernel spilled 66
+        // local stores per warp, and those, not the h rows, were half of its DRAM writes)
+        if (nm == 2 && F.mem_pos[k0] < 0 && F.mem_pos[k0 + 1] >= 0) {
+          const int row = F.node_datarow[v];
+          const int pa = F.mem_pos[k0 + 1];
+          const bool first = (fh >> 1) & 1;
+          double z[P];
+#pragma unroll
+          for (int t = 0; t < P; t++) z[t] = 0.0 + 1.0 * td[(int64_t)(row * P + t) * ldd];
+#pragma unroll
+          for (int t = 0; t < P; t++) if (z[t] != z[t]) status_fail(gen.status, e, PGBP_STATUS(0x7ffffa, t + 1));
+          const uint32_t ld8 = (uint32_t)(ld * 8);
+          char* stb = (char*)st;
+          double quad = 0.0;
+#pragma unroll
+          for (int r = 0; r < P; r++) {
+            double s = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < P; cc++) s += PGBP_JU(r, cc) * z[cc];
+            quad += z[r] * s;
+            double* dh = kaddr(stb, (uint32_t)(hs + pa + r), ld8);
+            if (first) *dh = 0.0 - (-1.0) * s;
+            else *dh = *dh - (-1.0) * s;
+#if defined(__CUDA_ARCH__)
+            asm volatile("" ::: "memory");  // keep the loads of row r + 1 behind the store of row r
+#endif
+          }
+          gv -= 0.5 * quad;
+          g += gv;
+          continue;
+        }
+      }
       // evidence: z = sum over fixed members of c_a * value_a
       bool anyfixed = false;
       double z[P], jz[P];
