@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(128, (CI <= 16 ? 3 : 2)) k_hmsg_bulk(HArgs a, 
 // Records are padded to whole 128-byte lines: a line never holds parts of two records, so reading a record after
 // its flag cannot see a stale L1 line from an earlier read of its neighbour.
 #define PGBP_SW_WIDE 8     // widest step (messages) of a walk run
-#define PGBP_SW_MINRUN 8   // shortest run worth a walk launch
+#define PGBP_SW_MINRUN 4   // shortest run worth a walk launch (C2's clique tree: 7 levels per direction)
 #ifndef PGBP_HOST_EMUL
 __global__ void __launch_bounds__(32 * PGBP_SW_WIDE) k_jwalk(JArgs a, const int32_t* __restrict__ step_off, int s0, int s1,
                                                             unsigned* flags, int maxM) {
@@ -550,8 +550,14 @@ __global__ void __launch_bounds__(32 * PGBP_SW_WIDE) k_jwalk(JArgs a, const int3
   }
 }
 
-template <int CH>
-__global__ void __launch_bounds__(128) k_hwalk(HArgs a, const int32_t* __restrict__ step_off, int s0, int s1,
+// (one out-of-line body per shape: inlined into one switch the nine small shapes cost 2 KB of spills and a 1 KB frame)
+template <int CI, int CH>
+__device__ __noinline__ void hmsg_call(const HArgs& a, int m, int64_t e) { hmsg_thread<CI, CH>(a, m, e); }
+
+// SMALL: every message of the run integrates at most 8 variables (C2-like graphs): exact small shapes, 128 registers,
+// four resident blocks per SM; otherwise the I = 0 / 16 / 32 shapes of the p = 16 workloads at 255 registers.
+template <int CH, bool SMALL>
+__global__ void __launch_bounds__(128, (SMALL ? 4 : 1)) k_hwalk(HArgs a, const int32_t* __restrict__ step_off, int s0, int s1,
                                                   const unsigned* flags, unsigned* hcount, unsigned* done_blocks, int64_t G) {
   __shared__ unsigned need;
   __shared__ int timed_out;
@@ -577,11 +583,25 @@ __global__ void __launch_bounds__(128) k_hwalk(HArgs a, const int32_t* __restric
       const int first = step_off[s], end = step_off[s + 1];
       for (int m = first; m < end; m++) {
         const int I = a.msgs[m].mF - a.msgs[m].s;
-        switch (I) {
-          case 0: hmsg_thread<0, CH>(a, m, e); break;
-          case 16: hmsg_thread<16, CH>(a, m, e); break;
-          case 32: hmsg_thread<32, CH>(a, m, e); break;
-          default: hmsg_thread<-1, CH>(a, m, e); break;
+        if constexpr (SMALL) {
+          switch (I) {
+            case 0: hmsg_call<0, CH>(a, m, e); break;
+            case 1: hmsg_call<1, CH>(a, m, e); break;
+            case 2: hmsg_call<2, CH>(a, m, e); break;
+            case 3: hmsg_call<3, CH>(a, m, e); break;
+            case 4: hmsg_call<4, CH>(a, m, e); break;
+            case 5: hmsg_call<5, CH>(a, m, e); break;
+            case 6: hmsg_call<6, CH>(a, m, e); break;
+            case 7: hmsg_call<7, CH>(a, m, e); break;
+            default: hmsg_call<8, CH>(a, m, e); break;
+          }
+        } else {
+          switch (I) {
+            case 0: hmsg_call<0, CH>(a, m, e); break;
+            case 16: hmsg_thread<16, CH>(a, m, e); break;
+            case 32: hmsg_thread<32, CH>(a, m, e); break;
+            default: hmsg_thread<-1, CH>(a, m, e); break;
+          }
         }
       }
     }
@@ -616,12 +636,12 @@ static int launch_jmsg(pgbp_batch* b, JArgs a, int nmsg, int maxM, pgbp_stream_t
 #else
     dim3 grid((unsigned)n, (unsigned)std::min<int64_t>(c.G, 65535));
     const size_t smem = sizeof(double) * (size_t)(tri(maxM) + 1 + 4) + 2 * (size_t)tri(maxM) + 8;
-    // sender dimension >= 23: a 128-thread block per (message, group) shortens the chain of dependent rank-1 updates
-    // -- the right trade on narrow levels, where that chain IS the run time.  On wide levels it is the wrong one:
-    // the block version spends 29.5k warp instructions per 32 x 32 message (ncu: issue slots 81 % busy, all 2,048
-    // thread slots of an SM taken, so the element pass on the other stream cannot overlap) against ~4.5k for one warp.
+    // sender dimension >= 23: a 128-thread block per (message, group) shortens the chain of dependent rank-1 updates.
+    // PGBP_JMSG_WIDE=n takes the one-warp kernel instead from n (message, group) pairs per launch upwards: 4.5k
+    // instead of 29.5k warp instructions per 32 x 32 message, but measured no faster on C5's wide levels (138.9 vs
+    // 137.1 ms per step) -- the group pass is bound by its scattered 8-byte accesses, not by instructions.
     const char* we = getenv("PGBP_JMSG_WIDE");  // (read per call: a test switches it)
-    const int64_t wide = we ? atoll(we) : 1024;
+    const int64_t wide = we ? atoll(we) : INT64_MAX;
     if (tri(maxM) >= 256 && (int64_t)n * c.G < wide) k_jmsg<128><<<grid, 128, smem, stream>>>(c, maxM);
     else k_jmsg<32><<<grid, 32, smem, stream>>>(c, maxM);
 #endif
@@ -784,8 +804,12 @@ int shared_run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_
   std::vector<int> walk_end(tv.nsteps + 1, 0);
 #ifndef PGBP_HOST_EMUL
   {
-    static const bool walk_on = [] { const char* e = getenv("PGBP_SHARED_WALK"); return !(e && atoi(e) == 0); }();
-    const bool ok = walk_on && !(opts & PGBP_CAL_RESIDKLDIV) && (b->B + 127) / 128 <= 64 && b->ngroups <= 16;
+    // PGBP_SHARED_WALK: 0 = per-step launches only, 2 = walks only where both run side by side (<= 64 element blocks)
+    static const int walk_mode = [] { const char* e = getenv("PGBP_SHARED_WALK"); return e ? atoi(e) : 1; }();
+    const bool walk_on = walk_mode == 1 || (walk_mode == 2 && (b->B + 127) / 128 <= 64);
+    // (<= 64 element blocks: the two walks run side by side, the element walk spinning on the group walk's counters;
+    // larger batches: the element walk is launched behind the group walk's event -- same kernels, nothing to spin on)
+    const bool ok = walk_on && !(opts & PGBP_CAL_RESIDKLDIV) && b->ngroups <= 16;
     for (int s = 0; ok && s < tv.nsteps;) {
       int t = s;
       while (t < tv.nsteps && tv.step_off[t + 1] - tv.step_off[t] <= PGBP_SW_WIDE) t++;
@@ -844,8 +868,17 @@ int shared_run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_
       c.msgs = b->d_msgs[td];
       c.cache_off = b->d_jcache_off[td];
       const unsigned grid = (unsigned)((b->B + 127) / 128);
-      if (hmsg_chunk() == 4) k_hwalk<4><<<grid, 128, 0, b->stream>>>(c, b->jb->d_step_off[td], g.step, s1, b->d_walkflags[td], b->d_walkcount[td], b->d_walkcount[td] + 1, b->ngroups);
-      else k_hwalk<8><<<grid, 128, 0, b->stream>>>(c, b->jb->d_step_off[td], g.step, s1, b->d_walkflags[td], b->d_walkcount[td], b->d_walkcount[td] + 1, b->ngroups);
+      if (grid > 64) {  // every SM may be taken by spinning blocks: order the element walk after the whole group walk
+        PGBP_CUDA(cudaStreamWaitEvent(b->stream, (cudaEvent_t)b->jstep_events[s1 - 1], 0));
+        waited = s1 - 1;
+      }
+      int maxI = 0;
+      for (int k = tv.step_off[g.step]; k < tv.step_off[s1]; k++) maxI = std::max(maxI, tv.msgs[k].mF - tv.msgs[k].s);
+#define PGBP_HWALK(CH_, SM_) k_hwalk<CH_, SM_><<<grid, 128, 0, b->stream>>>(c, b->jb->d_step_off[td], g.step, s1, b->d_walkflags[td], b->d_walkcount[td], b->d_walkcount[td] + 1, b->ngroups)
+      if (maxI <= 8) PGBP_HWALK(4, true);
+      else if (hmsg_chunk() == 4) PGBP_HWALK(4, false);
+      else PGBP_HWALK(8, false);
+#undef PGBP_HWALK
       b->launches++;
       PGBP_TRY(check_launch("k_hwalk"));
       walked_until = s1;

@@ -1514,3 +1514,33 @@ def test_shared_precision_groups_of_128_elements(backend):
     for x, y in zip(a[5], s_[5]):
         for u, v in zip(x, y):
             assert np.array_equal(u, v)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_shared_precision_large_batch_one_group(backend):
+    # 8,320 replicates under one parameter vector on the lazaridis clique tree (p = 3): 65 blocks of 128 elements, so on
+    # the GPU each traversal is one group-walk launch and one element-walk launch behind its event (the walks of
+    # batches of <= 64 blocks run side by side instead, covered by the small-batch tests); bit-identical to own-J batches
+    lib = get_lib(backend)
+    rng = np.random.default_rng(77)
+    taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
+    p, B = 3, 8320
+    A = rng.normal(size=(p, p))
+    R = A @ A.T / p + 0.1 * np.eye(p)
+    mu = rng.normal(size=p)
+    data = rng.normal(size=(B, 7, p))
+    model = M.MvFullBrownianMotion(R, mu)
+    case = Case(GOLD["lazaridis"], "cliquetree", data[0], taxa, model, lib, order_hint=GOLD["lazaridis_cluster_labels"])
+    params = pgbp_b200.bm_params([R], mu)[None, :]
+    out = {}
+    for name, group in (("own", 0), ("shared", B)):
+        bt = pgbp_b200.BatchedClusterGraphBelief(case.plan, B, shared_precision_group=group)
+        bt.assignfactors(params, data, pairing="product")
+        succ, iscal = bt.calibrate(case.sched, 2)
+        out[name] = (succ, iscal, bt.status(), bt.integratebelief(case.sched[0][2][0])[1], bt.factored_energy(),
+                     [bt.get_belief(j) for j in range(1, len(case.b) + 1)])
+    a, s_ = out["own"], out["shared"]
+    assert a[0].all() and all(np.array_equal(a[k], s_[k]) for k in range(5))
+    for x, y in zip(a[5], s_[5]):
+        for u, v in zip(x, y):
+            assert np.array_equal(u, v)
