@@ -95,7 +95,7 @@ class C2S(C2):
                 "ONE parameter vector, clique tree, SHARED-PRECISION batch (J stored once per group, h and g per element), "
                 "calibrate! (post+pre order, residual tracking) + integratebelief! [BASELINE configs[1], shared-J variant "
                 "of SURVEY 8f-1: own byte count 8*(m_F + 1 + 4*(s+1) + s) per message]")
-    kernel_text = "k_message<i,s> family, shared-precision mode (32 messages of a calibration)"
+    kernel_text = "k_hmsg<I> family (element pass of the 32 messages of a calibration; the group pass k_jmsg runs once per GPU)"
 
     def cost(self, plan):
         return shared_cost(self, plan, (0, 1))
@@ -292,7 +292,7 @@ class C5S(C5):
                 "x (1 + 0.001 k)), assignfactors! + calibrate! (post+pre order) + integratebelief!(root) "
                 "[BASELINE configs[4], shared-J path of SURVEY 8f-1: own byte count 8*(m_F + 1 + 4*(s+1)) per message]")
     step_text = "assign_factors (K1: J once, h / g per replicate) + calibrate (419,994 messages: group pass + element pass) + integrate(root)"
-    kernel_text = "k_hmsg<I> family (element pass of the 419,994 messages; the group pass k_jmsg runs once per GPU)"
+    kernel_text = "k_hmsg_bulk<I> / k_hmsg<I> family (element pass of the 419,994 messages; the group pass k_jmsg runs once per GPU)"
 
     def inputs(self, B, rank):
         params, base = C5.inputs(self, min(B, self.nsim), rank)

@@ -1518,9 +1518,9 @@ def test_shared_precision_groups_of_128_elements(backend):
 
 @pytest.mark.parametrize("backend", BACKENDS)
 def test_shared_precision_large_batch_one_group(backend):
-    # 8,320 replicates under one parameter vector on the lazaridis clique tree (p = 3): 65 blocks of 128 elements, so on
-    # the GPU each traversal is one group-walk launch and one element-walk launch behind its event (the walks of
-    # batches of <= 64 blocks run side by side instead, covered by the small-batch tests); bit-identical to own-J batches
+    # 8,320 replicates under one parameter vector on the lazaridis clique tree (p = 3): 65 blocks of 128 elements, the
+    # first size at which the walk kernels step aside for per-step launches (and, with PGBP_SHARED_WALK=1, the element
+    # walk runs behind the group walk's event); bit-identical to own-J batches
     lib = get_lib(backend)
     rng = np.random.default_rng(77)
     taxa = ["Mbuti", "Onge", "Karitiana", "MA1", "Loschbour", "European", "Stuttgart"]
