@@ -748,7 +748,8 @@ def measure(w, args, ctx, steps, headline, cpu_seconds, e2e_steps_cap, min_regio
     step = finish = None
     torch.cuda.empty_cache()
     free_b, total_b = torch.cuda.mem_get_info()
-    nb_e2e = max(1, min(args.e2e_batches, 1 + int(free_b / (bt.device_bytes() * 1.1))))
+    # (per extra batch: its state plus the device-side staging of one step's inputs, which device_bytes() may not hold yet)
+    nb_e2e = max(1, min(args.e2e_batches, 1 + int(free_b / (bt.device_bytes() * 1.1 + 2.5 * big.nbytes))))
     bts = [bt]
     for _ in range(nb_e2e - 1):
         bts.append(pgbp_b200.BatchedClusterGraphBelief(plan, B, device=local, factors=w.residuals, residuals=w.residuals,
@@ -777,14 +778,21 @@ def measure(w, args, ctx, steps, headline, cpu_seconds, e2e_steps_cap, min_regio
             succ = b_.propagate_1traversal_postorder(0, update_residualnorm=False)
         results[i] = b_.integratebelief(root, want_mu=False)[1]  # D2H of the result
 
+    errors = []
+
     def worker(i, n):
         torch.cuda.set_device(local)
-        for _ in range(n):
-            e2e_step(i)
+        try:
+            for _ in range(n):
+                e2e_step(i)
+        except Exception as ex:  # re-raised on the main thread after the join
+            errors.append(ex)
 
     def run_e2e(n):
         if len(bts) == 1:
             worker(0, n)
+            if errors:
+                raise errors[0]
             return
         nb = len(bts)
         ths = [threading.Thread(target=worker, args=(i, n // nb + (i < n % nb))) for i in range(nb)]
@@ -792,6 +800,8 @@ def measure(w, args, ctx, steps, headline, cpu_seconds, e2e_steps_cap, min_regio
             t.start()
         for t in ths:
             t.join()
+        if errors:
+            raise errors[0]
     run_e2e(2 * len(bts))
     barrier()
     t0e = time.perf_counter()
