@@ -146,7 +146,15 @@ PGBP_HD void jmsg_body(const JArgs& a, int mi, int64_t g, const W& w, double* A,
   const int32_t* __restrict__ gat = a.tab + md.gat;
   const int32_t* __restrict__ sca = a.tab + md.sca;
   double* rec = I > 0 ? a.cache + g * a.stride + a.cache_off[mi] : nullptr;
-  for (int q = w.lane; q < SM; q += W::n) A[q] = st[(md.fJ + gat[q]) * ld];
+  for (int q0 = w.lane; q0 < SM; q0 += 4 * W::n) {  // four independent (table, entry) load pairs in flight per lane
+    double v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (q0 + j * W::n < SM) v[j] = st[(md.fJ + gat[q0 + j * W::n]) * ld];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (q0 + j * W::n < SM) A[q0 + j * W::n] = v[j];
+  }
   w.sync();
   if (I > 0) {
     bool z = true;  // "Ji = Jki = 0", src/beliefupdates.jl:62-66 (the h_I part of the test is the elements')
@@ -192,18 +200,19 @@ PGBP_HD void jmsg_body(const JArgs& a, int mi, int64_t g, const W& w, double* A,
   const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;  // lazy sepset zero: the old sepset value is 0, not loaded
   double* rs = a.resid ? a.resid + g : nullptr;
   double maxJ = 0.0;
-  for (int c = 0; c < S; c++)
-    for (int r = w.lane; r <= c; r += W::n) {
-      const int q = pk(r, c);
-      const double nv = A[pk(I + r, I + c)];
-      double* sp = st + (md.sJ + q) * ld;
-      double* tp = st + (md.tJ + sca[q]) * ld;
-      const double d = nv - (sz ? 0.0 : *sp);
-      *sp = nv;
-      *tp = *tp + d;
-      if (rs) rs[(md.rJ + q) * ld] = d;
-      absmax(maxJ, d);
-    }
+  // (flattened over the packed entries: one pass of dependent global round trips per W::n entries instead of one per
+  // column -- on narrow levels these round trips ARE the group pass: C2S spent 17 us per level here)
+  for (int q = w.lane; q < tri(S); q += W::n) {
+    const int r = rc[2 * q], c = rc[2 * q + 1];
+    const double nv = A[pk(I + r, I + c)];
+    double* sp = st + (md.sJ + q) * ld;
+    double* tp = st + (md.tJ + sca[q]) * ld;
+    const double d = nv - (sz ? 0.0 : *sp);
+    *sp = nv;
+    *tp = *tp + d;
+    if (rs) rs[(md.rJ + q) * ld] = d;
+    absmax(maxJ, d);
+  }
   maxJ = w.maxnan(maxJ);
   if (w.lane == 0 && (a.opts & PGBP_CAL_RESIDNORM) && a.calflag)
     a.calflag[(int64_t)md.dmsg * ld + g] = (S > 0 ? (maxJ / (double)S <= 1e-5) : true) ? 1 : 0;
