@@ -691,7 +691,8 @@ def measure(w, args, ctx, steps, headline, cpu_seconds, e2e_steps_cap, min_regio
     pe1.record(stream)
     barrier()
     t_probe = pe0.elapsed_time(pe1) / 3 * 1e-3
-    inner = int(min(256, max(1, np.ceil(min_region_s / max(steps * t_probe, 1e-9)))))
+    # (15 % margin: the three probe passes run a little slower than the steady state)
+    inner = int(min(256, max(1, np.ceil(1.15 * min_region_s / max(steps * t_probe, 1e-9)))))
     inner = int(ctx.max_over_ranks([inner])[0])
     nsteps = steps * inner
     sampler = ClockSampler(local) if (rank == 0 and headline) else None
