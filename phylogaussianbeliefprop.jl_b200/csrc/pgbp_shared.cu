@@ -220,8 +220,9 @@ PGBP_HD void jmsg_body(const JArgs& a, int mi, int64_t g, const W& w, double* A,
 
 // h, g part of one message for one element.  CI >= 0: compile-time integrated dimension (w in registers);
 // CI < 0: runtime (thread-local array).
-// CH: kept entries per streaming chunk (3 CH loads in flight per thread).  Measured on B200: CH = 4 (168 registers,
-// 3 blocks per SM) beats CH = 8 (254 registers): c5s 4,801 vs 4,227 calibrations/s, c2s 137.7 vs 130.9 M/s
+// CH: kept entries per streaming chunk (3 CH loads in flight per thread).  Measured on B200: CH = 4 beats CH = 8 (254
+// registers): c5s 4,801 vs 4,227 calibrations/s, c2s 137.7 vs 130.9 M/s at that stage; with CH = 4 the kernel is capped
+// at 128 registers for I <= 16 (4 blocks per SM: 166.5 ms per C5S step against 178.6 with 3 and 194.0 with 5)
 // STAGED (device only): the block staged the message's record and its two index tables in dynamic shared memory
 // (k_hmsg); they are read through the shared window (LDS with immediate offsets), not through generic pointers.
 template <int CI, int CH, bool STAGED = false>
