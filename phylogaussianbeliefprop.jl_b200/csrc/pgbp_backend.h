@@ -4,6 +4,7 @@
 // exercise the plan compiler, index tables and ABI without a GPU.  The Python
 // package never loads it (see _lib.py: it refuses to run without the CUDA .so).
 #pragma once
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -102,6 +103,18 @@ inline int set_device(int d) {
   PGBP_CUDA(cudaSetDevice(d));
   return 0;
 }
+// cudaFuncSetAttribute applies to the CURRENT device only: one flag per (kernel instantiation, device), so that a
+// process that drives several GPUs raises the dynamic shared-memory limit on each of them.  Returns true the first
+// time it is called on the current device.
+struct AttrOnce {
+  std::atomic<uint64_t> mask{0};
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    return (mask.fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+  }
+};
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) PGBP_FAIL(PGBP_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));

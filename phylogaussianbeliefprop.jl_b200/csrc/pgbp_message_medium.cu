@@ -30,20 +30,13 @@ static int launch_smem(pgbp_batch* b, const MsgArgs& a, int nmsg, int I, int S) 
   for (int m = 0; m < nmsg; m++)
     for (int64_t e = a.e0; e < a.B; e++) message_thread_rt<PGBP_MAX_DIM>(a, m, e);
 #else
-  static bool attr_done = false;  // per instantiation
-  static bool attr8_done = false;
+  static AttrOnce attr_done, attr8_done;  // per instantiation and device
   const bool s8 = EXACT && S <= 8 && MAXI <= 10;  // fully unrolled kept-block loops (register budget: I <= 10)
   const void* fn;
   if constexpr (EXACT) fn = s8 ? (const void*)k_message_smem<MAXI, 8> : (const void*)k_message_smem<MAXI, 0>;
   else fn = (const void*)k_message_smem_rt<MAXI>;
-  if (s8 && !attr8_done) {
+  if (s8 ? attr8_done.first() : attr_done.first())
     PGBP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_LIMIT));
-    attr8_done = true;
-  }
-  if (!s8 && !attr_done) {
-    PGBP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_LIMIT));
-    attr_done = true;
-  }
   if (a.ld * 8 >= ((int64_t)1 << 32)) PGBP_FAIL(PGBP_ESTATE, "batch too large for 32-bit row pitch");
   const size_t bytes = smem_block_bytes(I, S);
   dim3 grid((unsigned)((a.B - a.e0 + 31) / 32), (unsigned)nmsg);
@@ -73,10 +66,9 @@ static int launch_smem_mw(pgbp_batch* b, const MsgArgs& a, int nmsg, int S) {
   for (int m = 0; m < nmsg; m++)
     for (int64_t e = a.e0; e < a.B; e++) message_thread_rt<PGBP_MAX_DIM>(a, m, e);
 #else
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  static AttrOnce attr_done;  // per instantiation and device
+  if (attr_done.first()) {
     PGBP_CUDA(cudaFuncSetAttribute((const void*)k_message_smem_mw<I, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_MW_LIMIT));
-    attr_done = true;
   }
   if (a.ld * 8 >= ((int64_t)1 << 32)) PGBP_FAIL(PGBP_ESTATE, "batch too large for 32-bit row pitch");
   dim3 grid((unsigned)((a.B - a.e0 + 31) / 32), (unsigned)nmsg), block(32, NW);
@@ -99,10 +91,9 @@ static int launch_smem_mwp(pgbp_batch* b, const MsgArgs& a, int nmsg, int S) {
   for (int m = 0; m < nmsg; m++)
     for (int64_t e = a.e0; e < a.B; e++) message_thread_rt<PGBP_MAX_DIM>(a, m, e);
 #else
-  static bool attr_done = false;
-  if (!attr_done) {
+  static AttrOnce attr_done;
+  if (attr_done.first()) {
     PGBP_CUDA(cudaFuncSetAttribute((const void*)k_message_smem_mwp<I, NW, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_MW_LIMIT));
-    attr_done = true;
   }
   if (a.ld * 8 >= ((int64_t)1 << 32)) PGBP_FAIL(PGBP_ESTATE, "batch too large for 32-bit row pitch");
   dim3 grid((unsigned)((a.B - a.e0 + TILE - 1) / TILE), (unsigned)nmsg), block(32, NW);
@@ -120,10 +111,9 @@ static int launch_smem_tile(pgbp_batch* b, const MsgArgs& a, int nmsg, int I, in
   for (int m = 0; m < nmsg; m++)
     for (int64_t e = a.e0; e < a.B; e++) message_thread_rt<PGBP_MAX_DIM>(a, m, e);
 #else
-  static bool attr_done = false;
-  if (!attr_done) {
+  static AttrOnce attr_done;
+  if (attr_done.first()) {
     PGBP_CUDA(cudaFuncSetAttribute((const void*)k_message_smem_rt<32, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGBP_SMEM_MW_LIMIT));
-    attr_done = true;
   }
   const size_t bytes = sizeof(double) * TILE * (size_t)(I * (I + 1) / 2 + I * S + I);
   dim3 grid((unsigned)((a.B - a.e0 + TILE - 1) / TILE), (unsigned)nmsg);

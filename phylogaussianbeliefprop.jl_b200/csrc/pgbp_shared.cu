@@ -687,12 +687,11 @@ static int launch_hmsg_t(pgbp_batch* b, const HArgs& a, int nmsg, int reclen) {
       const int nrows = CI + 3 * S + 3;
       const size_t smem = sizeof(double) * ((size_t)reclen16 + (size_t)nrows * 128) + sizeof(uint32_t) * (size_t)nrows;
       if (jrec_len(CI, S) == reclen && smem <= 100 * 1024) {
-        static const cudaError_t attr = cudaFuncSetAttribute(k_hmsg_bulk<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        if (attr == cudaSuccess) {
-          k_hmsg_bulk<CI><<<grid, 128, smem, b->stream>>>(a, reclen16);
-          b->launches++;
-          return check_launch("k_hmsg_bulk");
-        }
+        static AttrOnce attr;  // per instantiation and device
+        if (attr.first()) PGBP_CUDA(cudaFuncSetAttribute(k_hmsg_bulk<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        k_hmsg_bulk<CI><<<grid, 128, smem, b->stream>>>(a, reclen16);
+        b->launches++;
+        return check_launch("k_hmsg_bulk");
       }
     }
   }
@@ -847,8 +846,8 @@ int shared_run_traversal(pgbp_batch* b, int tree, int dir, uint32_t opts, int32_
       int maxM = 0;
       for (int k = tv.step_off[s]; k < tv.step_off[s1]; k++) maxM = std::max(maxM, tv.msgs[k].mF);
       const size_t smem = sizeof(double) * (size_t)PGBP_SW_WIDE * (size_t)(tri(maxM) + 1) + 2 * (size_t)tri(maxM) + 16;
-      static bool attr_done = false;
-      if (!attr_done) { PGBP_CUDA(cudaFuncSetAttribute((const void*)k_jwalk, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_done = true; }
+      static AttrOnce attr_done;
+      if (attr_done.first()) PGBP_CUDA(cudaFuncSetAttribute((const void*)k_jwalk, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       k_jwalk<<<(unsigned)std::min<int64_t>(b->ngroups, 1024), 32 * PGBP_SW_WIDE, smem, js>>>(ja, b->jb->d_step_off[td], s, s1, b->d_walkflags[td], maxM);
       b->launches++;
       PGBP_TRY(check_launch("k_jwalk"));

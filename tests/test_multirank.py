@@ -145,3 +145,36 @@ def test_peer_gather_two_ranks_in_process():
         sharding.PeerGather(lib, 0, 0, 1, 4, connect=False).integrate_gather(bts[0], 1, 0)  # window shorter than the batch
     for c in comms:
         c.close()
+
+
+@pytest.mark.gpu
+def test_two_devices_in_one_process_raise_their_own_kernel_limits():
+    # The kernels that need more than 48 KB of dynamic shared memory (k_message_smem*, k_hmsg_bulk, k_jwalk) get their
+    # limit raised per DEVICE (cudaFuncSetAttribute applies to the current device only): a process that drives two
+    # GPUs, as the Julia wrapper may, must be able to run the same shapes on the second one.  p = 16 on a small
+    # level-1 network: ordinary batch (shared-memory kernels) and shared-precision batch (bulk-copy element pass) on
+    # device 0, then on device 1; identical results.
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import bench
+    from harness import get_lib
+    import pgbp_b200
+    lib = get_lib("cuda")
+    w = bench.C5(ntips=60, nretic=6)
+    d = w.d
+    B = 200
+    params, tips = w.inputs(B, 0)
+    plan = pgbp_b200.ClusterGraphPlan(d["nclusters"], d["belief_dim"], d["sepset_clusters"], d["upind"], d["trees"],
+                                      d["ntraits"], d["families"], lib)
+    root = d["root_cluster"] + 1
+    out = {}
+    for dev in (0, 1):
+        for group in (0, B):
+            bt = pgbp_b200.BatchedClusterGraphBelief(plan, B, device=dev, shared_precision_group=group)
+            bt.assignfactors(params, tips)
+            succ, _ = bt.calibrate(None, 1)
+            assert succ.all()
+            out[dev, group] = bt.integratebelief(root)[1]
+    assert np.array_equal(out[0, 0], out[1, 0]) and np.array_equal(out[0, B], out[1, B])
+    assert np.array_equal(out[0, 0], out[0, B])
