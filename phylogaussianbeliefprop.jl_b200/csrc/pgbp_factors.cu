@@ -747,6 +747,25 @@ struct AssignFast {
           continue;
         }
       }
+      if constexpr (SH) {
+        // Family without evidence (every member free: the internal nodes, half of a big network's clusters): the h
+        // segments this family writes first are zero, nothing else moves on the element side.  Same stores as the
+        // general code below, without its z / j z arrays.
+        bool nofixed = true;
+        for (int a = 0; a < nm; a++) if (F.mem_pos[k0 + a] < 0) nofixed = false;
+        if (nofixed) {
+          g += gv;
+          const uint32_t ld8 = (uint32_t)(ld * 8);
+          char* stb = (char*)st;
+          for (int a = 0; a < nm; a++) {
+            if (!((fh >> a) & 1)) continue;
+            const int pa = F.mem_pos[k0 + a];
+#pragma unroll
+            for (int t = 0; t < P; t++) *kaddr(stb, (uint32_t)(hs + pa + t), ld8) = 0.0;
+          }
+          continue;
+        }
+      }
       // evidence: z = sum over fixed members of c_a * value_a
       bool anyfixed = false;
       double z[P], jz[P];
