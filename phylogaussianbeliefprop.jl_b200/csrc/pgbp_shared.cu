@@ -146,26 +146,6 @@ PGBP_HD void jmsg_body(const JArgs& a, int mi, int64_t g, const W& w, double* A,
   const int32_t* __restrict__ gat = a.tab + md.gat;
   const int32_t* __restrict__ sca = a.tab + md.sca;
   double* rec = I > 0 ? a.cache + g * a.stride + a.cache_off[mi] : nullptr;
-  // The old sepset and target entries that divide! / mult! need at the very end are fetched NOW, next to the gather
-  // (up to PF entries per lane in registers): nothing writes them before this message does -- the messages of a step
-  // touch disjoint beliefs -- and on narrow levels every dependent global round trip saved is ~0.7 us of the chain.
-  constexpr int PF = 2;
-  const int SS = tri(S);
-  const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;  // lazy sepset zero: the old sepset value is 0, not loaded
-  const bool pf = SS <= PF * W::n;
-  double so[PF], to[PF];
-  if (pf) {
-#pragma unroll
-    for (int j = 0; j < PF; j++) {
-      const int q = w.lane + j * W::n;
-      so[j] = 0.0;
-      to[j] = 0.0;
-      if (q < SS) {
-        if (!sz) so[j] = st[(md.sJ + q) * ld];
-        to[j] = st[(md.tJ + sca[q]) * ld];
-      }
-    }
-  }
   for (int q0 = w.lane; q0 < SM; q0 += 4 * W::n) {  // four independent (table, entry) load pairs in flight per lane
     double v[4];
 #pragma unroll
@@ -217,26 +197,21 @@ PGBP_HD void jmsg_body(const JArgs& a, int mi, int64_t g, const W& w, double* A,
     }
   }
   // divide! / mult! / residual of the J part (src/beliefupdates.jl:579-587, 483-488, 646-647)
+  const bool sz = (a.opts & PGBP_OPT_SEPZERO) != 0;  // lazy sepset zero: the old sepset value is 0, not loaded
   double* rs = a.resid ? a.resid + g : nullptr;
   double maxJ = 0.0;
   // (flattened over the packed entries: one pass of dependent global round trips per W::n entries instead of one per
   // column -- on narrow levels these round trips ARE the group pass: C2S spent 17 us per level here)
-  auto entry = [&](int q, double sold, double told) {
+  for (int q = w.lane; q < tri(S); q += W::n) {
     const int r = rc[2 * q], c = rc[2 * q + 1];
     const double nv = A[pk(I + r, I + c)];
-    const double d = nv - sold;
-    st[(md.sJ + q) * ld] = nv;
-    st[(md.tJ + sca[q]) * ld] = told + d;
+    double* sp = st + (md.sJ + q) * ld;
+    double* tp = st + (md.tJ + sca[q]) * ld;
+    const double d = nv - (sz ? 0.0 : *sp);
+    *sp = nv;
+    *tp = *tp + d;
     if (rs) rs[(md.rJ + q) * ld] = d;
     absmax(maxJ, d);
-  };
-  if (pf) {
-#pragma unroll
-    for (int j = 0; j < PF; j++)
-      if (w.lane + j * W::n < SS) entry(w.lane + j * W::n, so[j], to[j]);
-  } else {
-    for (int q = w.lane; q < SS; q += W::n)
-      entry(q, sz ? 0.0 : st[(md.sJ + q) * ld], st[(md.tJ + sca[q]) * ld]);
   }
   maxJ = w.maxnan(maxJ);
   if (w.lane == 0 && (a.opts & PGBP_CAL_RESIDNORM) && a.calflag)
